@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- VQ-encoded patches/sec of the fused vector-quantisation hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): the standalone VectorQuantizer forward on 2^24
+synthetic patch vectors per GPU, repo-default codebook K=256, D=32 (z = 0.1*randn, seed
+1234+rank; codebook U(-1/K, 1/K), seed 0).  One step = one pass of the hot path over that
+batch: distance + argmin + gather + straight-through value + loss + histogram/perplexity
+(z_q (N,D) fp32 and int64 ids written; the (N,K) one-hot is not materialised -- SURVEY.md
+section 8(d)).  Weak scaling: every rank quantises its own shard, the codebook is replicated,
+the only collective is the K-element all-reduce of the code histogram.
+
+One JSON line on stdout (rank 0).  `value` = device-timed whole-job patches/s with inputs
+resident in HBM; `e2e` = the same through the host-buffer C-ABI call (pinned host arrays in,
+z_q + ids + scalars back on the host, copies inside the timed region); `roofline` = the
+dominant kernel against the measured HBM peak; `cpu_baseline` = the reference's op sequence
+on this box's host cores (oracle port, bounded sample).
+
+--impl reference times that CPU port alone (the reference is a Python/PyTorch program whose
+own files cannot travel to the GPU box) on the same config and metric.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_CODES, DIM, BETA = 256, 32, 0.25
+N_VECTORS = 1 << 24
+METRIC = "vq_encoded_patches_per_sec"
+UNIT = "patches/s"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def workload_config(n_gpus: int, n_rows: int) -> dict:
+    return {
+        "workload": f"VectorQuantizer.forward, K={K_CODES} D={DIM} (repo default), N={n_rows} vectors per GPU "
+                    f"(BASELINE configs[1])",
+        "codebook": "U(-1/K,1/K) seed 0", "inputs": "0.1*randn seed 1234+rank",
+        "outputs": "z_q fp32 (N,D) + int64 ids + loss + perplexity + histogram; no (N,K) one-hot",
+        "parallelism": f"batch-sharded x{n_gpus}, codebook replicated",
+        "l2": f"inputs larger than L2 ({n_rows * DIM * 4 / 2**20:.0f} MiB read per step)",
+    }
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------
+# clocks / throttle sampling during the timed regions
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int, period: float = 0.02):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._index, self._period = index, period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _reason_names(self, mask: int):
+        nv = self._nv
+        table = [("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"),
+                 ("hw_power_brake", "nvmlClocksThrottleReasonHwPowerBrakeSlowdown"),
+                 ("sync_boost", "nvmlClocksThrottleReasonSyncBoost"),
+                 ("app_clocks", "nvmlClocksThrottleReasonApplicationsClocksSetting")]
+        return [name for name, attr in table if mask & int(getattr(nv, attr, 0))]
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                getter = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                    nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.reasons.update(self._reason_names(int(getter(self._h))))
+            except Exception:
+                pass
+            self._stop.wait(self._period)
+
+    def start(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's CPU path (oracle port): cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------
+def cpu_port_rate(rows_per_call: int, calls: int, warm: int):
+    """Times the reference's op sequence (oracle.torch_port_forward; model/vector_quantizer.py:
+    88-119) on host cores.  Returns (patches/s, seconds per call list, threads)."""
+    import torch
+    from oracle import vq_oracle as O
+
+    torch.set_float32_matmul_precision("highest")
+    g = torch.Generator().manual_seed(1234)
+    z = 0.1 * torch.randn(rows_per_call, DIM, generator=g)
+    g0 = torch.Generator().manual_seed(0)
+    weight = (torch.rand(K_CODES, DIM, generator=g0) * 2 - 1) / K_CODES
+    times = []
+    with torch.no_grad():
+        for i in range(warm + calls):
+            t0 = time.perf_counter()
+            O.torch_port_forward(z, weight, BETA)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    return rows_per_call * len(times) / sum(times), times, torch.get_num_threads()
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: size one step so that warmup+steps finish within ~2 minutes
+    probe_rows = 1 << 16
+    rate, _, threads = cpu_port_rate(probe_rows, 2, 1)
+    budget_s = 120.0 / max(1, args.steps + args.warmup)
+    rows = int(min(1 << 20, max(1 << 14, rate * budget_s)))
+    rows = 1 << (rows.bit_length() - 1)
+    rate, times, threads = cpu_port_rate(rows, args.steps, args.warmup)
+    ms = 1e3 * sum(times) / len(times)
+    sample = f"{rows} of the {N_VECTORS} vectors per step (2^{rows.bit_length() - 1}-vector chunk), scaled per vector"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, N_VECTORS),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference's op sequence (model/vector_quantizer.py:88-119) as torch CPU ops on all host threads; "
+                "the reference's own files are not present on the GPU box (oracle port, DESIGN.md)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import vqb200
+    from vqb200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = vqb200._lib.load()
+    n = args.rows
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    z = 0.1 * torch.randn(n, DIM, device=dev, generator=g)
+    g0 = torch.Generator().manual_seed(0)
+    weight = ((torch.rand(K_CODES, DIM, generator=g0) * 2 - 1) / K_CODES).to(dev)
+    if world > 1:
+        dist.broadcast(weight, 0)      # replicated codebook
+
+    def step():
+        out = ops.forward(z, weight, BETA, path=args.path)
+        if world > 1:
+            dist.all_reduce(out[4])    # global code histogram: the path's only collective
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.vqb_profile_enable(1)
+    launches0 = lib.vqb_launch_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step()
+    ev1.record()
+    barrier()
+    launches = lib.vqb_launch_counter() - launches0
+    lib.vqb_profile_enable(0)
+    ms_total = ev0.elapsed_time(ev1)
+    kms, kn = ctypes.c_double(), ctypes.c_int()
+    vqb200._lib.check(lib.vqb_profile_collect(ctypes.byref(kms), ctypes.byref(kn)), "vqb_profile_collect")
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    loss, zq, ppl, idx, counts = out
+
+    # ---- end to end through the host-buffer C-ABI call --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        z_host = torch.empty((n, DIM), dtype=torch.float32).pin_memory()
+        z_host.copy_(z)
+        zq_host = torch.empty((n, DIM), dtype=torch.float32).pin_memory()
+        idx_host = torch.empty((n,), dtype=torch.int64).pin_memory()
+        counts_host = np.zeros(K_CODES, np.uint64)
+        enc = ops.HostEncoder(weight, device=local_rank, chunk_rows=args.chunk_rows, depth=3)
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            enc.encode(z_host, BETA, zq_out=zq_host, idx_out=idx_host, counts_out=counts_host, path=args.path)
+        barrier()
+        dev_ms, wall = 0.0, 0.0
+        ms_buf = ctypes.c_float()
+        for _ in range(e2e_steps):
+            t0 = time.perf_counter()
+            h_loss, h_ppl = enc.encode(z_host, BETA, zq_out=zq_host, idx_out=idx_host, counts_out=counts_host,
+                                       path=args.path)
+            wall += time.perf_counter() - t0
+            lib.vqb_host_last_ms(enc._ctx, ctypes.byref(ms_buf))
+            dev_ms += ms_buf.value
+        barrier()
+        e2e_launches = enc.last_launches
+        # ids-only variant: what dataloader/latentspace_dataloader.py:160-161 actually consumes
+        ids_ms = 0.0
+        for _ in range(e2e_steps):
+            enc.encode(z_host, BETA, idx_out=idx_host, path=args.path)
+            lib.vqb_host_last_ms(enc._ctx, ctypes.byref(ms_buf))
+            ids_ms += ms_buf.value
+        barrier()
+        te = torch.tensor([dev_ms, wall * 1e3, ids_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, ids_ms = (float(v) for v in te.tolist())
+        assert torch.equal(idx_host.to(dev), idx.view(-1)), "host path and device path disagree"
+        e2e = {
+            "value": world * n * e2e_steps / (max(dev_ms, 1e-9) * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": n * DIM * 4,
+            "d2h_bytes_per_step": n * DIM * 4 + n * 8 + 8 + K_CODES * 8,
+            "ms_per_step": dev_ms / e2e_steps, "wall_ms_per_step": wall_ms / e2e_steps, "steps": e2e_steps,
+            "timing": "CUDA events inside vqb_encode_host, first H2D to last D2H; wall clock alongside",
+            "chunk_rows": args.chunk_rows, "gpu_launches_per_step": e2e_launches,
+            "ids_only": {"value": world * n * e2e_steps / (max(ids_ms, 1e-9) * 1e-3), "unit": UNIT,
+                         "d2h_bytes_per_step": n * 8 + 8},
+        }
+        enc.close()
+        del z_host, zq_host, idx_host
+    clocks = sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- index match rate vs the oracle on a sample (outside every timed region) ------
+    from oracle import vq_oracle as O
+    sample_rows = 1 << 16
+    ora = O.forward(z[:sample_rows].cpu().numpy(), weight.cpu().numpy(), BETA)
+    match = float((idx[:sample_rows].view(-1).cpu().numpy() == ora.indices.reshape(-1)).mean())
+
+    peak, peak_src = measured_peaks()
+    algo_bytes = n * (8 * DIM + 8)                     # read z, write z_q, int64 idx
+    k_ms = kms.value / max(1, kn.value)
+    achieved = algo_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get(f"K{K_CODES}_D{DIM}_N{n}_{args.path}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": traffic,
+                "kernel": "fused VQ forward (distance+argmin+gather+loss+histogram)", "kernel_ms": k_ms,
+                "kernel_share_of_step": k_ms * kn.value / ms_total if ms_total > 0 else None,
+                "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src}
+
+    cpu = None
+    if not args.no_cpu:
+        # bounded sample of the same workload: 2^18-vector chunks for about 10-20 s of CPU work
+        rows = 1 << 18
+        rate, times, threads = cpu_port_rate(rows, 1, 1)
+        calls = int(max(2, min(64, 12.0 / max(times[0], 1e-3))))
+        rate, times, threads = cpu_port_rate(rows, calls, 0)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{calls} x {rows}-vector chunks of the {n}-vector workload ({sum(times):.1f} s)"}
+
+    line = {
+        "metric": METRIC, "value": world * n * args.steps / (ms_total * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world, n), "path": args.path,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "index_match": {"vs": "oracle (oracle/vq_oracle.c)", "rows": sample_rows, "rate": match},
+        "check": {"loss": float(loss.item()), "perplexity": float(ppl.item()), "histogram_total": int(counts.sum().item())},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--path", choices=["auto", "fma", "tc"], default="auto")
+    ap.add_argument("--rows", type=int, default=N_VECTORS, help="vectors per GPU per step")
+    ap.add_argument("--chunk-rows", type=int, default=1 << 20, help="host-path pipeline chunk")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,175 @@
+/*
+ * vqb200.h -- C ABI of the B200-native vector-quantisation hot path.
+ *
+ * Drop-in boundary for tmdt-buw/VQ-VAE-Transformer-Arc-Welding.  The reference
+ * has no FFI of its own (it is pure PyTorch); the boundary it exposes for this
+ * path is the Python class VectorQuantizer (model/vector_quantizer.py:59-131).
+ * Each entry point below replaces one piece of that class and is what a ctypes
+ * binding inside the reference would call (INTEGRATION.md shows the stub):
+ *
+ *   vqb_forward   <- VectorQuantizer.forward                model/vector_quantizer.py:76-119
+ *   vqb_backward  <- autograd of :103-111 (straight-through + commitment/codebook loss)
+ *   vqb_gather    <- VectorQuantizer.get_embedding_from_one_hot          :121-131
+ *   vqb_one_hot   <- the (N, n_e) `min_encodings` matrix                 :98-100
+ *   vqb_encode_host / vqb_host_* <- the host-side encode call of
+ *                    dataloader/latentspace_dataloader.py:154-161,225-238
+ *                    (host buffers in, ids out, copies inside the call)
+ *
+ * Conventions
+ *   - Plain C: pointers and sizes only, no torch types, no C++ exceptions.
+ *   - Device entry points take DEVICE pointers owned by the caller (for the
+ *     PyTorch binding: tensors from the caching allocator).  The library never
+ *     allocates or frees device memory on those paths, never synchronises, and
+ *     enqueues everything on the caller's stream (a cudaStream_t passed as void*).
+ *   - Every function returns VQB_OK (0), a negative VQB_E_* argument error, or a
+ *     positive cudaError_t.  vqb_error_string() names any of them.
+ *   - Thread-safe for concurrent calls on different devices/streams.
+ *   - fp32 only, like the reference.
+ *
+ * Numerics contract (DESIGN.md section "Exactness")
+ *   idx[i] = argmin_k fl(fl(zz_i + ee_k) - fl(2 * dot_ik)) with every sum an
+ *   ascending fmaf chain from +0 ("oracle order", oracle/vq_oracle.c), lowest
+ *   index on ties, first NaN wins -- bit-identical to the oracle on every
+ *   kernel path, including the tensor-core path (which only FILTERS candidates
+ *   with tcgen05 and decides with the exact expression).
+ *   zq[i] = fl(z_i + fl(E[idx_i] - z_i)) elementwise           (:111)
+ *   loss  = m + beta*m, m = mean((E[idx]-z)^2)                  (:107-108)
+ *   perplexity = exp(-sum_k p_k log(p_k + 1e-10)), p = counts/N (:114-115)
+ */
+#ifndef VQB200_H
+#define VQB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQB_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ------------------------------------------------------- */
+#define VQB_OK 0
+#define VQB_E_ARG (-1)         /* null pointer / non-positive size / bad stride */
+#define VQB_E_WORKSPACE (-2)   /* workspace too small (see vqb_workspace_bytes) */
+#define VQB_E_UNSUPPORTED (-3) /* shape not supported by the requested kernel path */
+#define VQB_E_DEVICE (-4)      /* device is not sm_100 */
+#define VQB_E_DRIVER (-5)      /* driver entry point (tensor-map encode) unavailable */
+#define VQB_E_HOSTCTX (-6)     /* host context misuse */
+
+/* ---- flags for vqb_forward ---------------------------------------------- */
+#define VQB_PATH_AUTO 0u   /* tcgen05 filter+refine where the shape allows, else FMA */
+#define VQB_PATH_FMA 1u    /* force the CUDA-core FMA kernel (exact, any K/D/strides) */
+#define VQB_PATH_TC 2u     /* force the tcgen05 kernel; VQB_E_UNSUPPORTED if not possible */
+#define VQB_PATH_MASK 3u
+
+typedef struct vqb_device_info {
+    int device;
+    int cc_major;
+    int cc_minor;
+    int sm_count;
+    int max_smem_per_block; /* opt-in bytes */
+    size_t l2_bytes;
+    size_t total_mem;
+} vqb_device_info;
+
+int vqb_version(void);
+const char *vqb_error_string(int code);
+int vqb_query(int device, vqb_device_info *out);
+
+/* Bytes of caller-owned device scratch every device entry point needs for a
+ * codebook of (k, d).  Contents are private to the library and need not be
+ * preserved between calls.  The buffer must be 256-byte aligned. */
+size_t vqb_workspace_bytes(int k, int d);
+
+/* Which kernel path VQB_PATH_AUTO would take for this shape on `device`
+ * (returns VQB_PATH_FMA or VQB_PATH_TC, or a negative error). */
+int vqb_select_path(int device, int64_t n, int k, int d, int64_t stride_row, int64_t stride_d);
+
+/*
+ * Forward: quantise N = n_outer * n_inner vectors of dimension d.
+ *
+ * z addressing (element strides): vector (b, t), component j lives at
+ *     z[b * stride_outer + t * stride_inner + j * stride_d].
+ * Contiguous (N, d):            n_outer = N, n_inner = 1, stride_outer = d, stride_d = 1.
+ * The encoder's permuted view   (model/vq_vae_patch_embedd.py:91; physical (B, d, T)):
+ *                               n_outer = B, n_inner = T, stride_outer = d*T,
+ *                               stride_inner = 1, stride_d = T  -- read in place, no copy.
+ *
+ * Outputs (device; any of zq/idx/loss/perplexity/counts may be NULL):
+ *   zq          (N, d) contiguous fp32 -- straight-through value z + (E[idx] - z)
+ *   idx         (N)    int64           -- min_encoding_indices
+ *   loss        (1)    fp32
+ *   perplexity  (1)    fp32
+ *   counts      (k)    uint64          -- code-usage histogram of this call
+ *   stats       (4)    uint64 or NULL  -- [0] rows decided by the tcgen05 filter alone,
+ *                                         [1] rows re-evaluated exactly, [2] rows on the
+ *                                         non-finite path, [3] reserved
+ */
+int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, int d,
+                int64_t stride_outer, int64_t stride_inner, int64_t stride_d,
+                const float *codebook, int k, float beta,
+                float *zq, int64_t *idx, float *loss, float *perplexity,
+                unsigned long long *counts, unsigned long long *stats,
+                void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
+
+/*
+ * Backward of vqb_forward's (loss, zq) with respect to z and the codebook:
+ *   grad_z[i]        = g_zq[i] + g_loss * 2 * (z_i - E[idx_i]) / (N*d)
+ *   grad_codebook[c] = g_loss * beta * 2 / (N*d) * sum_{i: idx_i = c} (E[c] - z_i)
+ * g_zq: (N, d) contiguous or NULL (zeros); g_loss: device scalar or NULL (zero);
+ * grad_z: (N, d) contiguous or NULL; grad_codebook: (k, d), OVERWRITTEN, or NULL.
+ * z uses the same strided addressing as vqb_forward.
+ */
+int vqb_backward(int device, const float *g_zq, const float *g_loss,
+                 const float *z, int64_t n_outer, int64_t n_inner, int d,
+                 int64_t stride_outer, int64_t stride_inner, int64_t stride_d,
+                 const int64_t *idx, const float *codebook, int k, float beta,
+                 float *grad_z, float *grad_codebook,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* out[i] = codebook[idx[i]] (n, d).  Out-of-range indices yield NaN rows and set
+ * *bad_index (device int, may be NULL) to 1. */
+int vqb_gather(int device, const int64_t *idx, int64_t n, const float *codebook, int k, int d,
+               float *out, int *bad_index, void *stream);
+
+/* onehot (n, k) fp32 <- one_hot(idx).  4*k bytes per vector: not part of the
+ * hot path's roofline (no caller of the reference reads it). */
+int vqb_one_hot(int device, const int64_t *idx, int64_t n, int k, float *onehot, void *stream);
+
+/* ---- measurement hooks (bench.py) ---------------------------------------- */
+/* Cumulative number of kernels this library has launched in this process. */
+long long vqb_launch_counter(void);
+/* While enabled, vqb_forward brackets its dominant kernel (the fused distance/argmin/gather
+ * kernel) with CUDA events on the caller's stream; vqb_profile_collect waits for them and
+ * returns the summed duration and the number of bracketed launches, then forgets them. */
+int vqb_profile_enable(int on);
+int vqb_profile_collect(double *ms_sum, int *launches);
+
+/* ---- host-buffer path (copies inside the call) --------------------------- */
+typedef struct vqb_host_ctx vqb_host_ctx;
+
+/* Creates device staging for chunks of `chunk_rows` vectors of dimension d against
+ * a k-entry codebook: `depth` (>=2) in-flight chunks, each with its own stream.
+ * This is the only place the library owns device memory. */
+int vqb_host_create(int device, int64_t chunk_rows, int d, int k, int depth, vqb_host_ctx **out);
+int vqb_host_destroy(vqb_host_ctx *ctx);
+/* Upload the codebook (host pointer, (k, d) fp32). */
+int vqb_host_set_codebook(vqb_host_ctx *ctx, const float *codebook_host);
+/*
+ * Quantise n host vectors (contiguous (n, d) fp32; pinned memory gives async copies).
+ * H2D copy, kernels and D2H copy of successive chunks overlap.  zq_host / idx_host may
+ * be NULL (ids-only is what dataloader/latentspace_dataloader.py:160-161 consumes).
+ * Scalars are written to host on return (the call synchronises its own streams).
+ * launches_out (optional) receives the number of kernels launched.
+ */
+int vqb_encode_host(vqb_host_ctx *ctx, const float *z_host, int64_t n, float beta,
+                    float *zq_host, int64_t *idx_host, float *loss_host, float *perplexity_host,
+                    unsigned long long *counts_host, unsigned flags, int *launches_out);
+/* Device-timed duration (CUDA events, first H2D to last D2H) of the last vqb_encode_host. */
+int vqb_host_last_ms(vqb_host_ctx *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQB200_H */

@@ -1,0 +1,266 @@
+"""GPU parity tests proper (run with -m gpu on the B200 box): the CUDA path, called through
+the C ABI, against (1) the CPU oracle on the same seeded inputs -- indices and z_q bit-exact --
+and (2) the committed outputs of the unmodified reference (tests/golden/), where only
+documented fp32 near-ties may move.
+
+Tolerances (BASELINE.json north_star): indices bit-exact vs the oracle; z_q bit-exact vs the
+oracle; loss, perplexity, grad_z, grad_E within 1e-5 relative (fp32).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+import vqb200
+from vqb200 import ops
+from oracle import vq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+PATHS = ["fma", "auto"]
+
+
+def _dev():
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch.device("cuda:0")
+
+
+def _to_dev(case):
+    storage, logical, E = C.make_inputs(case)
+    st = torch.from_numpy(storage).to(_dev())
+    z = st.permute(0, 2, 1) if case["layout"] == "permuted" else st
+    assert tuple(z.shape) == tuple(case["shape"])
+    return z, logical, E
+
+
+def _module(case, path, one_hot="dense"):
+    vq = vqb200.VectorQuantizer(case["K"], case["D"], case["beta"], one_hot=one_hot, path=path).to(_dev())
+    return vq
+
+
+def _finite(case):
+    return case["z"] != "nonfinite" and case["cb"] != "nan_rows"
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("case", C.CASES, ids=[c["name"] for c in C.CASES])
+def test_forward_matches_oracle_and_reference(case, path, golden, manifest):
+    name = case["name"]
+    z, z_np, E = _to_dev(case)
+    vq = _module(case, path)
+    with torch.no_grad():
+        vq.embedding.weight.copy_(torch.from_numpy(E))
+        loss, zq, ppl, onehot, idx = vq(z)
+    torch.cuda.synchronize()
+    n = z.numel() // case["D"]
+    # ---- the reference's return contract (model/vector_quantizer.py:118-119) ----
+    assert loss.shape == () and ppl.shape == () and loss.dtype == torch.float32
+    assert zq.shape == z.shape and zq.is_contiguous() and zq.dtype == torch.float32
+    assert idx.shape == (n, 1) and idx.dtype == torch.int64
+    assert onehot.shape == (n, case["K"]) and onehot.dtype == torch.float32
+    got = idx.cpu().numpy().reshape(-1)
+    # ---- vs the oracle: bit-exact ----
+    ora = O.forward(z_np, E, case["beta"])
+    assert np.array_equal(got, ora.indices.reshape(-1)), "indices differ from the oracle"
+    zq_np = zq.cpu().numpy().reshape(n, case["D"])
+    assert np.array_equal(zq_np, ora.z_q.reshape(n, case["D"]), equal_nan=True), "z_q differs from the oracle"
+    assert np.array_equal(vq.code_counts.cpu().numpy(), ora.counts)
+    oh = onehot.cpu().numpy()
+    assert np.array_equal(oh.argmax(1), got) and np.array_equal(oh.sum(1), np.ones(n, np.float32))
+    if np.isnan(ora.loss):
+        assert torch.isnan(loss)
+    else:
+        assert loss.item() == pytest.approx(float(ora.loss), rel=REL)
+    assert ppl.item() == pytest.approx(float(ora.perplexity), rel=REL)
+    # ---- vs the reference's stored outputs ----
+    ref_idx = golden[f"{name}/idx"].astype(np.int64)
+    if _finite(case):
+        info = O.explain_mismatches(z_np, E, got, ref_idx, ulps=8.0)
+        assert info["explained"] == info["mismatch"], info
+        assert info["mismatch"] <= max(1, int(3e-2 * n)) if info["mismatch"] else True
+    else:
+        assert np.array_equal(got, ref_idx)
+    if np.array_equal(got, ref_idx):
+        if _finite(case):
+            assert hashlib.sha256(zq_np.tobytes()).hexdigest() == manifest["vq"][name]["zq_sha256"]
+        ref_loss = golden[f"{name}/loss"]
+        if not np.isnan(ref_loss):
+            assert loss.item() == pytest.approx(float(ref_loss), rel=REL)
+            assert ppl.item() == pytest.approx(float(golden[f"{name}/perplexity"]), rel=REL)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("case", [c for c in C.CASES if c["bwd"]], ids=[c["name"] for c in C.CASES if c["bwd"]])
+def test_backward_matches_reference_autograd(case, path, golden):
+    name = case["name"]
+    z, z_np, E = _to_dev(case)
+    vq = _module(case, path, one_hot="none")
+    with torch.no_grad():
+        vq.embedding.weight.copy_(torch.from_numpy(E))
+    z = z.detach().requires_grad_(True)
+    loss, zq, ppl, onehot, idx = vq(z)
+    assert onehot is None
+    assert loss.requires_grad and zq.requires_grad and not ppl.requires_grad and not idx.requires_grad
+    w = torch.from_numpy(C.upstream_weights(case)).to(_dev())
+    total = C.G_LOSS * loss + (w * zq).sum()
+    total.backward()
+    torch.cuda.synchronize()
+    n = z.numel() // case["D"]
+    assert z.grad.shape == z.shape
+    gz = z.grad.cpu().numpy().reshape(n, case["D"])
+    gE = vq.embedding.weight.grad.cpu().numpy()
+    got_idx = idx.cpu().numpy().reshape(-1)
+    ref_idx = golden[f"{name}/idx"].astype(np.int64)
+    # closed form in fp64 on the indices the kernel chose
+    ogz, ogE = O.backward(C.upstream_weights(case), C.G_LOSS, z_np, got_idx, E, case["beta"])
+    np.testing.assert_allclose(gz, ogz.reshape(n, case["D"]), rtol=REL, atol=1e-7)
+    scale = np.abs(ogE).max() + 1e-30
+    np.testing.assert_allclose(gE, ogE, rtol=1e-4, atol=REL * scale)
+    if np.array_equal(got_idx, ref_idx):   # and against the reference's autograd
+        head = golden[f"{name}/grad_z_head"]
+        np.testing.assert_allclose(gz[: head.shape[0]], head, rtol=REL, atol=1e-7)
+        rscale = np.abs(golden[f"{name}/grad_E"]).max() + 1e-30
+        np.testing.assert_allclose(gE, golden[f"{name}/grad_E"], rtol=1e-4, atol=REL * rscale)
+
+
+def test_gradient_routing_matches_reference_semantics():
+    """g_zq reaches z only (straight-through); the codebook only sees the beta term."""
+    dev = _dev()
+    torch.manual_seed(3)
+    vq = vqb200.VectorQuantizer(32, 8, 0.25, one_hot="none").to(dev)
+    z = (0.05 * torch.randn(64, 8, device=dev)).requires_grad_(True)
+    loss, zq, *_ = vq(z)
+    zq.sum().backward()
+    assert torch.equal(z.grad, torch.ones_like(z))
+    assert torch.count_nonzero(vq.embedding.weight.grad) == 0
+    z.grad = None
+    vq.zero_grad()
+    loss, zq, *_ = vq(z)
+    loss.backward()
+    assert torch.count_nonzero(vq.embedding.weight.grad) > 0
+    with torch.no_grad():
+        out = vq(z)
+    assert not out[0].requires_grad and not out[1].requires_grad
+
+
+def test_gather_and_bad_index():
+    dev = _dev()
+    vq = vqb200.VectorQuantizer(16, 8, 0.25).to(dev)
+    idx = torch.tensor([[3], [0], [15], [3]], device=dev)
+    out = vq.get_embedding_from_one_hot(idx, (2, 2, 8))
+    assert out.shape == (2, 2, 8) and out.is_contiguous()
+    assert torch.equal(out.view(4, 8), vq.embedding.weight.detach()[idx.view(-1)])
+    bad = ops.gather(torch.tensor([[16]], device=dev), vq.embedding.weight)
+    assert torch.isnan(bad).all()
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_encode_indices_and_empty_input(path):
+    dev = _dev()
+    vq = vqb200.VectorQuantizer(256, 32, 0.25, path=path).to(dev)
+    z = 0.1 * torch.randn(1000, 32, device=dev)
+    with torch.no_grad():
+        full = vq(z)[4]
+    ids = vq.encode_indices(z)
+    assert torch.equal(ids, full)
+    loss, zq, ppl, oh, idx = vq(torch.empty(0, 32, device=dev))
+    assert idx.shape == (0, 1) and zq.shape == (0, 32) and oh.shape == (0, 256)
+    assert torch.isnan(loss)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_random_shapes_against_oracle(path):
+    """Property test: random (K, D, N, layout) against the oracle, bit-exact."""
+    dev = _dev()
+    rs = np.random.RandomState(2024)
+    for trial in range(24):
+        K = int(rs.choice([1, 2, 3, 17, 64, 100, 256, 300, 1000]))
+        D = int(rs.choice([1, 2, 4, 7, 8, 16, 24, 32, 48, 64, 128]))
+        n = int(rs.choice([1, 31, 128, 129, 257, 1000, 4096]))
+        scale = float(rs.choice([0.1, 1.0]))
+        E = (rs.standard_normal((K, D)) * float(rs.choice([1.0 / K, 0.1]))).astype(np.float32)
+        z_np = (scale * rs.standard_normal((n, D))).astype(np.float32)
+        layout = rs.choice(["contig", "colmajor", "permuted"])
+        zt = torch.from_numpy(z_np).to(dev)
+        if layout == "colmajor":
+            zt = zt.t().contiguous().t()
+        elif layout == "permuted" and n % 4 == 0:
+            zt = zt.view(n // 4, 4, D).permute(0, 2, 1).contiguous().permute(0, 2, 1)
+        vq = vqb200.VectorQuantizer(K, D, 0.25, one_hot="none", path=path).to(dev)
+        with torch.no_grad():
+            vq.embedding.weight.copy_(torch.from_numpy(E))
+            loss, zq, ppl, _, idx = vq(zt)
+        ora = O.forward(z_np, E, 0.25)
+        tag = f"trial {trial}: K={K} D={D} n={n} {layout}"
+        assert np.array_equal(idx.cpu().numpy().reshape(-1), ora.indices.reshape(-1)), tag
+        assert np.array_equal(zq.cpu().numpy().reshape(n, D), ora.z_q.reshape(n, D)), tag
+        assert loss.item() == pytest.approx(float(ora.loss), rel=REL), tag
+        assert ppl.item() == pytest.approx(float(ora.perplexity), rel=REL), tag
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_full_size_properties(path):
+    """BASELINE config 2 at full size (2^24 vectors, K=256, D=32): size-independent properties
+    plus an oracle check on a 2^16-row sample."""
+    dev = _dev()
+    n, K, D = 1 << 24, 256, 32
+    g = torch.Generator(device=dev).manual_seed(1234)
+    z = 0.1 * torch.randn(n, D, device=dev, generator=g)
+    torch.manual_seed(0)
+    vq = vqb200.VectorQuantizer(K, D, 0.25, one_hot="none", path=path).to(dev)
+    with torch.no_grad():
+        loss, zq, ppl, _, idx = vq(z)
+    torch.cuda.synchronize()
+    E = vq.embedding.weight.detach()
+    flat = idx.view(-1)
+    assert int(flat.min()) >= 0 and int(flat.max()) < K
+    counts = vq.code_counts
+    assert int(counts.sum()) == n
+    assert torch.equal(counts, torch.bincount(flat, minlength=K))
+    # z_q is exactly z + (E[idx] - z); the loss is the mean of the squared residual
+    e = E[flat]
+    assert torch.equal(zq, z + (e - z))
+    m = ((e - z).double() ** 2).mean()
+    assert loss.item() == pytest.approx(float(m * 1.25), rel=REL)
+    p = counts.double() / n
+    assert ppl.item() == pytest.approx(float(torch.exp(-(p * torch.log(p + 1e-10)).sum())), rel=REL)
+    # optimality: no code is closer than the chosen one (fp64 check on a strided sample)
+    sample = torch.arange(0, n, n // 4096, device=dev)[:4096]
+    d64 = torch.cdist(z[sample].double(), E.double())
+    chosen = d64.gather(1, flat[sample].view(-1, 1)).view(-1)
+    assert torch.all(chosen <= d64.min(1).values + 1e-6)
+    # oracle on the first 2^16 rows: bit-exact
+    head = 1 << 16
+    ora = O.forward(z[:head].cpu().numpy(), E.cpu().numpy(), 0.25)
+    assert np.array_equal(flat[:head].cpu().numpy(), ora.indices.reshape(-1))
+    # idempotence: quantising the quantised vectors' code rows returns codes with identical rows
+    with torch.no_grad():
+        idx2 = vq.encode_indices(e[: 1 << 20].contiguous()).view(-1)
+    assert torch.equal(E[idx2], e[: 1 << 20])
+
+
+def test_host_buffer_path_matches_oracle():
+    rs = np.random.RandomState(7)
+    K, D, n = 256, 32, 300_000
+    E = rs.uniform(-1.0 / K, 1.0 / K, (K, D)).astype(np.float32)
+    z = torch.from_numpy((0.1 * rs.standard_normal((n, D))).astype(np.float32)).pin_memory()
+    zq = torch.empty_like(z).pin_memory()
+    idx = torch.empty(n, dtype=torch.int64).pin_memory()
+    counts = np.zeros(K, np.uint64)
+    enc = ops.HostEncoder(E, device=0, chunk_rows=65536, depth=3)
+    loss, ppl = enc.encode(z, 0.25, zq_out=zq, idx_out=idx, counts_out=counts)
+    assert enc.last_launches >= 2 + (n + 65535) // 65536
+    ora = O.forward(z.numpy(), E, 0.25)
+    assert np.array_equal(idx.numpy(), ora.indices.reshape(-1))
+    assert np.array_equal(zq.numpy(), ora.z_q)
+    assert np.array_equal(counts.astype(np.int64), ora.counts)
+    assert loss == pytest.approx(float(ora.loss), rel=REL)
+    assert ppl == pytest.approx(float(ora.perplexity), rel=REL)
+    # ids-only mode (what the latent-dataset builder consumes)
+    idx2 = torch.empty(n, dtype=torch.int64).pin_memory()
+    enc.encode(z, 0.25, idx_out=idx2)
+    assert torch.equal(idx, idx2)
+    enc.close()

@@ -1,0 +1,104 @@
+"""VQ-VAE-Patch with the fused VQ on the GPU against outputs of the unmodified reference
+model (tests/golden/patch_golden.npz): full forward, one training step, the id-encode call
+and the bulk latent-dataset loops (dataloader/latentspace_dataloader.py:144-263)."""
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+import vqb200
+from vqb200.dataloader import LatentSpaceEncoder
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _load(case, patch_golden):
+    model = vqb200.VQVAEPatch(hidden_dim=case["hidden_dim"], input_dim=case["input_dim"],
+                              num_embeddings=case["num_embeddings"], embedding_dim=case["embedding_dim"],
+                              n_resblocks=case["n_resblocks"], learning_rate=1e-3, dropout_p=0.0,
+                              patch_size=case["patch_size"], seq_len=case["seq_len"],
+                              batch_norm=case["batch_norm"], beta=case["beta"])
+    pre = f"{case['name']}/sd/"
+    sd = {k[len(pre):]: torch.from_numpy(patch_golden[k]) for k in patch_golden.files if k.startswith(pre)}
+    model.load_state_dict(sd, strict=True)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return model.to(DEV)
+
+
+@pytest.mark.parametrize("case", C.PATCH_CASES, ids=[c["name"] for c in C.PATCH_CASES])
+def test_forward_matches_reference(case, patch_golden):
+    name = case["name"]
+    model = _load(case, patch_golden).eval()
+    x = torch.from_numpy(C.make_cycles(case)).to(DEV)
+    with torch.no_grad():
+        z_e = model.encode(x)
+        emb_loss, x_hat, ppl = model(x)
+        ids = model.encode_ids(x)
+    assert not z_e.is_contiguous()                 # the permuted view is consumed in place
+    np.testing.assert_allclose(z_e.contiguous().cpu().numpy(), patch_golden[f"{name}/z_e"], rtol=1e-4, atol=1e-5)
+    ref_ids = patch_golden[f"{name}/idx"].astype(np.int64)
+    got = ids.cpu().numpy().reshape(-1)
+    assert ids.shape == (x.shape[0], model.enc_out_len)
+    # the encoder runs through cuBLAS here and MKL in the fixture: ids may differ only where the
+    # two nearest codes are equidistant to within the encoder's rounding
+    assert (got == ref_ids).mean() >= 0.97
+    if np.array_equal(got, ref_ids):
+        assert emb_loss.item() == pytest.approx(float(patch_golden[f"{name}/emb_loss"]), rel=1e-4)
+        assert ppl.item() == pytest.approx(float(patch_golden[f"{name}/perplexity"]), rel=1e-4)
+        np.testing.assert_allclose(x_hat.cpu().numpy(), patch_golden[f"{name}/x_hat"], rtol=1e-3, atol=1e-4)
+
+
+def test_training_step_matches_reference(patch_golden):
+    case = C.PATCH_CASES[0]
+    name = case["name"]
+    model = _load(case, patch_golden).train()
+    x = torch.from_numpy(C.make_cycles(case)).to(DEV)
+    out = model.training_step(x, 0)
+    out["loss"].backward()
+    assert out["loss"].item() == pytest.approx(float(patch_golden[f"{name}/train_total"]), rel=1e-4)
+    assert out["recon_error"].item() == pytest.approx(float(patch_golden[f"{name}/train_recon"]), rel=1e-4)
+    for key, param in (("grad_codebook", model.vector_quantization.embedding.weight),
+                       ("grad_enc_proj", model.encoder[1].shared_conv.weight),
+                       ("grad_patch_proj", model.patch_embed.proj.weight)):
+        ref = patch_golden[f"{name}/{key}"]
+        got = param.grad.cpu().numpy()
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=2e-3, atol=2e-4 * np.abs(ref).max())
+    # the two outer taps of the k=3 encoder convs only ever see zero padding (appendix A.7)
+    w = model.encoder[0].shared_conv[0].block[1].weight.grad
+    assert torch.count_nonzero(w[:, :, 0]) == 0 and torch.count_nonzero(w[:, :, 2]) == 0
+    opt = model.configure_optimizers()
+    opt.step()
+
+
+def test_bulk_loops_equal_per_cycle_reference_loop(patch_golden):
+    """create_latent_space_dataset_VQ_VAE_IDs over windows of 3 cycles == encoding each cycle
+    slice on its own, the way the reference loop does (:225-238)."""
+    case = C.PATCH_CASES[0]
+    model = _load(case, patch_golden).eval()
+    enc = LatentSpaceEncoder(model, window_size=200, device=DEV)
+    rs = np.random.RandomState(5)
+    seq_len, n_windows = 3, 10
+    data = torch.from_numpy(rs.standard_normal((n_windows, seq_len * 200, 2)).astype(np.float32))
+    labels = torch.from_numpy(rs.randint(0, 2, n_windows).astype(np.float32))
+    loader = [(data[i:i + 4], labels[i:i + 4]) for i in range(0, n_windows, 4)]
+    ids, y = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True)
+    assert ids.shape == (n_windows, seq_len, model.enc_out_len) and ids.dtype == np.int64
+    assert np.array_equal(y, labels.numpy().astype(np.float64))
+    want = np.empty_like(ids)
+    with torch.no_grad():
+        for i in range(seq_len):
+            x_i = data[:, i * 200:(i + 1) * 200, :].clone().to(DEV)
+            want[:, i, :] = enc.get_latent_space_IDs(x_i, True).cpu().numpy().reshape(n_windows, -1)
+    assert np.array_equal(ids, want)
+    assert int(enc.code_counts.sum()) == ids.size
+    flat, y2 = enc.create_latent_space_dataset_VQ_VAE_autoreggressive(
+        [d for d, _ in loader], seq_len=seq_len, has_patch_embed=True, task="autoregressive_ids")
+    assert flat.shape == (n_windows, seq_len * model.enc_out_len) and np.array_equal(flat, ids.reshape(n_windows, -1))
+    assert np.array_equal(y2, np.zeros(n_windows))
+    zq, y3 = enc.create_latent_space_dataset_VQ_VAE(loader, seq_len=seq_len, has_patch_embed=True)
+    assert zq.shape == (n_windows, seq_len, model.embedding_dim * model.enc_out_len) and zq.dtype == np.float64
+    E = model.vector_quantization.embedding.weight.detach().cpu().numpy()
+    np.testing.assert_allclose(zq.reshape(n_windows, seq_len, model.enc_out_len, -1), E[ids], rtol=0, atol=1e-6)

@@ -1,0 +1,90 @@
+"""Host-side logic of the drop-in that needs no GPU: argument checking, layout analysis,
+module surface and state-dict contract."""
+import numpy as np
+import pytest
+import torch
+
+import vqb200
+from vqb200 import ops
+
+
+def test_constructor_surface_and_init_range():
+    torch.manual_seed(0)
+    vq = vqb200.VectorQuantizer(256, 32, 0.25)
+    assert (vq.n_e, vq.e_dim, vq.beta) == (256, 32, 0.25)
+    assert isinstance(vq.embedding, torch.nn.Embedding)
+    w = vq.embedding.weight
+    assert w.shape == (256, 32) and w.dtype == torch.float32 and w.requires_grad
+    assert w.abs().max().item() <= 1.0 / 256          # model/vector_quantizer.py:74
+    assert list(vq.state_dict().keys()) == ["embedding.weight"]   # the only persistent key
+    assert [n for n, _ in vq.named_parameters()] == ["embedding.weight"]
+    assert hasattr(vq, "device")
+
+
+def test_same_seed_same_codebook_as_reference_init():
+    """uniform_(-1/K, 1/K) right after nn.Embedding's own normal_ init: same RNG consumption
+    as the reference constructor, so seeded runs start from the same codebook."""
+    torch.manual_seed(123)
+    a = vqb200.VectorQuantizer(64, 8, 0.25).embedding.weight.detach().clone()
+    torch.manual_seed(123)
+    emb = torch.nn.Embedding(64, 8)
+    emb.weight.data.uniform_(-1.0 / 64, 1.0 / 64)
+    assert torch.equal(a, emb.weight.detach())
+
+
+def test_cpu_tensors_raise_no_fallback():
+    vq = vqb200.VectorQuantizer(16, 8, 0.25)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vq(torch.randn(4, 8))
+
+
+def test_dtype_mismatch_raises_runtime_error():
+    vq = vqb200.VectorQuantizer(16, 8, 0.25)
+    with pytest.raises(RuntimeError, match="float32"):
+        vq(torch.randn(4, 8, dtype=torch.float64))
+
+
+def test_bad_options():
+    with pytest.raises(ValueError):
+        vqb200.VectorQuantizer(16, 8, 0.25, one_hot="sparse")
+    with pytest.raises(ValueError):
+        vqb200.VectorQuantizer(16, 8, 0.25, path="triton")
+
+
+def test_view_params_contiguous_and_permuted():
+    z = torch.randn(6, 16, 32)
+    t, n_outer, n_inner, so, si, sd = ops._view_params(z, 32)
+    assert (n_outer * n_inner, so, sd) == (96, 32, 1) and t is z
+    phys = torch.randn(6, 32, 16)
+    view = phys.permute(0, 2, 1)                      # the encoder's layout
+    t, n_outer, n_inner, so, si, sd = ops._view_params(view, 32)
+    assert t is view and (n_outer, n_inner, so, si, sd) == (6, 16, 512, 1, 16)
+    two_d = torch.randn(32, 10).t()                   # (10, 32) column-major
+    t, n_outer, n_inner, so, si, sd = ops._view_params(two_d, 32)
+    assert t is two_d and (n_outer, n_inner, so, sd) == (10, 1, 1, 10)
+    odd = torch.randn(2, 4, 4, 64)[..., ::2]          # 4-D strided: falls back to one copy
+    t, n_outer, n_inner, so, si, sd = ops._view_params(odd, 32)
+    assert t.is_contiguous() and (n_outer * n_inner, so, sd) == (32, 32, 1)
+
+
+def test_world_size_helpers_single_process():
+    assert vqb200.get_world_size() == 1
+    t = torch.arange(4)
+    assert vqb200.all_reduce(t) is t
+
+
+def test_lightning_hook_surface():
+    m = vqb200.VQVAEPatch(hidden_dim=16, input_dim=2, num_embeddings=8, embedding_dim=4, n_resblocks=1,
+                          learning_rate=1e-3, batch_norm=False)
+    for hook in ("training_step", "validation_step", "test_step", "configure_optimizers", "_forward_setp"):
+        assert callable(getattr(m, hook))
+    opt = m.configure_optimizers()
+    assert isinstance(opt, torch.optim.RAdam)
+    ids = {id(p) for g in opt.param_groups for p in g["params"]}
+    assert id(m.vector_quantization.embedding.weight) in ids
+    assert m.enc_out_len == 16 and m.patch_size == 25 and m.embedding_dim == 4 and m.num_embeddings == 8
+    hp = vars(m.hparams) if not isinstance(m.hparams, dict) else m.hparams
+    assert hp["hidden_dim"] == 16 and hp["patch_size"] == 25 and hp["beta"] == 0.25
+    with pytest.raises(NotImplementedError):
+        vqb200.VQVAEPatch(hidden_dim=16, input_dim=2, num_embeddings=8, embedding_dim=4, n_resblocks=1,
+                          learning_rate=1e-3, use_improved_vq=True)

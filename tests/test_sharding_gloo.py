@@ -1,0 +1,76 @@
+"""N>1 host logic on CPU: two gloo ranks shard a batch of cycles, encode their shards with a
+stand-in encoder, gather the ids and all-reduce the code histogram -- the same plumbing the
+B200 ranks run over NCCL."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import vqb200  # noqa: F401
+from vqb200.dataloader import bulk_encode_ids, gather_sharded, reduce_counts, shard_range
+
+
+def test_shard_range_partitions_in_order():
+    for n in (0, 1, 7, 16, 1000, 10_000_001):
+        for world in (1, 2, 3, 4, 8):
+            edges = [shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for (a, b), (c, d) in zip(edges, edges[1:]):
+                assert b == c and a <= b
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _fake_encode(cycles: torch.Tensor) -> torch.Tensor:
+    # deterministic stand-in for model.encode_ids: 4 "tokens" per cycle in [0, 16)
+    b = cycles.shape[0]
+    feat = cycles.reshape(b, 4, -1).sum(-1)
+    return (feat.abs() * 1000).long() % 16
+
+
+def _worker(rank, world, port, n, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(5)
+        cycles = torch.randn(n, 8, 2, generator=g)
+        ids = bulk_encode_ids(_fake_encode, cycles, batch=5)
+        local, (lo, hi) = bulk_encode_ids(_fake_encode, cycles, batch=5, gather=False)
+        counts = reduce_counts(torch.bincount(local.reshape(-1), minlength=16))
+        assert vqb200.get_world_size() == world
+        t = torch.ones(3)
+        assert vqb200.all_reduce(t) is t and torch.equal(t, torch.full((3,), float(world)))
+        torch.save(dict(ids=ids, counts=counts, lo=lo, hi=hi), os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [23, 16, 1])
+def test_two_rank_bulk_encode_equals_single_process(tmp_path, n):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
+    g = torch.Generator().manual_seed(5)
+    cycles = torch.randn(n, 8, 2, generator=g)
+    want = _fake_encode(cycles)
+    r0 = torch.load(os.path.join(tmp_path, "r0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "r1.pt"))
+    assert torch.equal(r0["ids"], want) and torch.equal(r1["ids"], want)
+    assert r0["hi"] == r1["lo"] and r0["lo"] == 0 and r1["hi"] == n
+    full = torch.bincount(want.reshape(-1), minlength=16)
+    assert torch.equal(r0["counts"], full) and torch.equal(r1["counts"], full)
+
+
+def test_single_process_paths():
+    cycles = torch.randn(10, 8, 2)
+    ids = bulk_encode_ids(_fake_encode, cycles, batch=3)
+    assert torch.equal(ids, _fake_encode(cycles))
+    assert gather_sharded(ids, 10) is ids
+    c = torch.ones(4, dtype=torch.int64)
+    assert reduce_counts(c) is c

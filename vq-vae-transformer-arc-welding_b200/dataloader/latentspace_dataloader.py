@@ -1,0 +1,189 @@
+"""The encode calls of the reference's offline tokeniser, on the B200 path.
+
+Mirror of the hot-path part of ``dataloader/latentspace_dataloader.py``:
+  get_latent_space / get_latent_space_IDs                       (:144-161)
+  create_latent_space_dataset_VQ_VAE[_IDs|_autoreggressive]      (:171-263)
+with the same method names, arguments and returned numpy arrays (shapes, dtypes, order),
+so ``LatentSpaceDataLoader`` can delegate to it.  Everything around it in that file (CSV
+loading, window bookkeeping, pickle cache, wandb artifacts) is data plumbing outside the hot
+path and is not rebuilt.
+
+What changes underneath:
+  * the reference encodes a batch of windows one 200-sample cycle at a time: per cycle one
+    H2D copy, one launch storm and one blocking ``.cpu()`` (:231-235), then ``np.append``s
+    (O(n^2) host copying, :238).  Here all cycles of a batch go through the encoder and the
+    fused VQ kernel in ONE call (cycles are independent: every op before the decoder is
+    per token), results land in preallocated arrays, and only ids cross PCIe for the id tasks;
+  * multi-GPU: batches are sharded across ranks (one process per GPU), the codebook and
+    encoder weights are replicated, the only collectives are an optional gather of the ids and
+    one K-element all-reduce of the code-usage histogram (bulk_encode_ids / gather_sharded).
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import distributed as dist
+
+
+class LatentSpaceEncoder:
+    """Encode-side of ``LatentSpaceDataLoader`` (reference :16-39 for the constructor fields
+    that matter here: the model, ``window_size`` and the device)."""
+
+    def __init__(self, latent_space_model, window_size: int = 200, device: Optional[str] = None):
+        if device is None:
+            # the reference hard-codes cuda:0 (:34); one process per GPU uses its own device
+            device = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"
+        self.device = device
+        self.latent_space_model = latent_space_model.to(self.device)
+        self.window_size = window_size
+        self.code_counts = None
+
+    # ---- single encode calls (:144-161) -------------------------------------------------
+    def _encode(self, x, has_patch_embed: bool):
+        model = self.latent_space_model
+        x = model.patch_embed(x) if has_patch_embed else x.permute(0, 2, 1)
+        return model.encoder(x)
+
+    def get_latent_space(self, x, has_patch_embed: bool = False):
+        z_e = self._encode(x, has_patch_embed)
+        _loss, z_q, _ppl, _oh, _idx = self.latent_space_model.vector_quantization(z_e)
+        return z_q
+
+    def get_latent_space_IDs(self, x, has_patch_embed: bool = False):
+        z_e = self._encode(x, has_patch_embed)
+        vq = self.latent_space_model.vector_quantization
+        if hasattr(vq, "encode_indices"):
+            return vq.encode_indices(z_e)
+        return vq(z_e)[4]
+
+    # ---- bulk loops (:171-263) ------------------------------------------------------------
+    def _cycles(self, x: torch.Tensor, seq_len: int) -> torch.Tensor:
+        """(B, >= seq_len*window, C) -> (B*seq_len, window, C): cycle i of window b at row b*seq_len+i."""
+        b = x.shape[0]
+        w = self.window_size
+        return x[:, : seq_len * w, :].reshape(b * seq_len, w, x.shape[2])
+
+    def create_latent_space_dataset_VQ_VAE(self, loader: Iterable, seq_len: int, has_patch_embed: bool = False):
+        """Quantised latents per window: (n, seq_len, embedding_dim*enc_out_len) float64, labels (n,)."""
+        model = self.latent_space_model
+        width = int(model.embedding_dim * model.enc_out_len)
+        xs, ys = [], []
+        model.eval()
+        with torch.no_grad():
+            for x, y in loader:
+                b = x.shape[0]
+                cyc = self._cycles(x, seq_len).to(self.device, non_blocking=True)
+                z_q = self.get_latent_space(cyc, has_patch_embed=has_patch_embed)
+                xs.append(z_q.reshape(b, seq_len, -1).cpu().numpy().astype(np.float64))
+                ys.append(np.asarray(y.cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64))
+        if not xs:
+            return np.empty((0, seq_len, width)), np.empty((0,))
+        return np.concatenate(xs, axis=0), np.concatenate(ys, axis=0)
+
+    def create_latent_space_dataset_VQ_VAE_IDs(self, loader: Iterable, seq_len: int, has_patch_embed: bool = False,
+                                               no_labels: bool = False):
+        """Token ids per window: (n, seq_len, enc_out_len) int64, labels (n,) (zeros when no_labels)."""
+        model = self.latent_space_model
+        enc_out_len = int(model.enc_out_len)
+        xs, ys = [], []
+        counts = None
+        model.eval()
+        with torch.no_grad():
+            for item in loader:
+                x, y = (item, None) if no_labels else item
+                b = x.shape[0]
+                cyc = self._cycles(x, seq_len).to(self.device, non_blocking=True)
+                ids = self.get_latent_space_IDs(cyc, has_patch_embed)
+                c = getattr(model.vector_quantization, "code_counts", None)
+                if c is not None:
+                    counts = c.clone() if counts is None else counts + c
+                xs.append(ids.view(b, seq_len, -1).cpu().numpy())
+                if y is not None:
+                    ys.append(np.asarray(y.cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64))
+        self.code_counts = counts
+        new_x = np.concatenate(xs, axis=0) if xs else np.empty((0, seq_len, enc_out_len), dtype=int)
+        new_y = np.zeros(new_x.shape[0]) if no_labels else (np.concatenate(ys, axis=0) if ys else np.empty((0,)))
+        return new_x, new_y
+
+    def create_latent_space_dataset_VQ_VAE_autoreggressive(self, loader: Iterable, seq_len: int = 1,
+                                                          has_patch_embed: bool = False, task: str = "autoregressive_ids"):
+        """Flattened ids (n, seq_len*enc_out_len) for the autoregressive task (:245-263)."""
+        new_x, new_y = self.create_latent_space_dataset_VQ_VAE_IDs(
+            loader, seq_len=seq_len, has_patch_embed=has_patch_embed, no_labels=(task == "autoregressive_ids"))
+        return new_x.reshape((new_x.shape[0], -1)), new_y
+
+
+# ---------------------------------------------------------------------------------------
+# batch sharding across ranks (one process per GPU)
+# ---------------------------------------------------------------------------------------
+def shard_range(n: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of n items owned by `rank`; the first n % world_size ranks
+    get one extra item, so concatenating the shards in rank order restores the input order."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _dist_ready() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def gather_sharded(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """All-gathers per-rank shards (split with shard_range along dim 0) into the full tensor
+    in input order, on every rank.  Ragged shards are padded by one row at most."""
+    if not _dist_ready():
+        return local
+    world = dist.get_world_size()
+    base, extra = divmod(n_total, world)
+    rows = base + (1 if extra else 0)
+    padded = local.new_zeros((rows,) + tuple(local.shape[1:]))
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    out = []
+    for r, part in enumerate(parts):
+        lo, hi = shard_range(n_total, r, world)
+        out.append(part[: hi - lo])
+    return torch.cat(out, dim=0)
+
+
+def reduce_counts(counts: torch.Tensor) -> torch.Tensor:
+    """Sum of the per-rank code-usage histograms (the one collective bulk encoding needs)."""
+    if _dist_ready():
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return counts
+
+
+def bulk_encode_ids(encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: torch.Tensor, batch: int = 65536,
+                    rank: Optional[int] = None, world_size: Optional[int] = None, gather: bool = True):
+    """Tokenise `cycles` (n, window, C) with `encode_fn` (cycles -> (b, T) int64 ids), this rank
+    encoding only its shard.  Returns the ids of all cycles in input order when gather=True
+    (every rank), else this rank's shard and its [lo, hi) range."""
+    if rank is None:
+        rank = dist.get_rank() if _dist_ready() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if _dist_ready() else 1
+    n = cycles.shape[0]
+    lo, hi = shard_range(n, rank, world_size)
+    outs = []
+    for s in range(lo, hi, batch):
+        outs.append(encode_fn(cycles[s: min(s + batch, hi)]))
+    local = torch.cat(outs, dim=0) if outs else None
+    if world_size > 1 and _dist_ready():
+        # a rank whose shard is empty learns the id layout (tokens per cycle, dtype) from its peers
+        meta = [None] * world_size
+        dist.all_gather_object(meta, None if local is None else (tuple(local.shape[1:]), local.dtype,
+                                                                 local.device.type))
+        known = next((m for m in meta if m is not None), ((0,), torch.int64, cycles.device.type))
+        if local is None:
+            dev = torch.device("cuda", torch.cuda.current_device()) if known[2] == "cuda" else torch.device("cpu")
+            local = torch.empty((0,) + known[0], dtype=known[1], device=dev)
+    elif local is None:
+        local = torch.empty((0, 0), dtype=torch.int64, device=cycles.device)
+    if gather and world_size > 1:
+        return gather_sharded(local, n)
+    return local if gather else (local, (lo, hi))

@@ -1,0 +1,98 @@
+"""Drop-in for the reference's ``model/vector_quantizer.py:VectorQuantizer`` (lines 59-131).
+
+Same constructor, attributes, ``forward`` signature, returned 5-tuple, ``embedding.weight``
+state-dict key and Lightning base class -- but ``forward`` is one fused CUDA kernel
+(libvqb200.so) instead of five (N, K) temporaries, two GEMMs and a CPU-built one-hot.
+There is no CPU path: calling it with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import torch
+from torch import distributed as dist
+from torch import nn
+
+from .. import ops
+from .._lightning_compat import LightningModule
+
+
+class VectorQuantizer(LightningModule):
+    """Discretisation bottleneck of the VQ-VAE.
+
+    Args (model/vector_quantizer.py:68):
+        n_e:   number of codebook entries
+        e_dim: dimension of one entry
+        beta:  weight of the codebook term, loss = mean((sg[e]-z)^2) + beta*mean((e-sg[z])^2)
+               (the reference's weighting, :107-108 -- reversed w.r.t. the VQ-VAE paper)
+    Extra keyword arguments (not in the reference, defaults keep its behaviour):
+        one_hot: "dense" materialises the (N, n_e) fp32 ``min_encodings`` like the reference;
+                 "none" returns None in its place (4*n_e bytes per vector saved; no caller
+                 in the reference reads it).
+        path:    "auto" | "fma" | "tc" kernel selection (see include/vqb200.h).
+    """
+
+    def __init__(self, n_e, e_dim, beta, one_hot: str = "dense", path: str = "auto"):
+        super().__init__()
+        if one_hot not in ("dense", "none"):
+            raise ValueError(f"one_hot must be 'dense' or 'none', got {one_hot!r}")
+        if path not in ops.PATHS:
+            raise ValueError(f"path must be one of {sorted(ops.PATHS)}, got {path!r}")
+        self.n_e = n_e
+        self.e_dim = e_dim
+        self.beta = beta
+        self.one_hot = one_hot
+        self.path = path
+        self.embedding = nn.Embedding(self.n_e, self.e_dim)
+        self.embedding.weight.data.uniform_(-1.0 / self.n_e, 1.0 / self.n_e)   # :74
+        # code-usage histogram of the last forward (int64, K): a plain attribute, so the state
+        # dict keeps its single key `embedding.weight` and DDP has no extra buffer to broadcast
+        self.code_counts = None
+
+    def forward(self, z):
+        """z: fp32 CUDA tensor whose trailing elements group into vectors of ``e_dim``
+        (any shape, may be a non-contiguous view; read in place).
+
+        Returns (loss, z_q, perplexity, min_encodings, min_encoding_indices), :119.
+        """
+        loss, z_q, perplexity, indices, counts = ops.VQStraightThrough.apply(
+            z, self.embedding.weight, self.beta, self.path)
+        self.code_counts = counts
+        min_encodings = ops.one_hot(indices, self.n_e) if self.one_hot == "dense" else None
+        return loss, z_q, perplexity, min_encodings, indices
+
+    def encode_indices(self, z):
+        """min_encoding_indices only (what dataloader/latentspace_dataloader.py:160-161 keeps):
+        no z_q write, no one-hot, no autograd graph."""
+        with torch.no_grad():
+            _, _, _, indices, counts = ops.forward(z, self.embedding.weight, self.beta, self.path, want_zq=False)
+        self.code_counts = counts
+        return indices
+
+    def get_embedding_from_one_hot(self, min_encoding_indices, target_shape):
+        """E[min_encoding_indices].view(target_shape), :121-131."""
+        return ops.gather(min_encoding_indices, self.embedding.weight, target_shape)
+
+    def global_perplexity(self):
+        """Perplexity of the code usage summed over all ranks (opt-in; the reference never
+        reduces it).  One K-element all-reduce over NCCL."""
+        if self.code_counts is None:
+            raise RuntimeError("global_perplexity() needs a forward pass first")
+        counts = self.code_counts.clone()
+        all_reduce(counts)
+        p = counts.to(torch.float32) / counts.sum().to(torch.float32)
+        return torch.exp(-torch.sum(p * torch.log(p + 1e-10)))
+
+
+def get_world_size():
+    """model/vector_quantizer.py:134-141."""
+    if not dist.is_available() or not dist.is_initialized():
+        return 1
+    return dist.get_world_size()
+
+
+def all_reduce(tensor, op=dist.ReduceOp.SUM):
+    """In-place all-reduce guarded for single-process runs (model/vector_quantizer.py:144-152).
+    Unlike the reference, the reduced tensor is returned in the multi-rank case too."""
+    if get_world_size() == 1:
+        return tensor
+    dist.all_reduce(tensor, op=op)
+    return tensor

@@ -1,0 +1,193 @@
+"""VQ-VAE-Patch with the B200 encode-and-quantise path -- mirror of the reference's
+``model/vq_vae_patch_embedd.py`` (same constructor, attributes, sub-module names and
+therefore the same 80-key state dict, so reference checkpoints load strictly).
+
+Encode half (the hot path):
+  * PatchEmbedding  : channel-major patchify + linear P -> H            (:7-17)
+  * CNNBlock        : per-token residual MLP.  The reference applies Conv1d(k=3, pad=1) to
+                      length-1 slices in a 16-iteration Python loop (:103-111), where only the
+                      centre tap W[:, :, 1] ever meets non-zero data; here the same weights are
+                      applied to all tokens at once as dense layers (one GEMM per conv instead
+                      of 16 tiny convolutions).  With BatchNorm in training mode the per-position
+                      batch statistics of the reference are kept by looping like it does.
+  * SepCNNBlock     : per-token linear H -> D, returned in the reference's permuted layout
+                      (physical (B, D, T), logical (B, T, D), :83-91)
+  * VectorQuantizer : fused CUDA kernel, reads the permuted view in place.
+Decode half (out of the hot-path scope, stock PyTorch modules): :19-57, :142-147.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .autencoder_lightning_base import Autoencoder
+from .vector_quantizer import VectorQuantizer
+
+
+class PatchEmbedding(nn.Module):
+    def __init__(self, patch_size, embed_dim):
+        super().__init__()
+        self.patch_size = patch_size
+        self.proj = nn.Conv1d(1, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+    def forward(self, x):
+        """(B, L, C) -> (B, H, T) with T = L*C/patch: channel-major, all patches of channel 0
+        first (:14-15).  A stride-P conv over the flattened signal is a linear map per patch."""
+        b = x.shape[0]
+        patches = x.permute(0, 2, 1).reshape(b, -1, self.patch_size)        # (B, T, P)
+        tokens = F.linear(patches, self.proj.weight[:, 0, :], self.proj.bias)  # (B, T, H)
+        return tokens.permute(0, 2, 1)
+
+
+class PatchEmbeddingInverse(nn.Module):
+    _KERNELS = {25: (5, 5), 10: (2, 5), 50: (10, 5)}   # (:24-45)
+
+    def __init__(self, patch_size, embed_dim, input_dim):
+        super().__init__()
+        if patch_size not in self._KERNELS:
+            raise NotImplementedError(f"Patch size not implemented: {patch_size}")
+        k0, k1 = self._KERNELS[patch_size]
+        self.patch_size = patch_size
+        self.input_dim = input_dim
+        self.proj = nn.Sequential(
+            nn.ConvTranspose1d(embed_dim, embed_dim, kernel_size=k0, stride=k0),
+            nn.BatchNorm1d(embed_dim),
+            nn.GELU(),
+            nn.ConvTranspose1d(embed_dim, 1, kernel_size=k1, stride=k1),
+        )
+
+    def forward(self, x):
+        x = self.proj(x)
+        return x.reshape(x.shape[0], -1, self.input_dim)   # (:56) not the inverse of the patchify; kept
+
+
+class ResBlock(nn.Module):
+    def __init__(self, channels: int, kernel_size: int = 3, stride: int = 1, padding: int = 1,
+                 dropout_p: float = 0.1, batch_norm: bool = True):
+        super().__init__()
+        def norm():
+            return nn.BatchNorm1d(channels) if batch_norm else nn.Identity()
+        self.block = nn.Sequential(
+            nn.GELU(),
+            nn.Conv1d(channels, channels, kernel_size=kernel_size, stride=stride, padding=padding),
+            norm(),
+            nn.GELU(),
+            nn.Conv1d(channels, channels, kernel_size=kernel_size, stride=stride, padding=padding),
+            norm(),
+            nn.Dropout(p=dropout_p),
+        )
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+
+    def forward(self, x):
+        return x + self.block(x)
+
+    def _centre_tap_ok(self) -> bool:
+        return self.stride == 1 and self.kernel_size == 2 * self.padding + 1
+
+    def forward_tokens(self, t):
+        """Same block applied to independent tokens t: (..., C).  On a length-1 sequence with
+        zero padding only the centre tap of each conv sees data."""
+        blk = self.block
+        c = self.padding
+        h = F.gelu(t)
+        h = F.linear(h, blk[1].weight[:, :, c], blk[1].bias)
+        h = _token_norm(blk[2], h)
+        h = F.gelu(h)
+        h = F.linear(h, blk[4].weight[:, :, c], blk[4].bias)
+        h = _token_norm(blk[5], h)
+        return t + blk[6](h)
+
+
+def _token_norm(norm, t):
+    """BatchNorm1d in eval mode is a per-channel affine map; Identity passes through."""
+    if isinstance(norm, nn.Identity):
+        return t
+    return F.batch_norm(t.reshape(-1, t.shape[-1]), norm.running_mean, norm.running_var,
+                        norm.weight, norm.bias, False, 0.0, norm.eps).reshape(t.shape)
+
+
+class SepCNNBlock(nn.Module):
+    def __init__(self, hidden_dim: int, embedding_dim: int) -> None:
+        super().__init__()
+        self.shared_conv = nn.Conv1d(hidden_dim, embedding_dim, kernel_size=1, stride=1, padding=0)
+
+    def forward(self, x):
+        """(B, H, T) -> logical (B, T, D) stored as (B, D, T): the same non-contiguous view the
+        reference returns (:91), which the fused VQ kernel reads without a copy."""
+        out = torch.matmul(self.shared_conv.weight[:, :, 0], x) + self.shared_conv.bias[:, None]  # (B, D, T)
+        return out.permute(0, 2, 1)
+
+
+class CNNBlock(nn.Module):
+    def __init__(self, embed_dim: int, seperate: bool = True, kernel_size: int = 3, stride: int = 1,
+                 padding: int = 1, dropout_p: float = 0.1, batch_norm: bool = True, n_resblocks: int = 1):
+        super().__init__()
+        self.seperate = seperate
+        self.shared_conv = nn.Sequential(
+            *[ResBlock(channels=embed_dim, kernel_size=kernel_size, stride=stride, padding=padding,
+                       dropout_p=dropout_p, batch_norm=batch_norm) for _ in range(n_resblocks)])
+        self._has_bn = batch_norm
+
+    def forward(self, x):
+        if not self.seperate:
+            return self.shared_conv(x)
+        per_position_stats = self._has_bn and self.training
+        if per_position_stats or not all(b._centre_tap_ok() for b in self.shared_conv):
+            # training-mode BatchNorm normalises each position with its own batch statistics and
+            # updates the running statistics once per position: do exactly what the reference does
+            cols = [self.shared_conv(x[:, :, i].unsqueeze(2)) for i in range(x.shape[2])]
+            return torch.cat(cols, dim=2)
+        t = x.permute(0, 2, 1)                     # (B, T, H) tokens
+        for blk in self.shared_conv:
+            t = blk.forward_tokens(t)
+        return t.permute(0, 2, 1)
+
+
+class VQVAEPatch(Autoencoder):
+
+    def __init__(self, hidden_dim: int, input_dim: int, num_embeddings: int, embedding_dim: int,
+                 n_resblocks: int, learning_rate: float, dropout_p: float = 0.1, patch_size: int = 25,
+                 seq_len: int = 200, batch_norm: bool = True, beta: float = 0.25,
+                 use_improved_vq: bool = False, kmeans_iters: int = 0, threshold_ema_dead_code: int = 2):
+        super().__init__(hidden_dim=hidden_dim, input_dim=input_dim, num_embeddings=num_embeddings,
+                         embedding_dim=embedding_dim, n_resblocks=n_resblocks, learning_rate=learning_rate,
+                         seq_len=seq_len, dropout_p=dropout_p)
+        if use_improved_vq:
+            # ResidualVQLightning wraps the un-vendored `vector-quantize-pytorch` package
+            # (model/vector_quantizer.py:9-56); out of scope, parity unpinned.
+            raise NotImplementedError("use_improved_vq=True (ResidualVQ) is outside the B200 hot path")
+        self.patch_embed = PatchEmbedding(patch_size=patch_size, embed_dim=hidden_dim)
+        self.encoder = nn.Sequential(
+            CNNBlock(embed_dim=hidden_dim, n_resblocks=n_resblocks, dropout_p=dropout_p, batch_norm=batch_norm),
+            SepCNNBlock(hidden_dim=hidden_dim, embedding_dim=embedding_dim),
+        )
+        self.vector_quantization = VectorQuantizer(n_e=num_embeddings, e_dim=embedding_dim, beta=beta)
+        self.decoder = nn.Sequential(
+            nn.Conv1d(embedding_dim, hidden_dim, kernel_size=1, stride=1, padding=0),
+            CNNBlock(embed_dim=hidden_dim, seperate=False, n_resblocks=n_resblocks, dropout_p=dropout_p,
+                     batch_norm=batch_norm),
+        )
+        self.reverse_patch_embed = PatchEmbeddingInverse(patch_size=patch_size, embed_dim=hidden_dim,
+                                                         input_dim=input_dim)
+        self.enc_out_len = seq_len // patch_size * input_dim
+        self.patch_size = patch_size
+        self.apply(self.weights_init)
+
+    # ---- encode half: the hot path ------------------------------------------------------
+    def encode(self, x):
+        """x (B, seq_len, input_dim) -> z_e, logical (B, T, D) on physical (B, D, T)."""
+        return self.encoder(self.patch_embed(x))
+
+    def encode_ids(self, x):
+        """Token ids (B, T) int64 -- the encode call of dataloader/latentspace_dataloader.py:154-161
+        without z_q, loss, one-hot or autograd."""
+        with torch.no_grad():
+            z_e = self.encode(x)
+            return self.vector_quantization.encode_indices(z_e).view(x.shape[0], -1)
+
+    def forward(self, x):
+        z_e = self.encode(x)
+        embedding_loss, z_q, perplexity, _, _ = self.vector_quantization(z_e)
+        x_hat = self.reverse_patch_embed(self.decoder(z_q.permute(0, 2, 1)))
+        return embedding_loss, x_hat, perplexity

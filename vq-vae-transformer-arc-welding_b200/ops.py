@@ -1,0 +1,244 @@
+"""Tensor-level entry points: torch tensors in, C-ABI calls out.
+
+PyTorch is plumbing here (device memory from the caching allocator, the current
+stream, autograd bookkeeping); all arithmetic happens inside libvqb200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+PATHS = {"auto": _lib.PATH_AUTO, "fma": _lib.PATH_FMA, "tc": _lib.PATH_TC}
+
+_workspaces = {}
+
+
+def _require_cuda_fp32(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if t.dtype != torch.float32:
+        # the reference module is fp32-only as well
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} lives on {t.device}: the B200 vector quantiser has no CPU fallback; "
+            "move the module and its input to a CUDA device")
+
+
+def _workspace(device: torch.device, k: int, d: int) -> torch.Tensor:
+    stream = torch.cuda.current_stream(device).cuda_stream
+    key = (device.index, k, d, stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = _lib.load().vqb_workspace_bytes(k, d)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _ws_ptr(ws: torch.Tensor) -> Tuple[int, int]:
+    p = ws.data_ptr()
+    a = (p + 255) // 256 * 256
+    return a, ws.numel() - (a - p)
+
+
+def _view_params(z: torch.Tensor, d: int):
+    """Express z (logical row-major order of reshape(-1, d)) as (n_outer, n_inner, d) with
+    element strides, without copying when the layout allows it.  Returns
+    (tensor_to_keep_alive, n_outer, n_inner, s_outer, s_inner, s_d)."""
+    n = z.numel() // d
+    if z.is_contiguous():
+        return z, n, 1, d, d, 1
+    if z.dim() >= 2 and z.shape[-1] == d:
+        if z.dim() == 2:
+            return z, z.shape[0], 1, z.stride(0), 0, z.stride(1)
+        if z.dim() == 3:  # e.g. the encoder's permuted view, strides (d*T, 1, T)
+            return z, z.shape[0], z.shape[1], z.stride(0), z.stride(1), z.stride(2)
+    zc = z.contiguous()  # exotic layout: same copy the reference's reshape makes (:88)
+    return zc, n, 1, d, d, 1
+
+
+def forward(z: torch.Tensor, weight: torch.Tensor, beta: float, path: str = "auto",
+            want_zq: bool = True, want_stats: bool = False):
+    """Fused nearest-code search.  Returns (loss, z_q, perplexity, indices (N,1) int64,
+    counts (K,) int64[, stats (4,) int64])."""
+    _require_cuda_fp32(z, "z")
+    _require_cuda_fp32(weight, "embedding.weight")
+    if weight.dim() != 2:
+        raise RuntimeError("embedding.weight must be (n_e, e_dim)")
+    if z.device != weight.device:
+        raise RuntimeError(f"z is on {z.device} but the codebook is on {weight.device}")
+    k, d = weight.shape
+    if z.numel() % d:
+        raise RuntimeError(f"shape '[-1, {d}]' is invalid for input of size {z.numel()}")
+    lib = _lib.load()
+    dev = z.device
+    w = weight.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    zsrc, n_outer, n_inner, s_outer, s_inner, s_d = _view_params(z.detach(), d)
+    n = n_outer * n_inner
+    with torch.cuda.device(dev):
+        zq = torch.empty(z.shape, dtype=torch.float32, device=dev) if want_zq else None
+        idx = torch.empty((n, 1), dtype=torch.int64, device=dev)
+        scal = torch.empty(2, dtype=torch.float32, device=dev)
+        counts = torch.empty(k, dtype=torch.int64, device=dev)
+        stats = torch.empty(4, dtype=torch.int64, device=dev) if want_stats else None
+        ws = _workspace(dev, k, d)
+        ws_ptr, ws_bytes = _ws_ptr(ws)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.vqb_forward(
+            dev.index, zsrc.data_ptr(), n_outer, n_inner, d, s_outer, s_inner, s_d,
+            w.data_ptr(), k, float(beta),
+            zq.data_ptr() if zq is not None else None, idx.data_ptr(),
+            scal.data_ptr(), scal.data_ptr() + 4, counts.data_ptr(),
+            stats.data_ptr() if stats is not None else None,
+            ws_ptr, ws_bytes, PATHS[path], stream)
+    _lib.check(rc, "vqb_forward")
+    out = (scal[0], zq, scal[1], idx, counts)
+    return out + (stats,) if want_stats else out
+
+
+def backward(g_zq: Optional[torch.Tensor], g_loss: Optional[torch.Tensor], z: torch.Tensor,
+             idx: torch.Tensor, weight: torch.Tensor, beta: float,
+             need_z: bool = True, need_e: bool = True):
+    """Fused straight-through backward.  Returns (grad_z or None, grad_E or None)."""
+    lib = _lib.load()
+    dev = z.device
+    k, d = weight.shape
+    w = weight.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    zsrc, n_outer, n_inner, s_outer, s_inner, s_d = _view_params(z.detach(), d)
+    if g_zq is not None:
+        _require_cuda_fp32(g_zq, "grad of z_q")
+        g_zq = g_zq.contiguous()
+    if g_loss is not None:
+        _require_cuda_fp32(g_loss, "grad of loss")
+        g_loss = g_loss.reshape(1).contiguous()
+    with torch.cuda.device(dev):
+        grad_z = torch.empty(z.shape, dtype=torch.float32, device=dev) if need_z else None
+        grad_e = torch.empty((k, d), dtype=torch.float32, device=dev) if need_e else None
+        ws = _workspace(dev, k, d)
+        ws_ptr, ws_bytes = _ws_ptr(ws)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.vqb_backward(
+            dev.index, g_zq.data_ptr() if g_zq is not None else None,
+            g_loss.data_ptr() if g_loss is not None else None,
+            zsrc.data_ptr(), n_outer, n_inner, d, s_outer, s_inner, s_d,
+            idx.data_ptr(), w.data_ptr(), k, float(beta),
+            grad_z.data_ptr() if grad_z is not None else None,
+            grad_e.data_ptr() if grad_e is not None else None,
+            ws_ptr, ws_bytes, stream)
+    _lib.check(rc, "vqb_backward")
+    return grad_z, grad_e
+
+
+def gather(indices: torch.Tensor, weight: torch.Tensor, target_shape=None) -> torch.Tensor:
+    """E[indices] (model/vector_quantizer.py:121-131)."""
+    _require_cuda_fp32(weight, "embedding.weight")
+    if indices.dtype != torch.int64:
+        raise RuntimeError(f"indices must be int64, got {indices.dtype}")
+    if indices.device != weight.device:
+        raise RuntimeError("indices and codebook must be on the same device")
+    lib = _lib.load()
+    dev = weight.device
+    k, d = weight.shape
+    flat = indices.reshape(-1).contiguous()
+    n = flat.numel()
+    w = weight.detach().contiguous()
+    with torch.cuda.device(dev):
+        out = torch.empty((n, d), dtype=torch.float32, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        rc = lib.vqb_gather(dev.index, flat.data_ptr(), n, w.data_ptr(), k, d, out.data_ptr(),
+                            bad.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "vqb_gather")
+    return out.view(target_shape) if target_shape is not None else out
+
+
+def one_hot(indices: torch.Tensor, k: int) -> torch.Tensor:
+    """(N, k) fp32 one-hot of (N, 1) int64 indices (model/vector_quantizer.py:98-100)."""
+    lib = _lib.load()
+    dev = indices.device
+    flat = indices.reshape(-1).contiguous()
+    n = flat.numel()
+    with torch.cuda.device(dev):
+        out = torch.empty((n, k), dtype=torch.float32, device=dev)
+        rc = lib.vqb_one_hot(dev.index, flat.data_ptr(), n, k, out.data_ptr(),
+                             torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "vqb_one_hot")
+    return out
+
+
+class VQStraightThrough(torch.autograd.Function):
+    """loss, z_q, perplexity, indices, counts = f(z, codebook).  Gradients follow the
+    reference's autograd exactly: z receives g_zq (straight-through)
+    plus the commitment term, the codebook receives the beta-weighted codebook term."""
+
+    @staticmethod
+    def forward(ctx, z, weight, beta, path):
+        loss, zq, ppl, idx, counts = forward(z, weight, beta, path)
+        ctx.save_for_backward(z, weight, idx)
+        ctx.beta = float(beta)
+        ctx.mark_non_differentiable(ppl, idx, counts)
+        return loss, zq, ppl, idx, counts
+
+    @staticmethod
+    def backward(ctx, g_loss, g_zq, _g_ppl, _g_idx, _g_counts):
+        z, weight, idx = ctx.saved_tensors
+        need_z, need_e = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        grad_z, grad_e = backward(g_zq, g_loss, z, idx, weight, ctx.beta, need_z, need_e)
+        return grad_z, grad_e, None, None
+
+
+class HostEncoder:
+    """Owns a vqb_host_ctx: host arrays in, ids / quantised vectors back on the host, with
+    H2D / kernel / D2H of successive chunks overlapped (vqb_encode_host)."""
+
+    def __init__(self, codebook, device: int = 0, chunk_rows: int = 1 << 20, depth: int = 3):
+        import numpy as np
+        self._np = np
+        self._lib = _lib.load()
+        cb = np.ascontiguousarray(codebook.detach().cpu().numpy() if isinstance(codebook, torch.Tensor) else codebook,
+                                  dtype=np.float32)
+        self.k, self.d = cb.shape
+        self.device = int(device)
+        self.chunk_rows = int(chunk_rows)
+        self._ctx = ctypes.c_void_p()
+        _lib.check(self._lib.vqb_host_create(self.device, self.chunk_rows, self.d, self.k, int(depth),
+                                             ctypes.byref(self._ctx)), "vqb_host_create")
+        _lib.check(self._lib.vqb_host_set_codebook(self._ctx, cb.ctypes.data), "vqb_host_set_codebook")
+        self.last_launches = 0
+
+    def encode(self, z_host, beta: float = 0.25, zq_out=None, idx_out=None, counts_out=None, path: str = "auto"):
+        """z_host: (n, d) fp32 contiguous numpy array or CPU tensor (pin it for async copies).
+        Returns (loss, perplexity)."""
+        def ptr(a):
+            if a is None:
+                return None
+            return a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data
+        n = z_host.shape[0] if z_host.ndim == 2 else z_host.size // self.d
+        loss = ctypes.c_float()
+        ppl = ctypes.c_float()
+        launches = ctypes.c_int()
+        rc = self._lib.vqb_encode_host(self._ctx, ptr(z_host), int(n), float(beta), ptr(zq_out), ptr(idx_out),
+                                       ctypes.addressof(loss), ctypes.addressof(ppl), ptr(counts_out),
+                                       PATHS[path], ctypes.byref(launches))
+        _lib.check(rc, "vqb_encode_host")
+        self.last_launches = launches.value
+        return loss.value, ppl.value
+
+    def close(self):
+        if self._ctx:
+            self._lib.vqb_host_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
