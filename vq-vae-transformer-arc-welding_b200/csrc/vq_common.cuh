@@ -41,8 +41,9 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // Extra floats the tcgen05 path keeps per codebook: B operand tile(s) + per-code data.
 __host__ inline size_t tc_scratch_floats(int k, int d)
 {
-    const size_t kpad = align_up((size_t)k, 16);
-    return kpad * ((size_t)d + 8) + 4 * kpad + 64;
+    // tcgen05 path: image of the constant operands (vq_fwd_tc.cu, tc::IMG_BYTES, for 256 codes)
+    (void)k; (void)d;
+    return (32768 + 8192 + 32768 + 1024 + 64) / sizeof(float) + 64;
 }
 
 __host__ inline WsLayout ws_layout(int k, int d)

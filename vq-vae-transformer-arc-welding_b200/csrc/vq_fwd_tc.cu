@@ -1,14 +1,703 @@
-// vq_fwd_tc.cu -- tcgen05 filter + exact refine forward path (placeholder until the
-// kernel lands: reports "unsupported" so that VQB_PATH_AUTO takes the FMA path).
+// vq_fwd_tc.cu -- tcgen05 "filter, then decide exactly" forward kernel (sm_100a).
+//
+// Replaces model/vector_quantizer.py:88-119 for contiguous (N, 32) inputs and K <= 256.
+//
+// Why tensor cores at all: K=256, D=32 needs 16 384 flop per 264 bytes; on the fp32 FMA
+// pipe that is 18 % of the HBM roofline at best (measured: 8.8 %, profiles/README.md).
+// Why not tensor cores alone: TF32/BF16 products flip indices.  So the
+// tensor cores only FILTER:
+//
+//   1. split  z = z1 + z2 (+r), E = E1 + E2 (+r) into bf16 pairs (|r| <= 2^-18 |x|) and let
+//      tcgen05.mma accumulate   s~[i][k] = ee_k - 2*(z1.E1 + z1.E2 + z2.E1)   in TMEM
+//      (7 MMAs of 128 x 256 x 16 per 128-vector tile; ee_k enters through a 7th K-slice of
+//      ones times its exact three-way bf16 split, E is pre-scaled by -2);
+//   2. per vector, the 256 approximate scores are reduced to 32 chunk minima (8 codes per
+//      chunk, FMNMX3) and a packed top-2 over the chunks;
+//   3. |s~ - s| <= eps  =>  the oracle's winner lies in the best chunk unless the runner-up
+//      chunk is within delta = 2*eps + rounding slack of it (rare: ~0.1 % of vectors);
+//   4. the 8 codes of the best chunk are evaluated with the oracle-order expression
+//      (ascending fmaf chain, fl(fl(zz+ee) - 2dot), lowest index wins) on the CUDA cores;
+//      ambiguous or non-finite vectors are scanned exactly over all K codes by their warp.
+//
+// The decision is therefore bit-identical to the FMA kernel and the CPU oracle.
+//
+// Pipeline per CTA (persistent, one CTA per SM, 512 threads):
+//   warp 0      TMA producer: z tile (128 x 32 fp32, SWIZZLE_128B) -> 4-deep smem ring
+//   warp 1      MMA issuer (one thread): 7 x tcgen05.mma.kind::f16 -> TMEM (2 x 256 columns)
+//   warp 2      TMEM allocator
+//   warps 4-7   converters: fp32 tile -> bf16 [z1|z2] tile in the UMMA K-major SW128 layout
+//   warps 8-15  two epilogue groups alternating tiles: TMEM -> chunk minima -> exact decision
+//               -> z_q written in place into the ring slot -> TMA store; idx, loss, histogram
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "vq_common.cuh"
 
 namespace vqb {
 
-bool tc_shape_supported(int, int) { return false; }
+namespace tc {
 
-cudaError_t launch_fwd_tc(const FwdParams &, float *, int, int, int *, int *, cudaStream_t, cudaEvent_t, cudaEvent_t)
+constexpr int D = 32;
+constexpr int TILE_M = 128;
+constexpr int KMAX = 256;
+constexpr int STAGES = 4;
+constexpr int THREADS = 512;
+
+// shared-memory map (bytes); SW128 operands need 1024-byte alignment
+constexpr int OFF_ZRING = 0;                              // STAGES x 16384  fp32 z tiles (TMA, SW128)
+constexpr int OFF_ARING = OFF_ZRING + STAGES * 16384;     // 2 x 16384       bf16 [z1|z2] tiles (SW128)
+constexpr int OFF_BMAIN = OFF_ARING + 2 * 16384;          // 32768           bf16 -2*[E1|E2] (SW128)
+constexpr int OFF_BAUG = OFF_BMAIN + 32768;               // 8192            bf16 ee split (SW32)
+constexpr int OFF_AAUG = OFF_BAUG + 8192;                 // 4096            bf16 ones (SW32)
+constexpr int OFF_EF32 = OFF_AAUG + 4096;                 // 32768           fp32 codebook, XOR-swizzled rows
+constexpr int OFF_EE = OFF_EF32 + 32768;                  // 1024            fp32 ||E_k||^2 (oracle order)
+constexpr int OFF_HIST = OFF_EE + 1024;                   // 1024            u32 histogram
+constexpr int OFF_BARS = OFF_HIST + 1024;                 // 256             mbarriers + tmem base
+constexpr int SMEM_BYTES = OFF_BARS + 256;
+constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;             // slack for manual 1024-byte alignment
+
+// image of the constant operands prepared once per call in global scratch
+constexpr int IMG_BMAIN = 0;
+constexpr int IMG_BAUG = IMG_BMAIN + 32768;
+constexpr int IMG_EF32 = IMG_BAUG + 8192;
+constexpr int IMG_EE = IMG_EF32 + 32768;
+constexpr int IMG_CONST = IMG_EE + 1024;                  // float emax_bits(as uint), eemax_bits, flags
+constexpr int IMG_BYTES = IMG_CONST + 64;
+
+struct Consts {
+    unsigned emax2_bits;   // max_k ee_k (finite ones), as float bits
+    unsigned nonfinite;    // some ee_k is not finite
+    unsigned pad[14];
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    return cudaErrorNotSupported;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must trap instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26))
+            __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float min3(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// K-major operand descriptors (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr)
+{   // 8-row x 128-byte swizzle atoms, 1024 bytes apart along M/N
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr)
+{   // 8-row x 32-byte swizzle atoms, 256 bytes apart along M/N
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
+// kind::f16, A = B = BF16, D = F32, both K-major, M = 128, N = n
+__host__ __device__ inline uint32_t idesc_bf16(int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// byte offset of 16-byte chunk `c` of row `r` in a 128-byte-row SW128 tile
+__device__ __forceinline__ int sw128(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+// fp32 codebook rows: chunk swizzle that also separates rows 8 apart (best-chunk gathers)
+__device__ __forceinline__ int ef32_off(int k, int c) { return k * 128 + ((c ^ ((k ^ (k >> 3)) & 7)) << 4); }
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------
+// prep: one thread per (padded) code builds the constant operand image in global scratch
+// ---------------------------------------------------------------------------------------
+__global__ void vq_tc_prep_kernel(const float *__restrict__ E, const float *__restrict__ ee, int K, int kp,
+                                  unsigned char *__restrict__ img)
+{
+    using namespace tc;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= KMAX)
+        return;
+    Consts *cst = reinterpret_cast<Consts *>(img + IMG_CONST);
+    const bool real = k < K;
+    float e[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+        e[j] = real ? __ldg(E + (size_t)k * D + j) : 0.0f;
+    // main B operand: row k = [-2*E1 (32 bf16) | -2*E2 (32 bf16)], SW128
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        __nv_bfloat16 out[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int j = (c & 3) * 8 + t;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(e[j]);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(e[j] - __bfloat162float(hi));
+            out[t] = __float2bfloat16_rn(-2.0f * __bfloat162float(c < 4 ? hi : lo));   // exact scaling
+        }
+        *reinterpret_cast<uint4 *>(img + IMG_BMAIN + sw128(k, c)) = *reinterpret_cast<uint4 *>(out);
+    }
+    // augmentation B operand: ee_k = a1 + a2 + a3 exactly (3 x 8 bits); pads get a huge score
+    const float eek = real ? ee[k] : 3.0e38f;
+    const bool fin = isfinite(eek);
+    const float eef = fin ? eek : 3.0e38f;
+    const __nv_bfloat16 a1 = __float2bfloat16_rn(eef);
+    const float r1 = eef - __bfloat162float(a1);
+    const __nv_bfloat16 a2 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
+    {
+        __nv_bfloat16 out[8] = {a1, a2, a3, __float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f),
+                                __float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f)};
+        const int sw = (k >> 2) & 1;   // SW32: 16-byte chunk index ^= bit 7 of the byte offset
+        *reinterpret_cast<uint4 *>(img + IMG_BAUG + k * 32 + ((0 ^ sw) << 4)) = *reinterpret_cast<uint4 *>(out);
+        *reinterpret_cast<uint4 *>(img + IMG_BAUG + k * 32 + ((1 ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+    }
+    // fp32 codebook for the exact decision + gather
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4 *>(img + IMG_EF32 + ef32_off(k, c)) =
+            make_float4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+    reinterpret_cast<float *>(img + IMG_EE)[k] = real ? ee[k] : __int_as_float(0x7f800000);
+    if (real) {
+        if (fin)
+            atomicMax(&cst->emax2_bits, __float_as_uint(eek));   // non-negative floats order like uints
+        else
+            atomicOr(&cst->nonfinite, 1u);
+    }
+    (void)kp;
+}
+
+// ---------------------------------------------------------------------------------------
+// exact pieces shared by the epilogue
+// ---------------------------------------------------------------------------------------
+namespace tc {
+
+// warp-cooperative exact scan of all K codes for the vector held by lane `src`
+// (zrow points at that vector's 128-byte row in the ring slot, SW128 layout).
+__device__ __noinline__ int warp_full_scan(const unsigned char *ztile, int row_in_tile, float zz,
+                                           const unsigned char *ef32, const float *ees, int K)
+{
+    const int lane = threadIdx.x & 31;
+    float z[D];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4 *>(ztile + sw128(row_in_tile, c));
+        z[4 * c] = v.x; z[4 * c + 1] = v.y; z[4 * c + 2] = v.z; z[4 * c + 3] = v.w;
+    }
+    float best = __int_as_float(0x7f800000);
+    int bidx = 0x7fffffff;
+    unsigned first_nan = 0xffffffffu;
+    for (int k = lane; k < K; k += 32) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 e = *reinterpret_cast<const float4 *>(ef32 + ef32_off(k, c));
+            acc = fmaf(z[4 * c], e.x, acc);
+            acc = fmaf(z[4 * c + 1], e.y, acc);
+            acc = fmaf(z[4 * c + 2], e.z, acc);
+            acc = fmaf(z[4 * c + 3], e.w, acc);
+        }
+        const float dist = ref_distance(zz, ees[k], acc);
+        if (dist != dist)
+            first_nan = min(first_nan, (unsigned)k);
+        if (dist < best || (dist == best && k < bidx)) {
+            best = dist;
+            bidx = k;
+        }
+    }
+    const unsigned nan_k = __reduce_min_sync(0xffffffffu, first_nan);
+    if (nan_k != 0xffffffffu)
+        return (int)nan_k;   // torch.argmin: the first NaN wins
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob < best || (ob == best && oi < bidx)) {
+            best = ob;
+            bidx = oi;
+        }
+    }
+    return bidx == 0x7fffffff ? 0 : bidx;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(tc::THREADS, 1)
+vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const __grid_constant__ CUtensorMap map_z,
+                 const __grid_constant__ CUtensorMap map_zq, int kp)
+{
+    using namespace tc;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);
+    // barrier indices
+    enum { Z_FULL = 0, Z_EMPTY = Z_FULL + STAGES, A_FULL = Z_EMPTY + STAGES, A_EMPTY = A_FULL + 2,
+           T_FULL = A_EMPTY + 2, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2 };
+    auto bar = [&](int i) { return sbase + OFF_BARS + 8 * i; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + 8 * N_BARS);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_rows = p.z.n_rows;
+    const int64_t n_tiles = (n_rows + TILE_M - 1) / TILE_M;
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int K = p.K;
+
+    // ---- one-time setup -----------------------------------------------------------------
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar(Z_FULL + s), 1);
+            mbar_init(bar(Z_EMPTY + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar(A_FULL + b), 128);
+            mbar_init(bar(A_EMPTY + b), 1);
+            mbar_init(bar(T_FULL + b), 1);
+            mbar_init(bar(T_EMPTY + b), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // constant operands: copy the prepared image, build the ones tile, clear the histogram
+    for (int i = tid; i < (IMG_EE + 1024) / 16; i += THREADS) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img) + i);
+        // image order = smem order for BMAIN | BAUG, then EF32 | EE live after the AAUG tile
+        const int off = i * 16;
+        const int dst = off < IMG_EF32 ? OFF_BMAIN + off : OFF_EF32 + (off - IMG_EF32);
+        *reinterpret_cast<uint4 *>(smem + dst) = v;
+    }
+    if (tid < TILE_M) {
+        const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
+        __nv_bfloat16 out[8] = {one, one, one, zero, zero, zero, zero, zero};
+        const int sw = (tid >> 2) & 1;
+        *reinterpret_cast<uint4 *>(smem + OFF_AAUG + tid * 32 + ((0 ^ sw) << 4)) = *reinterpret_cast<uint4 *>(out);
+        *reinterpret_cast<uint4 *>(smem + OFF_AAUG + tid * 32 + ((1 ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+    }
+    if (tid < KMAX)
+        reinterpret_cast<unsigned *>(smem + OFF_HIST)[tid] = 0u;
+    fence_proxy_async();          // generic-proxy writes of the operands -> visible to tcgen05/TMA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const Consts *cst = reinterpret_cast<const Consts *>(img + IMG_CONST);
+    double sq = 0.0;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int64_t i = 0; i < my_tiles; ++i) {
+                const int s = (int)(i % STAGES);
+                const uint32_t ph = (uint32_t)((i / STAGES) & 1);
+                mbar_wait(bar(Z_EMPTY + s), ph ^ 1);
+                mbar_expect_tx(bar(Z_FULL + s), TILE_M * D * 4);
+                const int64_t tile = blockIdx.x + i * gridDim.x;
+                tma_load_2d(sbase + OFF_ZRING + s * 16384, &map_z, bar(Z_FULL + s), 0, (int)(tile * TILE_M));
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_bf16(kp);
+            const uint64_t bmain = desc_sw128(sbase + OFF_BMAIN);
+            const uint64_t baug = desc_sw32(sbase + OFF_BAUG);
+            const uint64_t aaug = desc_sw32(sbase + OFF_AAUG);
+            for (int64_t i = 0; i < my_tiles; ++i) {
+                const int b = (int)(i & 1);
+                const uint32_t ph = (uint32_t)((i >> 1) & 1);
+                mbar_wait(bar(A_FULL + b), ph);
+                mbar_wait(bar(T_EMPTY + b), ph ^ 1);
+                tc_fence_after();
+                const uint64_t a = desc_sw128(sbase + OFF_ARING + b * 16384);
+                const uint32_t d = tmem_base + b * KMAX;
+                // K-slices of 16 bf16 = 32 bytes = +2 in the descriptor's address field
+                umma_bf16(d, a + 0, bmain + 0, idesc, 0);   // z1[0:16]  . E1[0:16]
+                umma_bf16(d, a + 2, bmain + 2, idesc, 1);   // z1[16:32] . E1[16:32]
+                umma_bf16(d, a + 0, bmain + 4, idesc, 1);   // z1[0:16]  . E2[0:16]
+                umma_bf16(d, a + 2, bmain + 6, idesc, 1);   // z1[16:32] . E2[16:32]
+                umma_bf16(d, a + 4, bmain + 0, idesc, 1);   // z2[0:16]  . E1[0:16]
+                umma_bf16(d, a + 6, bmain + 2, idesc, 1);   // z2[16:32] . E1[16:32]
+                umma_bf16(d, aaug, baug, idesc, 1);         // + ee_k
+                umma_commit(bar(A_EMPTY + b));
+                umma_commit(bar(T_FULL + b));
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================= converters: fp32 -> bf16 hi/lo, thread = row =================
+        const int r = tid - 128;
+        for (int64_t i = 0; i < my_tiles; ++i) {
+            const int s = (int)(i % STAGES);
+            const int b = (int)(i & 1);
+            mbar_wait(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));
+            mbar_wait(bar(A_EMPTY + b), (uint32_t)(((i >> 1) & 1) ^ 1));
+            const unsigned char *zt = smem + OFF_ZRING + s * 16384;
+            unsigned char *at = smem + OFF_ARING + b * 16384;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 v = *reinterpret_cast<const float4 *>(zt + sw128(r, c));
+                const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * h], x[2 * h + 1]);
+                    const float r0 = x[2 * h] - __low2float(h2);
+                    const float r1 = x[2 * h + 1] - __high2float(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+                    hi[2 * c + h] = *reinterpret_cast<const uint32_t *>(&h2);
+                    lo[2 * c + h] = *reinterpret_cast<const uint32_t *>(&l2);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                *reinterpret_cast<uint4 *>(at + sw128(r, c)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                *reinterpret_cast<uint4 *>(at + sw128(r, c + 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            }
+            fence_proxy_async();
+            mbar_arrive(bar(A_FULL + b));
+        }
+    } else if (warp >= 8) {
+        // ================= epilogue groups =================
+        const int g = (warp - 8) >> 2;            // group 0 / 1 <-> TMEM buffer 0 / 1
+        const int q = warp & 3;                   // TMEM lane quarter of this warp
+        const int r = q * 32 + lane;              // row in tile = TMEM lane
+        const unsigned char *ef32 = smem + OFF_EF32;
+        const float *ees = reinterpret_cast<const float *>(smem + OFF_EE);
+        unsigned *hist = reinterpret_cast<unsigned *>(smem + OFF_HIST);
+        const float eemax = __uint_as_float(cst->emax2_bits);
+        const float emax = sqrtf(eemax) * 1.0000002f;
+        const bool cb_bad = cst->nonfinite != 0 || p.hdr_in->poisoned_columns != 0;
+        const bool poisoned = p.hdr_in->poisoned_columns != 0;
+        const int n_chunk32 = kp >> 5;
+
+        for (int64_t i = g; i < my_tiles; i += 2) {
+            const int s = (int)(i % STAGES);
+            const uint32_t ph = (uint32_t)((i >> 1) & 1);
+            const int64_t tile = blockIdx.x + i * gridDim.x;
+            const int64_t row = tile * TILE_M + r;
+            const bool ok = row < n_rows;
+
+            // ---- filter: chunk minima of the approximate scores, packed top-2 ----
+            mbar_wait(bar(T_FULL + g), ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + g * KMAX + ((uint32_t)(q * 32) << 16);
+            float m1 = __int_as_float(0x7f800000), m2 = m1;
+            for (int c32 = 0; c32 < n_chunk32; ++c32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c32 * 32, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float t0 = min3(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1]), __uint_as_float(v[8 * u + 2]));
+                    const float t1 = min3(__uint_as_float(v[8 * u + 3]), __uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]));
+                    const float t2 = min3(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]), t0);
+                    const float m = fminf(t1, t2);
+                    const float key = __uint_as_float((__float_as_uint(m) & ~31u) | (unsigned)(c32 * 4 + u));
+                    m2 = fminf(m2, fmaxf(m1, key));
+                    m1 = fminf(m1, key);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(T_EMPTY + g));        // accumulator drained: the next MMA may overwrite it
+
+            // ---- exact decision ----
+            mbar_wait(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));   // acquire the TMA-written tile
+            unsigned char *zt = smem + OFF_ZRING + s * 16384;
+            float z[D];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 v = *reinterpret_cast<const float4 *>(zt + sw128(r, c));
+                z[4 * c] = v.x; z[4 * c + 1] = v.y; z[4 * c + 2] = v.z; z[4 * c + 3] = v.w;
+            }
+            float zz = 0.0f;
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                zz = fmaf(z[j], z[j], zz);
+            const float zn = sqrtf(zz) * 1.0000002f;
+            // Filter radius, see DESIGN.md "Exactness".  With |z| = zn, max|e| = emax, max ee = eemax:
+            //   2*eps  (bf16x3 residual 3*2^-18 per unit of sum|z_j e_j|, x2 for -2*dot, x2 both sides,
+            //           plus tensor-core accumulation slack)                 <= 2^-13.6 zn emax + 2^-19 eemax
+            //   2*H    (oracle fp32 roundings: fl(zz+ee), fl(t-u), D-step dot chain)
+            //                                                               <= 2^-22 (zn+emax)^2 + D 2^-22 zn emax
+            //   2*pack (chunk id in 5 mantissa bits of the key)             <= 2^-17 (2 zn emax + eemax)
+            const float delta = 9.6e-5f * zn * emax + 1.1e-5f * eemax + 3.0e-7f * (zn + emax) * (zn + emax);
+            const bool certain = (m2 > m1 + delta) && (zz <= 3.0e38f) && !cb_bad;
+            const int c1 = (int)(__float_as_uint(m1) & 31u);
+            float best = __int_as_float(0x7f800000);
+            int code = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = c1 * 8 + u;
+                float acc = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 e = *reinterpret_cast<const float4 *>(ef32 + ef32_off(k, c));
+                    acc = fmaf(z[4 * c], e.x, acc);
+                    acc = fmaf(z[4 * c + 1], e.y, acc);
+                    acc = fmaf(z[4 * c + 2], e.z, acc);
+                    acc = fmaf(z[4 * c + 3], e.w, acc);
+                }
+                const float dist = ref_distance(zz, ees[k], acc);
+                code = dist < best ? k : code;
+                best = fminf(best, dist);
+            }
+            if (code >= K)
+                code = 0;
+            // vectors the filter cannot certify (runner-up chunk too close, non-finite input or
+            // codebook): exact scan of all K codes, one vector at a time, by the whole warp
+            unsigned need = __ballot_sync(0xffffffffu, !certain);
+            const unsigned n_slow = __popc(need);
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const float zz_src = __shfl_sync(0xffffffffu, zz, src);
+                const int res = warp_full_scan(zt, q * 32 + src, zz_src, ef32, ees, K);
+                if (lane == src)
+                    code = res;
+            }
+            if (p.stats && lane == 0 && n_slow) {
+                atomicAdd(p.stats + 1, (unsigned long long)n_slow);
+            }
+
+            // ---- outputs: idx, histogram, loss, z_q (in place in the ring slot) ----
+            if (ok) {
+                if (p.idx)
+                    p.idx[row] = code;
+                atomicAdd(hist + code, 1u);
+            }
+            float rsq = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 e = *reinterpret_cast<const float4 *>(ef32 + ef32_off(code, c));
+                if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
+                    float *ev = reinterpret_cast<float *>(&e);
+                    for (int t = 0; t < 4; ++t) {
+                        const int j = 4 * c + t, cc = p.colcnt[j];
+                        if (!(cc == 0 || (cc == 1 && p.colwhich[j] == code + 1)))
+                            ev[t] = __int_as_float(0x7fc00000);
+                    }
+                }
+                float4 o;
+                float dj;
+                dj = __fsub_rn(e.x, z[4 * c]);     rsq = __fadd_rn(rsq, __fmul_rn(dj, dj)); o.x = __fadd_rn(z[4 * c], dj);
+                dj = __fsub_rn(e.y, z[4 * c + 1]); rsq = __fadd_rn(rsq, __fmul_rn(dj, dj)); o.y = __fadd_rn(z[4 * c + 1], dj);
+                dj = __fsub_rn(e.z, z[4 * c + 2]); rsq = __fadd_rn(rsq, __fmul_rn(dj, dj)); o.z = __fadd_rn(z[4 * c + 2], dj);
+                dj = __fsub_rn(e.w, z[4 * c + 3]); rsq = __fadd_rn(rsq, __fmul_rn(dj, dj)); o.w = __fadd_rn(z[4 * c + 3], dj);
+                if (p.zq)
+                    *reinterpret_cast<float4 *>(zt + sw128(r, c)) = o;
+            }
+            if (ok)
+                sq += (double)rsq;
+            if (p.zq)
+                fence_proxy_async();               // z_q rows (generic proxy) -> visible to the TMA store
+            named_bar_sync(1 + g, 128);            // all 128 rows of the tile are final
+            if ((warp & 3) == 0 && lane == 0) {
+                if (p.zq) {
+                    tma_store_2d(&map_zq, sbase + OFF_ZRING + s * 16384, 0, (int)(tile * TILE_M));
+                    tma_store_commit();
+                    tma_store_wait_read();         // the slot may be refilled once the store has read it
+                }
+                mbar_arrive(bar(Z_EMPTY + s));
+            }
+        }
+        if ((warp & 3) == 0 && lane == 0)
+            tma_store_wait_all();
+    }
+
+    // ---- teardown ----------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (tid < K) {
+        const unsigned c = reinterpret_cast<unsigned *>(smem + OFF_HIST)[tid];
+        if (c)
+            atomicAdd(p.counts + tid, (unsigned long long)c);
+    }
+    // per-CTA sum of squared residuals (deterministic order within the CTA)
+    __shared__ double red[16];
+    sq = warp_sum(sq);
+    if (lane == 0)
+        red[warp] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 16; ++w)
+            t += red[w];
+        p.partials[blockIdx.x] = p.accumulate ? p.partials[blockIdx.x] + t : t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+bool tc_shape_supported(int K, int D) { return D == tc::D && K >= 1 && K <= tc::KMAX; }
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+bool make_map(CUtensorMap *map, const float *base, int64_t n_rows)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc)
+        return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)tc::D, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)tc::D * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::D, (cuuint32_t)tc::TILE_M};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas,
+                          int *n_launches, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end)
+{
+    using namespace tc;
+    if (!tc_shape_supported(p.K, p.D) || !p.z.rows_contiguous(p.D) || SMEM_ALLOC > max_smem)
+        return cudaErrorNotSupported;
+    unsigned char *img = reinterpret_cast<unsigned char *>(tc_scratch);
+    CUtensorMap map_z, map_zq;
+    if (!make_map(&map_z, p.z.base, p.z.n_rows))
+        return cudaErrorNotSupported;
+    if (p.zq) {
+        if (!make_map(&map_zq, p.zq, p.z.n_rows))
+            return cudaErrorNotSupported;
+    } else {
+        map_zq = map_z;
+    }
+    const int kp = ((p.K + 31) / 32) * 32;
+    cudaError_t err = cudaMemsetAsync(img + IMG_CONST, 0, sizeof(Consts), st);
+    if (err != cudaSuccess)
+        return err;
+    vq_tc_prep_kernel<<<(KMAX + 127) / 128, 128, 0, st>>>(p.E, p.ee, p.K, kp, img);
+    if ((err = cudaGetLastError()) != cudaSuccess)
+        return err;
+    err = cudaFuncSetAttribute(vq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+    if (err != cudaSuccess)
+        return err;
+    const int64_t tiles = (p.z.n_rows + TILE_M - 1) / TILE_M;
+    int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    if (grid < 1)
+        grid = 1;
+    *n_ctas = grid;
+    if (ev_begin)
+        cudaEventRecord(ev_begin, st);
+    vq_fwd_tc_kernel<<<grid, THREADS, SMEM_ALLOC, st>>>(p, img, map_z, map_zq, kp);
+    err = cudaGetLastError();
+    if (ev_end)
+        cudaEventRecord(ev_end, st);
+    *n_launches = 2;
+    return err;
 }
 
 }  // namespace vqb
