@@ -264,3 +264,85 @@ def test_host_buffer_path_matches_oracle():
     enc.encode(z, 0.25, idx_out=idx2)
     assert torch.equal(idx, idx2)
     enc.close()
+
+
+# ---------------------------------------------------------------------------------------
+# tcgen05 path specifics (D = 32, K <= 256, contiguous rows): the cases the filter must hand
+# to the exact scan -- exact ties, near-ties, non-finite vectors and codebooks, pad codes
+# ---------------------------------------------------------------------------------------
+def _tc_vs_oracle(z_np, E, beta=0.25, path="tc"):
+    dev = _dev()
+    z = torch.from_numpy(z_np).to(dev)
+    out = ops.forward(z, torch.from_numpy(E).to(dev), beta, path=path, want_stats=True)
+    torch.cuda.synchronize()
+    ora = O.forward(z_np, E, beta)
+    n, d = z_np.shape
+    assert np.array_equal(out[3].cpu().numpy().reshape(-1), ora.indices.reshape(-1))
+    assert np.array_equal(out[1].cpu().numpy().reshape(n, d), ora.z_q.reshape(n, d), equal_nan=True)
+    assert np.array_equal(out[4].cpu().numpy(), ora.counts)
+    if np.isnan(ora.loss):
+        assert torch.isnan(out[0])
+    else:
+        assert out[0].item() == pytest.approx(float(ora.loss), rel=REL)
+    assert out[2].item() == pytest.approx(float(ora.perplexity), rel=REL)
+    return out[5].cpu().numpy()
+
+
+def test_tc_exact_ties_take_lowest_index():
+    rs = np.random.RandomState(31)
+    K, D, n = 256, 32, 1000
+    E = (0.1 * rs.standard_normal((K, D))).astype(np.float32)
+    E[200] = E[7]; E[201] = E[7]; E[16] = E[3]; E[255] = E[0]      # duplicates across A- and B-groups
+    pick = rs.randint(0, K, n)
+    z = E[pick].copy()
+    z[n // 2:] += (0.01 * rs.standard_normal((n - n // 2, D))).astype(np.float32)
+    z[:8] = (E[1] + E[2]) / 2                                       # equidistant from two codes
+    stats = _tc_vs_oracle(z, E)
+    assert stats[1] > 0                                             # ties went through the exact scan
+
+
+def test_tc_nonfinite_vectors_and_codebook():
+    rs = np.random.RandomState(32)
+    K, D, n = 256, 32, 640
+    E = rs.uniform(-1.0 / K, 1.0 / K, (K, D)).astype(np.float32)
+    z = (0.1 * rs.standard_normal((n, D))).astype(np.float32)
+    z[1, 2] = np.nan; z[2, 0] = np.inf; z[3, 1] = -np.inf; z[4, :] = np.nan
+    z[5, 0] = np.inf; z[5, 1] = -np.inf; z[6, :] = 0.0; z[7, 3] = 3.0e38; z[130, 31] = 1.0e30; z[639, 0] = np.nan
+    _tc_vs_oracle(z, E)
+    E2 = E.copy(); E2[5, 1] = np.nan; E2[2, 3] = np.inf; E2[77, 30] = -np.inf
+    _tc_vs_oracle((0.1 * rs.standard_normal((n, D))).astype(np.float32), E2)
+    E3 = E.copy(); E3[9] *= 1.0e20                                  # finite entries, ee overflows to inf
+    _tc_vs_oracle((0.1 * rs.standard_normal((n, D))).astype(np.float32), E3)
+
+
+@pytest.mark.parametrize("K", [1, 2, 15, 16, 17, 31, 33, 100, 255, 256])
+@pytest.mark.parametrize("n", [128, 129, 1000])
+def test_tc_pad_codes_and_ragged_tiles(K, n):
+    rs = np.random.RandomState(K * 1000 + n)
+    E = (0.1 * rs.standard_normal((K, 32))).astype(np.float32)
+    z = (0.1 * rs.standard_normal((n, 32))).astype(np.float32)
+    _tc_vs_oracle(z, E)
+
+
+def test_tc_scale_extremes():
+    """Tiny and huge magnitudes, and a codebook much larger than the vectors (the filter radius is
+    dominated by ee there: many vectors take the exact scan, results must not change)."""
+    rs = np.random.RandomState(33)
+    for zs, es in ((1e-20, 1e-20), (1e15, 1e15), (0.01, 10.0), (10.0, 0.001), (1e-3, 1.0)):
+        E = (es * rs.standard_normal((256, 32))).astype(np.float32)
+        z = (zs * rs.standard_normal((2000, 32))).astype(np.float32)
+        _tc_vs_oracle(z, E)
+
+
+def test_tc_matches_fma_on_4m_vectors():
+    """Bit-exact agreement of the two kernel paths on 2^22 vectors, trained-like and default codebooks."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(99)
+    for scale_e in (None, 0.1):
+        z = 0.1 * torch.randn(1 << 22, 32, device=dev, generator=g)
+        w = (torch.rand(256, 32, device=dev, generator=g) * 2 - 1) / 256 if scale_e is None else \
+            scale_e * torch.randn(256, 32, device=dev, generator=g)
+        a = ops.forward(z, w, 0.25, path="fma")
+        b = ops.forward(z, w, 0.25, path="tc")
+        assert torch.equal(a[3], b[3]) and torch.equal(a[1], b[1]) and torch.equal(a[4], b[4])
+        assert b[0].item() == pytest.approx(a[0].item(), rel=1e-6)

@@ -11,13 +11,17 @@
 //      tcgen05.mma accumulate   s~[i][k] = ee_k - 2*(z1.E1 + z1.E2 + z2.E1)   in TMEM
 //      (7 MMAs of 128 x 256 x 16 per 128-vector tile; ee_k enters through a 7th K-slice of
 //      ones times its exact three-way bf16 split, E is pre-scaled by -2);
-//   2. per vector, the 256 approximate scores are reduced to 32 chunk minima (8 codes per
-//      chunk, FMNMX3) and a packed top-2 over the chunks;
-//   3. |s~ - s| <= eps  =>  the oracle's winner lies in the best chunk unless the runner-up
-//      chunk is within delta = 2*eps + rounding slack of it (rare: ~0.1 % of vectors);
-//   4. the 8 codes of the best chunk are evaluated with the oracle-order expression
-//      (ascending fmaf chain, fl(fl(zz+ee) - 2dot), lowest index wins) on the CUDA cores;
-//      ambiguous or non-finite vectors are scanned exactly over all K codes by their warp.
+//   2. per vector, the 256 approximate scores are reduced along TWO orthogonal groupings:
+//      A-groups of 16 consecutive codes {16a .. 16a+15} and B-groups of 16 strided codes
+//      {b, b+16, b+32, ...}; each grouping keeps a packed (value | group id) top-2 (FMNMX3
+//      trees: 1.5 ALU ops per score in total).  Two codes that share an A-group never share
+//      a B-group, so min(runner-up A, runner-up B) bounds the second-smallest SCORE;
+//   3. |s~ - s| <= eps  =>  if that runner-up is more than delta = 2*eps + rounding slack
+//      above the best score, the oracle's argmin is the code (best A-group, best B-group)
+//      -- decided by the tensor cores alone (~99.8 % of vectors);
+//   4. otherwise, or for non-finite vectors / codebooks, the vector's warp scans all K codes
+//      with the oracle-order expression (ascending fmaf chain, fl(fl(zz+ee) - 2dot), lowest
+//      index wins, first NaN wins) on the CUDA cores.
 //
 // The decision is therefore bit-identical to the FMA kernel and the CPU oracle.
 //
@@ -25,6 +29,7 @@
 //   warp 0      TMA producer: z tile (128 x 32 fp32, SWIZZLE_128B) -> 4-deep smem ring
 //   warp 1      MMA issuer (one thread): 7 x tcgen05.mma.kind::f16 -> TMEM (2 x 256 columns)
 //   warp 2      TMEM allocator
+//   warp 3      z_q TMA store + ring-slot release
 //   warps 4-7   converters: fp32 tile -> bf16 [z1|z2] tile in the UMMA K-major SW128 layout
 //   warps 8-15  two epilogue groups alternating tiles: TMEM -> chunk minima -> exact decision
 //               -> z_q written in place into the ring slot -> TMA store; idx, loss, histogram
@@ -40,7 +45,7 @@ namespace tc {
 constexpr int D = 32;
 constexpr int TILE_M = 128;
 constexpr int KMAX = 256;
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 constexpr int THREADS = 512;
 
 // shared-memory map (bytes); SW128 operands need 1024-byte alignment
@@ -54,7 +59,7 @@ constexpr int OFF_EE = OFF_EF32 + 32768;                  // 1024            fp3
 constexpr int OFF_HIST = OFF_EE + 1024;                   // 1024            u32 histogram
 constexpr int OFF_BARS = OFF_HIST + 1024;                 // 256             mbarriers + tmem base
 constexpr int SMEM_BYTES = OFF_BARS + 256;
-constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;             // slack for manual 1024-byte alignment
+constexpr int SMEM_ALLOC = SMEM_BYTES;
 
 // image of the constant operands prepared once per call in global scratch
 constexpr int IMG_BMAIN = 0;
@@ -102,7 +107,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26))
+        __nanosleep(32);
+        if (++spins > (1u << 24))
             __trap();
     }
 }
@@ -254,9 +260,10 @@ __global__ void vq_tc_prep_kernel(const float *__restrict__ E, const float *__re
 // ---------------------------------------------------------------------------------------
 namespace tc {
 
-// warp-cooperative exact scan of all K codes for the vector held by lane `src`
-// (zrow points at that vector's 128-byte row in the ring slot, SW128 layout).
-__device__ __noinline__ int warp_full_scan(const unsigned char *ztile, int row_in_tile, float zz,
+// Warp-cooperative exact scan of all K codes for one vector (row `row_in_tile` of the ring
+// slot `ztile`, SW128 layout): the oracle-order expression, lowest index on ties, first NaN
+// wins.  Every lane returns the same code.
+__device__ __noinline__ int warp_full_scan(const unsigned char *ztile, int row_in_tile,
                                            const unsigned char *ef32, const float *ees, int K)
 {
     const int lane = threadIdx.x & 31;
@@ -266,6 +273,10 @@ __device__ __noinline__ int warp_full_scan(const unsigned char *ztile, int row_i
         const float4 v = *reinterpret_cast<const float4 *>(ztile + sw128(row_in_tile, c));
         z[4 * c] = v.x; z[4 * c + 1] = v.y; z[4 * c + 2] = v.z; z[4 * c + 3] = v.w;
     }
+    float zz = 0.0f;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+        zz = fmaf(z[j], z[j], zz);          // oracle-order ||z||^2
     float best = __int_as_float(0x7f800000);
     int bidx = 0x7fffffff;
     unsigned first_nan = 0xffffffffu;
@@ -282,14 +293,14 @@ __device__ __noinline__ int warp_full_scan(const unsigned char *ztile, int row_i
         const float dist = ref_distance(zz, ees[k], acc);
         if (dist != dist)
             first_nan = min(first_nan, (unsigned)k);
-        if (dist < best || (dist == best && k < bidx)) {
+        if (dist < best) {                  // k ascends per lane: strict < keeps the lowest index
             best = dist;
             bidx = k;
         }
     }
     const unsigned nan_k = __reduce_min_sync(0xffffffffu, first_nan);
     if (nan_k != 0xffffffffu)
-        return (int)nan_k;   // torch.argmin: the first NaN wins
+        return (int)nan_k;                  // torch.argmin: the first NaN wins
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -302,6 +313,54 @@ __device__ __noinline__ int warp_full_scan(const unsigned char *ztile, int row_i
     return bidx == 0x7fffffff ? 0 : bidx;
 }
 
+// packed top-2 update: key = value with a group id in its 4 low mantissa bits
+__device__ __forceinline__ void top2(float &m1, float &m2, float v, unsigned id)
+{
+    const float key = __uint_as_float((__float_as_uint(v) & ~15u) | id);
+    m2 = fminf(m2, fmaxf(m1, key));
+    m1 = fminf(m1, key);
+}
+
+// minimum of 16 registers with 3-input FMNMX: 8 instructions
+__device__ __forceinline__ float min16(const uint32_t *v)
+{
+    const float t0 = min3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+    const float t1 = min3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+    const float t2 = min3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+    const float t3 = min3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+    const float t4 = min3(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]));
+    const float t5 = min3(__uint_as_float(v[15]), t0, t1);
+    const float t6 = min3(t2, t3, t4);
+    return fminf(t5, t6);
+}
+
+// One 32-column slab of approximate scores: two A-groups (16 consecutive codes each) and a
+// contribution to each of the 16 B-groups (code mod 16).
+__device__ __forceinline__ void filter_slab(const uint32_t (&v)[32], int slab, float (&bmin)[16], float &a1, float &a2)
+{
+    top2(a1, a2, min16(&v[0]), (unsigned)(2 * slab));
+    top2(a1, a2, min16(&v[16]), (unsigned)(2 * slab + 1));
+#pragma unroll
+    for (int b = 0; b < 16; ++b)
+        bmin[b] = min3(bmin[b], __uint_as_float(v[b]), __uint_as_float(v[b + 16]));
+}
+
+// tcgen05.wait::ld, with the freshly loaded registers threaded through the statement so that
+// no use of them can be scheduled before the wait
+__device__ __forceinline__ void tmem_wait_ld_fence(uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+    asm volatile(""
+                 : "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------
@@ -312,13 +371,14 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                  const __grid_constant__ CUtensorMap map_zq, int kp)
 {
     using namespace tc;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);
+    if ((sbase & 1023u) != 0)
+        __trap();                  // SW128 operands and TMA boxes need a 1024-byte aligned base
     // barrier indices
-    enum { Z_FULL = 0, Z_EMPTY = Z_FULL + STAGES, A_FULL = Z_EMPTY + STAGES, A_EMPTY = A_FULL + 2,
-           T_FULL = A_EMPTY + 2, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2 };
+    enum { Z_FULL = 0, Z_EMPTY = Z_FULL + STAGES, Q_DONE = Z_EMPTY + STAGES, A_FULL = Q_DONE + STAGES,
+           A_EMPTY = A_FULL + 2, T_FULL = A_EMPTY + 2, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2 };
+    static_assert(8 * N_BARS + 8 <= 256, "barrier area");
     auto bar = [&](int i) { return sbase + OFF_BARS + 8 * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + 8 * N_BARS);
 
@@ -333,6 +393,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar(Z_FULL + s), 1);
             mbar_init(bar(Z_EMPTY + s), 1);
+            mbar_init(bar(Q_DONE + s), 128);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar(A_FULL + b), 128);
@@ -411,26 +472,43 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 umma_commit(bar(T_FULL + b));
             }
         }
+    } else if (warp == 3) {
+        // ================= z_q store + slot release =================
+        if (lane == 0) {
+            for (int64_t i = 0; i < my_tiles; ++i) {
+                const int s = (int)(i % STAGES);
+                mbar_wait(bar(Q_DONE + s), (uint32_t)((i / STAGES) & 1));
+                if (p.zq) {
+                    const int64_t tile = blockIdx.x + i * gridDim.x;
+                    tma_store_2d(&map_zq, sbase + OFF_ZRING + s * 16384, 0, (int)(tile * TILE_M));
+                    tma_store_commit();
+                    tma_store_wait_read();     // the slot may be refilled once the store has read it
+                }
+                mbar_arrive(bar(Z_EMPTY + s));
+            }
+            tma_store_wait_all();
+        }
     } else if (warp >= 4 && warp < 8) {
         // ================= converters: fp32 -> bf16 hi/lo, thread = row =================
         const int r = tid - 128;
+        const int x = (r & 7) << 4;
         for (int64_t i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % STAGES);
             const int b = (int)(i & 1);
             mbar_wait(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));
             mbar_wait(bar(A_EMPTY + b), (uint32_t)(((i >> 1) & 1) ^ 1));
-            const unsigned char *zt = smem + OFF_ZRING + s * 16384;
-            unsigned char *at = smem + OFF_ARING + b * 16384;
+            const unsigned char *zrow = smem + OFF_ZRING + s * 16384 + r * 128;
+            unsigned char *arow = smem + OFF_ARING + b * 16384 + r * 128;
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const float4 v = *reinterpret_cast<const float4 *>(zt + sw128(r, c));
-                const float x[4] = {v.x, v.y, v.z, v.w};
+                const float4 v = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ x));
+                const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * h], x[2 * h + 1]);
-                    const float r0 = x[2 * h] - __low2float(h2);
-                    const float r1 = x[2 * h + 1] - __high2float(h2);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(xs[2 * h], xs[2 * h + 1]);
+                    const float r0 = xs[2 * h] - __low2float(h2);
+                    const float r1 = xs[2 * h + 1] - __high2float(h2);
                     const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
                     hi[2 * c + h] = *reinterpret_cast<const uint32_t *>(&h2);
                     lo[2 * c + h] = *reinterpret_cast<const uint32_t *>(&l2);
@@ -438,8 +516,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                *reinterpret_cast<uint4 *>(at + sw128(r, c)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                *reinterpret_cast<uint4 *>(at + sw128(r, c + 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                *reinterpret_cast<uint4 *>(arow + ((c << 4) ^ x)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                *reinterpret_cast<uint4 *>(arow + (((c + 4) << 4) ^ x)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
             }
             fence_proxy_async();
             mbar_arrive(bar(A_FULL + b));
@@ -449,14 +527,16 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         const int g = (warp - 8) >> 2;            // group 0 / 1 <-> TMEM buffer 0 / 1
         const int q = warp & 3;                   // TMEM lane quarter of this warp
         const int r = q * 32 + lane;              // row in tile = TMEM lane
+        const int x = (r & 7) << 4;
         const unsigned char *ef32 = smem + OFF_EF32;
         const float *ees = reinterpret_cast<const float *>(smem + OFF_EE);
         unsigned *hist = reinterpret_cast<unsigned *>(smem + OFF_HIST);
         const float eemax = __uint_as_float(cst->emax2_bits);
         const float emax = sqrtf(eemax) * 1.0000002f;
-        const bool cb_bad = cst->nonfinite != 0 || p.hdr_in->poisoned_columns != 0;
         const bool poisoned = p.hdr_in->poisoned_columns != 0;
-        const int n_chunk32 = kp >> 5;
+        const bool cb_bad = cst->nonfinite != 0 || poisoned;
+        const int n_slab = kp >> 5;
+        unsigned long long n_slow_total = 0;
 
         for (int64_t i = g; i < my_tiles; i += 2) {
             const int s = (int)(i % STAGES);
@@ -465,86 +545,76 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             const int64_t row = tile * TILE_M + r;
             const bool ok = row < n_rows;
 
-            // ---- filter: chunk minima of the approximate scores, packed top-2 ----
+            // ---- filter: A/B group minima of the approximate scores, packed top-2 each ----
             mbar_wait(bar(T_FULL + g), ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + g * KMAX + ((uint32_t)(q * 32) << 16);
-            float m1 = __int_as_float(0x7f800000), m2 = m1;
-            for (int c32 = 0; c32 < n_chunk32; ++c32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c32 * 32, v);
-                tmem_wait_ld();
+            const float inf = __int_as_float(0x7f800000);
+            float a1 = inf, a2 = inf;
+            float bmin[16];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float t0 = min3(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1]), __uint_as_float(v[8 * u + 2]));
-                    const float t1 = min3(__uint_as_float(v[8 * u + 3]), __uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]));
-                    const float t2 = min3(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]), t0);
-                    const float m = fminf(t1, t2);
-                    const float key = __uint_as_float((__float_as_uint(m) & ~31u) | (unsigned)(c32 * 4 + u));
-                    m2 = fminf(m2, fmaxf(m1, key));
-                    m1 = fminf(m1, key);
+            for (int b = 0; b < 16; ++b)
+                bmin[b] = inf;
+            {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr, v0);
+                for (int sl = 0; sl < n_slab; sl += 2) {       // software pipelined: next slab in flight
+                    tmem_wait_ld_fence(v0);
+                    if (sl + 1 < n_slab)
+                        tmem_ld32(taddr + (sl + 1) * 32, v1);
+                    filter_slab(v0, sl, bmin, a1, a2);
+                    if (sl + 1 < n_slab) {
+                        tmem_wait_ld_fence(v1);
+                        if (sl + 2 < n_slab)
+                            tmem_ld32(taddr + (sl + 2) * 32, v0);
+                        filter_slab(v1, sl + 1, bmin, a1, a2);
+                    }
                 }
             }
             tc_fence_before();
             mbar_arrive(bar(T_EMPTY + g));        // accumulator drained: the next MMA may overwrite it
+            float b1 = inf, b2 = inf;
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                top2(b1, b2, bmin[b], (unsigned)b);
 
-            // ---- exact decision ----
-            mbar_wait(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));   // acquire the TMA-written tile
+            // ---- the vector itself (TMA-written ring slot) ----
+            mbar_wait(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));   // acquire the tile
             unsigned char *zt = smem + OFF_ZRING + s * 16384;
+            unsigned char *zrow = zt + r * 128;
             float z[D];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const float4 v = *reinterpret_cast<const float4 *>(zt + sw128(r, c));
+                const float4 v = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ x));
                 z[4 * c] = v.x; z[4 * c + 1] = v.y; z[4 * c + 2] = v.z; z[4 * c + 3] = v.w;
             }
-            float zz = 0.0f;
+            float zp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < D; ++j)
-                zz = fmaf(z[j], z[j], zz);
-            const float zn = sqrtf(zz) * 1.0000002f;
+                zp[j & 3] = fmaf(z[j], z[j], zp[j & 3]);
+            const float zz = (zp[0] + zp[1]) + (zp[2] + zp[3]);     // only bounds ||z||, not part of the decision
+            const float zn = sqrtf(zz) * 1.000001f;
             // Filter radius, see DESIGN.md "Exactness".  With |z| = zn, max|e| = emax, max ee = eemax:
             //   2*eps  (bf16x3 residual 3*2^-18 per unit of sum|z_j e_j|, x2 for -2*dot, x2 both sides,
             //           plus tensor-core accumulation slack)                 <= 2^-13.6 zn emax + 2^-19 eemax
             //   2*H    (oracle fp32 roundings: fl(zz+ee), fl(t-u), D-step dot chain)
             //                                                               <= 2^-22 (zn+emax)^2 + D 2^-22 zn emax
-            //   2*pack (chunk id in 5 mantissa bits of the key)             <= 2^-17 (2 zn emax + eemax)
+            //   2*pack (group id in 4 mantissa bits of the keys)             <= 2^-17 (2 zn emax + eemax)
             const float delta = 9.6e-5f * zn * emax + 1.1e-5f * eemax + 3.0e-7f * (zn + emax) * (zn + emax);
-            const bool certain = (m2 > m1 + delta) && (zz <= 3.0e38f) && !cb_bad;
-            const int c1 = (int)(__float_as_uint(m1) & 31u);
-            float best = __int_as_float(0x7f800000);
-            int code = 0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int k = c1 * 8 + u;
-                float acc = 0.0f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 e = *reinterpret_cast<const float4 *>(ef32 + ef32_off(k, c));
-                    acc = fmaf(z[4 * c], e.x, acc);
-                    acc = fmaf(z[4 * c + 1], e.y, acc);
-                    acc = fmaf(z[4 * c + 2], e.z, acc);
-                    acc = fmaf(z[4 * c + 3], e.w, acc);
-                }
-                const float dist = ref_distance(zz, ees[k], acc);
-                code = dist < best ? k : code;
-                best = fminf(best, dist);
-            }
+            const float best = fmaxf(a1, b1), second = fminf(a2, b2);
+            const bool certain = (second > best + delta) && (zz <= 3.0e38f) && !cb_bad;
+            int code = (int)(((__float_as_uint(a1) & 15u) << 4) | (__float_as_uint(b1) & 15u));
             if (code >= K)
                 code = 0;
-            // vectors the filter cannot certify (runner-up chunk too close, non-finite input or
-            // codebook): exact scan of all K codes, one vector at a time, by the whole warp
+            // vectors the filter cannot certify: exact scan of all K codes by the whole warp
             unsigned need = __ballot_sync(0xffffffffu, !certain);
-            const unsigned n_slow = __popc(need);
+            n_slow_total += __popc(need);
             while (need) {
                 const int src = __ffs(need) - 1;
                 need &= need - 1;
-                const float zz_src = __shfl_sync(0xffffffffu, zz, src);
-                const int res = warp_full_scan(zt, q * 32 + src, zz_src, ef32, ees, K);
+                const int res = warp_full_scan(zt, q * 32 + src, ef32, ees, K);
                 if (lane == src)
                     code = res;
-            }
-            if (p.stats && lane == 0 && n_slow) {
-                atomicAdd(p.stats + 1, (unsigned long long)n_slow);
             }
 
             // ---- outputs: idx, histogram, loss, z_q (in place in the ring slot) ----
@@ -553,10 +623,12 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     p.idx[row] = code;
                 atomicAdd(hist + code, 1u);
             }
-            float rsq = 0.0f;
+            const unsigned char *erow = ef32 + code * 128;
+            const int xe = ((code ^ (code >> 3)) & 7) << 4;
+            float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                float4 e = *reinterpret_cast<const float4 *>(ef32 + ef32_off(code, c));
+                float4 e = *reinterpret_cast<const float4 *>(erow + ((c << 4) ^ xe));
                 if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
                     float *ev = reinterpret_cast<float *>(&e);
                     for (int t = 0; t < 4; ++t) {
@@ -567,29 +639,21 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 }
                 float4 o;
                 float dj;
-                dj = __fsub_rn(e.x, z[4 * c]);     rsq = __fadd_rn(rsq, __fmul_rn(dj, dj)); o.x = __fadd_rn(z[4 * c], dj);
-                dj = __fsub_rn(e.y, z[4 * c + 1]); rsq = __fadd_rn(rsq, __fmul_rn(dj, dj)); o.y = __fadd_rn(z[4 * c + 1], dj);
-                dj = __fsub_rn(e.z, z[4 * c + 2]); rsq = __fadd_rn(rsq, __fmul_rn(dj, dj)); o.z = __fadd_rn(z[4 * c + 2], dj);
-                dj = __fsub_rn(e.w, z[4 * c + 3]); rsq = __fadd_rn(rsq, __fmul_rn(dj, dj)); o.w = __fadd_rn(z[4 * c + 3], dj);
+                dj = __fsub_rn(e.x, z[4 * c]);     rs[0] = fmaf(dj, dj, rs[0]); o.x = __fadd_rn(z[4 * c], dj);
+                dj = __fsub_rn(e.y, z[4 * c + 1]); rs[1] = fmaf(dj, dj, rs[1]); o.y = __fadd_rn(z[4 * c + 1], dj);
+                dj = __fsub_rn(e.z, z[4 * c + 2]); rs[2] = fmaf(dj, dj, rs[2]); o.z = __fadd_rn(z[4 * c + 2], dj);
+                dj = __fsub_rn(e.w, z[4 * c + 3]); rs[3] = fmaf(dj, dj, rs[3]); o.w = __fadd_rn(z[4 * c + 3], dj);
                 if (p.zq)
-                    *reinterpret_cast<float4 *>(zt + sw128(r, c)) = o;
+                    *reinterpret_cast<float4 *>(zrow + ((c << 4) ^ x)) = o;
             }
             if (ok)
-                sq += (double)rsq;
+                sq += (double)((rs[0] + rs[1]) + (rs[2] + rs[3]));
             if (p.zq)
                 fence_proxy_async();               // z_q rows (generic proxy) -> visible to the TMA store
-            named_bar_sync(1 + g, 128);            // all 128 rows of the tile are final
-            if ((warp & 3) == 0 && lane == 0) {
-                if (p.zq) {
-                    tma_store_2d(&map_zq, sbase + OFF_ZRING + s * 16384, 0, (int)(tile * TILE_M));
-                    tma_store_commit();
-                    tma_store_wait_read();         // the slot may be refilled once the store has read it
-                }
-                mbar_arrive(bar(Z_EMPTY + s));
-            }
+            mbar_arrive(bar(Q_DONE + s));          // warp 3 stores the tile and frees the slot
         }
-        if ((warp & 3) == 0 && lane == 0)
-            tma_store_wait_all();
+        if (p.stats && n_slow_total && lane == 0)
+            atomicAdd(p.stats + 1, n_slow_total);
     }
 
     // ---- teardown ----------------------------------------------------------------------
