@@ -31,7 +31,7 @@
 //   warp 2      TMEM allocator
 //   warp 3      z_q TMA store + ring-slot release
 //   warps 4-7   converters: fp32 tile -> bf16 [z1|z2] tile in the UMMA K-major SW128 layout
-//   warps 8-15  two epilogue groups alternating tiles: TMEM -> chunk minima -> exact decision
+//   warps 8-23  four epilogue groups (tile i -> group i % 4, TMEM buffer i & 1): TMEM -> chunk minima -> exact decision
 //               -> z_q written in place into the ring slot -> TMA store; idx, loss, histogram
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -46,7 +46,8 @@ constexpr int D = 32;
 constexpr int TILE_M = 128;
 constexpr int KMAX = 256;
 constexpr int STAGES = 6;
-constexpr int THREADS = 512;
+constexpr int GROUPS = 4;                 // epilogue groups (4 warps each) rotating over the 2 TMEM buffers
+constexpr int THREADS = 256 + 128 * GROUPS;
 
 // shared-memory map (bytes); SW128 operands need 1024-byte alignment
 constexpr int OFF_ZRING = 0;                              // STAGES x 16384  fp32 z tiles (TMA, SW128)
@@ -103,15 +104,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
     return ok != 0;
 }
 // Bounded wait: a pipeline bug must trap instead of hanging the GPU.
+template <int SLEEP_NS = 32>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(32);
+        if (SLEEP_NS > 0)
+            __nanosleep(SLEEP_NS);      // waiting warps must not eat the issue slots of working ones
         if (++spins > (1u << 24))
             __trap();
     }
 }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -377,7 +382,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         __trap();                  // SW128 operands and TMA boxes need a 1024-byte aligned base
     // barrier indices
     enum { Z_FULL = 0, Z_EMPTY = Z_FULL + STAGES, Q_DONE = Z_EMPTY + STAGES, A_FULL = Q_DONE + STAGES,
-           A_EMPTY = A_FULL + 2, T_FULL = A_EMPTY + 2, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2 };
+           A_EMPTY = A_FULL + 2, T_FULL = A_EMPTY + 2, T_EMPTY = T_FULL + GROUPS, N_BARS = T_EMPTY + 2 };
+    // T_FULL is per epilogue GROUP (a waiter must see every phase of its barrier), T_EMPTY per TMEM buffer
     static_assert(8 * N_BARS + 8 <= 256, "barrier area");
     auto bar = [&](int i) { return sbase + OFF_BARS + 8 * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + 8 * N_BARS);
@@ -398,9 +404,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar(A_FULL + b), 128);
             mbar_init(bar(A_EMPTY + b), 1);
-            mbar_init(bar(T_FULL + b), 1);
             mbar_init(bar(T_EMPTY + b), 128);
         }
+        for (int g = 0; g < GROUPS; ++g)
+            mbar_init(bar(T_FULL + g), 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -433,13 +440,15 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     const Consts *cst = reinterpret_cast<const Consts *>(img + IMG_CONST);
     double sq = 0.0;
 
+    if (warp < 4)
+        reg_dec<40>();
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             for (int64_t i = 0; i < my_tiles; ++i) {
                 const int s = (int)(i % STAGES);
                 const uint32_t ph = (uint32_t)((i / STAGES) & 1);
-                mbar_wait(bar(Z_EMPTY + s), ph ^ 1);
+                mbar_wait<128>(bar(Z_EMPTY + s), ph ^ 1);
                 mbar_expect_tx(bar(Z_FULL + s), TILE_M * D * 4);
                 const int64_t tile = blockIdx.x + i * gridDim.x;
                 tma_load_2d(sbase + OFF_ZRING + s * 16384, &map_z, bar(Z_FULL + s), 0, (int)(tile * TILE_M));
@@ -455,8 +464,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             for (int64_t i = 0; i < my_tiles; ++i) {
                 const int b = (int)(i & 1);
                 const uint32_t ph = (uint32_t)((i >> 1) & 1);
-                mbar_wait(bar(A_FULL + b), ph);
-                mbar_wait(bar(T_EMPTY + b), ph ^ 1);
+                mbar_wait<32>(bar(A_FULL + b), ph);
+                mbar_wait<32>(bar(T_EMPTY + b), ph ^ 1);
                 tc_fence_after();
                 const uint64_t a = desc_sw128(sbase + OFF_ARING + b * 16384);
                 const uint32_t d = tmem_base + b * KMAX;
@@ -469,7 +478,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 umma_bf16(d, a + 6, bmain + 2, idesc, 1);   // z2[16:32] . E1[16:32]
                 umma_bf16(d, aaug, baug, idesc, 1);         // + ee_k
                 umma_commit(bar(A_EMPTY + b));
-                umma_commit(bar(T_FULL + b));
+                umma_commit(bar(T_FULL + (int)(i % GROUPS)));
             }
         }
     } else if (warp == 3) {
@@ -477,7 +486,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         if (lane == 0) {
             for (int64_t i = 0; i < my_tiles; ++i) {
                 const int s = (int)(i % STAGES);
-                mbar_wait(bar(Q_DONE + s), (uint32_t)((i / STAGES) & 1));
+                mbar_wait<128>(bar(Q_DONE + s), (uint32_t)((i / STAGES) & 1));
                 if (p.zq) {
                     const int64_t tile = blockIdx.x + i * gridDim.x;
                     tma_store_2d(&map_zq, sbase + OFF_ZRING + s * 16384, 0, (int)(tile * TILE_M));
@@ -490,13 +499,14 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         }
     } else if (warp >= 4 && warp < 8) {
         // ================= converters: fp32 -> bf16 hi/lo, thread = row =================
+        reg_dec<72>();
         const int r = tid - 128;
         const int x = (r & 7) << 4;
         for (int64_t i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % STAGES);
             const int b = (int)(i & 1);
-            mbar_wait(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));
-            mbar_wait(bar(A_EMPTY + b), (uint32_t)(((i >> 1) & 1) ^ 1));
+            mbar_wait<128>(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));
+            mbar_wait<128>(bar(A_EMPTY + b), (uint32_t)(((i >> 1) & 1) ^ 1));
             const unsigned char *zrow = smem + OFF_ZRING + s * 16384 + r * 128;
             unsigned char *arow = smem + OFF_ARING + b * 16384 + r * 128;
             uint32_t hi[16], lo[16];
@@ -524,7 +534,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         }
     } else if (warp >= 8) {
         // ================= epilogue groups =================
-        const int g = (warp - 8) >> 2;            // group 0 / 1 <-> TMEM buffer 0 / 1
+        reg_inc<88>();
+        const int g = (warp - 8) >> 2;            // tile i is handled by group i % GROUPS, TMEM buffer i & 1
         const int q = warp & 3;                   // TMEM lane quarter of this warp
         const int r = q * 32 + lane;              // row in tile = TMEM lane
         const int x = (r & 7) << 4;
@@ -538,48 +549,40 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         const int n_slab = kp >> 5;
         unsigned long long n_slow_total = 0;
 
-        for (int64_t i = g; i < my_tiles; i += 2) {
+        float sqf = 0.0f;
+        for (int64_t i = g; i < my_tiles; i += GROUPS) {
             const int s = (int)(i % STAGES);
-            const uint32_t ph = (uint32_t)((i >> 1) & 1);
+            const int b = (int)(i & 1);
+            const uint32_t ph = (uint32_t)((i / GROUPS) & 1);
             const int64_t tile = blockIdx.x + i * gridDim.x;
             const int64_t row = tile * TILE_M + r;
             const bool ok = row < n_rows;
 
             // ---- filter: A/B group minima of the approximate scores, packed top-2 each ----
-            mbar_wait(bar(T_FULL + g), ph);
+            mbar_wait<64>(bar(T_FULL + g), ph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + g * KMAX + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + b * KMAX + ((uint32_t)(q * 32) << 16);
             const float inf = __int_as_float(0x7f800000);
             float a1 = inf, a2 = inf;
             float bmin[16];
 #pragma unroll
-            for (int b = 0; b < 16; ++b)
-                bmin[b] = inf;
-            {
-                uint32_t v0[32], v1[32];
-                tmem_ld32(taddr, v0);
-                for (int sl = 0; sl < n_slab; sl += 2) {       // software pipelined: next slab in flight
-                    tmem_wait_ld_fence(v0);
-                    if (sl + 1 < n_slab)
-                        tmem_ld32(taddr + (sl + 1) * 32, v1);
-                    filter_slab(v0, sl, bmin, a1, a2);
-                    if (sl + 1 < n_slab) {
-                        tmem_wait_ld_fence(v1);
-                        if (sl + 2 < n_slab)
-                            tmem_ld32(taddr + (sl + 2) * 32, v0);
-                        filter_slab(v1, sl + 1, bmin, a1, a2);
-                    }
-                }
+            for (int bb = 0; bb < 16; ++bb)
+                bmin[bb] = inf;
+            for (int sl = 0; sl < n_slab; ++sl) {
+                uint32_t v[32];
+                tmem_ld32(taddr + sl * 32, v);
+                tmem_wait_ld_fence(v);
+                filter_slab(v, sl, bmin, a1, a2);
             }
             tc_fence_before();
-            mbar_arrive(bar(T_EMPTY + g));        // accumulator drained: the next MMA may overwrite it
+            mbar_arrive(bar(T_EMPTY + b));        // accumulator drained: the next MMA may overwrite it
             float b1 = inf, b2 = inf;
 #pragma unroll
-            for (int b = 0; b < 16; ++b)
-                top2(b1, b2, bmin[b], (unsigned)b);
+            for (int bb = 0; bb < 16; ++bb)
+                top2(b1, b2, bmin[bb], (unsigned)bb);
 
             // ---- the vector itself (TMA-written ring slot) ----
-            mbar_wait(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));   // acquire the tile
+            mbar_wait<32>(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));   // acquire the tile
             unsigned char *zt = smem + OFF_ZRING + s * 16384;
             unsigned char *zrow = zt + r * 128;
             float z[D];
@@ -600,7 +603,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             //   2*H    (oracle fp32 roundings: fl(zz+ee), fl(t-u), D-step dot chain)
             //                                                               <= 2^-22 (zn+emax)^2 + D 2^-22 zn emax
             //   2*pack (group id in 4 mantissa bits of the keys)             <= 2^-17 (2 zn emax + eemax)
-            const float delta = 9.6e-5f * zn * emax + 1.1e-5f * eemax + 3.0e-7f * (zn + emax) * (zn + emax);
+            //   + an absolute floor: the tensor core may flush sub-normal operands/products (|x| < 2^-126)
+            const float delta = 9.6e-5f * zn * emax + 1.1e-5f * eemax + 3.0e-7f * (zn + emax) * (zn + emax) + 1.0e-35f;
             const float best = fmaxf(a1, b1), second = fminf(a2, b2);
             const bool certain = (second > best + delta) && (zz <= 3.0e38f) && !cb_bad;
             int code = (int)(((__float_as_uint(a1) & 15u) << 4) | (__float_as_uint(b1) & 15u));
@@ -647,11 +651,16 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     *reinterpret_cast<float4 *>(zrow + ((c << 4) ^ x)) = o;
             }
             if (ok)
-                sq += (double)((rs[0] + rs[1]) + (rs[2] + rs[3]));
+                sqf += (rs[0] + rs[1]) + (rs[2] + rs[3]);
+            if (((i / GROUPS) & 15) == 15) {      // bounded fp32 run lengths, fp64 across them
+                sq += (double)sqf;
+                sqf = 0.0f;
+            }
             if (p.zq)
                 fence_proxy_async();               // z_q rows (generic proxy) -> visible to the TMA store
             mbar_arrive(bar(Q_DONE + s));          // warp 3 stores the tile and frees the slot
         }
+        sq += (double)sqf;
         if (p.stats && n_slow_total && lane == 0)
             atomicAdd(p.stats + 1, n_slow_total);
     }
@@ -668,14 +677,14 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             atomicAdd(p.counts + tid, (unsigned long long)c);
     }
     // per-CTA sum of squared residuals (deterministic order within the CTA)
-    __shared__ double red[16];
+    __shared__ double red[THREADS / 32];
     sq = warp_sum(sq);
     if (lane == 0)
         red[warp] = sq;
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;
-        for (int w = 0; w < 16; ++w)
+        for (int w = 0; w < THREADS / 32; ++w)
             t += red[w];
         p.partials[blockIdx.x] = p.accumulate ? p.partials[blockIdx.x] + t : t;
     }
