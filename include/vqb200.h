@@ -146,6 +146,11 @@ long long vqb_launch_counter(void);
 int vqb_profile_enable(int on);
 int vqb_profile_collect(double *ms_sum, int *launches);
 
+/* Debug only: while a device buffer of vqb_debug_tc_trace_words() uint64 is set, the tcgen05
+ * kernel records clock64() of eight pipeline events per tile there (tools/tc_trace.py). */
+int vqb_debug_set_tc_trace(unsigned long long *buf);
+size_t vqb_debug_tc_trace_words(void);
+
 /* ---- host-buffer path (copies inside the call) --------------------------- */
 typedef struct vqb_host_ctx vqb_host_ctx;
 

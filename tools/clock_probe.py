@@ -1,0 +1,26 @@
+"""GPU box: SM clock / power while the tcgen05 forward runs back to back for a few seconds."""
+import os, sys, time, threading
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, pynvml, vqb200
+from vqb200 import ops
+pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0)
+dev = torch.device("cuda:0")
+n = 1 << 24
+z = 0.1 * torch.randn(n, 32, device=dev); w = (torch.rand(256, 32, device=dev) * 2 - 1) / 256
+samples = []; stop = False
+def sampler():
+    while not stop:
+        samples.append((time.time(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                        pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+        time.sleep(0.05)
+for path in (sys.argv[1:] or ["tc", "fma"]):
+    samples.clear(); stop = False
+    t = threading.Thread(target=sampler); t.start()
+    torch.cuda.synchronize(); t0 = time.time(); it = 0
+    while time.time() - t0 < 3.0:
+        for _ in range(50): ops.forward(z, w, 0.25, path=path)
+        torch.cuda.synchronize(); it += 50
+    dt = time.time() - t0; stop = True; t.join()
+    mid = samples[len(samples)//4:]
+    print(f"{path}: {dt/it*1e3:.3f} ms/call; sm clock min/median/max {min(s[1] for s in mid)}/{sorted(s[1] for s in mid)[len(mid)//2]}/{max(s[1] for s in mid)} MHz; "
+          f"power median {sorted(s[2] for s in mid)[len(mid)//2]:.0f} W; throttle reasons {sorted(set(hex(s[3]) for s in mid))}")

@@ -34,7 +34,7 @@ def run(n, K, D=32, zscale=0.1, cb="default", reps=1):
             torch.cuda.synchronize()
             print(f"  {path}: {(time.perf_counter()-t0)/reps*1e3:.3f} ms/call")
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--timing" not in sys.argv:
     run(128, 256)
     run(1000, 256)
     run(4096, 256, cb="randn")
@@ -42,3 +42,23 @@ if __name__ == "__main__":
     run(65536, 256, zscale=1.0)
     run(1 << 20, 256, reps=5)
     run(1 << 24, 256, reps=5)
+
+
+def timing(n=1 << 24, K=256, reps=10):
+    z = 0.1 * torch.randn(n, 32, device=dev)
+    w = (torch.rand(K, 32, device=dev) * 2 - 1) / K
+    for want_zq in (True, False):
+        for _ in range(3):
+            ops.forward(z, w, 0.25, path="tc", want_zq=want_zq)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ops.forward(z, w, 0.25, path="tc", want_zq=want_zq)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        bytes_ = n * (264 if want_zq else 136)
+        print(f"timing n={n} zq={want_zq}: {ms:.3f} ms/call  {bytes_/ms/1e6:.0f} GB/s algorithmic", flush=True)
+
+if __name__ == "__main__" and "--timing" in sys.argv:
+    timing()

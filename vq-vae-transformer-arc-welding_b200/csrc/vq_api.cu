@@ -65,6 +65,15 @@ extern "C" {
 
 long long vqb_launch_counter(void) { return g_launches.load(std::memory_order_relaxed); }
 
+/* Debug: route the tcgen05 kernel through its tracing build; `buf` is a device buffer of
+ * vqb_debug_tc_trace_words() uint64 (NULL switches tracing off). */
+int vqb_debug_set_tc_trace(unsigned long long *buf)
+{
+    set_tc_trace(buf);
+    return VQB_OK;
+}
+size_t vqb_debug_tc_trace_words(void) { return tc_trace_words(); }
+
 int vqb_profile_enable(int on)
 {
     g_profile.store(on ? 1 : 0);

@@ -41,9 +41,10 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // Extra floats the tcgen05 path keeps per codebook: B operand tile(s) + per-code data.
 __host__ inline size_t tc_scratch_floats(int k, int d)
 {
-    // tcgen05 path: image of the constant operands (vq_fwd_tc.cu, tc::IMG_BYTES, for 256 codes)
+    // tcgen05 path (vq_fwd_tc.cu, tc::IMG_BYTES): image of the constant operands for 256 codes,
+    // the scalar constants, and the per-CTA queues of vectors deferred to the fix-up kernel
     (void)k; (void)d;
-    return (32768 + 8192 + 32768 + 1024 + 64) / sizeof(float) + 64;
+    return (32768 + 8192 + 32768 + 1024 + 64 + 192 * 4 + 192 * 2048 * 4) / sizeof(float) + 64;
 }
 
 __host__ inline WsLayout ws_layout(int k, int d)
@@ -120,6 +121,8 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
                           int *n_launches, cudaStream_t st, cudaEvent_t ev_begin = nullptr,
                           cudaEvent_t ev_end = nullptr);
 void count_launches(int n);
+void set_tc_trace(unsigned long long *buf);
+size_t tc_trace_words();
 
 // ---------------------------------------------------------------------------------------
 // Device helpers

@@ -58,8 +58,8 @@ constexpr int OFF_AAUG = OFF_BAUG + 8192;                 // 4096            bf1
 constexpr int OFF_EF32 = OFF_AAUG + 4096;                 // 32768           fp32 codebook, XOR-swizzled rows
 constexpr int OFF_EE = OFF_EF32 + 32768;                  // 1024            fp32 ||E_k||^2 (oracle order)
 constexpr int OFF_HIST = OFF_EE + 1024;                   // 1024            u32 histogram
-constexpr int OFF_BARS = OFF_HIST + 1024;                 // 256             mbarriers + tmem base
-constexpr int SMEM_BYTES = OFF_BARS + 256;
+constexpr int OFF_BARS = OFF_HIST + 1024;                 // 512             mbarriers + tmem base
+constexpr int SMEM_BYTES = OFF_BARS + 512;
 constexpr int SMEM_ALLOC = SMEM_BYTES;
 
 // image of the constant operands prepared once per call in global scratch
@@ -68,7 +68,11 @@ constexpr int IMG_BAUG = IMG_BMAIN + 32768;
 constexpr int IMG_EF32 = IMG_BAUG + 8192;
 constexpr int IMG_EE = IMG_EF32 + 32768;
 constexpr int IMG_CONST = IMG_EE + 1024;                  // float emax_bits(as uint), eemax_bits, flags
-constexpr int IMG_BYTES = IMG_CONST + 64;
+constexpr int IMG_WLCOUNT = IMG_CONST + 64;               // u32 [WL_CTAS]  deferred vectors per CTA
+constexpr int WL_CTAS = 192;                              // >= number of CTAs (one per SM)
+constexpr int WL_CAP = 2048;                              // deferred vectors a CTA can queue
+constexpr int IMG_WL = IMG_WLCOUNT + WL_CTAS * 4;         // u32 [WL_CTAS][WL_CAP] row indices
+constexpr int IMG_BYTES = IMG_WL + WL_CTAS * WL_CAP * 4;
 
 struct Consts {
     unsigned emax2_bits;   // max_k ee_k (finite ones), as float bits
@@ -91,15 +95,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or
+// ~`hint_ns` elapse, so a long wait costs a handful of instructions instead of a polling storm.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns)
 {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
         : "memory");
     return ok != 0;
 }
@@ -107,13 +113,43 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 template <int SLEEP_NS = 32>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
+    // Polling costs issue slots and power (the kernel runs at the board's power cap): sleep between
+    // polls, and let one warp poll on behalf of its group (group_wait below).
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait(bar, parity, 1000u)) {
         if (SLEEP_NS > 0)
-            __nanosleep(SLEEP_NS);      // waiting warps must not eat the issue slots of working ones
-        if (++spins > (1u << 24))
+            __nanosleep(SLEEP_NS);
+        if (++spins > (1u << 22))       // seconds: a pipeline bug traps instead of hanging the GPU
             __trap();
     }
+}
+// latency-critical waits (accumulator ready, operands ready): plain try_wait loop, the hardware
+// suspends the thread inside try_wait and wakes it on completion
+__device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok)
+            break;
+        if (++spins > (1u << 26))
+            __trap();
+    }
+}
+// One warp (`leader`) polls the mbarrier, the other warps of the 128-thread group block in hardware
+// on a named barrier until it has seen the phase complete.
+template <int SLEEP_NS>
+__device__ __forceinline__ void group_wait(bool leader, uint32_t bar, uint32_t parity, int bar_id)
+{
+    if (leader)
+        mbar_wait<SLEEP_NS>(bar, parity);
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -171,6 +207,15 @@ __device__ __forceinline__ float min3(float a, float b, float c)
 {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// MUFU.SQRT: 1 instruction, ~2^-22 relative error; callers scale the result up a little because it
+// only feeds upper bounds
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
@@ -371,11 +416,19 @@ __device__ __forceinline__ void tmem_wait_ld_fence(uint32_t (&v)[32])
 // ---------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------
+// TRACE: debug build of the same kernel that records clock64() of eight pipeline events per tile
+// (first kTraceTiles tiles of the first kTraceCtas CTAs) -- tools/tc_trace.py turns them into a timeline.
+constexpr int kTraceCtas = 4, kTraceTiles = 256, kTraceEvents = 8;
+template <bool TRACE>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const __grid_constant__ CUtensorMap map_z,
-                 const __grid_constant__ CUtensorMap map_zq, int kp)
+                 const __grid_constant__ CUtensorMap map_zq, int kp, unsigned long long *trace)
 {
     using namespace tc;
+    auto stamp = [&](int64_t i, int ev) {
+        if (TRACE && blockIdx.x < kTraceCtas && i < kTraceTiles)
+            trace[((size_t)blockIdx.x * kTraceTiles + i) * kTraceEvents + ev] = (unsigned long long)clock64();
+    };
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     if ((sbase & 1023u) != 0)
@@ -384,7 +437,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     enum { Z_FULL = 0, Z_EMPTY = Z_FULL + STAGES, Q_DONE = Z_EMPTY + STAGES, A_FULL = Q_DONE + STAGES,
            A_EMPTY = A_FULL + 2, T_FULL = A_EMPTY + 2, T_EMPTY = T_FULL + GROUPS, N_BARS = T_EMPTY + 2 };
     // T_FULL is per epilogue GROUP (a waiter must see every phase of its barrier), T_EMPTY per TMEM buffer
-    static_assert(8 * N_BARS + 8 <= 256, "barrier area");
+    static_assert(8 * N_BARS + 8 <= 512, "barrier area");
     auto bar = [&](int i) { return sbase + OFF_BARS + 8 * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + 8 * N_BARS);
 
@@ -431,6 +484,9 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     }
     if (tid < KMAX)
         reinterpret_cast<unsigned *>(smem + OFF_HIST)[tid] = 0u;
+    unsigned *wl_count_s = reinterpret_cast<unsigned *>(smem + OFF_BARS + 8 * N_BARS + 4);
+    if (tid == 0)
+        *wl_count_s = 0u;
     fence_proxy_async();          // generic-proxy writes of the operands -> visible to tcgen05/TMA
     tc_fence_before();
     __syncthreads();
@@ -452,21 +508,26 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 mbar_expect_tx(bar(Z_FULL + s), TILE_M * D * 4);
                 const int64_t tile = blockIdx.x + i * gridDim.x;
                 tma_load_2d(sbase + OFF_ZRING + s * 16384, &map_z, bar(Z_FULL + s), 0, (int)(tile * TILE_M));
+                stamp(i, 0);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
+            // (Issuing the codebook as two N = kp/2 halves with an early commit was measured: the 14
+            // half-width MMAs take ~2x the tensor time of 7 full-width ones, a net loss.)
             const uint32_t idesc = idesc_bf16(kp);
             const uint64_t bmain = desc_sw128(sbase + OFF_BMAIN);
             const uint64_t baug = desc_sw32(sbase + OFF_BAUG);
             const uint64_t aaug = desc_sw32(sbase + OFF_AAUG);
             for (int64_t i = 0; i < my_tiles; ++i) {
                 const int b = (int)(i & 1);
+                const int g = (int)(i % GROUPS);
                 const uint32_t ph = (uint32_t)((i >> 1) & 1);
                 mbar_wait<32>(bar(A_FULL + b), ph);
                 mbar_wait<32>(bar(T_EMPTY + b), ph ^ 1);
                 tc_fence_after();
+                stamp(i, 3);
                 const uint64_t a = desc_sw128(sbase + OFF_ARING + b * 16384);
                 const uint32_t d = tmem_base + b * KMAX;
                 // K-slices of 16 bf16 = 32 bytes = +2 in the descriptor's address field
@@ -478,11 +539,13 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 umma_bf16(d, a + 6, bmain + 2, idesc, 1);   // z2[16:32] . E1[16:32]
                 umma_bf16(d, aaug, baug, idesc, 1);         // + ee_k
                 umma_commit(bar(A_EMPTY + b));
-                umma_commit(bar(T_FULL + (int)(i % GROUPS)));
+                umma_commit(bar(T_FULL + g));
             }
         }
     } else if (warp == 3) {
         // ================= z_q store + slot release =================
+        // (Keeping one store in flight and releasing slot i when store i+1 is issued was measured:
+        // the extra tile period of slot hold time costs more than the wait it hides.)
         if (lane == 0) {
             for (int64_t i = 0; i < my_tiles; ++i) {
                 const int s = (int)(i % STAGES);
@@ -494,6 +557,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     tma_store_wait_read();     // the slot may be refilled once the store has read it
                 }
                 mbar_arrive(bar(Z_EMPTY + s));
+                stamp(i, 7);
             }
             tma_store_wait_all();
         }
@@ -505,8 +569,12 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         for (int64_t i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % STAGES);
             const int b = (int)(i & 1);
-            mbar_wait<128>(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));
-            mbar_wait<128>(bar(A_EMPTY + b), (uint32_t)(((i >> 1) & 1) ^ 1));
+            if (warp == 4) {
+                mbar_wait<128>(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));
+                if (r == 0) stamp(i, 1);
+                mbar_wait<128>(bar(A_EMPTY + b), (uint32_t)(((i >> 1) & 1) ^ 1));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             const unsigned char *zrow = smem + OFF_ZRING + s * 16384 + r * 128;
             unsigned char *arow = smem + OFF_ARING + b * 16384 + r * 128;
             uint32_t hi[16], lo[16];
@@ -531,6 +599,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
             fence_proxy_async();
             mbar_arrive(bar(A_FULL + b));
+            if (r == 0) stamp(i, 2);
         }
     } else if (warp >= 8) {
         // ================= epilogue groups =================
@@ -543,11 +612,12 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         const float *ees = reinterpret_cast<const float *>(smem + OFF_EE);
         unsigned *hist = reinterpret_cast<unsigned *>(smem + OFF_HIST);
         const float eemax = __uint_as_float(cst->emax2_bits);
-        const float emax = sqrtf(eemax) * 1.0000002f;
+        const float emax = sqrt_approx(eemax) * 1.00001f;
         const bool poisoned = p.hdr_in->poisoned_columns != 0;
         const bool cb_bad = cst->nonfinite != 0 || poisoned;
         const int n_slab = kp >> 5;
         unsigned long long n_slow_total = 0;
+        unsigned *wl = reinterpret_cast<unsigned *>(const_cast<unsigned char *>(img) + IMG_WL) + (size_t)blockIdx.x * WL_CAP;
 
         float sqf = 0.0f;
         for (int64_t i = g; i < my_tiles; i += GROUPS) {
@@ -559,8 +629,9 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             const bool ok = row < n_rows;
 
             // ---- filter: A/B group minima of the approximate scores, packed top-2 each ----
-            mbar_wait<64>(bar(T_FULL + g), ph);
+            group_wait<64>(q == 0, bar(T_FULL + g), ph, 2 + g);
             tc_fence_after();
+            if (r == 0) stamp(i, 4);
             const uint32_t taddr = tmem_base + b * KMAX + ((uint32_t)(q * 32) << 16);
             const float inf = __int_as_float(0x7f800000);
             float a1 = inf, a2 = inf;
@@ -576,27 +647,28 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
             tc_fence_before();
             mbar_arrive(bar(T_EMPTY + b));        // accumulator drained: the next MMA may overwrite it
+            if (r == 0) stamp(i, 5);
             float b1 = inf, b2 = inf;
 #pragma unroll
             for (int bb = 0; bb < 16; ++bb)
                 top2(b1, b2, bmin[bb], (unsigned)bb);
 
             // ---- the vector itself (TMA-written ring slot) ----
-            mbar_wait<32>(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));   // acquire the tile
+            // (the tile itself was TMA-written before the converters read it, i.e. long before T_FULL)
             unsigned char *zt = smem + OFF_ZRING + s * 16384;
             unsigned char *zrow = zt + r * 128;
-            float z[D];
+            // pass 1 over the row: only ||z||^2 (bounds the filter radius; not part of the decision).
+            // The row is re-read for the outputs below so that nothing wide stays live across the
+            // rare exact-scan call.
+            float zp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 v = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ x));
-                z[4 * c] = v.x; z[4 * c + 1] = v.y; z[4 * c + 2] = v.z; z[4 * c + 3] = v.w;
+                zp[0] = fmaf(v.x, v.x, zp[0]); zp[1] = fmaf(v.y, v.y, zp[1]);
+                zp[2] = fmaf(v.z, v.z, zp[2]); zp[3] = fmaf(v.w, v.w, zp[3]);
             }
-            float zp[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j < D; ++j)
-                zp[j & 3] = fmaf(z[j], z[j], zp[j & 3]);
-            const float zz = (zp[0] + zp[1]) + (zp[2] + zp[3]);     // only bounds ||z||, not part of the decision
-            const float zn = sqrtf(zz) * 1.000001f;
+            const float zz = (zp[0] + zp[1]) + (zp[2] + zp[3]);
+            const float zn = sqrt_approx(zz) * 1.00001f;
             // Filter radius, see DESIGN.md "Exactness".  With |z| = zn, max|e| = emax, max ee = eemax:
             //   2*eps  (bf16x3 residual 3*2^-18 per unit of sum|z_j e_j|, x2 for -2*dot, x2 both sides,
             //           plus tensor-core accumulation slack)                 <= 2^-13.6 zn emax + 2^-19 eemax
@@ -610,9 +682,19 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             int code = (int)(((__float_as_uint(a1) & 15u) << 4) | (__float_as_uint(b1) & 15u));
             if (code >= K)
                 code = 0;
-            // vectors the filter cannot certify: exact scan of all K codes by the whole warp
-            unsigned need = __ballot_sync(0xffffffffu, !certain);
-            n_slow_total += __popc(need);
+            // Vectors the filter cannot certify (~0.1 %) are queued for the fix-up kernel, which decides
+            // them with the exact expression after this kernel: no slow path inside the pipeline.  Only
+            // when the CTA's queue is full are they scanned here, by the whole warp.
+            bool deferred = false;
+            if (!certain && ok) {
+                const unsigned pos = atomicAdd(wl_count_s, 1u);
+                if (pos < (unsigned)WL_CAP) {
+                    wl[pos] = (unsigned)row;
+                    deferred = true;
+                }
+            }
+            unsigned need = __ballot_sync(0xffffffffu, !certain && ok && !deferred);
+            n_slow_total += __popc(__ballot_sync(0xffffffffu, !certain && ok));
             while (need) {
                 const int src = __ffs(need) - 1;
                 need &= need - 1;
@@ -622,7 +704,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
 
             // ---- outputs: idx, histogram, loss, z_q (in place in the ring slot) ----
-            if (ok) {
+            const bool emit = ok && !deferred;
+            if (emit) {
                 if (p.idx)
                     p.idx[row] = code;
                 atomicAdd(hist + code, 1u);
@@ -632,6 +715,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
+                const float4 zv = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ x));
                 float4 e = *reinterpret_cast<const float4 *>(erow + ((c << 4) ^ xe));
                 if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
                     float *ev = reinterpret_cast<float *>(&e);
@@ -643,14 +727,14 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 }
                 float4 o;
                 float dj;
-                dj = __fsub_rn(e.x, z[4 * c]);     rs[0] = fmaf(dj, dj, rs[0]); o.x = __fadd_rn(z[4 * c], dj);
-                dj = __fsub_rn(e.y, z[4 * c + 1]); rs[1] = fmaf(dj, dj, rs[1]); o.y = __fadd_rn(z[4 * c + 1], dj);
-                dj = __fsub_rn(e.z, z[4 * c + 2]); rs[2] = fmaf(dj, dj, rs[2]); o.z = __fadd_rn(z[4 * c + 2], dj);
-                dj = __fsub_rn(e.w, z[4 * c + 3]); rs[3] = fmaf(dj, dj, rs[3]); o.w = __fadd_rn(z[4 * c + 3], dj);
+                dj = __fsub_rn(e.x, zv.x); rs[0] = fmaf(dj, dj, rs[0]); o.x = __fadd_rn(zv.x, dj);
+                dj = __fsub_rn(e.y, zv.y); rs[1] = fmaf(dj, dj, rs[1]); o.y = __fadd_rn(zv.y, dj);
+                dj = __fsub_rn(e.z, zv.z); rs[2] = fmaf(dj, dj, rs[2]); o.z = __fadd_rn(zv.z, dj);
+                dj = __fsub_rn(e.w, zv.w); rs[3] = fmaf(dj, dj, rs[3]); o.w = __fadd_rn(zv.w, dj);
                 if (p.zq)
                     *reinterpret_cast<float4 *>(zrow + ((c << 4) ^ x)) = o;
             }
-            if (ok)
+            if (emit)
                 sqf += (rs[0] + rs[1]) + (rs[2] + rs[3]);
             if (((i / GROUPS) & 15) == 15) {      // bounded fp32 run lengths, fp64 across them
                 sq += (double)sqf;
@@ -659,6 +743,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             if (p.zq)
                 fence_proxy_async();               // z_q rows (generic proxy) -> visible to the TMA store
             mbar_arrive(bar(Q_DONE + s));          // warp 3 stores the tile and frees the slot
+            if (r == 0) stamp(i, 6);
         }
         sq += (double)sqf;
         if (p.stats && n_slow_total && lane == 0)
@@ -671,6 +756,11 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     tc_fence_after();
     if (warp == 2)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (tid == 0) {
+        const unsigned n = *wl_count_s;
+        reinterpret_cast<unsigned *>(const_cast<unsigned char *>(img) + IMG_WLCOUNT)[blockIdx.x] =
+            n < (unsigned)WL_CAP ? n : (unsigned)WL_CAP;
+    }
     if (tid < K) {
         const unsigned c = reinterpret_cast<unsigned *>(smem + OFF_HIST)[tid];
         if (c)
@@ -687,6 +777,102 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         for (int w = 0; w < THREADS / 32; ++w)
             t += red[w];
         p.partials[blockIdx.x] = p.accumulate ? p.partials[blockIdx.x] + t : t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// fix-up: the queued vectors are decided with the exact expression (warp per vector), and
+// their idx / z_q / histogram / loss contributions are written here.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vq_tc_fixup_kernel(const FwdParams p, const unsigned char *__restrict__ img,
+                                                           double *__restrict__ partial_out)
+{
+    using namespace tc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned count = reinterpret_cast<const unsigned *>(img + IMG_WLCOUNT)[blockIdx.x];
+    const unsigned *wl = reinterpret_cast<const unsigned *>(img + IMG_WL) + (size_t)blockIdx.x * WL_CAP;
+    const bool poisoned = p.hdr_in->poisoned_columns != 0;
+    const int K = p.K;
+    double sq = 0.0;
+    for (unsigned e = warp; e < count; e += 8) {
+        const int64_t row = wl[e];
+        const float *zrow = p.z.base + row * D;
+        const float zj = __ldg(zrow + lane);
+        float zv[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j)          // whole vector in every lane (uniform control flow here)
+            zv[j] = __shfl_sync(0xffffffffu, zj, j);
+        float zz = 0.0f;
+#pragma unroll
+        for (int j = 0; j < D; ++j)          // oracle-order chain
+            zz = fmaf(zv[j], zv[j], zz);
+        float best = __int_as_float(0x7f800000);
+        int bidx = 0x7fffffff;
+        unsigned first_nan = 0xffffffffu;
+        for (int k = lane; k < K; k += 32) { // lane-dependent trip count: no warp collectives inside
+            const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k * D);
+            float acc = 0.0f;
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c) {
+                const float4 ev4 = __ldg(er + c);
+                acc = fmaf(zv[4 * c], ev4.x, acc);
+                acc = fmaf(zv[4 * c + 1], ev4.y, acc);
+                acc = fmaf(zv[4 * c + 2], ev4.z, acc);
+                acc = fmaf(zv[4 * c + 3], ev4.w, acc);
+            }
+            const float dist = ref_distance(zz, p.ee[k], acc);
+            if (dist != dist)
+                first_nan = min(first_nan, (unsigned)k);
+            if (dist < best) {
+                best = dist;
+                bidx = k;
+            }
+        }
+        int code;
+        const unsigned nan_k = __reduce_min_sync(0xffffffffu, first_nan);
+        if (nan_k != 0xffffffffu) {
+            code = (int)nan_k;
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+                if (ob < best || (ob == best && oi < bidx)) {
+                    best = ob;
+                    bidx = oi;
+                }
+            }
+            code = bidx == 0x7fffffff ? 0 : bidx;
+        }
+        float ev = __ldg(p.E + (size_t)code * D + lane);
+        if (poisoned) {
+            const int cc = p.colcnt[lane];
+            if (!(cc == 0 || (cc == 1 && p.colwhich[lane] == code + 1)))
+                ev = __int_as_float(0x7fc00000);
+        }
+        const float diff = __fsub_rn(ev, zj);
+        if (p.zq)
+            p.zq[row * D + lane] = __fadd_rn(zj, diff);
+        float r2 = __fmul_rn(diff, diff);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        if (lane == 0) {
+            if (p.idx)
+                p.idx[row] = code;
+            atomicAdd(p.counts + code, 1ULL);
+            sq += (double)r2;
+        }
+    }
+    __shared__ double red[8];
+    if (lane == 0)
+        red[warp] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w)
+            t += red[w];
+        partial_out[blockIdx.x] = p.accumulate ? partial_out[blockIdx.x] + t : t;
     }
 }
 
@@ -732,6 +918,10 @@ bool make_map(CUtensorMap *map, const float *base, int64_t n_rows)
 
 }  // namespace
 
+static unsigned long long *g_trace_buf = nullptr;   // debug only, see vqb_debug_set_tc_trace
+void set_tc_trace(unsigned long long *buf) { g_trace_buf = buf; }
+size_t tc_trace_words() { return (size_t)kTraceCtas * kTraceTiles * kTraceEvents; }
+
 cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas,
                           int *n_launches, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end)
 {
@@ -749,27 +939,39 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
         map_zq = map_z;
     }
     const int kp = ((p.K + 31) / 32) * 32;
-    cudaError_t err = cudaMemsetAsync(img + IMG_CONST, 0, sizeof(Consts), st);
+    cudaError_t err = cudaMemsetAsync(img + IMG_CONST, 0, sizeof(Consts) + WL_CTAS * 4, st);
     if (err != cudaSuccess)
         return err;
     vq_tc_prep_kernel<<<(KMAX + 127) / 128, 128, 0, st>>>(p.E, p.ee, p.K, kp, img);
     if ((err = cudaGetLastError()) != cudaSuccess)
         return err;
-    err = cudaFuncSetAttribute(vq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+    err = cudaFuncSetAttribute(vq_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+    if (err != cudaSuccess)
+        return err;
+    err = cudaFuncSetAttribute(vq_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
     if (err != cudaSuccess)
         return err;
     const int64_t tiles = (p.z.n_rows + TILE_M - 1) / TILE_M;
     int grid = (int)(tiles < sm_count ? tiles : sm_count);
     if (grid < 1)
         grid = 1;
-    *n_ctas = grid;
+    if (grid > WL_CTAS)
+        grid = WL_CTAS;
+    *n_ctas = 2 * grid;    // partials [0, grid): main kernel, [grid, 2*grid): fix-up kernel
     if (ev_begin)
         cudaEventRecord(ev_begin, st);
-    vq_fwd_tc_kernel<<<grid, THREADS, SMEM_ALLOC, st>>>(p, img, map_z, map_zq, kp);
+    if (g_trace_buf)
+        vq_fwd_tc_kernel<true><<<grid, THREADS, SMEM_ALLOC, st>>>(p, img, map_z, map_zq, kp, g_trace_buf);
+    else
+        vq_fwd_tc_kernel<false><<<grid, THREADS, SMEM_ALLOC, st>>>(p, img, map_z, map_zq, kp, nullptr);
+    err = cudaGetLastError();
+    if (err != cudaSuccess)
+        return err;
+    vq_tc_fixup_kernel<<<grid, 256, 0, st>>>(p, img, p.partials + grid);
     err = cudaGetLastError();
     if (ev_end)
         cudaEventRecord(ev_end, st);
-    *n_launches = 2;
+    *n_launches = 3;
     return err;
 }
 
