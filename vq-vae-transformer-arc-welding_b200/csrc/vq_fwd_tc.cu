@@ -58,7 +58,8 @@ constexpr int OFF_AAUG = OFF_BAUG + 8192;                 // 4096            bf1
 constexpr int OFF_EF32 = OFF_AAUG + 4096;                 // 32768           fp32 codebook, XOR-swizzled rows
 constexpr int OFF_EE = OFF_EF32 + 32768;                  // 1024            fp32 ||E_k||^2 (oracle order)
 constexpr int OFF_HIST = OFF_EE + 1024;                   // 1024            u32 histogram
-constexpr int OFF_BARS = OFF_HIST + 1024;                 // 512             mbarriers + tmem base
+constexpr int OFF_ZZ = OFF_HIST + 1024;                   // STAGES x 512    ||z||^2 bound per row (from the converters)
+constexpr int OFF_BARS = OFF_ZZ + STAGES * 512;           // 512             mbarriers + tmem base
 constexpr int SMEM_BYTES = OFF_BARS + 512;
 constexpr int SMEM_ALLOC = SMEM_BYTES;
 
@@ -578,10 +579,13 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             const unsigned char *zrow = smem + OFF_ZRING + s * 16384 + r * 128;
             unsigned char *arow = smem + OFF_ARING + b * 16384 + r * 128;
             uint32_t hi[16], lo[16];
+            float zp[4] = {0.f, 0.f, 0.f, 0.f};     // ||z||^2 for the epilogue's filter radius (a bound, not the decision)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 v = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ x));
                 const float xs[4] = {v.x, v.y, v.z, v.w};
+                zp[0] = fmaf(v.x, v.x, zp[0]); zp[1] = fmaf(v.y, v.y, zp[1]);
+                zp[2] = fmaf(v.z, v.z, zp[2]); zp[3] = fmaf(v.w, v.w, zp[3]);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(xs[2 * h], xs[2 * h + 1]);
@@ -597,6 +601,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 *reinterpret_cast<uint4 *>(arow + ((c << 4) ^ x)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
                 *reinterpret_cast<uint4 *>(arow + (((c + 4) << 4) ^ x)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
             }
+            reinterpret_cast<float *>(smem + OFF_ZZ + s * 512)[r] = (zp[0] + zp[1]) + (zp[2] + zp[3]);
             fence_proxy_async();
             mbar_arrive(bar(A_FULL + b));
             if (r == 0) stamp(i, 2);
@@ -657,17 +662,9 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             // (the tile itself was TMA-written before the converters read it, i.e. long before T_FULL)
             unsigned char *zt = smem + OFF_ZRING + s * 16384;
             unsigned char *zrow = zt + r * 128;
-            // pass 1 over the row: only ||z||^2 (bounds the filter radius; not part of the decision).
-            // The row is re-read for the outputs below so that nothing wide stays live across the
-            // rare exact-scan call.
-            float zp[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 v = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ x));
-                zp[0] = fmaf(v.x, v.x, zp[0]); zp[1] = fmaf(v.y, v.y, zp[1]);
-                zp[2] = fmaf(v.z, v.z, zp[2]); zp[3] = fmaf(v.w, v.w, zp[3]);
-            }
-            const float zz = (zp[0] + zp[1]) + (zp[2] + zp[3]);
+            // ||z||^2 comes from the converter that already had the row in registers (ordered before us
+            // by A_FULL -> MMA -> T_FULL); it only bounds the filter radius, it is not part of the decision
+            const float zz = reinterpret_cast<const float *>(smem + OFF_ZZ + s * 512)[r];
             const float zn = sqrt_approx(zz) * 1.00001f;
             // Filter radius, see DESIGN.md "Exactness".  With |z| = zn, max|e| = emax, max ee = eemax:
             //   2*eps  (bf16x3 residual 3*2^-18 per unit of sum|z_j e_j|, x2 for -2*dot, x2 both sides,
@@ -788,80 +785,99 @@ __global__ void __launch_bounds__(256) vq_tc_fixup_kernel(const FwdParams p, con
                                                            double *__restrict__ partial_out)
 {
     using namespace tc;
+    extern __shared__ __align__(16) unsigned char fsm[];     // [EF32 32 KB | EE 1 KB], same layout as the image
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned count = reinterpret_cast<const unsigned *>(img + IMG_WLCOUNT)[blockIdx.x];
     const unsigned *wl = reinterpret_cast<const unsigned *>(img + IMG_WL) + (size_t)blockIdx.x * WL_CAP;
-    const bool poisoned = p.hdr_in->poisoned_columns != 0;
-    const int K = p.K;
     double sq = 0.0;
-    for (unsigned e = warp; e < count; e += 8) {
-        const int64_t row = wl[e];
-        const float *zrow = p.z.base + row * D;
-        const float zj = __ldg(zrow + lane);
-        float zv[D];
+    if (count > 0) {                                          // block-uniform
+        for (int i = threadIdx.x; i < (32768 + 1024) / 16; i += 256)
+            reinterpret_cast<uint4 *>(fsm)[i] = __ldg(reinterpret_cast<const uint4 *>(img + IMG_EF32) + i);
+        __syncthreads();
+        const unsigned char *ef32 = fsm;
+        const float *ees = reinterpret_cast<const float *>(fsm + 32768);
+        const bool poisoned = p.hdr_in->poisoned_columns != 0;
+        const int K = p.K;
+        const int kp = (K + 31) & ~31;
+        for (unsigned e = warp; e < count; e += 8) {
+            const int64_t row = wl[e];
+            const float zj = __ldg(p.z.base + row * D + lane);
+            float zv[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j)          // whole vector in every lane (uniform control flow here)
-            zv[j] = __shfl_sync(0xffffffffu, zj, j);
-        float zz = 0.0f;
+            for (int j = 0; j < D; ++j)          // whole vector in every lane (uniform control flow)
+                zv[j] = __shfl_sync(0xffffffffu, zj, j);
+            float zz = 0.0f;
 #pragma unroll
-        for (int j = 0; j < D; ++j)          // oracle-order chain
-            zz = fmaf(zv[j], zv[j], zz);
-        float best = __int_as_float(0x7f800000);
-        int bidx = 0x7fffffff;
-        unsigned first_nan = 0xffffffffu;
-        for (int k = lane; k < K; k += 32) { // lane-dependent trip count: no warp collectives inside
-            const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k * D);
-            float acc = 0.0f;
+            for (int j = 0; j < D; ++j)          // oracle-order chain
+                zz = fmaf(zv[j], zv[j], zz);
+            // lane owns codes lane, lane+32, ...; their chains are interleaved four at a time (each
+            // still ascends j = 0..31, so the values are the oracle's)
+            float best = __int_as_float(0x7f800000);
+            int bidx = 0x7fffffff;
+            unsigned first_nan = 0xffffffffu;
+            for (int k0 = 0; k0 < kp; k0 += 128) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < D / 4; ++c) {
-                const float4 ev4 = __ldg(er + c);
-                acc = fmaf(zv[4 * c], ev4.x, acc);
-                acc = fmaf(zv[4 * c + 1], ev4.y, acc);
-                acc = fmaf(zv[4 * c + 2], ev4.z, acc);
-                acc = fmaf(zv[4 * c + 3], ev4.w, acc);
-            }
-            const float dist = ref_distance(zz, p.ee[k], acc);
-            if (dist != dist)
-                first_nan = min(first_nan, (unsigned)k);
-            if (dist < best) {
-                best = dist;
-                bidx = k;
-            }
-        }
-        int code;
-        const unsigned nan_k = __reduce_min_sync(0xffffffffu, first_nan);
-        if (nan_k != 0xffffffffu) {
-            code = (int)nan_k;
-        } else {
+                for (int c = 0; c < 8; ++c) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-                if (ob < best || (ob == best && oi < bidx)) {
-                    best = ob;
-                    bidx = oi;
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + lane + 32 * u;
+                        const float4 ev4 = *reinterpret_cast<const float4 *>(ef32 + ef32_off(k & (KMAX - 1), c));
+                        acc[u] = fmaf(zv[4 * c], ev4.x, acc[u]);
+                        acc[u] = fmaf(zv[4 * c + 1], ev4.y, acc[u]);
+                        acc[u] = fmaf(zv[4 * c + 2], ev4.z, acc[u]);
+                        acc[u] = fmaf(zv[4 * c + 3], ev4.w, acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + lane + 32 * u;
+                    if (k < K) {
+                        const float dist = ref_distance(zz, ees[k], acc[u]);
+                        if (dist != dist)
+                            first_nan = min(first_nan, (unsigned)k);
+                        if (dist < best) {          // k ascends per lane: strict < keeps the lowest index
+                            best = dist;
+                            bidx = k;
+                        }
+                    }
                 }
             }
-            code = bidx == 0x7fffffff ? 0 : bidx;
-        }
-        float ev = __ldg(p.E + (size_t)code * D + lane);
-        if (poisoned) {
-            const int cc = p.colcnt[lane];
-            if (!(cc == 0 || (cc == 1 && p.colwhich[lane] == code + 1)))
-                ev = __int_as_float(0x7fc00000);
-        }
-        const float diff = __fsub_rn(ev, zj);
-        if (p.zq)
-            p.zq[row * D + lane] = __fadd_rn(zj, diff);
-        float r2 = __fmul_rn(diff, diff);
+            int code;
+            const unsigned nan_k = __reduce_min_sync(0xffffffffu, first_nan);
+            if (nan_k != 0xffffffffu) {
+                code = (int)nan_k;                  // torch.argmin: the first NaN wins
+            } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-        if (lane == 0) {
-            if (p.idx)
-                p.idx[row] = code;
-            atomicAdd(p.counts + code, 1ULL);
-            sq += (double)r2;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+                    if (ob < best || (ob == best && oi < bidx)) {
+                        best = ob;
+                        bidx = oi;
+                    }
+                }
+                code = bidx == 0x7fffffff ? 0 : bidx;
+            }
+            float ev = __ldg(p.E + (size_t)code * D + lane);
+            if (poisoned) {
+                const int cc = p.colcnt[lane];
+                if (!(cc == 0 || (cc == 1 && p.colwhich[lane] == code + 1)))
+                    ev = __int_as_float(0x7fc00000);
+            }
+            const float diff = __fsub_rn(ev, zj);
+            if (p.zq)
+                p.zq[row * D + lane] = __fadd_rn(zj, diff);
+            float r2 = __fmul_rn(diff, diff);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+            if (lane == 0) {
+                if (p.idx)
+                    p.idx[row] = code;
+                atomicAdd(p.counts + code, 1ULL);
+                sq += (double)r2;
+            }
         }
     }
     __shared__ double red[8];
@@ -967,7 +983,7 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
     err = cudaGetLastError();
     if (err != cudaSuccess)
         return err;
-    vq_tc_fixup_kernel<<<grid, 256, 0, st>>>(p, img, p.partials + grid);
+    vq_tc_fixup_kernel<<<grid, 256, 32768 + 1024, st>>>(p, img, p.partials + grid);
     err = cudaGetLastError();
     if (ev_end)
         cudaEventRecord(ev_end, st);
