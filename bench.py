@@ -127,6 +127,10 @@ def cpu_port_rate(rows_per_call: int, calls: int, warm: int):
     from oracle import vq_oracle as O
 
     torch.set_float32_matmul_precision("highest")
+    try:   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core it may run on
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     g = torch.Generator().manual_seed(1234)
     z = 0.1 * torch.randn(rows_per_call, DIM, generator=g)
     g0 = torch.Generator().manual_seed(0)
