@@ -26,10 +26,10 @@
 // The decision is therefore bit-identical to the FMA kernel and the CPU oracle.
 //
 // Pipeline per CTA (persistent, one CTA per SM, 512 threads):
-//   warp 0      TMA producer: z tile (128 x 32 fp32, SWIZZLE_128B) -> 4-deep smem ring
+//   warp 3      ring owner: TMA loads of z tiles (128 x 32 fp32, SWIZZLE_128B) into a 6-deep ring,
+//               z_q TMA store out of the same slot, refill of the slot it just released
 //   warp 1      MMA issuer (one thread): 7 x tcgen05.mma.kind::f16 -> TMEM (2 x 256 columns)
 //   warp 2      TMEM allocator
-//   warp 3      z_q TMA store + ring-slot release
 //   warps 4-7   converters: fp32 tile -> bf16 [z1|z2] tile in the UMMA K-major SW128 layout
 //   warps 8-23  four epilogue groups (tile i -> group i % 4, TMEM buffer i & 1): TMEM -> chunk minima -> exact decision
 //               -> z_q written in place into the ring slot -> TMA store; idx, loss, histogram
@@ -435,7 +435,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     if ((sbase & 1023u) != 0)
         __trap();                  // SW128 operands and TMA boxes need a 1024-byte aligned base
     // barrier indices
-    enum { Z_FULL = 0, Z_EMPTY = Z_FULL + STAGES, Q_DONE = Z_EMPTY + STAGES, A_FULL = Q_DONE + STAGES,
+    enum { Z_FULL = 0, Q_DONE = Z_FULL + STAGES, A_FULL = Q_DONE + STAGES,
            A_EMPTY = A_FULL + 2, T_FULL = A_EMPTY + 2, T_EMPTY = T_FULL + GROUPS, N_BARS = T_EMPTY + 2 };
     // T_FULL is per epilogue GROUP (a waiter must see every phase of its barrier), T_EMPTY per TMEM buffer
     static_assert(8 * N_BARS + 8 <= 512, "barrier area");
@@ -452,7 +452,6 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar(Z_FULL + s), 1);
-            mbar_init(bar(Z_EMPTY + s), 1);
             mbar_init(bar(Q_DONE + s), 128);
         }
         for (int b = 0; b < 2; ++b) {
@@ -500,18 +499,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     if (warp < 4)
         reg_dec<40>();
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            for (int64_t i = 0; i < my_tiles; ++i) {
-                const int s = (int)(i % STAGES);
-                const uint32_t ph = (uint32_t)((i / STAGES) & 1);
-                mbar_wait<128>(bar(Z_EMPTY + s), ph ^ 1);
-                mbar_expect_tx(bar(Z_FULL + s), TILE_M * D * 4);
-                const int64_t tile = blockIdx.x + i * gridDim.x;
-                tma_load_2d(sbase + OFF_ZRING + s * 16384, &map_z, bar(Z_FULL + s), 0, (int)(tile * TILE_M));
-                stamp(i, 0);
-            }
-        }
+        // (idle: the ring is refilled by the store warp the moment it has released a slot)
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
@@ -544,21 +532,31 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
         }
     } else if (warp == 3) {
-        // ================= z_q store + slot release =================
+        // ================= ring owner: z_q TMA store, slot release, TMA refill =================
         // (Keeping one store in flight and releasing slot i when store i+1 is issued was measured:
         // the extra tile period of slot hold time costs more than the wait it hides.)
         if (lane == 0) {
+            auto load_tile = [&](int64_t i) {
+                const int s = (int)(i % STAGES);
+                mbar_expect_tx(bar(Z_FULL + s), TILE_M * D * 4);
+                const int64_t tile = blockIdx.x + i * gridDim.x;
+                tma_load_2d(sbase + OFF_ZRING + s * 16384, &map_z, bar(Z_FULL + s), 0, (int)(tile * TILE_M));
+                stamp(i, 0);
+            };
+            for (int64_t i = 0; i < my_tiles && i < STAGES; ++i)
+                load_tile(i);
             for (int64_t i = 0; i < my_tiles; ++i) {
                 const int s = (int)(i % STAGES);
-                mbar_wait<128>(bar(Q_DONE + s), (uint32_t)((i / STAGES) & 1));
+                mbar_wait<64>(bar(Q_DONE + s), (uint32_t)((i / STAGES) & 1));
                 if (p.zq) {
                     const int64_t tile = blockIdx.x + i * gridDim.x;
                     tma_store_2d(&map_zq, sbase + OFF_ZRING + s * 16384, 0, (int)(tile * TILE_M));
                     tma_store_commit();
                     tma_store_wait_read();     // the slot may be refilled once the store has read it
                 }
-                mbar_arrive(bar(Z_EMPTY + s));
                 stamp(i, 7);
+                if (i + STAGES < my_tiles)
+                    load_tile(i + STAGES);
             }
             tma_store_wait_all();
         }
@@ -588,8 +586,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 zp[2] = fmaf(v.z, v.z, zp[2]); zp[3] = fmaf(v.w, v.w, zp[3]);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    // z1 = rn_bf16(z), z2 = rn_bf16(z - z1)  (truncating instead of rounding saves two
+                    // ALU ops per pair but widens the filter radius by 60 %: more vectors to fix up)
                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(xs[2 * h], xs[2 * h + 1]);
-                    const float r0 = xs[2 * h] - __low2float(h2);
+                    const float r0 = xs[2 * h] - __low2float(h2);              // exact
                     const float r1 = xs[2 * h + 1] - __high2float(h2);
                     const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
                     hi[2 * c + h] = *reinterpret_cast<const uint32_t *>(&h2);
@@ -666,14 +666,16 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             // by A_FULL -> MMA -> T_FULL); it only bounds the filter radius, it is not part of the decision
             const float zz = reinterpret_cast<const float *>(smem + OFF_ZZ + s * 512)[r];
             const float zn = sqrt_approx(zz) * 1.00001f;
-            // Filter radius, see DESIGN.md "Exactness".  With |z| = zn, max|e| = emax, max ee = eemax:
-            //   2*eps  (bf16x3 residual 3*2^-18 per unit of sum|z_j e_j|, x2 for -2*dot, x2 both sides,
-            //           plus tensor-core accumulation slack)                 <= 2^-13.6 zn emax + 2^-19 eemax
-            //   2*H    (oracle fp32 roundings: fl(zz+ee), fl(t-u), D-step dot chain)
-            //                                                               <= 2^-22 (zn+emax)^2 + D 2^-22 zn emax
-            //   2*pack (group id in 4 mantissa bits of the keys)             <= 2^-17 (2 zn emax + eemax)
+            // Filter radius delta = 2*eps + 2*H + 2*pack (DESIGN.md "Exactness"), u = 2^-8 the bf16 unit
+            // roundoff, zn >= |z|, emax >= max|e_k|, eemax = max ee_k, S = sum_j |z_j e_j| <= zn*emax:
+            //   eps : terms the three products leave out, z2.E2 + r_z.E + z.r_E <= (u*u + u*u + u*u) S = 3*2^-16 S,
+            //         doubled by the -2 scaling, plus tensor-core accumulation slack 2^-19 (2S + ee)
+            //   H   : the oracle's own fp32 roundings fl(zz+ee), fl(t-u) and its D-step fmaf chain:
+            //         <= 2^-24 [2 (zn+emax)^2 + 2 D S]
+            //   pack: group ids in 4 mantissa bits of the keys: <= 2^-19 (2S + ee)
+            //   =>  delta <= (12*2^-16 + 2^-17 + 2^-17 + D*2^-22) zn*emax + 2^-17 eemax + 2^-22 (zn+emax)^2
             //   + an absolute floor: the tensor core may flush sub-normal operands/products (|x| < 2^-126)
-            const float delta = 9.6e-5f * zn * emax + 1.1e-5f * eemax + 3.0e-7f * (zn + emax) * (zn + emax) + 1.0e-35f;
+            const float delta = 2.1e-4f * zn * emax + 8.0e-6f * eemax + 3.0e-7f * (zn + emax) * (zn + emax) + 1.0e-35f;
             const float best = fmaxf(a1, b1), second = fminf(a2, b2);
             const bool certain = (second > best + delta) && (zz <= 3.0e38f) && !cb_bad;
             int code = (int)(((__float_as_uint(a1) & 15u) << 4) | (__float_as_uint(b1) & 15u));
@@ -707,12 +709,15 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     p.idx[row] = code;
                 atomicAdd(hist + code, 1u);
             }
+            // (Walking the row in physical chunk order would save the swizzle XORs, but then the 8 lanes of a
+            // quarter-warp hit the same bank group: measured 2x slower.  Logical order is conflict-free.)
             const unsigned char *erow = ef32 + code * 128;
             const int xe = ((code ^ (code >> 3)) & 7) << 4;
             float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const float4 zv = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ x));
+                float4 *zp4 = reinterpret_cast<float4 *>(zrow + ((c << 4) ^ x));
+                const float4 zv = *zp4;
                 float4 e = *reinterpret_cast<const float4 *>(erow + ((c << 4) ^ xe));
                 if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
                     float *ev = reinterpret_cast<float *>(&e);
@@ -729,7 +734,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 dj = __fsub_rn(e.z, zv.z); rs[2] = fmaf(dj, dj, rs[2]); o.z = __fadd_rn(zv.z, dj);
                 dj = __fsub_rn(e.w, zv.w); rs[3] = fmaf(dj, dj, rs[3]); o.w = __fadd_rn(zv.w, dj);
                 if (p.zq)
-                    *reinterpret_cast<float4 *>(zrow + ((c << 4) ^ x)) = o;
+                    *zp4 = o;
             }
             if (emit)
                 sqf += (rs[0] + rs[1]) + (rs[2] + rs[3]);
