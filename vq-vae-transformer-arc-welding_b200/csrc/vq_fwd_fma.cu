@@ -454,15 +454,30 @@ cudaError_t launch_gather(const int64_t *idx, int64_t n, const float *E, int K, 
     return cudaGetLastError();
 }
 
-// one CTA-wide pass: each row of K floats is written once (zeros, and the single 1)
+// each row of K floats is written once (zeros and the single 1); 16-byte stores when K % 4 == 0
+template <bool VEC>
 __global__ void __launch_bounds__(256) vq_one_hot_kernel(const int64_t *__restrict__ idx, int64_t n, int K,
                                                           float *__restrict__ onehot)
 {
-    const int64_t total = n * K;
-    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
-        const int64_t i = t / K;
-        const int c = (int)(t - i * K);
-        onehot[t] = (idx[i] == c) ? 1.0f : 0.0f;
+    if (VEC) {
+        const int kq = K >> 2;
+        const int64_t total = n * kq;
+        for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+            const int64_t i = t / kq;
+            const int c = (int)(t - i * kq) << 2;
+            const int hit = (int)(idx[i] - c);      // 0..3 when the 1 falls into this quad
+            float4 v;
+            v.x = hit == 0 ? 1.0f : 0.0f; v.y = hit == 1 ? 1.0f : 0.0f;
+            v.z = hit == 2 ? 1.0f : 0.0f; v.w = hit == 3 ? 1.0f : 0.0f;
+            reinterpret_cast<float4 *>(onehot)[t] = v;
+        }
+    } else {
+        const int64_t total = n * K;
+        for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+            const int64_t i = t / K;
+            const int c = (int)(t - i * K);
+            onehot[t] = (idx[i] == c) ? 1.0f : 0.0f;
+        }
     }
 }
 
@@ -470,8 +485,14 @@ cudaError_t launch_one_hot(const int64_t *idx, int64_t n, int K, float *onehot, 
 {
     if (n == 0)
         return cudaSuccess;
-    const int64_t blocks = (n * K + 255) / 256;
-    vq_one_hot_kernel<<<(int)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, st>>>(idx, n, K, onehot);
+    const bool vec = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(onehot) & 15) == 0);
+    const int64_t work = vec ? n * (K / 4) : n * K;
+    const int64_t blocks = (work + 255) / 256;
+    const int grid = (int)(blocks < 148 * 32 ? blocks : 148 * 32);
+    if (vec)
+        vq_one_hot_kernel<true><<<grid, 256, 0, st>>>(idx, n, K, onehot);
+    else
+        vq_one_hot_kernel<false><<<grid, 256, 0, st>>>(idx, n, K, onehot);
     return cudaGetLastError();
 }
 
