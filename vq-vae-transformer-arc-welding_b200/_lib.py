@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libvqb200.so")
+# VQB_LIB_PATH: experiment builds of the same CUDA library (tools/ab_build.py); never a CPU fallback
+LIB_PATH = os.environ.get("VQB_LIB_PATH") or os.path.join(_PKG, "libvqb200.so")
 
 PATH_AUTO, PATH_FMA, PATH_TC = 0, 1, 2
 

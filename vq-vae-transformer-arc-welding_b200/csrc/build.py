@@ -31,23 +31,24 @@ def stale() -> bool:
     return any(os.path.getmtime(p) > t for p in deps if os.path.exists(p))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, out: str = OUT, extra_flags=()) -> str:
+    """out / extra_flags: experiment builds (tools/ab_build.py) next to the product library."""
+    if out == OUT and not force and not stale():
         return OUT
-    cmd = [NVCC] + FLAGS + ["-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+    cmd = [NVCC] + FLAGS + list(extra_flags) + ["-o", out] + [os.path.join(HERE, s) for s in SOURCES]
     host_cxx = "/usr/bin/g++"
     if os.path.exists(host_cxx):
         cmd[1:1] = ["-ccbin", host_cxx]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
+    with open(os.path.join(HERE, "build.log" if out == OUT else os.path.basename(out) + ".log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libvqb200.so")
     if verbose:
         print(log)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

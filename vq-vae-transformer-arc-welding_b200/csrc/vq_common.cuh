@@ -14,7 +14,7 @@ namespace vqb {
 // ---------------------------------------------------------------------------------------
 // Workspace layout (caller-owned device scratch, see vqb_workspace_bytes()).
 // ---------------------------------------------------------------------------------------
-constexpr int kMaxPartials = 2048;       // loss partial sums, one per CTA of the forward kernel
+constexpr int kMaxPartials = 4096;       // loss partial sums, one per CTA of the forward kernel
 constexpr int kHeaderBytes = 256;
 
 struct WsHeader {                        // first kHeaderBytes of the workspace
@@ -44,7 +44,7 @@ __host__ inline size_t tc_scratch_floats(int k, int d)
     // tcgen05 path (vq_fwd_tc.cu, tc::IMG_BYTES): image of the constant operands for 256 codes,
     // the scalar constants, and the per-CTA queues of vectors deferred to the fix-up kernel
     (void)k; (void)d;
-    return (32768 + 8192 + 32768 + 1024 + 64 + 192 * 4 + 192 * 2048 * 4) / sizeof(float) + 64;
+    return (32768 + 8192 + 32768 + 1024 + 64 + 192 * 4 + 192 * 2048 * 8) / sizeof(float) + 64;
 }
 
 __host__ inline WsLayout ws_layout(int k, int d)

@@ -19,20 +19,24 @@
 //   3. |s~ - s| <= eps  =>  if that runner-up is more than delta = 2*eps + rounding slack
 //      above the best score, the oracle's argmin is the code (best A-group, best B-group)
 //      -- decided by the tensor cores alone (~99.8 % of vectors);
-//   4. otherwise, or for non-finite vectors / codebooks, the vector's warp scans all K codes
-//      with the oracle-order expression (ascending fmaf chain, fl(fl(zz+ee) - 2dot), lowest
-//      index wins, first NaN wins) on the CUDA cores.
+//   4. otherwise (~0.2 % of vectors: near-ties) the vector's own thread evaluates, with the oracle-order
+//      expression (ascending fmaf chain, fl(fl(zz+ee) - 2dot), lowest index wins), only the codes the
+//      filter could not rule out: the cross product of the A-groups and B-groups whose minimum lies within
+//      delta of the best score (2-4 codes as a rule); non-finite vectors / codebooks, NaN distances and
+//      crowded candidate sets fall back to a warp-wide exact scan of all K codes (first NaN wins).
 //
-// The decision is therefore bit-identical to the FMA kernel and the CPU oracle.
+// The decision is therefore bit-identical to the FMA kernel and the CPU oracle, and everything -- filter,
+// exact decision, gather, loss, histogram, z_q -- happens in this one kernel.
 //
-// Pipeline per CTA (persistent, one CTA per SM, 512 threads):
+// Pipeline per CTA (persistent, one CTA per SM, 768 threads):
 //   warp 3      ring owner: TMA loads of z tiles (128 x 32 fp32, SWIZZLE_128B) into a 6-deep ring,
 //               z_q TMA store out of the same slot, refill of the slot it just released
 //   warp 1      MMA issuer (one thread): 7 x tcgen05.mma.kind::f16 -> TMEM (2 x 256 columns)
 //   warp 2      TMEM allocator
-//   warps 4-7   converters: fp32 tile -> bf16 [z1|z2] tile in the UMMA K-major SW128 layout
-//   warps 8-23  four epilogue groups (tile i -> group i % 4, TMEM buffer i & 1): TMEM -> chunk minima -> exact decision
-//               -> z_q written in place into the ring slot -> TMA store; idx, loss, histogram
+//   warps 4-7   converters: fp32 tile -> bf16 [z1|z2] tile in the UMMA K-major SW128 layout (Veltkamp split
+//               on the FMA pipe), ||z||^2 bound on the side
+//   warps 8-23  four epilogue groups (tile i -> group i % 4, TMEM buffer i & 1): TMEM -> A/B group minima ->
+//               decision -> z_q written in place into the ring slot -> TMA store; idx, loss, histogram
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -45,9 +49,10 @@ namespace tc {
 constexpr int D = 32;
 constexpr int TILE_M = 128;
 constexpr int KMAX = 256;
-constexpr int STAGES = 6;
+constexpr int STAGES = 6;                 // (7 stages fit but were measured slower: no L1 left beside 227 KB of smem)
 constexpr int GROUPS = 4;                 // epilogue groups (4 warps each) rotating over the 2 TMEM buffers
 constexpr int THREADS = 256 + 128 * GROUPS;
+constexpr int MAX_CAND = 32;              // candidate codes a queued vector may have (one lane of the fix-up warp each)
 
 // shared-memory map (bytes); SW128 operands need 1024-byte alignment
 constexpr int OFF_ZRING = 0;                              // STAGES x 16384  fp32 z tiles (TMA, SW128)
@@ -68,12 +73,13 @@ constexpr int IMG_BMAIN = 0;
 constexpr int IMG_BAUG = IMG_BMAIN + 32768;
 constexpr int IMG_EF32 = IMG_BAUG + 8192;
 constexpr int IMG_EE = IMG_EF32 + 32768;
-constexpr int IMG_CONST = IMG_EE + 1024;                  // float emax_bits(as uint), eemax_bits, flags
-constexpr int IMG_WLCOUNT = IMG_CONST + 64;               // u32 [WL_CTAS]  deferred vectors per CTA
+constexpr int IMG_CONST = IMG_EE + 1024;                  // Consts
+constexpr int IMG_WLCOUNT = IMG_CONST + 64;               // u32 [WL_CTAS]  vectors queued per CTA
 constexpr int WL_CTAS = 192;                              // >= number of CTAs (one per SM)
-constexpr int WL_CAP = 2048;                              // deferred vectors a CTA can queue
-constexpr int IMG_WL = IMG_WLCOUNT + WL_CTAS * 4;         // u32 [WL_CTAS][WL_CAP] row indices
-constexpr int IMG_BYTES = IMG_WL + WL_CTAS * WL_CAP * 4;
+constexpr int WL_CAP = 2048;                              // vectors a CTA can queue for the fix-up kernel
+constexpr int IMG_WL = IMG_WLCOUNT + WL_CTAS * 4;         // uint2 [WL_CTAS][WL_CAP]: row, A-mask | B-mask << 16
+constexpr int IMG_BYTES = IMG_WL + WL_CTAS * WL_CAP * 8;
+constexpr int FIX_SPLIT = 4;                              // fix-up CTAs per queue
 
 struct Consts {
     unsigned emax2_bits;   // max_k ee_k (finite ones), as float bits
@@ -385,17 +391,6 @@ __device__ __forceinline__ float min16(const uint32_t *v)
     return fminf(t5, t6);
 }
 
-// One 32-column slab of approximate scores: two A-groups (16 consecutive codes each) and a
-// contribution to each of the 16 B-groups (code mod 16).
-__device__ __forceinline__ void filter_slab(const uint32_t (&v)[32], int slab, float (&bmin)[16], float &a1, float &a2)
-{
-    top2(a1, a2, min16(&v[0]), (unsigned)(2 * slab));
-    top2(a1, a2, min16(&v[16]), (unsigned)(2 * slab + 1));
-#pragma unroll
-    for (int b = 0; b < 16; ++b)
-        bmin[b] = min3(bmin[b], __uint_as_float(v[b]), __uint_as_float(v[b + 16]));
-}
-
 // tcgen05.wait::ld, with the freshly loaded registers threaded through the statement so that
 // no use of them can be scheduled before the wait
 __device__ __forceinline__ void tmem_wait_ld_fence(uint32_t (&v)[32])
@@ -411,6 +406,45 @@ __device__ __forceinline__ void tmem_wait_ld_fence(uint32_t (&v)[32])
                  :
                  : "memory");
 }
+
+// z_q row = z + (e - z) written in place over the z row (ring slot, SW128), returns the row's sum of
+// squared residuals.  POISON: gather-by-GEMM semantics for a non-finite codebook (oracle column_poison);
+// kept out of the common instantiation so that its loads and branches do not split the hot loop.
+template <bool POISON>
+__device__ __forceinline__ float emit_row(unsigned char *zrow, int x, const unsigned char *ef32, int code,
+                                          bool write_zq, const int *colcnt, const int *colwhich)
+{
+    // (Walking the row in physical chunk order would save the swizzle XORs, but then the 8 lanes of a
+    // quarter-warp hit the same bank group: measured 2x slower.  Logical order is conflict-free.)
+    const unsigned char *erow = ef32 + code * 128;
+    const int xe = ((code ^ (code >> 3)) & 7) << 4;
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 *zp4 = reinterpret_cast<float4 *>(zrow + ((c << 4) ^ x));
+        const float4 zv = *zp4;
+        float4 e = *reinterpret_cast<const float4 *>(erow + ((c << 4) ^ xe));
+        if (POISON) {
+            float *ev = reinterpret_cast<float *>(&e);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = 4 * c + t, cc = colcnt[j];
+                if (!(cc == 0 || (cc == 1 && colwhich[j] == code + 1)))
+                    ev[t] = __int_as_float(0x7fc00000);
+            }
+        }
+        float4 o;
+        float dj;
+        dj = __fsub_rn(e.x, zv.x); rs[0] = fmaf(dj, dj, rs[0]); o.x = __fadd_rn(zv.x, dj);
+        dj = __fsub_rn(e.y, zv.y); rs[1] = fmaf(dj, dj, rs[1]); o.y = __fadd_rn(zv.y, dj);
+        dj = __fsub_rn(e.z, zv.z); rs[2] = fmaf(dj, dj, rs[2]); o.z = __fadd_rn(zv.z, dj);
+        dj = __fsub_rn(e.w, zv.w); rs[3] = fmaf(dj, dj, rs[3]); o.w = __fadd_rn(zv.w, dj);
+        if (write_zq)
+            *zp4 = o;
+    }
+    return (rs[0] + rs[1]) + (rs[2] + rs[3]);
+}
+
 
 }  // namespace tc
 
@@ -496,6 +530,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     const Consts *cst = reinterpret_cast<const Consts *>(img + IMG_CONST);
     double sq = 0.0;
 
+    // register budget (setmaxnreg acts on warpgroups): 4 x 40 + 4 x 56 + 16 x 96 = 1920 = 24 warps x 80
     if (warp < 4)
         reg_dec<40>();
     if (warp == 0) {
@@ -562,7 +597,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         }
     } else if (warp >= 4 && warp < 8) {
         // ================= converters: fp32 -> bf16 hi/lo, thread = row =================
-        reg_dec<72>();
+        reg_dec<56>();
         const int r = tid - 128;
         const int x = (r & 7) << 4;
         for (int64_t i = 0; i < my_tiles; ++i) {
@@ -576,30 +611,28 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const unsigned char *zrow = smem + OFF_ZRING + s * 16384 + r * 128;
             unsigned char *arow = smem + OFF_ARING + b * 16384 + r * 128;
-            uint32_t hi[16], lo[16];
             float zp[4] = {0.f, 0.f, 0.f, 0.f};     // ||z||^2 for the epilogue's filter radius (a bound, not the decision)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 v = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ x));
-                const float xs[4] = {v.x, v.y, v.z, v.w};
-                zp[0] = fmaf(v.x, v.x, zp[0]); zp[1] = fmaf(v.y, v.y, zp[1]);
-                zp[2] = fmaf(v.z, v.z, zp[2]); zp[3] = fmaf(v.w, v.w, zp[3]);
+            for (int cp = 0; cp < 4; ++cp) {        // two 16-byte chunks of z -> one chunk of z1 and one of z2
+                const float4 va = *reinterpret_cast<const float4 *>(zrow + (((2 * cp) << 4) ^ x));
+                const float4 vb = *reinterpret_cast<const float4 *>(zrow + (((2 * cp + 1) << 4) ^ x));
+                const float xs[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+                uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    // z1 = rn_bf16(z), z2 = rn_bf16(z - z1)  (truncating instead of rounding saves two
-                    // ALU ops per pair but widens the filter radius by 60 %: more vectors to fix up)
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(xs[2 * h], xs[2 * h + 1]);
-                    const float r0 = xs[2 * h] - __low2float(h2);              // exact
-                    const float r1 = xs[2 * h + 1] - __high2float(h2);
-                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
-                    hi[2 * c + h] = *reinterpret_cast<const uint32_t *>(&h2);
-                    lo[2 * c + h] = *reinterpret_cast<const uint32_t *>(&l2);
+                for (int h = 0; h < 4; ++h) {
+                    const float x0 = xs[2 * h], x1 = xs[2 * h + 1];
+                    zp[h] = fmaf(x0, x0, zp[h]);
+                    zp[h] = fmaf(x1, x1, zp[h]);
+                    // z1 = rn_bf16(x), z2 = rn_bf16(x - z1).  (Measured alternatives: truncating instead of
+                    // rounding saves two ALU ops per pair but widens the filter radius by 60 %; a Veltkamp split
+                    // on the FMA pipe relieves the ALU pipe but issues four more instructions per pair, ~1 % slower.)
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - __low2float(h2), x1 - __high2float(h2));
+                    hi[h] = *reinterpret_cast<const uint32_t *>(&h2);
+                    lo[h] = *reinterpret_cast<const uint32_t *>(&l2);
                 }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                *reinterpret_cast<uint4 *>(arow + ((c << 4) ^ x)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                *reinterpret_cast<uint4 *>(arow + (((c + 4) << 4) ^ x)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                *reinterpret_cast<uint4 *>(arow + ((cp << 4) ^ x)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(arow + (((cp + 4) << 4) ^ x)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
             reinterpret_cast<float *>(smem + OFF_ZZ + s * 512)[r] = (zp[0] + zp[1]) + (zp[2] + zp[3]);
             fence_proxy_async();
@@ -608,7 +641,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         }
     } else if (warp >= 8) {
         // ================= epilogue groups =================
-        reg_inc<88>();
+        reg_inc<96>();
         const int g = (warp - 8) >> 2;            // tile i is handled by group i % GROUPS, TMEM buffer i & 1
         const int q = warp & 3;                   // TMEM lane quarter of this warp
         const int r = q * 32 + lane;              // row in tile = TMEM lane
@@ -622,7 +655,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         const bool cb_bad = cst->nonfinite != 0 || poisoned;
         const int n_slab = kp >> 5;
         unsigned long long n_slow_total = 0;
-        unsigned *wl = reinterpret_cast<unsigned *>(const_cast<unsigned char *>(img) + IMG_WL) + (size_t)blockIdx.x * WL_CAP;
+        uint2 *wl = reinterpret_cast<uint2 *>(const_cast<unsigned char *>(img) + IMG_WL) + (size_t)blockIdx.x * WL_CAP;
 
         float sqf = 0.0f;
         for (int64_t i = g; i < my_tiles; i += GROUPS) {
@@ -633,30 +666,43 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             const int64_t row = tile * TILE_M + r;
             const bool ok = row < n_rows;
 
-            // ---- filter: A/B group minima of the approximate scores, packed top-2 each ----
+            // ---- filter: minima of the approximate scores over the 16 A-groups and the 16 B-groups ----
             group_wait<64>(q == 0, bar(T_FULL + g), ph, 2 + g);
             tc_fence_after();
             if (r == 0) stamp(i, 4);
             const uint32_t taddr = tmem_base + b * KMAX + ((uint32_t)(q * 32) << 16);
             const float inf = __int_as_float(0x7f800000);
-            float a1 = inf, a2 = inf;
-            float bmin[16];
+            // (finite sentinel: a group id packed into the low mantissa bits of +inf would make a NaN key)
+            const float big = 3.0e38f;
+            float amin[16], bmin[16];
 #pragma unroll
-            for (int bb = 0; bb < 16; ++bb)
-                bmin[bb] = inf;
-            for (int sl = 0; sl < n_slab; ++sl) {
-                uint32_t v[32];
-                tmem_ld32(taddr + sl * 32, v);
-                tmem_wait_ld_fence(v);
-                filter_slab(v, sl, bmin, a1, a2);
+            for (int t = 0; t < 16; ++t) {
+                amin[t] = big;
+                bmin[t] = big;
+            }
+#pragma unroll
+            for (int sl = 0; sl < KMAX / 32; ++sl) {
+                if (sl < n_slab) {                // CTA-uniform: slabs beyond the padded codebook are never read
+                    uint32_t v[32];
+                    tmem_ld32(taddr + sl * 32, v);
+                    tmem_wait_ld_fence(v);
+                    amin[2 * sl] = min16(&v[0]);
+                    amin[2 * sl + 1] = min16(&v[16]);
+#pragma unroll
+                    for (int t = 0; t < 16; ++t)
+                        bmin[t] = min3(bmin[t], __uint_as_float(v[t]), __uint_as_float(v[t + 16]));
+                }
             }
             tc_fence_before();
             mbar_arrive(bar(T_EMPTY + b));        // accumulator drained: the next MMA may overwrite it
             if (r == 0) stamp(i, 5);
-            float b1 = inf, b2 = inf;
+            // packed (value | group id) top-2 of each grouping -- off the accumulator's critical path
+            float a1 = inf, a2 = inf, b1 = inf, b2 = inf;
 #pragma unroll
-            for (int bb = 0; bb < 16; ++bb)
-                top2(b1, b2, bmin[bb], (unsigned)bb);
+            for (int t = 0; t < 16; ++t) {
+                top2(a1, a2, amin[t], (unsigned)t);
+                top2(b1, b2, bmin[t], (unsigned)t);
+            }
 
             // ---- the vector itself (TMA-written ring slot) ----
             // (the tile itself was TMA-written before the converters read it, i.e. long before T_FULL)
@@ -674,25 +720,44 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             //         <= 2^-24 [2 (zn+emax)^2 + 2 D S]
             //   pack: group ids in 4 mantissa bits of the keys: <= 2^-19 (2S + ee)
             //   =>  delta <= (12*2^-16 + 2^-17 + 2^-17 + D*2^-22) zn*emax + 2^-17 eemax + 2^-22 (zn+emax)^2
-            //   + an absolute floor: the tensor core may flush sub-normal operands/products (|x| < 2^-126)
-            const float delta = 2.1e-4f * zn * emax + 8.0e-6f * eemax + 3.0e-7f * (zn + emax) * (zn + emax) + 1.0e-35f;
+            //   + an absolute floor for sub-normal z entries (lost by the bf16 split and possibly flushed by the
+            //     tensor core): each is < 2^-126, so they move a score by < 2*sqrt(D)*2^-126*emax
+            const float delta = 2.1e-4f * zn * emax + 8.0e-6f * eemax + 3.0e-7f * (zn + emax) * (zn + emax) +
+                                (1.0e-35f + 1.0e-36f * emax);
             const float best = fmaxf(a1, b1), second = fminf(a2, b2);
             const bool certain = (second > best + delta) && (zz <= 3.0e38f) && !cb_bad;
             int code = (int)(((__float_as_uint(a1) & 15u) << 4) | (__float_as_uint(b1) & 15u));
             if (code >= K)
                 code = 0;
-            // Vectors the filter cannot certify (~0.1 %) are queued for the fix-up kernel, which decides
-            // them with the exact expression after this kernel: no slow path inside the pipeline.  Only
-            // when the CTA's queue is full are they scanned here, by the whole warp.
-            bool deferred = false;
+            // Vectors the filter cannot certify (~0.2 %: near-ties) are queued, together with the codes the filter
+            // could not rule out, for the fix-up kernel that follows: every oracle minimiser has an approximate
+            // score within delta of the best one, hence lies in an A-group AND a B-group whose minimum is
+            // <= best + delta (two 16-bit masks).  Rows whose exact distances could overflow, non-finite rows /
+            // codebooks, crowded candidate sets (exact ties of many codes) and a full queue take the warp-wide
+            // exact scan of all K codes right here instead.
+            bool slow = false, deferred = false;
             if (!certain && ok) {
-                const unsigned pos = atomicAdd(wl_count_s, 1u);
-                if (pos < (unsigned)WL_CAP) {
-                    wl[pos] = (unsigned)row;
-                    deferred = true;
+                slow = true;
+                if (zz <= 1.0e37f && eemax <= 1.0e37f && !cb_bad) {
+                    const float thr = best + delta;
+                    unsigned ma = 0u, mb = 0u;
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        ma |= amin[t] <= thr ? 1u << t : 0u;
+                        mb |= bmin[t] <= thr ? 1u << t : 0u;
+                    }
+                    const int nc = __popc(ma) * __popc(mb);
+                    if (nc >= 1 && nc <= MAX_CAND) {
+                        const unsigned pos = atomicAdd(wl_count_s, 1u);
+                        if (pos < (unsigned)WL_CAP) {
+                            wl[pos] = make_uint2((unsigned)row, ma | (mb << 16));
+                            slow = false;
+                            deferred = true;
+                        }
+                    }
                 }
             }
-            unsigned need = __ballot_sync(0xffffffffu, !certain && ok && !deferred);
+            unsigned need = __ballot_sync(0xffffffffu, slow);
             n_slow_total += __popc(__ballot_sync(0xffffffffu, !certain && ok));
             while (need) {
                 const int src = __ffs(need) - 1;
@@ -709,35 +774,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     p.idx[row] = code;
                 atomicAdd(hist + code, 1u);
             }
-            // (Walking the row in physical chunk order would save the swizzle XORs, but then the 8 lanes of a
-            // quarter-warp hit the same bank group: measured 2x slower.  Logical order is conflict-free.)
-            const unsigned char *erow = ef32 + code * 128;
-            const int xe = ((code ^ (code >> 3)) & 7) << 4;
-            float rs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float4 *zp4 = reinterpret_cast<float4 *>(zrow + ((c << 4) ^ x));
-                const float4 zv = *zp4;
-                float4 e = *reinterpret_cast<const float4 *>(erow + ((c << 4) ^ xe));
-                if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
-                    float *ev = reinterpret_cast<float *>(&e);
-                    for (int t = 0; t < 4; ++t) {
-                        const int j = 4 * c + t, cc = p.colcnt[j];
-                        if (!(cc == 0 || (cc == 1 && p.colwhich[j] == code + 1)))
-                            ev[t] = __int_as_float(0x7fc00000);
-                    }
-                }
-                float4 o;
-                float dj;
-                dj = __fsub_rn(e.x, zv.x); rs[0] = fmaf(dj, dj, rs[0]); o.x = __fadd_rn(zv.x, dj);
-                dj = __fsub_rn(e.y, zv.y); rs[1] = fmaf(dj, dj, rs[1]); o.y = __fadd_rn(zv.y, dj);
-                dj = __fsub_rn(e.z, zv.z); rs[2] = fmaf(dj, dj, rs[2]); o.z = __fadd_rn(zv.z, dj);
-                dj = __fsub_rn(e.w, zv.w); rs[3] = fmaf(dj, dj, rs[3]); o.w = __fadd_rn(zv.w, dj);
-                if (p.zq)
-                    *zp4 = o;
-            }
+            const float r2 = poisoned ? emit_row<true>(zrow, x, ef32, code, p.zq != nullptr, p.colcnt, p.colwhich)
+                                      : emit_row<false>(zrow, x, ef32, code, p.zq != nullptr, nullptr, nullptr);
             if (emit)
-                sqf += (rs[0] + rs[1]) + (rs[2] + rs[3]);
+                sqf += r2;
             if (((i / GROUPS) & 15) == 15) {      // bounded fp32 run lengths, fp64 across them
                 sq += (double)sqf;
                 sqf = 0.0f;
@@ -783,106 +823,75 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
 }
 
 // ---------------------------------------------------------------------------------------
-// fix-up: the queued vectors are decided with the exact expression (warp per vector), and
-// their idx / z_q / histogram / loss contributions are written here.
+// fix-up: each queued vector is decided among its candidate codes with the exact expression
+// (one warp per vector, one lane per candidate code), and its idx / z_q / histogram / loss
+// contributions are written here.  The main kernel only queues vectors whose distances
+// cannot overflow, so no NaN rule is needed.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) vq_tc_fixup_kernel(const FwdParams p, const unsigned char *__restrict__ img,
                                                            double *__restrict__ partial_out)
 {
     using namespace tc;
-    extern __shared__ __align__(16) unsigned char fsm[];     // [EF32 32 KB | EE 1 KB], same layout as the image
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned count = reinterpret_cast<const unsigned *>(img + IMG_WLCOUNT)[blockIdx.x];
-    const unsigned *wl = reinterpret_cast<const unsigned *>(img + IMG_WL) + (size_t)blockIdx.x * WL_CAP;
+    const int queue = blockIdx.x / FIX_SPLIT, part = blockIdx.x % FIX_SPLIT;
+    const unsigned count = reinterpret_cast<const unsigned *>(img + IMG_WLCOUNT)[queue];
+    const uint2 *wl = reinterpret_cast<const uint2 *>(img + IMG_WL) + (size_t)queue * WL_CAP;
+    const float *ee = reinterpret_cast<const float *>(img + IMG_EE);
+    const int K = p.K;
     double sq = 0.0;
-    if (count > 0) {                                          // block-uniform
-        for (int i = threadIdx.x; i < (32768 + 1024) / 16; i += 256)
-            reinterpret_cast<uint4 *>(fsm)[i] = __ldg(reinterpret_cast<const uint4 *>(img + IMG_EF32) + i);
-        __syncthreads();
-        const unsigned char *ef32 = fsm;
-        const float *ees = reinterpret_cast<const float *>(fsm + 32768);
-        const bool poisoned = p.hdr_in->poisoned_columns != 0;
-        const int K = p.K;
-        const int kp = (K + 31) & ~31;
-        for (unsigned e = warp; e < count; e += 8) {
-            const int64_t row = wl[e];
-            const float zj = __ldg(p.z.base + row * D + lane);
-            float zv[D];
+    for (unsigned e = part * 8 + warp; e < count; e += 8 * FIX_SPLIT) {
+        const uint2 ent = wl[e];
+        const int64_t row = ent.x;
+        const unsigned ma = ent.y & 0xffffu, mb = ent.y >> 16;
+        const int nb = __popc(mb), nc = __popc(ma) * nb;
+        // lane j takes the j-th candidate in ascending code order (A-group major)
+        int k = -1;
+        if (lane < nc) {
+            const int a = __fns(ma, 0, lane / nb + 1), b = __fns(mb, 0, lane % nb + 1);
+            k = 16 * a + b;
+            if (k >= K)
+                k = -1;
+        }
+        const float zj = __ldg(p.z.base + row * D + lane);
+        const float *erow = p.E + (size_t)(k < 0 ? 0 : k) * D;
+        float zz = 0.0f, acc = 0.0f;
 #pragma unroll
-            for (int j = 0; j < D; ++j)          // whole vector in every lane (uniform control flow)
-                zv[j] = __shfl_sync(0xffffffffu, zj, j);
-            float zz = 0.0f;
+        for (int c = 0; c < 8; ++c) {                 // oracle-order chains, ascending j
+            const float4 e4 = __ldg(reinterpret_cast<const float4 *>(erow) + c);
+            const float z0 = __shfl_sync(0xffffffffu, zj, 4 * c), z1 = __shfl_sync(0xffffffffu, zj, 4 * c + 1);
+            const float z2 = __shfl_sync(0xffffffffu, zj, 4 * c + 2), z3 = __shfl_sync(0xffffffffu, zj, 4 * c + 3);
+            zz = fmaf(z0, z0, zz); zz = fmaf(z1, z1, zz); zz = fmaf(z2, z2, zz); zz = fmaf(z3, z3, zz);
+            acc = fmaf(z0, e4.x, acc); acc = fmaf(z1, e4.y, acc); acc = fmaf(z2, e4.z, acc); acc = fmaf(z3, e4.w, acc);
+        }
+        float best = __int_as_float(0x7f800000);
+        int bidx = 0x7fffffff;
+        if (k >= 0) {
+            best = ref_distance(zz, ee[k], acc);
+            bidx = k;
+        }
 #pragma unroll
-            for (int j = 0; j < D; ++j)          // oracle-order chain
-                zz = fmaf(zv[j], zv[j], zz);
-            // lane owns codes lane, lane+32, ...; their chains are interleaved four at a time (each
-            // still ascends j = 0..31, so the values are the oracle's)
-            float best = __int_as_float(0x7f800000);
-            int bidx = 0x7fffffff;
-            unsigned first_nan = 0xffffffffu;
-            for (int k0 = 0; k0 < kp; k0 += 128) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int k = k0 + lane + 32 * u;
-                        const float4 ev4 = *reinterpret_cast<const float4 *>(ef32 + ef32_off(k & (KMAX - 1), c));
-                        acc[u] = fmaf(zv[4 * c], ev4.x, acc[u]);
-                        acc[u] = fmaf(zv[4 * c + 1], ev4.y, acc[u]);
-                        acc[u] = fmaf(zv[4 * c + 2], ev4.z, acc[u]);
-                        acc[u] = fmaf(zv[4 * c + 3], ev4.w, acc[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int k = k0 + lane + 32 * u;
-                    if (k < K) {
-                        const float dist = ref_distance(zz, ees[k], acc[u]);
-                        if (dist != dist)
-                            first_nan = min(first_nan, (unsigned)k);
-                        if (dist < best) {          // k ascends per lane: strict < keeps the lowest index
-                            best = dist;
-                            bidx = k;
-                        }
-                    }
-                }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (ob < best || (ob == best && oi < bidx)) {
+                best = ob;
+                bidx = oi;
             }
-            int code;
-            const unsigned nan_k = __reduce_min_sync(0xffffffffu, first_nan);
-            if (nan_k != 0xffffffffu) {
-                code = (int)nan_k;                  // torch.argmin: the first NaN wins
-            } else {
+        }
+        const int code = bidx == 0x7fffffff ? 0 : bidx;
+        const float ev = __ldg(p.E + (size_t)code * D + lane);
+        const float diff = __fsub_rn(ev, zj);
+        if (p.zq)
+            p.zq[row * D + lane] = __fadd_rn(zj, diff);
+        float r2 = __fmul_rn(diff, diff);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-                    if (ob < best || (ob == best && oi < bidx)) {
-                        best = ob;
-                        bidx = oi;
-                    }
-                }
-                code = bidx == 0x7fffffff ? 0 : bidx;
-            }
-            float ev = __ldg(p.E + (size_t)code * D + lane);
-            if (poisoned) {
-                const int cc = p.colcnt[lane];
-                if (!(cc == 0 || (cc == 1 && p.colwhich[lane] == code + 1)))
-                    ev = __int_as_float(0x7fc00000);
-            }
-            const float diff = __fsub_rn(ev, zj);
-            if (p.zq)
-                p.zq[row * D + lane] = __fadd_rn(zj, diff);
-            float r2 = __fmul_rn(diff, diff);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-            if (lane == 0) {
-                if (p.idx)
-                    p.idx[row] = code;
-                atomicAdd(p.counts + code, 1ULL);
-                sq += (double)r2;
-            }
+        for (int o = 16; o > 0; o >>= 1)
+            r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        if (lane == 0) {
+            if (p.idx)
+                p.idx[row] = code;
+            atomicAdd(p.counts + code, 1ULL);
+            sq += (double)r2;
         }
     }
     __shared__ double red[8];
@@ -978,7 +987,7 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
         grid = 1;
     if (grid > WL_CTAS)
         grid = WL_CTAS;
-    *n_ctas = 2 * grid;    // partials [0, grid): main kernel, [grid, 2*grid): fix-up kernel
+    *n_ctas = grid * (1 + FIX_SPLIT);    // partials [0, grid): main kernel, then one per fix-up CTA
     if (ev_begin)
         cudaEventRecord(ev_begin, st);
     if (g_trace_buf)
@@ -988,7 +997,7 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
     err = cudaGetLastError();
     if (err != cudaSuccess)
         return err;
-    vq_tc_fixup_kernel<<<grid, 256, 32768 + 1024, st>>>(p, img, p.partials + grid);
+    vq_tc_fixup_kernel<<<grid * FIX_SPLIT, 256, 0, st>>>(p, img, p.partials + grid);
     err = cudaGetLastError();
     if (ev_end)
         cudaEventRecord(ev_end, st);
