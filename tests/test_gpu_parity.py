@@ -346,3 +346,52 @@ def test_tc_matches_fma_on_4m_vectors():
         b = ops.forward(z, w, 0.25, path="tc")
         assert torch.equal(a[3], b[3]) and torch.equal(a[1], b[1]) and torch.equal(a[4], b[4])
         assert b[0].item() == pytest.approx(a[0].item(), rel=1e-6)
+
+
+def test_tc_crowded_candidates_and_queue_overflow():
+    """The fix-up queue takes vectors with at most 32 candidate codes and 2048 vectors per CTA; everything
+    beyond that is decided by the warp-wide exact scan inside the main kernel.  Both routes must agree with
+    the oracle: (a) a codebook of 256 identical rows (every code is a candidate, lowest index wins),
+    (b) a codebook of 8 distinct rows repeated 32 times (cross product of several A- and B-groups),
+    (c) 2^19 vectors that are ALL uncertain (each one the midpoint of two codes), which overflows every queue."""
+    rs = np.random.RandomState(34)
+    K, D = 256, 32
+    z = (0.1 * rs.standard_normal((1500, D))).astype(np.float32)
+    E = np.tile((0.1 * rs.standard_normal((1, D))).astype(np.float32), (K, 1))
+    stats = _tc_vs_oracle(z, E)
+    assert stats[1] == 1500
+    E = np.tile((0.1 * rs.standard_normal((8, D))).astype(np.float32), (32, 1))
+    stats = _tc_vs_oracle(z, E)
+    assert stats[1] == 1500
+    E = (0.1 * rs.standard_normal((K, D))).astype(np.float32)
+    a, b = rs.randint(0, K, 1 << 19), rs.randint(0, K, 1 << 19)
+    z = ((E[a] + E[b]) * 0.5).astype(np.float32)
+    stats = _tc_vs_oracle(z, E)
+    assert stats[1] > (1 << 18)
+
+
+def test_tc_subnormal_inputs():
+    """Sub-normal components are lost by the bf16 split (and may be flushed by the tensor core): the
+    absolute floor of the filter radius must send such near-ties to the exact path."""
+    rs = np.random.RandomState(35)
+    E = (rs.standard_normal((256, 32)) * 1e-38).astype(np.float32)
+    z = (rs.standard_normal((2000, 32)) * 1e-38).astype(np.float32)
+    _tc_vs_oracle(z, E)
+    E = (rs.standard_normal((256, 32))).astype(np.float32)
+    z = (rs.standard_normal((2000, 32)) * 1e-39).astype(np.float32)
+    z[:, 0] = 0.0
+    _tc_vs_oracle(z, E)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_ids_only_mode_skips_nothing_that_matters(path):
+    """want_zq=False, want_loss=False (encode_indices): ids and histogram equal those of the full call."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(5)
+    z = 0.1 * torch.randn(70000, 32, device=dev, generator=g)
+    w = (torch.rand(256, 32, device=dev, generator=g) * 2 - 1) / 256
+    full = ops.forward(z, w, 0.25, path=path)
+    ids = ops.forward(z, w, 0.25, path=path, want_zq=False, want_loss=False)
+    assert ids[0] is None and ids[1] is None
+    assert torch.equal(full[3], ids[3]) and torch.equal(full[4], ids[4])
+    assert ids[2].item() == pytest.approx(full[2].item(), rel=1e-6)

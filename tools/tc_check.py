@@ -49,12 +49,12 @@ def timing(n=1 << 24, K=256, reps=10):
     w = (torch.rand(K, 32, device=dev) * 2 - 1) / K
     for want_zq in (True, False):
         for _ in range(3):
-            ops.forward(z, w, 0.25, path="tc", want_zq=want_zq)
+            ops.forward(z, w, 0.25, path="tc", want_zq=want_zq, want_loss=want_zq)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            ops.forward(z, w, 0.25, path="tc", want_zq=want_zq)
+            ops.forward(z, w, 0.25, path="tc", want_zq=want_zq, want_loss=want_zq)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         bytes_ = n * (264 if want_zq else 136)

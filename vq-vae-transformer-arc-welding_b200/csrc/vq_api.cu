@@ -204,6 +204,7 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
         p.E = codebook; p.K = k; p.D = d; p.ee = ee; p.colcnt = colcnt; p.colwhich = colwhich; p.hdr_in = hdr;
         p.zq = zq; p.idx = idx; p.counts = cnt; p.partials = partials; p.accumulate = 0;
         p.stats = stats;
+        p.need_sq = loss != nullptr;
 
         unsigned path = flags & VQB_PATH_MASK;
         const bool tc_ok = p.z.rows_contiguous(d) && tc_shape_supported(k, d) && aligned(z, 16);

@@ -98,6 +98,7 @@ struct FwdParams {
     double *partials;     // [gridDim.x] sum of squared residuals per CTA
     int accumulate;       // partials[b] += instead of =
     int kt;               // codes per shared-memory tile (multiple of 4)
+    int need_sq;          // the caller wants the loss: residual sums are needed even when zq == nullptr
     unsigned long long *stats;
 };
 

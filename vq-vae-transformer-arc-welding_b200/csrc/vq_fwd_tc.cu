@@ -774,8 +774,11 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     p.idx[row] = code;
                 atomicAdd(hist + code, 1u);
             }
-            const float r2 = poisoned ? emit_row<true>(zrow, x, ef32, code, p.zq != nullptr, p.colcnt, p.colwhich)
-                                      : emit_row<false>(zrow, x, ef32, code, p.zq != nullptr, nullptr, nullptr);
+            // (ids-only calls -- no z_q, no loss -- skip the gather and the residual altogether)
+            float r2 = 0.0f;
+            if (p.zq || p.need_sq)
+                r2 = poisoned ? emit_row<true>(zrow, x, ef32, code, p.zq != nullptr, p.colcnt, p.colwhich)
+                              : emit_row<false>(zrow, x, ef32, code, p.zq != nullptr, nullptr, nullptr);
             if (emit)
                 sqf += r2;
             if (((i / GROUPS) & 15) == 15) {      // bounded fp32 run lengths, fp64 across them

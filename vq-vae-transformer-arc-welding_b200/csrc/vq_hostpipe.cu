@@ -171,6 +171,7 @@ int vqb_encode_host(vqb_host_ctx *ctx, const float *z_host, int64_t n, float bet
         p.partials = ctx->d_partials + (size_t)(c % ctx->depth) * kMaxPartials;
         p.accumulate = 1;
         p.stats = ctx->d_stats;
+        p.need_sq = loss_host != nullptr;
         unsigned path = flags & VQB_PATH_MASK;
         const bool tc_ok = tc_shape_supported(k, d);
         if (path == VQB_PATH_TC && !tc_ok)

@@ -63,7 +63,8 @@ class VectorQuantizer(LightningModule):
         """min_encoding_indices only (what dataloader/latentspace_dataloader.py:160-161 keeps):
         no z_q write, no one-hot, no autograd graph."""
         with torch.no_grad():
-            _, _, _, indices, counts = ops.forward(z, self.embedding.weight, self.beta, self.path, want_zq=False)
+            _, _, _, indices, counts = ops.forward(z, self.embedding.weight, self.beta, self.path, want_zq=False,
+                                                    want_loss=False)
         self.code_counts = counts
         return indices
 

@@ -10,9 +10,10 @@ Encode half (the hot path):
                       applied to all tokens at once as dense layers (one GEMM per conv instead
                       of 16 tiny convolutions).  With BatchNorm in training mode the per-position
                       batch statistics of the reference are kept by looping like it does.
-  * SepCNNBlock     : per-token linear H -> D, returned in the reference's permuted layout
-                      (physical (B, D, T), logical (B, T, D), :83-91)
-  * VectorQuantizer : fused CUDA kernel, reads the permuted view in place.
+  * SepCNNBlock     : per-token linear H -> D, written as contiguous (B, T, D) rows (the reference returns
+                      the same values as a permuted view of (B, D, T), :83-91)
+  * VectorQuantizer : fused CUDA kernel; contiguous rows go straight to the tcgen05 path, any strided view
+                      (e.g. the reference encoder's permuted output) is accepted too.
 Decode half (out of the hot-path scope, stock PyTorch modules): :19-57, :142-147.
 """
 from __future__ import annotations
@@ -113,10 +114,11 @@ class SepCNNBlock(nn.Module):
         self.shared_conv = nn.Conv1d(hidden_dim, embedding_dim, kernel_size=1, stride=1, padding=0)
 
     def forward(self, x):
-        """(B, H, T) -> logical (B, T, D) stored as (B, D, T): the same non-contiguous view the
-        reference returns (:91), which the fused VQ kernel reads without a copy."""
-        out = torch.matmul(self.shared_conv.weight[:, :, 0], x) + self.shared_conv.bias[:, None]  # (B, D, T)
-        return out.permute(0, 2, 1)
+        """(B, H, T) -> (B, T, D).  The reference returns the same values as a permuted view of a
+        (B, D, T) tensor (:91); here the per-token projection writes (B, T, D) rows directly, which is
+        the layout the tcgen05 quantiser streams with TMA (a permuted view would cost a packing copy)."""
+        tokens = x.permute(0, 2, 1)                # a view of the contiguous token rows CNNBlock produced
+        return F.linear(tokens, self.shared_conv.weight[:, :, 0], self.shared_conv.bias)
 
 
 class CNNBlock(nn.Module):
@@ -176,7 +178,7 @@ class VQVAEPatch(Autoencoder):
 
     # ---- encode half: the hot path ------------------------------------------------------
     def encode(self, x):
-        """x (B, seq_len, input_dim) -> z_e, logical (B, T, D) on physical (B, D, T)."""
+        """x (B, seq_len, input_dim) -> z_e (B, T, D)."""
         return self.encoder(self.patch_embed(x))
 
     def encode_ids(self, x):

@@ -74,9 +74,10 @@ def _view_params(z: torch.Tensor, d: int, k: int = 0, path: str = "fma"):
 
 
 def forward(z: torch.Tensor, weight: torch.Tensor, beta: float, path: str = "auto",
-            want_zq: bool = True, want_stats: bool = False):
+            want_zq: bool = True, want_stats: bool = False, want_loss: bool = True):
     """Fused nearest-code search.  Returns (loss, z_q, perplexity, indices (N,1) int64,
-    counts (K,) int64[, stats (4,) int64])."""
+    counts (K,) int64[, stats (4,) int64]).  want_zq=False / want_loss=False: that output is None and
+    the kernel skips the work behind it (ids-only encoding, dataloader/latentspace_dataloader.py:160-161)."""
     _require_cuda_fp32(z, "z")
     _require_cuda_fp32(weight, "embedding.weight")
     if weight.dim() != 2:
@@ -106,11 +107,11 @@ def forward(z: torch.Tensor, weight: torch.Tensor, beta: float, path: str = "aut
             dev.index, zsrc.data_ptr(), n_outer, n_inner, d, s_outer, s_inner, s_d,
             w.data_ptr(), k, float(beta),
             zq.data_ptr() if zq is not None else None, idx.data_ptr(),
-            scal.data_ptr(), scal.data_ptr() + 4, counts.data_ptr(),
+            scal.data_ptr() if want_loss else None, scal.data_ptr() + 4, counts.data_ptr(),
             stats.data_ptr() if stats is not None else None,
             ws_ptr, ws_bytes, PATHS[path], stream)
     _lib.check(rc, "vqb_forward")
-    out = (scal[0], zq, scal[1], idx, counts)
+    out = (scal[0] if want_loss else None, zq, scal[1], idx, counts)
     return out + (stats,) if want_stats else out
 
 
