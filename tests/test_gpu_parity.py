@@ -395,3 +395,25 @@ def test_ids_only_mode_skips_nothing_that_matters(path):
     assert ids[0] is None and ids[1] is None
     assert torch.equal(full[3], ids[3]) and torch.equal(full[4], ids[4])
     assert ids[2].item() == pytest.approx(full[2].item(), rel=1e-6)
+
+
+@pytest.mark.parametrize("D", [4, 8, 12, 16, 20, 28])
+@pytest.mark.parametrize("K", [5, 64, 256])
+def test_tc_narrow_vectors(D, K):
+    """D < 32 (multiples of 4) runs on the tcgen05 path as D = 32 with zero columns: the TMA boxes
+    zero-fill on load and clip on store; results stay bit-identical to the oracle."""
+    rs = np.random.RandomState(D * 1000 + K)
+    E = (0.1 * rs.standard_normal((K, D))).astype(np.float32)
+    if K > 2:
+        E[K - 1] = E[0]                                   # an exact tie across the codebook
+    for n in (128, 777):
+        z = (0.1 * rs.standard_normal((n, D))).astype(np.float32)
+        z[0] = E[0]
+        dev = _dev()
+        assert ops._tc_eligible(n, K, D)
+        out = ops.forward(torch.from_numpy(z).to(dev), torch.from_numpy(E).to(dev), 0.25, path="tc", want_stats=True)
+        ora = O.forward(z, E, 0.25)
+        assert np.array_equal(out[3].cpu().numpy().reshape(-1), ora.indices.reshape(-1))
+        assert np.array_equal(out[1].cpu().numpy(), ora.z_q.reshape(n, D))
+        assert np.array_equal(out[4].cpu().numpy(), ora.counts)
+        assert out[0].item() == pytest.approx(float(ora.loss), rel=REL)

@@ -256,7 +256,7 @@ __device__ __forceinline__ int ef32_off(int k, int c) { return k * 128 + ((c ^ (
 // ---------------------------------------------------------------------------------------
 // prep: one thread per (padded) code builds the constant operand image in global scratch
 // ---------------------------------------------------------------------------------------
-__global__ void vq_tc_prep_kernel(const float *__restrict__ E, const float *__restrict__ ee, int K, int kp,
+__global__ void vq_tc_prep_kernel(const float *__restrict__ E, const float *__restrict__ ee, int K, int d, int kp,
                                   unsigned char *__restrict__ img)
 {
     using namespace tc;
@@ -268,7 +268,7 @@ __global__ void vq_tc_prep_kernel(const float *__restrict__ E, const float *__re
     float e[D];
 #pragma unroll
     for (int j = 0; j < D; ++j)
-        e[j] = real ? __ldg(E + (size_t)k * D + j) : 0.0f;
+        e[j] = (real && j < d) ? __ldg(E + (size_t)k * d + j) : 0.0f;   // d < 32: zero columns change no sum
     // main B operand: row k = [-2*E1 (32 bf16) | -2*E2 (32 bf16)], SW128
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -544,6 +544,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             const uint64_t bmain = desc_sw128(sbase + OFF_BMAIN);
             const uint64_t baug = desc_sw32(sbase + OFF_BAUG);
             const uint64_t aaug = desc_sw32(sbase + OFF_AAUG);
+            const bool wide = p.D > 16;
             for (int64_t i = 0; i < my_tiles; ++i) {
                 const int b = (int)(i & 1);
                 const int g = (int)(i % GROUPS);
@@ -555,13 +556,14 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 const uint64_t a = desc_sw128(sbase + OFF_ARING + b * 16384);
                 const uint32_t d = tmem_base + b * KMAX;
                 // K-slices of 16 bf16 = 32 bytes = +2 in the descriptor's address field
-                umma_bf16(d, a + 0, bmain + 0, idesc, 0);   // z1[0:16]  . E1[0:16]
-                umma_bf16(d, a + 2, bmain + 2, idesc, 1);   // z1[16:32] . E1[16:32]
-                umma_bf16(d, a + 0, bmain + 4, idesc, 1);   // z1[0:16]  . E2[0:16]
-                umma_bf16(d, a + 2, bmain + 6, idesc, 1);   // z1[16:32] . E2[16:32]
-                umma_bf16(d, a + 4, bmain + 0, idesc, 1);   // z2[0:16]  . E1[0:16]
-                umma_bf16(d, a + 6, bmain + 2, idesc, 1);   // z2[16:32] . E1[16:32]
-                umma_bf16(d, aaug, baug, idesc, 1);         // + ee_k
+                // (D <= 16: components 16..31 are zero padding, their K-slices are skipped)
+                umma_bf16(d, a + 0, bmain + 0, idesc, 0);             // z1[0:16]  . E1[0:16]
+                if (wide) umma_bf16(d, a + 2, bmain + 2, idesc, 1);   // z1[16:32] . E1[16:32]
+                umma_bf16(d, a + 0, bmain + 4, idesc, 1);             // z1[0:16]  . E2[0:16]
+                if (wide) umma_bf16(d, a + 2, bmain + 6, idesc, 1);   // z1[16:32] . E2[16:32]
+                umma_bf16(d, a + 4, bmain + 0, idesc, 1);             // z2[0:16]  . E1[0:16]
+                if (wide) umma_bf16(d, a + 6, bmain + 2, idesc, 1);   // z2[16:32] . E1[16:32]
+                umma_bf16(d, aaug, baug, idesc, 1);                   // + ee_k
                 umma_commit(bar(A_EMPTY + b));
                 umma_commit(bar(T_FULL + g));
             }
@@ -855,12 +857,14 @@ __global__ void __launch_bounds__(256) vq_tc_fixup_kernel(const FwdParams p, con
             if (k >= K)
                 k = -1;
         }
-        const float zj = __ldg(p.z.base + row * D + lane);
-        const float *erow = p.E + (size_t)(k < 0 ? 0 : k) * D;
+        const int d = p.D;                            // real row width (<= 32); the image rows are zero-padded
+        const float zj = lane < d ? __ldg(p.z.base + row * d + lane) : 0.0f;
+        const unsigned char *ef32 = img + IMG_EF32;
+        const int kk = k < 0 ? 0 : k;
         float zz = 0.0f, acc = 0.0f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {                 // oracle-order chains, ascending j
-            const float4 e4 = __ldg(reinterpret_cast<const float4 *>(erow) + c);
+            const float4 e4 = __ldg(reinterpret_cast<const float4 *>(ef32 + ef32_off(kk, c)));
             const float z0 = __shfl_sync(0xffffffffu, zj, 4 * c), z1 = __shfl_sync(0xffffffffu, zj, 4 * c + 1);
             const float z2 = __shfl_sync(0xffffffffu, zj, 4 * c + 2), z3 = __shfl_sync(0xffffffffu, zj, 4 * c + 3);
             zz = fmaf(z0, z0, zz); zz = fmaf(z1, z1, zz); zz = fmaf(z2, z2, zz); zz = fmaf(z3, z3, zz);
@@ -882,10 +886,10 @@ __global__ void __launch_bounds__(256) vq_tc_fixup_kernel(const FwdParams p, con
             }
         }
         const int code = bidx == 0x7fffffff ? 0 : bidx;
-        const float ev = __ldg(p.E + (size_t)code * D + lane);
+        const float ev = __ldg(reinterpret_cast<const float *>(ef32 + ef32_off(code, lane >> 2)) + (lane & 3));
         const float diff = __fsub_rn(ev, zj);
-        if (p.zq)
-            p.zq[row * D + lane] = __fadd_rn(zj, diff);
+        if (p.zq && lane < d)
+            p.zq[row * d + lane] = __fadd_rn(zj, diff);
         float r2 = __fmul_rn(diff, diff);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
@@ -912,7 +916,9 @@ __global__ void __launch_bounds__(256) vq_tc_fixup_kernel(const FwdParams p, con
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-bool tc_shape_supported(int K, int D) { return D == tc::D && K >= 1 && K <= tc::KMAX; }
+// D < 32 (a multiple of 4: TMA needs 16-byte row pitches) runs as D = 32 with zero columns: the tensor maps
+// describe (N, D) tensors under 32-wide boxes, so loads zero-fill and stores clip the columns beyond D.
+bool tc_shape_supported(int K, int D) { return D >= 4 && D <= tc::D && D % 4 == 0 && K >= 1 && K <= tc::KMAX; }
 
 namespace {
 
@@ -935,13 +941,13 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
-bool make_map(CUtensorMap *map, const float *base, int64_t n_rows)
+bool make_map(CUtensorMap *map, const float *base, int64_t n_rows, int d)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc)
         return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)tc::D, (cuuint64_t)n_rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)tc::D * sizeof(float)};
+    const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)d * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)tc::D, (cuuint32_t)tc::TILE_M};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
@@ -963,10 +969,10 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
         return cudaErrorNotSupported;
     unsigned char *img = reinterpret_cast<unsigned char *>(tc_scratch);
     CUtensorMap map_z, map_zq;
-    if (!make_map(&map_z, p.z.base, p.z.n_rows))
+    if (!make_map(&map_z, p.z.base, p.z.n_rows, p.D))
         return cudaErrorNotSupported;
     if (p.zq) {
-        if (!make_map(&map_zq, p.zq, p.z.n_rows))
+        if (!make_map(&map_zq, p.zq, p.z.n_rows, p.D))
             return cudaErrorNotSupported;
     } else {
         map_zq = map_z;
@@ -975,7 +981,7 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
     cudaError_t err = cudaMemsetAsync(img + IMG_CONST, 0, sizeof(Consts) + WL_CTAS * 4, st);
     if (err != cudaSuccess)
         return err;
-    vq_tc_prep_kernel<<<(KMAX + 127) / 128, 128, 0, st>>>(p.E, p.ee, p.K, kp, img);
+    vq_tc_prep_kernel<<<(KMAX + 127) / 128, 128, 0, st>>>(p.E, p.ee, p.K, p.D, kp, img);
     if ((err = cudaGetLastError()) != cudaSuccess)
         return err;
     err = cudaFuncSetAttribute(vq_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
