@@ -417,3 +417,32 @@ def test_tc_narrow_vectors(D, K):
         assert np.array_equal(out[1].cpu().numpy(), ora.z_q.reshape(n, D))
         assert np.array_equal(out[4].cpu().numpy(), ora.counts)
         assert out[0].item() == pytest.approx(float(ora.loss), rel=REL)
+
+
+@pytest.mark.parametrize("K,D", [(257, 32), (300, 32), (512, 32), (1000, 16), (1024, 32), (2048, 8), (4100, 32)])
+def test_tc_chunked_large_codebooks(K, D):
+    """K > 256 on the tcgen05 path: one pass per 256-code chunk, the chunk winners compared by their
+    oracle-order distances (first NaN wins, ties keep the lower index), then the finish kernel.  Covers a
+    ragged last chunk, duplicated rows across chunks, NaN rows and a non-finite code in a late chunk."""
+    rs = np.random.RandomState(K + D)
+    n = 3000
+    E = (0.1 * rs.standard_normal((K, D))).astype(np.float32)
+    E[K - 1] = E[3]                                       # tie between the first and the last chunk
+    E[260 % K] = E[10]
+    z = (0.1 * rs.standard_normal((n, D))).astype(np.float32)
+    z[0] = E[3]; z[1] = E[10]; z[2] = (E[5] + E[K - 2]) / 2
+    z[7, 1] = np.nan; z[8, 0] = np.inf
+    dev = _dev()
+    assert ops._tc_eligible(n, K, D)
+    for Eb in (E, None):
+        if Eb is None:
+            Eb = E.copy(); Eb[K - 5, D - 1] = np.nan; Eb[2, 0] = np.inf     # poisoned columns
+        out = ops.forward(torch.from_numpy(z).to(dev), torch.from_numpy(Eb).to(dev), 0.25, path="tc")
+        ora = O.forward(z, Eb, 0.25)
+        assert np.array_equal(out[3].cpu().numpy().reshape(-1), ora.indices.reshape(-1))
+        assert np.array_equal(out[1].cpu().numpy(), ora.z_q.reshape(n, D), equal_nan=True)
+        assert np.array_equal(out[4].cpu().numpy(), ora.counts)
+        if np.isnan(ora.loss):
+            assert torch.isnan(out[0])
+        else:
+            assert out[0].item() == pytest.approx(float(ora.loss), rel=REL)

@@ -147,7 +147,7 @@ int vqb_select_path(int device, int64_t n, int k, int d, int64_t stride_row, int
     if (n <= 0 || k <= 0 || d <= 0)
         return VQB_E_ARG;
     const bool contiguous = stride_d == 1 && stride_row == d;
-    if (info.cc_major == 10 && contiguous && tc_shape_supported(k, d) && n >= 128)
+    if (info.cc_major == 10 && contiguous && (tc_shape_supported(k, d) || tc_chunked_supported(k, d)) && n >= 128)
         return (int)VQB_PATH_TC;
     return (int)VQB_PATH_FMA;
 }
@@ -207,7 +207,9 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
         p.need_sq = loss != nullptr;
 
         unsigned path = flags & VQB_PATH_MASK;
-        const bool tc_ok = p.z.rows_contiguous(d) && tc_shape_supported(k, d) && aligned(z, 16);
+        // K > 256 runs as one tcgen05 pass per 256-code chunk; the running best lives in the idx buffer
+        const bool tc_chunked = tc_chunked_supported(k, d) && idx != nullptr;
+        const bool tc_ok = p.z.rows_contiguous(d) && (tc_shape_supported(k, d) || tc_chunked) && aligned(z, 16);
         if (path == VQB_PATH_TC && !tc_ok)
             return VQB_E_UNSUPPORTED;
         if (path == VQB_PATH_AUTO)
@@ -221,8 +223,8 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
         if (path == VQB_PATH_TC) {
             launches = 0;
             // the tcgen05 launcher brackets only its main kernel (after its own codebook prep)
-            err = launch_fwd_tc(p, (float *)(ws + L.off_tc), info.sm_count, info.max_smem_per_block, &n_ctas,
-                                &launches, st, ev0, ev1);
+            err = (tc_shape_supported(k, d) ? launch_fwd_tc : launch_fwd_tc_chunked)(
+                p, (float *)(ws + L.off_tc), info.sm_count, info.max_smem_per_block, &n_ctas, &launches, st, ev0, ev1);
         } else {
             if (ev0) cudaEventRecord(ev0, st);
             err = launch_fwd_fma(p, info.sm_count, info.max_smem_per_block, &n_ctas, st);

@@ -100,6 +100,10 @@ struct FwdParams {
     int kt;               // codes per shared-memory tile (multiple of 4)
     int need_sq;          // the caller wants the loss: residual sums are needed even when zq == nullptr
     unsigned long long *stats;
+    // tcgen05 path, codebooks of more than 256 codes (one pass per 256-code chunk, vq_fwd_tc.cu):
+    unsigned long long *run;     // running best per vector: float bits of the exact distance << 32 | code
+    int code_base;               // first code of this pass's chunk
+    int chunk_mode;              // 0: single pass with all outputs; 1: first chunk; 2: later chunk
 };
 
 // launchers implemented in the .cu files -------------------------------------------------
@@ -121,6 +125,10 @@ bool tc_shape_supported(int K, int D);
 cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas,
                           int *n_launches, cudaStream_t st, cudaEvent_t ev_begin = nullptr,
                           cudaEvent_t ev_end = nullptr);
+bool tc_chunked_supported(int K, int D);
+cudaError_t launch_fwd_tc_chunked(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas,
+                                  int *n_launches, cudaStream_t st, cudaEvent_t ev_begin = nullptr,
+                                  cudaEvent_t ev_end = nullptr);
 void count_launches(int n);
 void set_tc_trace(unsigned long long *buf);
 size_t tc_trace_words();

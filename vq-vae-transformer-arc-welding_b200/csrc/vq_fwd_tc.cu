@@ -446,6 +446,35 @@ __device__ __forceinline__ float emit_row(unsigned char *zrow, int x, const unsi
 }
 
 
+// Oracle-order distance of one code for the vector in ring-slot row `zrow` (chunk passes of large codebooks:
+// the winners of the 256-code chunks are compared by their exact distances).
+__device__ __forceinline__ float exact_distance(const unsigned char *zrow, int x, const unsigned char *ef32,
+                                                const float *ees, int code)
+{
+    float zz = 0.0f, acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ x));
+        const float4 e = *reinterpret_cast<const float4 *>(ef32 + ef32_off(code, c));
+        zz = fmaf(v.x, v.x, zz); zz = fmaf(v.y, v.y, zz); zz = fmaf(v.z, v.z, zz); zz = fmaf(v.w, v.w, zz);
+        acc = fmaf(v.x, e.x, acc); acc = fmaf(v.y, e.y, acc); acc = fmaf(v.z, e.z, acc); acc = fmaf(v.w, e.w, acc);
+    }
+    return ref_distance(zz, ees[code], acc);
+}
+
+// Running argmin over the chunks of a large codebook, torch.argmin semantics: the first NaN wins, a tie keeps
+// the earlier chunk (= the lower index).
+__device__ __forceinline__ void merge_running(unsigned long long *run, int64_t row, float dist, int code, int chunk_mode)
+{
+    const unsigned long long cur = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)code;
+    if (chunk_mode == 2) {
+        const float dp = __uint_as_float((unsigned)(run[row] >> 32));
+        if ((dp != dp) || !((dist != dist) || dist < dp))
+            return;
+    }
+    run[row] = cur;
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------
@@ -769,6 +798,15 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     code = res;
             }
 
+            // ---- chunk pass of a large codebook: the chunk's winner and its exact distance join the running best ----
+            if (p.chunk_mode) {
+                if (ok && !deferred)
+                    merge_running(p.run, row, exact_distance(zrow, x, ef32, ees, code), p.code_base + code, p.chunk_mode);
+                mbar_arrive(bar(Q_DONE + s));
+                if (r == 0) stamp(i, 6);
+                continue;
+            }
+
             // ---- outputs: idx, histogram, loss, z_q (in place in the ring slot) ----
             const bool emit = ok && !deferred;
             if (emit) {
@@ -886,6 +924,11 @@ __global__ void __launch_bounds__(256) vq_tc_fixup_kernel(const FwdParams p, con
             }
         }
         const int code = bidx == 0x7fffffff ? 0 : bidx;
+        if (p.chunk_mode) {
+            if (lane == 0)
+                merge_running(p.run, row, best, p.code_base + code, p.chunk_mode);
+            continue;
+        }
         const float ev = __ldg(reinterpret_cast<const float *>(ef32 + ef32_off(code, lane >> 2)) + (lane & 3));
         const float diff = __fsub_rn(ev, zj);
         if (p.zq && lane < d)
@@ -957,6 +1000,68 @@ bool make_map(CUtensorMap *map, const float *base, int64_t n_rows, int d)
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------
+// finish kernel of the chunked path: the running best holds every vector's code; gather, z_q, loss,
+// histogram and the int64 index are produced in one streaming pass (eight threads per vector).
+// ---------------------------------------------------------------------------------------
+constexpr int kFinishMaxK = 16384;     // shared-memory histogram (u32 per code)
+__global__ void __launch_bounds__(256) vq_tc_finish_kernel(const FwdParams p, double *__restrict__ partial_out)
+{
+    extern __shared__ unsigned fhist[];
+    const int tid = threadIdx.x, sub = tid & 7, d = p.D;
+    for (int t = tid; t < p.K; t += 256)
+        fhist[t] = 0u;
+    __syncthreads();
+    const bool poisoned = p.hdr_in->poisoned_columns != 0;
+    const bool live = 4 * sub < d;
+    double sq = 0.0;
+    for (int64_t row = (int64_t)blockIdx.x * 32 + (tid >> 3); row < p.z.n_rows; row += (int64_t)gridDim.x * 32) {
+        const int code = (int)(unsigned)(p.run[row] & 0xffffffffull);
+        if (live) {
+            const float4 zv = __ldg(reinterpret_cast<const float4 *>(p.z.base + row * d) + sub);
+            float4 e = __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)code * d) + sub);
+            if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
+                float *ev = reinterpret_cast<float *>(&e);
+                for (int t = 0; t < 4; ++t) {
+                    const int j = 4 * sub + t, cc = p.colcnt[j];
+                    if (!(cc == 0 || (cc == 1 && p.colwhich[j] == code + 1)))
+                        ev[t] = __int_as_float(0x7fc00000);
+                }
+            }
+            float4 o;
+            float dj, rs = 0.0f;
+            dj = __fsub_rn(e.x, zv.x); rs = fmaf(dj, dj, rs); o.x = __fadd_rn(zv.x, dj);
+            dj = __fsub_rn(e.y, zv.y); rs = fmaf(dj, dj, rs); o.y = __fadd_rn(zv.y, dj);
+            dj = __fsub_rn(e.z, zv.z); rs = fmaf(dj, dj, rs); o.z = __fadd_rn(zv.z, dj);
+            dj = __fsub_rn(e.w, zv.w); rs = fmaf(dj, dj, rs); o.w = __fadd_rn(zv.w, dj);
+            if (p.zq)
+                __stcs(reinterpret_cast<float4 *>(p.zq + row * d) + sub, o);
+            sq += (double)rs;
+        }
+        if (sub == 0) {
+            p.idx[row] = code;            // same 8 bytes the running best lived in
+            atomicAdd(fhist + code, 1u);
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < p.K; t += 256) {
+        const unsigned c = fhist[t];
+        if (c)
+            atomicAdd(p.counts + t, (unsigned long long)c);
+    }
+    __shared__ double red[8];
+    sq = warp_sum(sq);
+    if ((tid & 31) == 0)
+        red[tid >> 5] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w)
+            t += red[w];
+        partial_out[blockIdx.x] = p.accumulate ? partial_out[blockIdx.x] + t : t;
+    }
+}
+
 static unsigned long long *g_trace_buf = nullptr;   // debug only, see vqb_debug_set_tc_trace
 void set_tc_trace(unsigned long long *buf) { g_trace_buf = buf; }
 size_t tc_trace_words() { return (size_t)kTraceCtas * kTraceTiles * kTraceEvents; }
@@ -1011,6 +1116,66 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
     if (ev_end)
         cudaEventRecord(ev_end, st);
     *n_launches = 3;
+    return err;
+}
+
+// ---------------------------------------------------------------------------------------
+// K > 256: one pass of the kernels above per 256-code chunk (codebook operands re-prepared per pass), each
+// merging the chunk's exact winner into the running best that lives in the caller's idx buffer, then the
+// finish kernel.  Exactness carries over: every chunk winner is the oracle's argmin within its chunk, and
+// the chunks are compared by oracle-order distances with the lower chunk winning ties.
+// ---------------------------------------------------------------------------------------
+bool tc_chunked_supported(int K, int D)
+{
+    return tc_shape_supported(tc::KMAX, D) && K > tc::KMAX && K <= kFinishMaxK;
+}
+
+cudaError_t launch_fwd_tc_chunked(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas,
+                                  int *n_launches, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end)
+{
+    using namespace tc;
+    if (!tc_chunked_supported(p.K, p.D) || !p.idx)
+        return cudaErrorNotSupported;
+    if (ev_begin)
+        cudaEventRecord(ev_begin, st);
+    int launches = 0, pass_ctas = 1;
+    const int n_chunks = (p.K + KMAX - 1) / KMAX;
+    for (int c = 0; c < n_chunks; ++c) {
+        FwdParams pc = p;
+        pc.E = p.E + (size_t)c * KMAX * p.D;
+        pc.ee = p.ee + c * KMAX;
+        pc.K = p.K - c * KMAX < KMAX ? p.K - c * KMAX : KMAX;
+        pc.zq = nullptr;
+        pc.idx = nullptr;
+        pc.need_sq = 0;
+        pc.run = reinterpret_cast<unsigned long long *>(p.idx);
+        pc.code_base = c * KMAX;
+        pc.chunk_mode = c == 0 ? 1 : 2;
+        int nl = 0;
+        cudaError_t err = launch_fwd_tc(pc, tc_scratch, sm_count, max_smem, &pass_ctas, &nl, st, nullptr, nullptr);
+        if (err != cudaSuccess)
+            return err;
+        launches += nl;
+    }
+    FwdParams pf = p;
+    pf.run = reinterpret_cast<unsigned long long *>(p.idx);
+    const int64_t groups = (p.z.n_rows + 31) / 32;
+    int grid = (int)(groups < (int64_t)sm_count * 6 ? groups : (int64_t)sm_count * 6);
+    if (grid < 1)
+        grid = 1;
+    if (grid > kMaxPartials)
+        grid = kMaxPartials;
+    cudaError_t err = cudaFuncSetAttribute(vq_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(unsigned) * kFinishMaxK));
+    if (err != cudaSuccess)
+        return err;
+    vq_tc_finish_kernel<<<grid, 256, sizeof(unsigned) * (size_t)p.K, st>>>(pf, p.partials);
+    err = cudaGetLastError();
+    if (ev_end)
+        cudaEventRecord(ev_end, st);
+    // the pass kernels left zeros in partials [0, pass_ctas); the finish kernel owns [0, grid)
+    *n_ctas = pass_ctas > grid ? pass_ctas : grid;
+    *n_launches = launches + 1;
     return err;
 }
 
