@@ -446,3 +446,30 @@ def test_tc_chunked_large_codebooks(K, D):
             assert torch.isnan(out[0])
         else:
             assert out[0].item() == pytest.approx(float(ora.loss), rel=REL)
+
+
+@pytest.mark.parametrize("D", [36, 48, 64])
+@pytest.mark.parametrize("K", [7, 256, 700])
+def test_tc_wide_vectors(D, K):
+    """32 < D <= 64 on the tcgen05 path: two 32-component D-chunks per tile accumulated in one TMEM buffer,
+    fp32 codebook rows from global memory; also through the chunked large-K passes (K = 700)."""
+    rs = np.random.RandomState(D * 7 + K)
+    E = (0.1 * rs.standard_normal((K, D))).astype(np.float32)
+    E[K - 1] = E[0]
+    dev = _dev()
+    for n in (128, 1500):
+        z = (0.1 * rs.standard_normal((n, D))).astype(np.float32)
+        z[0] = E[0]; z[1] = (E[1] + E[2]) / 2; z[5, D - 1] = np.nan; z[6, 33] = np.inf
+        assert ops._tc_eligible(n, K, D)
+        for Eb in (E, None):
+            if Eb is None:
+                Eb = E.copy(); Eb[min(3, K - 1), D - 2] = np.nan          # poisoned column in the second chunk
+            out = ops.forward(torch.from_numpy(z).to(dev), torch.from_numpy(Eb).to(dev), 0.25, path="tc", want_stats=True)
+            ora = O.forward(z, Eb, 0.25)
+            assert np.array_equal(out[3].cpu().numpy().reshape(-1), ora.indices.reshape(-1))
+            assert np.array_equal(out[1].cpu().numpy(), ora.z_q.reshape(n, D), equal_nan=True)
+            assert np.array_equal(out[4].cpu().numpy(), ora.counts)
+            if np.isnan(ora.loss):
+                assert torch.isnan(out[0])
+            else:
+                assert out[0].item() == pytest.approx(float(ora.loss), rel=REL)

@@ -265,22 +265,27 @@ __global__ void vq_tc_prep_kernel(const float *__restrict__ E, const float *__re
         return;
     Consts *cst = reinterpret_cast<Consts *>(img + IMG_CONST);
     const bool real = k < K;
+    // components [32*dc, 32*dc + 32) per D-chunk dc; columns beyond d are zero (they change no sum)
     float e[D];
+    for (int dc = 0; dc < (d > D ? 2 : 1); ++dc) {
 #pragma unroll
-    for (int j = 0; j < D; ++j)
-        e[j] = (real && j < d) ? __ldg(E + (size_t)k * d + j) : 0.0f;   // d < 32: zero columns change no sum
-    // main B operand: row k = [-2*E1 (32 bf16) | -2*E2 (32 bf16)], SW128
+        for (int j = 0; j < D; ++j)
+            e[j] = (real && dc * D + j < d) ? __ldg(E + (size_t)k * d + dc * D + j) : 0.0f;
+        // main B operand: row k = [-2*E1 (32 bf16) | -2*E2 (32 bf16)], SW128; the second D-chunk of a wide
+        // codebook (d > 32) takes the place of the fp32 copy, which wide codebooks read from global memory
+        unsigned char *bm = img + (dc == 0 ? IMG_BMAIN : IMG_EF32);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        __nv_bfloat16 out[8];
+        for (int c = 0; c < 8; ++c) {
+            __nv_bfloat16 out[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int j = (c & 3) * 8 + t;
-            const __nv_bfloat16 hi = __float2bfloat16_rn(e[j]);
-            const __nv_bfloat16 lo = __float2bfloat16_rn(e[j] - __bfloat162float(hi));
-            out[t] = __float2bfloat16_rn(-2.0f * __bfloat162float(c < 4 ? hi : lo));   // exact scaling
+            for (int t = 0; t < 8; ++t) {
+                const int j = (c & 3) * 8 + t;
+                const __nv_bfloat16 hi = __float2bfloat16_rn(e[j]);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(e[j] - __bfloat162float(hi));
+                out[t] = __float2bfloat16_rn(-2.0f * __bfloat162float(c < 4 ? hi : lo));   // exact scaling
+            }
+            *reinterpret_cast<uint4 *>(bm + sw128(k, c)) = *reinterpret_cast<uint4 *>(out);
         }
-        *reinterpret_cast<uint4 *>(img + IMG_BMAIN + sw128(k, c)) = *reinterpret_cast<uint4 *>(out);
     }
     // augmentation B operand: ee_k = a1 + a2 + a3 exactly (3 x 8 bits); pads get a huge score
     const float eek = real ? ee[k] : 3.0e38f;
@@ -297,11 +302,13 @@ __global__ void vq_tc_prep_kernel(const float *__restrict__ E, const float *__re
         *reinterpret_cast<uint4 *>(img + IMG_BAUG + k * 32 + ((0 ^ sw) << 4)) = *reinterpret_cast<uint4 *>(out);
         *reinterpret_cast<uint4 *>(img + IMG_BAUG + k * 32 + ((1 ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
     }
-    // fp32 codebook for the exact decision + gather
+    // fp32 codebook for the exact decision + gather (d <= 32)
+    if (d <= D) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<float4 *>(img + IMG_EF32 + ef32_off(k, c)) =
-            make_float4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4 *>(img + IMG_EF32 + ef32_off(k, c)) =
+                make_float4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+    }
     reinterpret_cast<float *>(img + IMG_EE)[k] = real ? ee[k] : __int_as_float(0x7f800000);
     if (real) {
         if (fin)
@@ -462,6 +469,99 @@ __device__ __forceinline__ float exact_distance(const unsigned char *zrow, int x
     return ref_distance(zz, ees[code], acc);
 }
 
+// ---- wide vectors (32 < d <= 64): a tile occupies two ring slots (components 0..31 and 32..63, the second one
+// zero-filled beyond d) and the fp32 codebook is read from global memory (L2) instead of shared memory ----
+__device__ __forceinline__ float4 ld_e4(const float *E, int code, int d, int j)
+{   // E[code][j .. j+3], zero beyond the row (d is a multiple of 4)
+    return j < d ? __ldg(reinterpret_cast<const float4 *>(E + (size_t)code * d + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__device__ __forceinline__ float exact_distance_wide(const unsigned char *zrow0, const unsigned char *zrow1, int x,
+                                                     const float *E, int d, const float *ees, int code)
+{
+    float zz = 0.0f, acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const float4 v = *reinterpret_cast<const float4 *>((c < 8 ? zrow0 : zrow1) + (((c & 7) << 4) ^ x));
+        const float4 e = ld_e4(E, code, d, 4 * c);
+        zz = fmaf(v.x, v.x, zz); zz = fmaf(v.y, v.y, zz); zz = fmaf(v.z, v.z, zz); zz = fmaf(v.w, v.w, zz);
+        acc = fmaf(v.x, e.x, acc); acc = fmaf(v.y, e.y, acc); acc = fmaf(v.z, e.z, acc); acc = fmaf(v.w, e.w, acc);
+    }
+    return ref_distance(zz, ees[code], acc);
+}
+
+// warp-wide exact scan of all K codes for one wide vector (rare path: codebook rows come from L2)
+__device__ __noinline__ int warp_full_scan_wide(const unsigned char *zt0, const unsigned char *zt1, int row_in_tile,
+                                                const float *E, int d, const float *ees, int K)
+{
+    const int lane = threadIdx.x & 31;
+    const int x = (row_in_tile & 7) << 4;
+    const unsigned char *zrow0 = zt0 + row_in_tile * 128, *zrow1 = zt1 + row_in_tile * 128;
+    float best = __int_as_float(0x7f800000);
+    int bidx = 0x7fffffff;
+    unsigned first_nan = 0xffffffffu;
+    for (int k = lane; k < K; k += 32) {
+        const float dist = exact_distance_wide(zrow0, zrow1, x, E, d, ees, k);
+        if (dist != dist)
+            first_nan = min(first_nan, (unsigned)k);
+        if (dist < best) {
+            best = dist;
+            bidx = k;
+        }
+    }
+    const unsigned nan_k = __reduce_min_sync(0xffffffffu, first_nan);
+    if (nan_k != 0xffffffffu)
+        return (int)nan_k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob < best || (ob == best && oi < bidx)) {
+            best = ob;
+            bidx = oi;
+        }
+    }
+    return bidx == 0x7fffffff ? 0 : bidx;
+}
+
+// z_q for one 32-component half of a wide row, codebook row from global memory
+template <bool POISON>
+__device__ __forceinline__ float emit_row_wide(unsigned char *zrow, int x, const float *E, int d, int j0, int code,
+                                               bool write_zq, const int *colcnt, const int *colwhich)
+{
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 e[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        e[c] = ld_e4(E, code, d, j0 + 4 * c);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 *zp4 = reinterpret_cast<float4 *>(zrow + ((c << 4) ^ x));
+        const float4 zv = *zp4;
+        if (POISON) {
+            float *ev = reinterpret_cast<float *>(&e[c]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = j0 + 4 * c + t;
+                if (j < d) {
+                    const int cc = colcnt[j];
+                    if (!(cc == 0 || (cc == 1 && colwhich[j] == code + 1)))
+                        ev[t] = __int_as_float(0x7fc00000);
+                }
+            }
+        }
+        float4 o;
+        float dj;
+        dj = __fsub_rn(e[c].x, zv.x); rs[0] = fmaf(dj, dj, rs[0]); o.x = __fadd_rn(zv.x, dj);
+        dj = __fsub_rn(e[c].y, zv.y); rs[1] = fmaf(dj, dj, rs[1]); o.y = __fadd_rn(zv.y, dj);
+        dj = __fsub_rn(e[c].z, zv.z); rs[2] = fmaf(dj, dj, rs[2]); o.z = __fadd_rn(zv.z, dj);
+        dj = __fsub_rn(e[c].w, zv.w); rs[3] = fmaf(dj, dj, rs[3]); o.w = __fadd_rn(zv.w, dj);
+        if (write_zq)
+            *zp4 = o;
+    }
+    return (rs[0] + rs[1]) + (rs[2] + rs[3]);
+}
+
 // Running argmin over the chunks of a large codebook, torch.argmin semantics: the first NaN wins, a tie keeps
 // the earlier chunk (= the lower index).
 __device__ __forceinline__ void merge_running(unsigned long long *run, int64_t row, float dist, int code, int chunk_mode)
@@ -483,7 +583,9 @@ __device__ __forceinline__ void merge_running(unsigned long long *run, int64_t r
 // TRACE: debug build of the same kernel that records clock64() of eight pipeline events per tile
 // (first kTraceTiles tiles of the first kTraceCtas CTAs) -- tools/tc_trace.py turns them into a timeline.
 constexpr int kTraceCtas = 4, kTraceTiles = 256, kTraceEvents = 8;
-template <bool TRACE>
+// WIDE: 32 < D <= 64 (two pipeline items per tile); a separate instantiation keeps the D <= 32 kernel's hot loops free
+// of the wide-vector code.
+template <bool TRACE, bool WIDE>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const __grid_constant__ CUtensorMap map_z,
                  const __grid_constant__ CUtensorMap map_zq, int kp, unsigned long long *trace)
@@ -509,6 +611,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     const int64_t n_rows = p.z.n_rows;
     const int64_t n_tiles = (n_rows + TILE_M - 1) / TILE_M;
     const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // wide vectors (32 < D <= 64): every tile is two pipeline items (D-chunks of 32 components), each with its own
+    // ring slot and converter pass; their products accumulate in the same TMEM buffer
+    constexpr int nd = WIDE ? 2 : 1;
+    const int64_t my_items = my_tiles * nd;
     const int K = p.K;
 
     // ---- one-time setup -----------------------------------------------------------------
@@ -573,28 +679,34 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             const uint64_t bmain = desc_sw128(sbase + OFF_BMAIN);
             const uint64_t baug = desc_sw32(sbase + OFF_BAUG);
             const uint64_t aaug = desc_sw32(sbase + OFF_AAUG);
-            const bool wide = p.D > 16;
-            for (int64_t i = 0; i < my_tiles; ++i) {
-                const int b = (int)(i & 1);
+            const uint64_t bmain1 = desc_sw128(sbase + OFF_EF32);      // second D-chunk of a wide codebook
+            for (int64_t it = 0; it < my_items; ++it) {
+                const int64_t i = nd == 2 ? it >> 1 : it;              // tile
+                const int dc = nd == 2 ? (int)(it & 1) : 0;            // D-chunk
+                const int ba = (int)(it & 1);                          // A buffer
+                const int b = (int)(i & 1);                            // TMEM buffer
                 const int g = (int)(i % GROUPS);
-                const uint32_t ph = (uint32_t)((i >> 1) & 1);
-                mbar_wait<32>(bar(A_FULL + b), ph);
-                mbar_wait<32>(bar(T_EMPTY + b), ph ^ 1);
+                mbar_wait<32>(bar(A_FULL + ba), (uint32_t)((it >> 1) & 1));
+                if (dc == 0)
+                    mbar_wait<32>(bar(T_EMPTY + b), (uint32_t)(((i >> 1) & 1) ^ 1));
                 tc_fence_after();
-                stamp(i, 3);
-                const uint64_t a = desc_sw128(sbase + OFF_ARING + b * 16384);
+                if (dc == 0) stamp(i, 3);
+                const uint64_t a = desc_sw128(sbase + OFF_ARING + ba * 16384);
+                const uint64_t bm = dc ? bmain1 : bmain;
                 const uint32_t d = tmem_base + b * KMAX;
+                const bool wide = p.D - 32 * dc > 16;                  // else components 16..31 of this chunk are padding
                 // K-slices of 16 bf16 = 32 bytes = +2 in the descriptor's address field
-                // (D <= 16: components 16..31 are zero padding, their K-slices are skipped)
-                umma_bf16(d, a + 0, bmain + 0, idesc, 0);             // z1[0:16]  . E1[0:16]
-                if (wide) umma_bf16(d, a + 2, bmain + 2, idesc, 1);   // z1[16:32] . E1[16:32]
-                umma_bf16(d, a + 0, bmain + 4, idesc, 1);             // z1[0:16]  . E2[0:16]
-                if (wide) umma_bf16(d, a + 2, bmain + 6, idesc, 1);   // z1[16:32] . E2[16:32]
-                umma_bf16(d, a + 4, bmain + 0, idesc, 1);             // z2[0:16]  . E1[0:16]
-                if (wide) umma_bf16(d, a + 6, bmain + 2, idesc, 1);   // z2[16:32] . E1[16:32]
-                umma_bf16(d, aaug, baug, idesc, 1);                   // + ee_k
-                umma_commit(bar(A_EMPTY + b));
-                umma_commit(bar(T_FULL + g));
+                umma_bf16(d, a + 0, bm + 0, idesc, dc);                // z1[0:16]  . E1[0:16]
+                if (wide) umma_bf16(d, a + 2, bm + 2, idesc, 1);       // z1[16:32] . E1[16:32]
+                umma_bf16(d, a + 0, bm + 4, idesc, 1);                 // z1[0:16]  . E2[0:16]
+                if (wide) umma_bf16(d, a + 2, bm + 6, idesc, 1);       // z1[16:32] . E2[16:32]
+                umma_bf16(d, a + 4, bm + 0, idesc, 1);                 // z2[0:16]  . E1[0:16]
+                if (wide) umma_bf16(d, a + 6, bm + 2, idesc, 1);       // z2[16:32] . E1[16:32]
+                umma_commit(bar(A_EMPTY + ba));
+                if (dc == nd - 1) {
+                    umma_bf16(d, aaug, baug, idesc, 1);                // + ee_k
+                    umma_commit(bar(T_FULL + g));
+                }
             }
         }
     } else if (warp == 3) {
@@ -602,27 +714,31 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         // (Keeping one store in flight and releasing slot i when store i+1 is issued was measured:
         // the extra tile period of slot hold time costs more than the wait it hides.)
         if (lane == 0) {
-            auto load_tile = [&](int64_t i) {
-                const int s = (int)(i % STAGES);
+            auto load_item = [&](int64_t it) {
+                const int s = (int)(it % STAGES);
                 mbar_expect_tx(bar(Z_FULL + s), TILE_M * D * 4);
+                const int64_t i = nd == 2 ? it >> 1 : it;
+                const int dc = nd == 2 ? (int)(it & 1) : 0;
                 const int64_t tile = blockIdx.x + i * gridDim.x;
-                tma_load_2d(sbase + OFF_ZRING + s * 16384, &map_z, bar(Z_FULL + s), 0, (int)(tile * TILE_M));
-                stamp(i, 0);
+                tma_load_2d(sbase + OFF_ZRING + s * 16384, &map_z, bar(Z_FULL + s), dc * D, (int)(tile * TILE_M));
+                if (dc == 0) stamp(i, 0);
             };
-            for (int64_t i = 0; i < my_tiles && i < STAGES; ++i)
-                load_tile(i);
-            for (int64_t i = 0; i < my_tiles; ++i) {
-                const int s = (int)(i % STAGES);
-                mbar_wait<64>(bar(Q_DONE + s), (uint32_t)((i / STAGES) & 1));
+            for (int64_t it = 0; it < my_items && it < STAGES; ++it)
+                load_item(it);
+            for (int64_t it = 0; it < my_items; ++it) {
+                const int s = (int)(it % STAGES);
+                mbar_wait<64>(bar(Q_DONE + s), (uint32_t)((it / STAGES) & 1));
                 if (p.zq) {
+                    const int64_t i = nd == 2 ? it >> 1 : it;
+                    const int dc = nd == 2 ? (int)(it & 1) : 0;
                     const int64_t tile = blockIdx.x + i * gridDim.x;
-                    tma_store_2d(&map_zq, sbase + OFF_ZRING + s * 16384, 0, (int)(tile * TILE_M));
+                    tma_store_2d(&map_zq, sbase + OFF_ZRING + s * 16384, dc * D, (int)(tile * TILE_M));
                     tma_store_commit();
                     tma_store_wait_read();     // the slot may be refilled once the store has read it
                 }
-                stamp(i, 7);
-                if (i + STAGES < my_tiles)
-                    load_tile(i + STAGES);
+                if (nd == 1 || (it & 1)) stamp(nd == 2 ? it >> 1 : it, 7);
+                if (it + STAGES < my_items)
+                    load_item(it + STAGES);
             }
             tma_store_wait_all();
         }
@@ -631,12 +747,12 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         reg_dec<56>();
         const int r = tid - 128;
         const int x = (r & 7) << 4;
-        for (int64_t i = 0; i < my_tiles; ++i) {
+        for (int64_t i = 0; i < my_items; ++i) {         // i: pipeline item (= tile, or half a wide tile)
             const int s = (int)(i % STAGES);
             const int b = (int)(i & 1);
             if (warp == 4) {
                 mbar_wait<128>(bar(Z_FULL + s), (uint32_t)((i / STAGES) & 1));
-                if (r == 0) stamp(i, 1);
+                if (r == 0 && nd == 1) stamp(i, 1);
                 mbar_wait<128>(bar(A_EMPTY + b), (uint32_t)(((i >> 1) & 1) ^ 1));
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -668,7 +784,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             reinterpret_cast<float *>(smem + OFF_ZZ + s * 512)[r] = (zp[0] + zp[1]) + (zp[2] + zp[3]);
             fence_proxy_async();
             mbar_arrive(bar(A_FULL + b));
-            if (r == 0) stamp(i, 2);
+            if (r == 0 && nd == 1) stamp(i, 2);
         }
     } else if (warp >= 8) {
         // ================= epilogue groups =================
@@ -690,7 +806,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
 
         float sqf = 0.0f;
         for (int64_t i = g; i < my_tiles; i += GROUPS) {
-            const int s = (int)(i % STAGES);
+            const int s = (int)((i * nd) % STAGES);          // ring slot of the tile (its first half if wide)
+            const int s1 = (int)((i * nd + 1) % STAGES);     // second half of a wide tile
             const int b = (int)(i & 1);
             const uint32_t ph = (uint32_t)((i / GROUPS) & 1);
             const int64_t tile = blockIdx.x + i * gridDim.x;
@@ -739,9 +856,13 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             // (the tile itself was TMA-written before the converters read it, i.e. long before T_FULL)
             unsigned char *zt = smem + OFF_ZRING + s * 16384;
             unsigned char *zrow = zt + r * 128;
+            unsigned char *zt1 = smem + OFF_ZRING + s1 * 16384;
+            unsigned char *zrow1 = zt1 + r * 128;
             // ||z||^2 comes from the converter that already had the row in registers (ordered before us
             // by A_FULL -> MMA -> T_FULL); it only bounds the filter radius, it is not part of the decision
-            const float zz = reinterpret_cast<const float *>(smem + OFF_ZZ + s * 512)[r];
+            float zz = reinterpret_cast<const float *>(smem + OFF_ZZ + s * 512)[r];
+            if (nd == 2)
+                zz += reinterpret_cast<const float *>(smem + OFF_ZZ + s1 * 512)[r];
             const float zn = sqrt_approx(zz) * 1.00001f;
             // Filter radius delta = 2*eps + 2*H + 2*pack (DESIGN.md "Exactness"), u = 2^-8 the bf16 unit
             // roundoff, zn >= |z|, emax >= max|e_k|, eemax = max ee_k, S = sum_j |z_j e_j| <= zn*emax:
@@ -793,7 +914,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             while (need) {
                 const int src = __ffs(need) - 1;
                 need &= need - 1;
-                const int res = warp_full_scan(zt, q * 32 + src, ef32, ees, K);
+                const int res = nd == 2 ? warp_full_scan_wide(zt, zt1, q * 32 + src, p.E, p.D, ees, K)
+                                        : warp_full_scan(zt, q * 32 + src, ef32, ees, K);
                 if (lane == src)
                     code = res;
             }
@@ -801,8 +923,13 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             // ---- chunk pass of a large codebook: the chunk's winner and its exact distance join the running best ----
             if (p.chunk_mode) {
                 if (ok && !deferred)
-                    merge_running(p.run, row, exact_distance(zrow, x, ef32, ees, code), p.code_base + code, p.chunk_mode);
+                    merge_running(p.run, row,
+                                  nd == 2 ? exact_distance_wide(zrow, zrow1, x, p.E, p.D, ees, code)
+                                          : exact_distance(zrow, x, ef32, ees, code),
+                                  p.code_base + code, p.chunk_mode);
                 mbar_arrive(bar(Q_DONE + s));
+                if (nd == 2)
+                    mbar_arrive(bar(Q_DONE + s1));
                 if (r == 0) stamp(i, 6);
                 continue;
             }
@@ -816,9 +943,18 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
             // (ids-only calls -- no z_q, no loss -- skip the gather and the residual altogether)
             float r2 = 0.0f;
-            if (p.zq || p.need_sq)
-                r2 = poisoned ? emit_row<true>(zrow, x, ef32, code, p.zq != nullptr, p.colcnt, p.colwhich)
-                              : emit_row<false>(zrow, x, ef32, code, p.zq != nullptr, nullptr, nullptr);
+            if (p.zq || p.need_sq) {
+                if (nd == 1) {
+                    r2 = poisoned ? emit_row<true>(zrow, x, ef32, code, p.zq != nullptr, p.colcnt, p.colwhich)
+                                  : emit_row<false>(zrow, x, ef32, code, p.zq != nullptr, nullptr, nullptr);
+                } else if (poisoned) {
+                    r2 = emit_row_wide<true>(zrow, x, p.E, p.D, 0, code, p.zq != nullptr, p.colcnt, p.colwhich) +
+                         emit_row_wide<true>(zrow1, x, p.E, p.D, D, code, p.zq != nullptr, p.colcnt, p.colwhich);
+                } else {
+                    r2 = emit_row_wide<false>(zrow, x, p.E, p.D, 0, code, p.zq != nullptr, nullptr, nullptr) +
+                         emit_row_wide<false>(zrow1, x, p.E, p.D, D, code, p.zq != nullptr, nullptr, nullptr);
+                }
+            }
             if (emit)
                 sqf += r2;
             if (((i / GROUPS) & 15) == 15) {      // bounded fp32 run lengths, fp64 across them
@@ -828,6 +964,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             if (p.zq)
                 fence_proxy_async();               // z_q rows (generic proxy) -> visible to the TMA store
             mbar_arrive(bar(Q_DONE + s));          // warp 3 stores the tile and frees the slot
+            if (nd == 2)
+                mbar_arrive(bar(Q_DONE + s1));
             if (r == 0) stamp(i, 6);
         }
         sq += (double)sqf;
@@ -895,18 +1033,22 @@ __global__ void __launch_bounds__(256) vq_tc_fixup_kernel(const FwdParams p, con
             if (k >= K)
                 k = -1;
         }
-        const int d = p.D;                            // real row width (<= 32); the image rows are zero-padded
-        const float zj = lane < d ? __ldg(p.z.base + row * d + lane) : 0.0f;
-        const unsigned char *ef32 = img + IMG_EF32;
+        const int d = p.D;                            // real row width (<= 64, a multiple of 4)
+        const float zj0 = lane < d ? __ldg(p.z.base + row * d + lane) : 0.0f;
+        const float zj1 = lane + 32 < d ? __ldg(p.z.base + row * d + lane + 32) : 0.0f;
         const int kk = k < 0 ? 0 : k;
         float zz = 0.0f, acc = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {                 // oracle-order chains, ascending j
-            const float4 e4 = __ldg(reinterpret_cast<const float4 *>(ef32 + ef32_off(kk, c)));
-            const float z0 = __shfl_sync(0xffffffffu, zj, 4 * c), z1 = __shfl_sync(0xffffffffu, zj, 4 * c + 1);
-            const float z2 = __shfl_sync(0xffffffffu, zj, 4 * c + 2), z3 = __shfl_sync(0xffffffffu, zj, 4 * c + 3);
-            zz = fmaf(z0, z0, zz); zz = fmaf(z1, z1, zz); zz = fmaf(z2, z2, zz); zz = fmaf(z3, z3, zz);
-            acc = fmaf(z0, e4.x, acc); acc = fmaf(z1, e4.y, acc); acc = fmaf(z2, e4.z, acc); acc = fmaf(z3, e4.w, acc);
+        for (int c = 0; c < 16; ++c) {                // oracle-order chains, ascending j
+            if (4 * c < d) {                          // warp-uniform
+                const float4 e4 = __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)kk * d) + c);
+                const float src = c < 8 ? zj0 : zj1;
+                const int j = (4 * c) & 31;
+                const float z0 = __shfl_sync(0xffffffffu, src, j), z1 = __shfl_sync(0xffffffffu, src, j + 1);
+                const float z2 = __shfl_sync(0xffffffffu, src, j + 2), z3 = __shfl_sync(0xffffffffu, src, j + 3);
+                zz = fmaf(z0, z0, zz); zz = fmaf(z1, z1, zz); zz = fmaf(z2, z2, zz); zz = fmaf(z3, z3, zz);
+                acc = fmaf(z0, e4.x, acc); acc = fmaf(z1, e4.y, acc); acc = fmaf(z2, e4.z, acc); acc = fmaf(z3, e4.w, acc);
+            }
         }
         float best = __int_as_float(0x7f800000);
         int bidx = 0x7fffffff;
@@ -929,11 +1071,18 @@ __global__ void __launch_bounds__(256) vq_tc_fixup_kernel(const FwdParams p, con
                 merge_running(p.run, row, best, p.code_base + code, p.chunk_mode);
             continue;
         }
-        const float ev = __ldg(reinterpret_cast<const float *>(ef32 + ef32_off(code, lane >> 2)) + (lane & 3));
-        const float diff = __fsub_rn(ev, zj);
-        if (p.zq && lane < d)
-            p.zq[row * d + lane] = __fadd_rn(zj, diff);
-        float r2 = __fmul_rn(diff, diff);
+        float r2 = 0.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = lane + 32 * h;
+            if (j < d) {
+                const float zj = h ? zj1 : zj0;
+                const float diff = __fsub_rn(__ldg(p.E + (size_t)code * d + j), zj);
+                if (p.zq)
+                    p.zq[row * d + j] = __fadd_rn(zj, diff);
+                r2 = fmaf(diff, diff, r2);
+            }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
             r2 += __shfl_xor_sync(0xffffffffu, r2, o);
@@ -961,7 +1110,8 @@ __global__ void __launch_bounds__(256) vq_tc_fixup_kernel(const FwdParams p, con
 // ---------------------------------------------------------------------------------------
 // D < 32 (a multiple of 4: TMA needs 16-byte row pitches) runs as D = 32 with zero columns: the tensor maps
 // describe (N, D) tensors under 32-wide boxes, so loads zero-fill and stores clip the columns beyond D.
-bool tc_shape_supported(int K, int D) { return D >= 4 && D <= tc::D && D % 4 == 0 && K >= 1 && K <= tc::KMAX; }
+// 32 < D <= 64: two 32-component D-chunks per tile (two ring slots, products accumulated in the same TMEM buffer).
+bool tc_shape_supported(int K, int D) { return D >= 4 && D <= 2 * tc::D && D % 4 == 0 && K >= 1 && K <= tc::KMAX; }
 
 namespace {
 
@@ -1013,17 +1163,16 @@ __global__ void __launch_bounds__(256) vq_tc_finish_kernel(const FwdParams p, do
         fhist[t] = 0u;
     __syncthreads();
     const bool poisoned = p.hdr_in->poisoned_columns != 0;
-    const bool live = 4 * sub < d;
     double sq = 0.0;
     for (int64_t row = (int64_t)blockIdx.x * 32 + (tid >> 3); row < p.z.n_rows; row += (int64_t)gridDim.x * 32) {
         const int code = (int)(unsigned)(p.run[row] & 0xffffffffull);
-        if (live) {
-            const float4 zv = __ldg(reinterpret_cast<const float4 *>(p.z.base + row * d) + sub);
-            float4 e = __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)code * d) + sub);
+        for (int f = sub; 4 * f < d; f += 8) {        // this thread's float4 columns of the row
+            const float4 zv = __ldg(reinterpret_cast<const float4 *>(p.z.base + row * d) + f);
+            float4 e = __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)code * d) + f);
             if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
                 float *ev = reinterpret_cast<float *>(&e);
                 for (int t = 0; t < 4; ++t) {
-                    const int j = 4 * sub + t, cc = p.colcnt[j];
+                    const int j = 4 * f + t, cc = p.colcnt[j];
                     if (!(cc == 0 || (cc == 1 && p.colwhich[j] == code + 1)))
                         ev[t] = __int_as_float(0x7fc00000);
                 }
@@ -1035,7 +1184,7 @@ __global__ void __launch_bounds__(256) vq_tc_finish_kernel(const FwdParams p, do
             dj = __fsub_rn(e.z, zv.z); rs = fmaf(dj, dj, rs); o.z = __fadd_rn(zv.z, dj);
             dj = __fsub_rn(e.w, zv.w); rs = fmaf(dj, dj, rs); o.w = __fadd_rn(zv.w, dj);
             if (p.zq)
-                __stcs(reinterpret_cast<float4 *>(p.zq + row * d) + sub, o);
+                __stcs(reinterpret_cast<float4 *>(p.zq + row * d) + f, o);
             sq += (double)rs;
         }
         if (sub == 0) {
@@ -1089,10 +1238,9 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
     vq_tc_prep_kernel<<<(KMAX + 127) / 128, 128, 0, st>>>(p.E, p.ee, p.K, p.D, kp, img);
     if ((err = cudaGetLastError()) != cudaSuccess)
         return err;
-    err = cudaFuncSetAttribute(vq_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
-    if (err != cudaSuccess)
-        return err;
-    err = cudaFuncSetAttribute(vq_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+    const bool wide = p.D > tc::D;
+    auto kern = wide ? vq_fwd_tc_kernel<false, true> : g_trace_buf ? vq_fwd_tc_kernel<true, false> : vq_fwd_tc_kernel<false, false>;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
     if (err != cudaSuccess)
         return err;
     const int64_t tiles = (p.z.n_rows + TILE_M - 1) / TILE_M;
@@ -1104,10 +1252,7 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
     *n_ctas = grid * (1 + FIX_SPLIT);    // partials [0, grid): main kernel, then one per fix-up CTA
     if (ev_begin)
         cudaEventRecord(ev_begin, st);
-    if (g_trace_buf)
-        vq_fwd_tc_kernel<true><<<grid, THREADS, SMEM_ALLOC, st>>>(p, img, map_z, map_zq, kp, g_trace_buf);
-    else
-        vq_fwd_tc_kernel<false><<<grid, THREADS, SMEM_ALLOC, st>>>(p, img, map_z, map_zq, kp, nullptr);
+    kern<<<grid, THREADS, SMEM_ALLOC, st>>>(p, img, map_z, map_zq, kp, wide ? nullptr : g_trace_buf);
     err = cudaGetLastError();
     if (err != cudaSuccess)
         return err;

@@ -48,7 +48,7 @@ def _ws_ptr(ws: torch.Tensor) -> Tuple[int, int]:
 
 def _tc_eligible(n: int, k: int, d: int) -> bool:
     """Shapes the tcgen05 kernel takes (vq_fwd_tc.cu: tc_shape_supported) once rows are contiguous."""
-    return 4 <= d <= 32 and d % 4 == 0 and 1 <= k <= 16384 and n >= 128
+    return 4 <= d <= 64 and d % 4 == 0 and 1 <= k <= 16384 and n >= 128
 
 
 def _view_params(z: torch.Tensor, d: int, k: int = 0, path: str = "fma"):
