@@ -242,9 +242,10 @@ def test_full_size_properties(path):
     assert torch.equal(E[idx2], e[: 1 << 20])
 
 
-def test_host_buffer_path_matches_oracle():
+@pytest.mark.parametrize("K,D,n", [(256, 32, 300_000), (600, 32, 150_000), (256, 64, 150_000), (100, 16, 150_000)])
+def test_host_buffer_path_matches_oracle(K, D, n):
+    """vqb_encode_host (pinned host buffers, pipelined copies) on the plain, chunked-K, wide-D and narrow-D shapes."""
     rs = np.random.RandomState(7)
-    K, D, n = 256, 32, 300_000
     E = rs.uniform(-1.0 / K, 1.0 / K, (K, D)).astype(np.float32)
     z = torch.from_numpy((0.1 * rs.standard_normal((n, D))).astype(np.float32)).pin_memory()
     zq = torch.empty_like(z).pin_memory()

@@ -1164,32 +1164,69 @@ __global__ void __launch_bounds__(256) vq_tc_finish_kernel(const FwdParams p, do
     __syncthreads();
     const bool poisoned = p.hdr_in->poisoned_columns != 0;
     double sq = 0.0;
-    for (int64_t row = (int64_t)blockIdx.x * 32 + (tid >> 3); row < p.z.n_rows; row += (int64_t)gridDim.x * 32) {
-        const int code = (int)(unsigned)(p.run[row] & 0xffffffffull);
-        for (int f = sub; 4 * f < d; f += 8) {        // this thread's float4 columns of the row
-            const float4 zv = __ldg(reinterpret_cast<const float4 *>(p.z.base + row * d) + f);
-            float4 e = __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)code * d) + f);
-            if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
-                float *ev = reinterpret_cast<float *>(&e);
-                for (int t = 0; t < 4; ++t) {
-                    const int j = 4 * f + t, cc = p.colcnt[j];
-                    if (!(cc == 0 || (cc == 1 && p.colwhich[j] == code + 1)))
-                        ev[t] = __int_as_float(0x7fc00000);
-                }
+    // four vectors per thread and step, all of a step's loads issued before anything depends on them
+    // (code -> E[code] is a dependent chain: one vector at a time is latency-bound, measured 1.48 ms -> see profiles)
+    const int nf = d > 32 ? 2 : 1;                    // float4 columns per thread: sub (and sub + 8 for wide rows)
+    for (int64_t row0 = (int64_t)blockIdx.x * 128 + (tid >> 3); row0 < p.z.n_rows; row0 += (int64_t)gridDim.x * 128) {
+        int code[4];
+        float4 zv[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t row = row0 + 32 * u;
+            code[u] = row < p.z.n_rows ? (int)(unsigned)(p.run[row] & 0xffffffffull) : -1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int f = sub + 8 * h;
+                zv[u][h] = (row < p.z.n_rows && h < nf && 4 * f < d)
+                               ? __ldg(reinterpret_cast<const float4 *>(p.z.base + row * d) + f)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            float4 o;
-            float dj, rs = 0.0f;
-            dj = __fsub_rn(e.x, zv.x); rs = fmaf(dj, dj, rs); o.x = __fadd_rn(zv.x, dj);
-            dj = __fsub_rn(e.y, zv.y); rs = fmaf(dj, dj, rs); o.y = __fadd_rn(zv.y, dj);
-            dj = __fsub_rn(e.z, zv.z); rs = fmaf(dj, dj, rs); o.z = __fadd_rn(zv.z, dj);
-            dj = __fsub_rn(e.w, zv.w); rs = fmaf(dj, dj, rs); o.w = __fadd_rn(zv.w, dj);
-            if (p.zq)
-                __stcs(reinterpret_cast<float4 *>(p.zq + row * d) + f, o);
-            sq += (double)rs;
         }
-        if (sub == 0) {
-            p.idx[row] = code;            // same 8 bytes the running best lived in
-            atomicAdd(fhist + code, 1u);
+        float4 ev[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int f = sub + 8 * h;
+                ev[u][h] = (code[u] >= 0 && h < nf && 4 * f < d)
+                               ? __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)code[u] * d) + f)
+                               : zv[u][h];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t row = row0 + 32 * u;
+            if (code[u] < 0)
+                continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int f = sub + 8 * h;
+                if (h >= nf || 4 * f >= d)
+                    continue;
+                float4 e = ev[u][h];
+                if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
+                    float *evp = reinterpret_cast<float *>(&e);
+                    for (int t = 0; t < 4; ++t) {
+                        const int j = 4 * f + t, cc = p.colcnt[j];
+                        if (!(cc == 0 || (cc == 1 && p.colwhich[j] == code[u] + 1)))
+                            evp[t] = __int_as_float(0x7fc00000);
+                    }
+                }
+                const float4 z4 = zv[u][h];
+                float4 o;
+                float dj, rs = 0.0f;
+                dj = __fsub_rn(e.x, z4.x); rs = fmaf(dj, dj, rs); o.x = __fadd_rn(z4.x, dj);
+                dj = __fsub_rn(e.y, z4.y); rs = fmaf(dj, dj, rs); o.y = __fadd_rn(z4.y, dj);
+                dj = __fsub_rn(e.z, z4.z); rs = fmaf(dj, dj, rs); o.z = __fadd_rn(z4.z, dj);
+                dj = __fsub_rn(e.w, z4.w); rs = fmaf(dj, dj, rs); o.w = __fadd_rn(z4.w, dj);
+                if (p.zq)
+                    __stcs(reinterpret_cast<float4 *>(p.zq + row * d) + f, o);
+                sq += (double)rs;
+            }
+            if (sub == 0) {
+                p.idx[row] = code[u];     // same 8 bytes the running best lived in
+                atomicAdd(fhist + code[u], 1u);
+            }
         }
     }
     __syncthreads();
@@ -1304,7 +1341,7 @@ cudaError_t launch_fwd_tc_chunked(const FwdParams &p, float *tc_scratch, int sm_
     }
     FwdParams pf = p;
     pf.run = reinterpret_cast<unsigned long long *>(p.idx);
-    const int64_t groups = (p.z.n_rows + 31) / 32;
+    const int64_t groups = (p.z.n_rows + 127) / 128;
     int grid = (int)(groups < (int64_t)sm_count * 6 ? groups : (int64_t)sm_count * 6);
     if (grid < 1)
         grid = 1;

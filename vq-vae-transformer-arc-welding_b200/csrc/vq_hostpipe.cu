@@ -173,7 +173,8 @@ int vqb_encode_host(vqb_host_ctx *ctx, const float *z_host, int64_t n, float bet
         p.stats = ctx->d_stats;
         p.need_sq = loss_host != nullptr;
         unsigned path = flags & VQB_PATH_MASK;
-        const bool tc_ok = tc_shape_supported(k, d);
+        const bool tc_chunked = tc_chunked_supported(k, d) && p.idx != nullptr;   // running best lives in d_idx
+        const bool tc_ok = tc_shape_supported(k, d) || tc_chunked;
         if (path == VQB_PATH_TC && !tc_ok)
             return VQB_E_UNSUPPORTED;
         if (path == VQB_PATH_AUTO)
@@ -181,8 +182,9 @@ int vqb_encode_host(vqb_host_ctx *ctx, const float *z_host, int64_t n, float bet
         int n_ctas = 0;
         if (path == VQB_PATH_TC) {
             int nl = 0;
-            VQB_TRY(launch_fwd_tc(p, sl.tc_scratch, ctx->info.sm_count, ctx->info.max_smem_per_block, &n_ctas, &nl,
-                                  sl.stream));
+            VQB_TRY((tc_chunked ? launch_fwd_tc_chunked : launch_fwd_tc)(
+                p, sl.tc_scratch, ctx->info.sm_count, ctx->info.max_smem_per_block, &n_ctas, &nl, sl.stream,
+                nullptr, nullptr));
             launches += nl;
         } else {
             VQB_TRY(launch_fwd_fma(p, ctx->info.sm_count, ctx->info.max_smem_per_block, &n_ctas, sl.stream));
