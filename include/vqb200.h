@@ -128,6 +128,19 @@ int vqb_backward(int device, const float *g_zq, const float *g_loss,
                  float *grad_z, float *grad_codebook,
                  void *workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * One per-token linear layer of the patch encoder's residual blocks with the element-wise work around it fused
+ * (model/vq_vae_patch_embedd.py:60-74 ResBlock, :103-111 CNNBlock: Conv1d(k=3, pad=1) on a length-1 slice is a
+ * dense layer with the centre tap W[:, :, 1]).  bf16 operands, fp32 accumulation (tcgen05), erf-form GELU to
+ * bf16 accuracy (|error| <= 2.5e-5 + 2.5e-4 |x| before the bf16 rounding):
+ *   mode 0:  out = bf16(gelu(a w^T + bias))                                   first conv of a block
+ *   mode 1:  h += a w^T + bias (fp32, in place);  out = bf16(gelu(h)) or NULL second conv + residual + next GELU
+ * a: (n_tokens, k) bf16 row-major, w: (n, k) bf16 row-major, bias: (n) fp32, h: (n_tokens, n) fp32,
+ * out: (n_tokens, n) bf16.  k a multiple of 64, n a multiple of 256; all pointers 16-byte aligned.
+ */
+int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const float *bias, float *h, void *out_bf16,
+                     int64_t n_tokens, int k, int n, unsigned mode, void *stream);
+
 /* out[i] = codebook[idx[i]] (n, d).  Out-of-range indices yield NaN rows and set
  * *bad_index (device int, may be NULL) to 1. */
 int vqb_gather(int device, const int64_t *idx, int64_t n, const float *codebook, int k, int d,

@@ -1,0 +1,105 @@
+"""GPU tests of the fused per-token linear layer (csrc/tok_linear.cu) against a plain PyTorch fp32 reference of the
+same op on the same bf16-rounded operands (tolerances: fp32 accumulation order + one bf16 rounding of the output)."""
+import numpy as np
+import pytest
+import torch
+
+import vqb200
+from vqb200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _ref(a, w, bias, h, mode):
+    acc = a.float() @ w.float().t() + bias
+    if mode == 1:
+        acc = acc + h
+    return acc, torch.nn.functional.gelu(acc)
+
+
+@pytest.mark.parametrize("T", [1, 127, 128, 129, 1000, 4096 + 77])
+@pytest.mark.parametrize("K,N", [(512, 512), (64, 256), (128, 768)])
+def test_token_linear_matches_fp32_reference(T, K, N):
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(T * 7 + K + N)
+    a = torch.randn(T, K, device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=dev, generator=g) * (2.0 / K) ** 0.5).to(torch.bfloat16)
+    bias = 0.1 * torch.randn(N, device=dev, generator=g)
+    # mode 0
+    out = ops.token_linear(a, w, bias, mode=0)
+    _, ref = _ref(a, w, bias, None, 0)
+    torch.testing.assert_close(out.float(), ref, rtol=1.0 / 128, atol=2e-3)      # bf16 output: 2^-8 relative
+    # mode 1: residual stream updated in place, next activation written
+    h = torch.randn(T, N, device=dev, generator=g)
+    h0 = h.clone()
+    nxt = torch.empty(T, N, dtype=torch.bfloat16, device=dev)
+    ops.token_linear(a, w, bias, h=h, out=nxt, mode=1)
+    acc, ref = _ref(a, w, bias, h0, 1)
+    torch.testing.assert_close(h, acc, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(nxt.float(), ref, rtol=1.0 / 128, atol=2e-3)
+    # mode 1 without the activation output (last block)
+    h2 = h0.clone()
+    ops.token_linear(a, w, bias, h=h2, out=None, mode=1)
+    assert torch.equal(h2, h)
+
+
+def test_token_linear_gelu_is_the_erf_form():
+    """The epilogue's GELU is the exact (erf) form to bf16 accuracy, not the textbook two-term tanh approximation:
+    |error| <= 2.5e-5 + 2.5e-4 |x| before the bf16 rounding (csrc/tok_linear.cu gelu_fast)."""
+    dev = _dev()
+    K, N, T = 64, 256, 256
+    a = torch.zeros(T, K, device=dev, dtype=torch.bfloat16)
+    w = torch.zeros(N, K, device=dev, dtype=torch.bfloat16)
+    x = torch.linspace(-6, 6, N, device=dev)
+    h = x.repeat(T, 1).contiguous()
+    out = torch.empty(T, N, dtype=torch.bfloat16, device=dev)
+    ops.token_linear(a, w, torch.zeros(N, device=dev), h=h, out=out, mode=1)
+    ref = torch.nn.functional.gelu(x)
+    bound = 2.5e-5 + 2.5e-4 * x.abs() + 2.0 ** -8 * ref.abs()      # formula + MUFU.TANH + bf16 rounding
+    assert bool(((out[0].float() - ref).abs() <= bound).all())
+
+
+def test_token_linear_rejects_bad_arguments():
+    dev = _dev()
+    a = torch.zeros(8, 64, device=dev, dtype=torch.bfloat16)
+    w = torch.zeros(256, 64, device=dev, dtype=torch.bfloat16)
+    b = torch.zeros(256, device=dev)
+    with pytest.raises(RuntimeError):
+        ops.token_linear(a.float(), w, b)
+    with pytest.raises(RuntimeError):
+        ops.token_linear(a, w, b, mode=1)                        # no residual stream
+    with pytest.raises(RuntimeError):
+        ops.token_linear(torch.zeros(8, 48, device=dev, dtype=torch.bfloat16),
+                         torch.zeros(256, 48, device=dev, dtype=torch.bfloat16), b)   # K not a multiple of 64
+
+
+def test_fused_bf16_encoder_tracks_the_fp32_encoder():
+    """VQVAEPatch.encode in 'fused_bf16' mode: same shapes, z_e within bf16-operand error of the fp32 encoder,
+    ids equal for the overwhelming majority of tokens (the quantiser itself is exact on whatever z_e it gets)."""
+    dev = _dev()
+    torch.manual_seed(0)
+    model = vqb200.VQVAEPatch(hidden_dim=512, input_dim=2, num_embeddings=256, embedding_dim=32, n_resblocks=8,
+                              learning_rate=1e-3, dropout_p=0.1, patch_size=25, batch_norm=False).to(dev).eval()
+    x = torch.randn(300, 200, 2, device=dev)
+    with torch.no_grad():
+        torch.backends.cuda.matmul.allow_tf32 = False
+        z_ref = model.encode(x)
+        ids_ref = model.encode_ids(x)
+        model.encoder_mode = "fused_bf16"
+        z_fused = model.encode(x)
+        ids_fused = model.encode_ids(x)
+        model.encoder_mode = "torch"
+    assert z_fused.shape == z_ref.shape and z_fused.is_contiguous()
+    err = (z_fused - z_ref).abs().max().item()
+    assert err <= 0.05 * z_ref.abs().max().item(), err
+    assert (ids_fused == ids_ref).float().mean().item() > 0.97
+    # training mode / autograd never takes the fused path
+    model.train()
+    model.encoder_mode = "fused_bf16"
+    assert not model._fused_ok(x)

@@ -29,6 +29,7 @@ T = model.enc_out_len
 def encode_all(mode):
     torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
     torch.set_float32_matmul_precision("high" if mode == "tf32" else "highest")
+    model.encoder_mode = "fused_bf16" if mode == "fused_bf16" else "torch"
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     counts = torch.zeros(256, dtype=torch.int64, device=dev)
     first = None
@@ -59,7 +60,7 @@ def encode_all(mode):
 
 out = {}
 ref_ids = None
-for mode in ("fp32", "tf32", "bf16"):
+for mode in ("fp32", "tf32", "bf16", "fused_bf16"):
     pairs = []
     encode_all(mode) if mode == "fp32" and n_cycles <= chunk else None     # warm-up for tiny runs
     pairs = []

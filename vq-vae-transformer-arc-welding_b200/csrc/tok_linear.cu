@@ -1,0 +1,316 @@
+// tok_linear.cu -- per-token linear layer of the patch encoder with its element-wise neighbours fused
+// (sm_100a, tcgen05 + TMA + TMEM).
+//
+// The reference's encoder (model/vq_vae_patch_embedd.py:60-74, 103-111) applies, to every token
+// independently, eight residual blocks  h <- h + W2 gelu(W1 gelu(h) + b1) + b2  with 512 x 512 weights
+// (the centre tap of Conv1d(k=3, pad=1) on a length-1 slice).  Run as stock PyTorch ops that is 16 GEMMs
+// plus ~40 element-wise passes over the (tokens x 512) activations, and the passes -- not the GEMMs --
+// bound it (profiles/README.md: bulk encoding).  This kernel is one of those GEMMs with the passes around it
+// folded into its epilogue:
+//     mode 0:  out = bf16( gelu( A W^T + b ) )                      (first GEMM of a block)
+//     mode 1:  h  += A W^T + b  (fp32, in place);  out = bf16( gelu(h) )   (second GEMM + residual + the
+//              next block's leading GELU; out may be NULL after the last block)
+// A: (T, K) bf16 row-major activations, W: (N, K) bf16 row-major, fp32 accumulation in TMEM, erf-form GELU
+// evaluated through a fitted tanh argument (gelu_fast below, |error| <= 2.5e-5 + 2.5e-4 |x|, then rounded to bf16).  bf16 operands make this the reduced-precision encoder mode
+// (same operand precision as the reference under its own torch.set_float32_matmul_precision('medium'));
+// the quantiser behind it stays exact.
+//
+// Tile 128 tokens x 256 outputs, K streamed in 64-element chunks through a 4-stage TMA ring (A 16 KB + W 32 KB per
+// stage, SWIZZLE_128B), 4 tcgen05.mma (128 x 256 x 16) per chunk into one of two 256-column TMEM accumulators,
+// eight epilogue warps (TMEM lane quarter x column half) that overlap with the next tile's MMAs.
+#include "vq_common.cuh"
+#include "vq_ptx.cuh"
+
+namespace vqb {
+
+namespace tl {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int THREADS = 128 + 256;                       // 4 service warps + 8 epilogue warps
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
+constexpr int OFF_XPOSE = OFF_B + STAGES * B_BYTES;      // 8 x 4096: per epilogue warp, a 32 x 128-byte transposing buffer
+constexpr int OFF_BARS = OFF_XPOSE + 8 * 4096;
+constexpr int SMEM_BYTES = OFF_BARS + 256;
+
+// GELU(x) = x Phi(x) as 0.5 x (1 + tanh(x (c1 + c3 x^2 + c5 x^4))): the odd polynomial is a minimax fit of
+// atanh(erf(x / sqrt 2)) (max |error| of the formula 2.5e-5, against 4.7e-4 for the textbook two-term "tanh GELU");
+// MUFU.TANH adds up to 2^-11 relative on the tanh, i.e. <= 2.5e-4 |x| on the result -- below a tenth of the bf16
+// spacing of the value it is rounded to.  7 FMA-pipe instructions + 1 MUFU per element: the A&S erf form (2 MUFU, ~30
+// instructions with IEEE reciprocal / exp) made the epilogue 2.6x longer than the tile's MMAs (profiles/README.md).
+__device__ __forceinline__ float gelu_fast(float x)
+{
+    const float u = x * x;
+    float p = fmaf(-3.51517534e-4f, u, 3.70056510e-2f);
+    p = fmaf(p, u, 7.97507878e-1f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+}
+
+}  // namespace tl
+
+template <int MODE>
+__global__ void __launch_bounds__(tl::THREADS, 1)
+tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                  const float *__restrict__ bias, float *__restrict__ h, __nv_bfloat16 *__restrict__ out,
+                  int64_t n_tokens, int K, int N)
+{
+    using namespace tc;
+    using namespace tl;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    if ((sbase & 1023u) != 0)
+        __trap();
+    enum { FULL = 0, EMPTY = FULL + STAGES, T_FULL = EMPTY + STAGES, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2 };
+    auto bar = [&](int i) { return sbase + OFF_BARS + 8 * i; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + 8 * N_BARS);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const int n_ntiles = N / BN;
+    const int64_t n_mtiles = (n_tokens + BM - 1) / BM;
+    const int64_t n_items = n_mtiles * n_ntiles;            // item = (m tile, n tile), n fastest: A is re-read from L2
+    const int64_t my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int n_k = K / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar(FULL + s), 1);
+            mbar_init(bar(EMPTY + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar(T_FULL + b), 1);
+            mbar_init(bar(T_EMPTY + b), 256);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int64_t step = 0;
+            for (int64_t it = 0; it < my_items; ++it) {
+                const int64_t item = blockIdx.x + it * gridDim.x;
+                const int64_t mt = item / n_ntiles;
+                const int nt = (int)(item % n_ntiles);
+                for (int k = 0; k < n_k; ++k, ++step) {
+                    const int s = (int)(step % STAGES);
+                    mbar_wait<32>(bar(EMPTY + s), (uint32_t)(((step / STAGES) & 1) ^ 1));
+                    mbar_expect_tx(bar(FULL + s), A_BYTES + B_BYTES);
+                    tma_load_2d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), k * BK, (int)(mt * BM));
+                    tma_load_2d(sbase + OFF_B + s * B_BYTES, &map_w, bar(FULL + s), k * BK, nt * BN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_bf16(BN);
+            int64_t step = 0;
+            for (int64_t it = 0; it < my_items; ++it) {
+                const int b = (int)(it & 1);
+                mbar_wait<32>(bar(T_EMPTY + b), (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t d = tmem_base + b * BN;
+                for (int k = 0; k < n_k; ++k, ++step) {
+                    const int s = (int)(step % STAGES);
+                    mbar_wait<32>(bar(FULL + s), (uint32_t)((step / STAGES) & 1));
+                    tc_fence_after();
+                    const uint64_t a = desc_sw128(sbase + OFF_A + s * A_BYTES);
+                    const uint64_t w = desc_sw128(sbase + OFF_B + s * B_BYTES);
+#pragma unroll
+                    for (int j = 0; j < BK / 16; ++j)    // K-slices of 16 bf16 = 32 bytes = +2 in the address field
+                        umma_bf16(d, a + 2 * j, w + 2 * j, idesc, (k | j) != 0);
+                    umma_commit(bar(EMPTY + s));
+                }
+                umma_commit(bar(T_FULL + b));
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: TMEM -> bias (+ residual) -> GELU -> bf16 =================
+        const int q = warp & 3;                           // TMEM lane quarter
+        const int ch = (warp - 4) >> 2;                   // column half of the 256-column accumulator
+        unsigned char *xp = smem + OFF_XPOSE + (warp - 4) * 4096;
+        for (int64_t it = 0; it < my_items; ++it) {
+            const int b = (int)(it & 1);
+            const int64_t item = blockIdx.x + it * gridDim.x;
+            const int64_t mt = item / n_ntiles;
+            const int nt = (int)(item % n_ntiles);
+            if (warp == 4)                                // one warp polls, the other seven block on a named barrier
+                mbar_wait<32>(bar(T_FULL + b), (uint32_t)((it >> 1) & 1));
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + b * BN + ch * 128 + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int sl = 0; sl < 4; ++sl) {
+                uint32_t v[32];
+                tmem_ld32(taddr + sl * 32, v);
+                tmem_wait_ld_fence(v);
+                const int col0 = nt * BN + ch * 128 + sl * 32;
+                // TMEM hands every thread one ROW of the slab (32 columns); global memory wants every warp instruction
+                // to cover whole 128-byte row segments.  The slab is therefore turned through a warp-private 4 KB
+                // buffer (16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4): conflict-free both ways):
+                // global <-> buffer moves use lane -> (row 4i + lane/8, chunk lane%8), i.e. 4 full lines per instruction.
+                float hv[32];
+                const int64_t row0 = mt * BM + q * 32;
+                if (MODE == 1) {
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + (lane >> 3), cc = lane & 7;
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row0 + rr < n_tokens)
+                            t = *reinterpret_cast<const float4 *>(h + (row0 + rr) * N + col0 + 4 * cc);
+                        *reinterpret_cast<float4 *>(xp + rr * 128 + ((cc ^ (rr & 7)) << 4)) = t;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 t = *reinterpret_cast<const float4 *>(xp + lane * 128 + ((c ^ (lane & 7)) << 4));
+                        hv[4 * c] = t.x; hv[4 * c + 1] = t.y; hv[4 * c + 2] = t.z; hv[4 * c + 3] = t.w;
+                    }
+                }
+                uint32_t packed[16];
+                float bv[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(bias + col0) + c);
+                    bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w;
+                }
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    float x0 = __uint_as_float(v[c]) + bv[c];
+                    float x1 = __uint_as_float(v[c + 1]) + bv[c + 1];
+                    if (MODE == 1) {
+                        x0 += hv[c];
+                        x1 += hv[c + 1];
+                        hv[c] = x0;
+                        hv[c + 1] = x1;
+                    }
+                    const __nv_bfloat162 pk = __floats2bfloat162_rn(gelu_fast(x0), gelu_fast(x1));
+                    packed[c >> 1] = *reinterpret_cast<const uint32_t *>(&pk);
+                }
+                if (MODE == 1) {
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<float4 *>(xp + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                            make_float4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + (lane >> 3), cc = lane & 7;
+                        const float4 t = *reinterpret_cast<const float4 *>(xp + rr * 128 + ((cc ^ (rr & 7)) << 4));
+                        if (row0 + rr < n_tokens)
+                            *reinterpret_cast<float4 *>(h + (row0 + rr) * N + col0 + 4 * cc) = t;
+                    }
+                }
+                if (out) {
+                    // bf16 rows are 64 bytes: chunk c of row r at r*64 + ((c ^ ((r >> 1) & 3)) << 4); global moves use
+                    // lane -> (row 8i + lane/4, chunk lane%4): 8 row segments of 64 bytes per instruction
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4 *>(xp + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                            make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = 8 * i + (lane >> 2), cc = lane & 3;
+                        const uint4 t = *reinterpret_cast<const uint4 *>(xp + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+                        if (row0 + rr < n_tokens)
+                            *reinterpret_cast<uint4 *>(out + (row0 + rr) * N + col0 + 8 * cc) = t;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(T_EMPTY + b));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tl_get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// (rows, cols) bf16 row-major tensor under boxes of `box_rows` x 64 columns (128 bytes, SWIZZLE_128B)
+bool make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int cols, int box_rows)
+{
+    EncodeTiledFn enc = tl_get_encode();
+    if (!enc)
+        return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)tl::BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool tok_linear_supported(int K, int N) { return K >= tl::BK && K % tl::BK == 0 && N >= tl::BN && N % tl::BN == 0; }
+
+cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, float *h, void *out, int64_t n_tokens,
+                              int K, int N, int mode, int sm_count, int max_smem, cudaStream_t st)
+{
+    using namespace tl;
+    if (!tok_linear_supported(K, N) || SMEM_BYTES > max_smem || (mode == 1 && !h) || (mode == 0 && !out))
+        return cudaErrorNotSupported;
+    if (n_tokens == 0)
+        return cudaSuccess;
+    CUtensorMap map_a, map_w;
+    if (!make_bf16_map(&map_a, a, n_tokens, K, BM) || !make_bf16_map(&map_w, w, N, K, BN))
+        return cudaErrorNotSupported;
+    const int64_t items = (n_tokens + BM - 1) / BM * (N / BN);
+    const int grid = (int)(items < sm_count ? items : sm_count);
+    cudaError_t err;
+    if (mode == 0) {
+        err = cudaFuncSetAttribute(tok_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (err != cudaSuccess)
+            return err;
+        tok_linear_kernel<0><<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, K, N);
+    } else {
+        err = cudaFuncSetAttribute(tok_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (err != cudaSuccess)
+            return err;
+        tok_linear_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, K, N);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace vqb

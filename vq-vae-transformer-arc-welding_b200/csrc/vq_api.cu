@@ -247,6 +247,34 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
     return VQB_OK;
 }
 
+int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const float *bias, float *h, void *out_bf16,
+                     int64_t n_tokens, int k, int n, unsigned mode, void *stream)
+{
+    if (!a_bf16 || !w_bf16 || !bias || n_tokens < 0 || mode > 1u || (mode == 1u && !h) || (mode == 0u && !out_bf16))
+        return VQB_E_ARG;
+    if (!tok_linear_supported(k, n) || !aligned(a_bf16, 16) || !aligned(w_bf16, 16) || !aligned(bias, 16) ||
+        (h && !aligned(h, 16)) || (out_bf16 && !aligned(out_bf16, 16)))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_tok_linear(a_bf16, w_bf16, bias, h, out_bf16, n_tokens, k, n, (int)mode, info.sm_count,
+                            info.max_smem_per_block, (cudaStream_t)stream);
+    if (err == cudaErrorNotSupported)
+        return VQB_E_UNSUPPORTED;
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_tokens > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
 int vqb_backward(int device, const float *g_zq, const float *g_loss,
                  const float *z, int64_t n_outer, int64_t n_inner, int d,
                  int64_t stride_outer, int64_t stride_inner, int64_t stride_d,

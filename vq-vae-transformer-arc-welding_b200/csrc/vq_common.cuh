@@ -129,6 +129,9 @@ bool tc_chunked_supported(int K, int D);
 cudaError_t launch_fwd_tc_chunked(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas,
                                   int *n_launches, cudaStream_t st, cudaEvent_t ev_begin = nullptr,
                                   cudaEvent_t ev_end = nullptr);
+bool tok_linear_supported(int K, int N);
+cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, float *h, void *out, int64_t n_tokens,
+                              int K, int N, int mode, int sm_count, int max_smem, cudaStream_t st);
 void count_launches(int n);
 void set_tc_trace(unsigned long long *buf);
 size_t tc_trace_words();

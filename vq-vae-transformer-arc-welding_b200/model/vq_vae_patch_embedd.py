@@ -177,9 +177,56 @@ class VQVAEPatch(Autoencoder):
         self.apply(self.weights_init)
 
     # ---- encode half: the hot path ------------------------------------------------------
+    #: "torch": stock PyTorch layers in the ambient matmul precision (default, fp32-faithful);
+    #: "fused_bf16": the residual blocks run on the fused tcgen05 layer kernel (csrc/tok_linear.cu) with bf16
+    #: operands / fp32 accumulation -- the operand precision the reference itself selects with
+    #: torch.set_float32_matmul_precision('medium') (train_*.py), without the element-wise passes.
+    encoder_mode = "torch"
+
     def encode(self, x):
         """x (B, seq_len, input_dim) -> z_e (B, T, D)."""
+        if self.encoder_mode == "fused_bf16" and self._fused_ok(x):
+            return self.encode_fused_bf16(x)
         return self.encoder(self.patch_embed(x))
+
+    def _fused_ok(self, x) -> bool:
+        cnn = self.encoder[0]
+        return (x.is_cuda and x.dtype == torch.float32 and not self.training and not torch.is_grad_enabled()
+                and cnn.seperate and not cnn._has_bn and all(b._centre_tap_ok() for b in cnn.shared_conv)
+                and self.patch_embed.proj.out_channels % 256 == 0)
+
+    def _fused_weights(self):
+        """bf16 centre-tap weights of the residual blocks, rebuilt when a parameter changes."""
+        params = [p for blk in self.encoder[0].shared_conv for p in (blk.block[1].weight, blk.block[4].weight)]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        cache = getattr(self, "_fused_cache", None)
+        if cache is None or cache[0] != key:
+            ws = []
+            for blk in self.encoder[0].shared_conv:
+                c = blk.padding
+                ws.append((blk.block[1].weight[:, :, c].to(torch.bfloat16).contiguous(), blk.block[1].bias.float().contiguous(),
+                           blk.block[4].weight[:, :, c].to(torch.bfloat16).contiguous(), blk.block[4].bias.float().contiguous()))
+            cache = (key, ws)
+            object.__setattr__(self, "_fused_cache", cache)
+        return cache[1]
+
+    def encode_fused_bf16(self, x):
+        """The encoder with its 16 hidden x hidden layers on the fused kernel: tokens (B*T, H) stay row-major,
+        the residual stream h is fp32 and updated in place, activations between the layers are bf16."""
+        from .. import ops
+        b = x.shape[0]
+        pe = self.patch_embed
+        patches = x.permute(0, 2, 1).reshape(-1, pe.patch_size)                       # (B*T, P)
+        h = F.linear(patches, pe.proj.weight[:, 0, :], pe.proj.bias).contiguous()     # (B*T, H) fp32
+        a = F.gelu(h).to(torch.bfloat16)
+        u = torch.empty_like(a)
+        blocks = self._fused_weights()
+        for i, (w1, b1, w2, b2) in enumerate(blocks):
+            ops.token_linear(a, w1, b1, out=u, mode=0)                                 # u = gelu(W1 a + b1)
+            ops.token_linear(u, w2, b2, h=h, out=a if i + 1 < len(blocks) else None, mode=1)   # h += W2 u + b2; a = gelu(h)
+        proj = self.encoder[1].shared_conv
+        z_e = F.linear(h, proj.weight[:, :, 0], proj.bias)
+        return z_e.view(b, -1, z_e.shape[-1])
 
     def encode_ids(self, x):
         """Token ids (B, T) int64 -- the encode call of dataloader/latentspace_dataloader.py:154-161
