@@ -135,6 +135,8 @@ int vqb_backward(int device, const float *g_zq, const float *g_loss,
  * bf16 accuracy (|error| <= 2.5e-5 + 2.5e-4 |x| before the bf16 rounding):
  *   mode 0:  out = bf16(gelu(a w^T + bias))                                   first conv of a block
  *   mode 1:  h += a w^T + bias (fp32, in place);  out = bf16(gelu(h)) or NULL second conv + residual + next GELU
+ *   mode 2:  h  = a w^T + bias (fp32, written);   out = bf16(gelu(h)) or NULL patch embedding (:13-17, k zero-padded
+ *            to 64) + the first block's leading GELU
  * a: (n_tokens, k) bf16 row-major, w: (n, k) bf16 row-major, bias: (n) fp32, h: (n_tokens, n) fp32,
  * out: (n_tokens, n) bf16.  k a multiple of 64, n a multiple of 256; all pointers 16-byte aligned.
  */

@@ -43,6 +43,13 @@ def test_token_linear_matches_fp32_reference(T, K, N):
     acc, ref = _ref(a, w, bias, h0, 1)
     torch.testing.assert_close(h, acc, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(nxt.float(), ref, rtol=1.0 / 128, atol=2e-3)
+    # mode 2: h written (not read), next activation written
+    h3 = torch.full((T, N), float("nan"), device=dev)
+    nxt3 = torch.empty(T, N, dtype=torch.bfloat16, device=dev)
+    ops.token_linear(a, w, bias, h=h3, out=nxt3, mode=2)
+    acc3, ref3 = _ref(a, w, bias, None, 0)
+    torch.testing.assert_close(h3, acc3, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(nxt3.float(), ref3, rtol=1.0 / 128, atol=2e-3)
     # mode 1 without the activation output (last block)
     h2 = h0.clone()
     ops.token_linear(a, w, bias, h=h2, out=None, mode=1)

@@ -10,6 +10,8 @@
 //     mode 0:  out = bf16( gelu( A W^T + b ) )                      (first GEMM of a block)
 //     mode 1:  h  += A W^T + b  (fp32, in place);  out = bf16( gelu(h) )   (second GEMM + residual + the
 //              next block's leading GELU; out may be NULL after the last block)
+//     mode 2:  h   = A W^T + b  (fp32, written);   out = bf16( gelu(h) )   (patch embedding, K zero-padded to 64,
+//              + the first block's leading GELU)
 // A: (T, K) bf16 row-major activations, W: (N, K) bf16 row-major, fp32 accumulation in TMEM, erf-form GELU
 // evaluated through a fitted tanh argument (gelu_fast below, |error| <= 2.5e-5 + 2.5e-4 |x|, then rounded to bf16).  bf16 operands make this the reduced-precision encoder mode
 // (same operand precision as the reference under its own torch.set_float32_matmul_precision('medium'));
@@ -26,13 +28,13 @@ namespace vqb {
 namespace tl {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;                               // (the fourth stage made room for the residual prefetch buffers)
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
 constexpr int THREADS = 128 + 256;                       // 4 service warps + 8 epilogue warps
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
-constexpr int OFF_XPOSE = OFF_B + STAGES * B_BYTES;      // 8 x 4096: per epilogue warp, a 32 x 128-byte transposing buffer
-constexpr int OFF_BARS = OFF_XPOSE + 8 * 4096;
+constexpr int OFF_XPOSE = OFF_B + STAGES * B_BYTES;      // 8 x 2 x 4096: per epilogue warp, two 32 x 128-byte transposing buffers
+constexpr int OFF_BARS = OFF_XPOSE + 8 * 8192;
 constexpr int SMEM_BYTES = OFF_BARS + 256;
 
 // GELU(x) = x Phi(x) as 0.5 x (1 + tanh(x (c1 + c3 x^2 + c5 x^4))): the odd polynomial is a minimax fit of
@@ -141,12 +143,27 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ================= epilogue: TMEM -> bias (+ residual) -> GELU -> bf16 =================
         const int q = warp & 3;                           // TMEM lane quarter
         const int ch = (warp - 4) >> 2;                   // column half of the 256-column accumulator
-        unsigned char *xp = smem + OFF_XPOSE + (warp - 4) * 4096;
+        unsigned char *xp0 = smem + OFF_XPOSE + (warp - 4) * 8192;
+        // cp.async of the residual slab `sl` of the current item into buffer `buf` (lane -> row 4i + lane/8, chunk lane%8;
+        // rows beyond the tensor are zero-filled): in flight while the tile's MMAs / the previous slab are worked on
+        auto prefetch_h = [&](int64_t row0, int col0, int buf) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = 4 * i + (lane >> 3), cc = lane & 7;
+                const bool in = row0 + rr < n_tokens;
+                const float *src = in ? h + (row0 + rr) * N + col0 + 4 * cc : h;
+                const uint32_t dst = smem_u32(xp0 + buf * 4096 + rr * 128 + ((cc ^ (rr & 7)) << 4));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
         for (int64_t it = 0; it < my_items; ++it) {
             const int b = (int)(it & 1);
             const int64_t item = blockIdx.x + it * gridDim.x;
             const int64_t mt = item / n_ntiles;
             const int nt = (int)(item % n_ntiles);
+            if (MODE == 1)
+                prefetch_h(mt * BM + q * 32, nt * BN + ch * 128, 0);
             if (warp == 4)                                // one warp polls, the other seven block on a named barrier
                 mbar_wait<32>(bar(T_FULL + b), (uint32_t)((it >> 1) & 1));
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -164,15 +181,14 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 // global <-> buffer moves use lane -> (row 4i + lane/8, chunk lane%8), i.e. 4 full lines per instruction.
                 float hv[32];
                 const int64_t row0 = mt * BM + q * 32;
+                unsigned char *xp = xp0 + (MODE == 1 ? (sl & 1) * 4096 : 0);
                 if (MODE == 1) {
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rr = 4 * i + (lane >> 3), cc = lane & 7;
-                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row0 + rr < n_tokens)
-                            t = *reinterpret_cast<const float4 *>(h + (row0 + rr) * N + col0 + 4 * cc);
-                        *reinterpret_cast<float4 *>(xp + rr * 128 + ((cc ^ (rr & 7)) << 4)) = t;
+                    __syncwarp();                         // every lane is done with the buffer the next slab lands in
+                    if (sl < 3) {
+                        prefetch_h(row0, col0 + 32, (sl + 1) & 1);
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    } else {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
                     }
                     __syncwarp();
 #pragma unroll
@@ -195,13 +211,15 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (MODE == 1) {
                         x0 += hv[c];
                         x1 += hv[c + 1];
+                    }
+                    if (MODE != 0) {
                         hv[c] = x0;
                         hv[c + 1] = x1;
                     }
                     const __nv_bfloat162 pk = __floats2bfloat162_rn(gelu_fast(x0), gelu_fast(x1));
                     packed[c >> 1] = *reinterpret_cast<const uint32_t *>(&pk);
                 }
-                if (MODE == 1) {
+                if (MODE != 0) {
                     __syncwarp();
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -289,7 +307,7 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
                               int K, int N, int mode, int sm_count, int max_smem, cudaStream_t st)
 {
     using namespace tl;
-    if (!tok_linear_supported(K, N) || SMEM_BYTES > max_smem || (mode == 1 && !h) || (mode == 0 && !out))
+    if (!tok_linear_supported(K, N) || SMEM_BYTES > max_smem || (mode != 0 && !h) || (mode == 0 && !out))
         return cudaErrorNotSupported;
     if (n_tokens == 0)
         return cudaSuccess;
@@ -298,18 +316,11 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
         return cudaErrorNotSupported;
     const int64_t items = (n_tokens + BM - 1) / BM * (N / BN);
     const int grid = (int)(items < sm_count ? items : sm_count);
-    cudaError_t err;
-    if (mode == 0) {
-        err = cudaFuncSetAttribute(tok_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (err != cudaSuccess)
-            return err;
-        tok_linear_kernel<0><<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, K, N);
-    } else {
-        err = cudaFuncSetAttribute(tok_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (err != cudaSuccess)
-            return err;
-        tok_linear_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, K, N);
-    }
+    auto kern = mode == 0 ? tok_linear_kernel<0> : mode == 1 ? tok_linear_kernel<1> : tok_linear_kernel<2>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (err != cudaSuccess)
+        return err;
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, K, N);
     return cudaGetLastError();
 }
 

@@ -250,7 +250,7 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
 int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const float *bias, float *h, void *out_bf16,
                      int64_t n_tokens, int k, int n, unsigned mode, void *stream)
 {
-    if (!a_bf16 || !w_bf16 || !bias || n_tokens < 0 || mode > 1u || (mode == 1u && !h) || (mode == 0u && !out_bf16))
+    if (!a_bf16 || !w_bf16 || !bias || n_tokens < 0 || mode > 2u || (mode != 0u && !h) || (mode == 0u && !out_bf16))
         return VQB_E_ARG;
     if (!tok_linear_supported(k, n) || !aligned(a_bf16, 16) || !aligned(w_bf16, 16) || !aligned(bias, 16) ||
         (h && !aligned(h, 16)) || (out_bf16 && !aligned(out_bf16, 16)))

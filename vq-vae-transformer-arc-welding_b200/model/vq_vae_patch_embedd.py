@@ -217,6 +217,8 @@ class VQVAEPatch(Autoencoder):
         b = x.shape[0]
         pe = self.patch_embed
         patches = x.permute(0, 2, 1).reshape(-1, pe.patch_size)                       # (B*T, P)
+        # (the patch embedding stays an fp32 PyTorch GEMM: K = 25 is 0.3 % of the FLOPs, and feeding the raw signal
+        # as bf16 through vqb_token_linear mode 2 was measured to cost index matches -- 99.86 % -> 99.59 %)
         h = F.linear(patches, pe.proj.weight[:, 0, :], pe.proj.bias).contiguous()     # (B*T, H) fp32
         a = F.gelu(h).to(torch.bfloat16)
         u = torch.empty_like(a)

@@ -259,7 +259,8 @@ class HostEncoder:
 def token_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Optional[torch.Tensor] = None,
                  out: Optional[torch.Tensor] = None, mode: int = 0) -> Optional[torch.Tensor]:
     """One fused per-token linear layer of the encoder's residual blocks (vqb_token_linear, csrc/tok_linear.cu):
-    mode 0: out = bf16(gelu(a @ w.T + bias));  mode 1: h += a @ w.T + bias (in place), out = bf16(gelu(h)) if given.
+    mode 0: out = bf16(gelu(a @ w.T + bias));  mode 1: h += a @ w.T + bias (in place), out = bf16(gelu(h)) if given;
+    mode 2: h = a @ w.T + bias (written), out = bf16(gelu(h)) if given.
     a (T, K) bf16, w (N, K) bf16, bias (N,) fp32, h (T, N) fp32, out (T, N) bf16 -- all CUDA, contiguous."""
     for t, name, dt in ((a, "a", torch.bfloat16), (w, "w", torch.bfloat16), (bias, "bias", torch.float32)):
         if not t.is_cuda or t.dtype != dt or not t.is_contiguous():
@@ -270,8 +271,8 @@ def token_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Option
         raise RuntimeError("token_linear: shape mismatch")
     if mode == 0 and out is None:
         out = torch.empty((t_rows, n), dtype=torch.bfloat16, device=a.device)
-    if mode == 1 and (h is None or h.dtype != torch.float32 or not h.is_contiguous() or tuple(h.shape) != (t_rows, n)):
-        raise RuntimeError("token_linear mode 1 needs a contiguous fp32 h of shape (T, N)")
+    if mode != 0 and (h is None or h.dtype != torch.float32 or not h.is_contiguous() or tuple(h.shape) != (t_rows, n)):
+        raise RuntimeError("token_linear modes 1 and 2 need a contiguous fp32 h of shape (T, N)")
     if out is not None and (out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape) != (t_rows, n)):
         raise RuntimeError("token_linear: out must be a contiguous bf16 (T, N) tensor")
     lib = _lib.load()
