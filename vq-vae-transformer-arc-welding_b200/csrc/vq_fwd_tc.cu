@@ -688,7 +688,9 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             float zz = reinterpret_cast<const float *>(smem + OFF_ZZ + s * 512)[r];
             if (nd == 2)
                 zz += reinterpret_cast<const float *>(smem + OFF_ZZ + s1 * 512)[r];
-            const float zn = sqrt_approx(zz) * 1.00001f;
+            // (sums of squares below 2^-120 are treated as 2^-120: the fp32 sum loses bits there -- it underflows to 0 for
+            // components below 2^-75 -- and sqrt.approx.ftz would flush a sub-normal sum to 0; 2^-60 still bounds the norm)
+            const float zn = sqrt_approx(fmaxf(zz, 7.52316385e-37f)) * 1.00001f;
             // Filter radius delta = 2*eps + 2*H + 2*pack (DESIGN.md "Exactness"), u = 2^-8 the bf16 unit
             // roundoff, zn >= |z|, emax >= max|e_k|, eemax = max ee_k, S = sum_j |z_j e_j| <= zn*emax:
             //   eps : terms the three products leave out, z2.E2 + r_z.E + z.r_E <= (u*u + u*u + u*u) S = 3*2^-16 S,
