@@ -31,3 +31,7 @@ ms = timeit(lambda: ops.backward(g, gl, zperm, idx, w, 0.25))
 print(f"bwd permuted z      : {ms:.3f} ms")
 ms = timeit(lambda: ops.one_hot(idx, K), 3)
 print(f"one-hot (N,K) fp32  : {ms:.3f} ms -> {n * K * 4 / ms / 1e6:.0f} GB/s")
+ms = timeit(lambda: ops.backward(g, gl, zc, idx, w, 0.25, need_e=False))
+print(f"bwd grad_z only     : {ms:.3f} ms -> {n * (12 * D + 8) / ms / 1e6:.0f} GB/s algorithmic (phase 1 alone)")
+ms = timeit(lambda: ops.backward(g, gl, zc, idx, w, 0.25, need_z=False))
+print(f"bwd grad_E only     : {ms:.3f} ms (reads z, idx; no g_zq read? no grad_z write)")
