@@ -143,6 +143,10 @@ int vqb_backward(int device, const float *g_zq, const float *g_loss,
 int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const float *bias, float *h, void *out_bf16,
                      int64_t n_tokens, int k, int n, unsigned mode, void *stream);
 
+/* h += bias (fp32 (n_tokens, n), in place); out = bf16(gelu(h)): the element-wise step between the fp32 patch
+ * embedding (model/vq_vae_patch_embedd.py:13-17) and the first fused layer, in one pass.  n a multiple of 4. */
+int vqb_token_bias_gelu(int device, float *h, const float *bias, void *out_bf16, int64_t n_tokens, int n, void *stream);
+
 /* out[i] = codebook[idx[i]] (n, d).  Out-of-range indices yield NaN rows and set
  * *bad_index (device int, may be NULL) to 1. */
 int vqb_gather(int device, const int64_t *idx, int64_t n, const float *codebook, int k, int d,

@@ -110,3 +110,16 @@ def test_fused_bf16_encoder_tracks_the_fp32_encoder():
     model.train()
     model.encoder_mode = "fused_bf16"
     assert not model._fused_ok(x)
+
+
+def test_token_bias_gelu():
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(3)
+    h = torch.randn(1000, 512, device=dev, generator=g) * 2
+    b = torch.randn(512, device=dev, generator=g)
+    ref_h = h + b
+    out = ops.token_bias_gelu(h, b)
+    assert torch.equal(h, ref_h)
+    ref = torch.nn.functional.gelu(ref_h)
+    bound = 5e-5 + 3e-4 * ref_h.abs() + 2.0 ** -8 * ref.abs()     # MUFU.TANH (2^-11 on the tanh) + bf16 rounding
+    assert bool(((out.float() - ref).abs() <= bound).all())

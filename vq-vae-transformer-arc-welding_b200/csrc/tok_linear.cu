@@ -263,6 +263,37 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// h += bias (fp32, in place); out = bf16(gelu(h)) -- the element-wise step between the fp32 patch embedding GEMM
+// (K = 25, stock cuBLAS without bias) and the first fused layer: one pass instead of bias + GELU + cast (three).
+__global__ void __launch_bounds__(256) tok_bias_gelu_kernel(float *__restrict__ h, const float *__restrict__ bias,
+                                                            __nv_bfloat16 *__restrict__ out, int64_t n_vec4, int n4)
+{
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n_vec4; t += (int64_t)gridDim.x * 256) {
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + (int)(t % n4));
+        float4 v = reinterpret_cast<float4 *>(h)[t];
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        reinterpret_cast<float4 *>(h)[t] = v;
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(tl::gelu_fast(v.x), tl::gelu_fast(v.y));
+        const __nv_bfloat162 p1 = __floats2bfloat162_rn(tl::gelu_fast(v.z), tl::gelu_fast(v.w));
+        reinterpret_cast<uint2 *>(out)[t] = make_uint2(*reinterpret_cast<const uint32_t *>(&p0),
+                                                       *reinterpret_cast<const uint32_t *>(&p1));
+    }
+}
+
+cudaError_t launch_tok_bias_gelu(float *h, const float *bias, void *out, int64_t n_tokens, int N, int sm_count,
+                                 cudaStream_t st)
+{
+    if (N % 4 != 0)
+        return cudaErrorNotSupported;
+    const int64_t n_vec4 = n_tokens * (N / 4);
+    if (n_vec4 == 0)
+        return cudaSuccess;
+    const int64_t blocks = (n_vec4 + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)sm_count * 16 ? blocks : (int64_t)sm_count * 16);
+    tok_bias_gelu_kernel<<<grid, 256, 0, st>>>(h, bias, (__nv_bfloat16 *)out, n_vec4, N / 4);
+    return cudaGetLastError();
+}
+
 namespace {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,

@@ -275,6 +275,29 @@ int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const f
     return VQB_OK;
 }
 
+int vqb_token_bias_gelu(int device, float *h, const float *bias, void *out_bf16, int64_t n_tokens, int n, void *stream)
+{
+    if (!h || !bias || !out_bf16 || n_tokens < 0 || n <= 0)
+        return VQB_E_ARG;
+    if (n % 4 != 0 || !aligned(h, 16) || !aligned(bias, 16) || !aligned(out_bf16, 8))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_tok_bias_gelu(h, bias, out_bf16, n_tokens, n, info.sm_count, (cudaStream_t)stream);
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_tokens > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
 int vqb_backward(int device, const float *g_zq, const float *g_loss,
                  const float *z, int64_t n_outer, int64_t n_inner, int d,
                  int64_t stride_outer, int64_t stride_inner, int64_t stride_d,

@@ -132,6 +132,8 @@ cudaError_t launch_fwd_tc_chunked(const FwdParams &p, float *tc_scratch, int sm_
 bool tok_linear_supported(int K, int N);
 cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, float *h, void *out, int64_t n_tokens,
                               int K, int N, int mode, int sm_count, int max_smem, cudaStream_t st);
+cudaError_t launch_tok_bias_gelu(float *h, const float *bias, void *out, int64_t n_tokens, int N, int sm_count,
+                                 cudaStream_t st);
 void count_launches(int n);
 void set_tc_trace(unsigned long long *buf);
 size_t tc_trace_words();

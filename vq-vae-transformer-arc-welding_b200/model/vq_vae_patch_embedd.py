@@ -219,8 +219,8 @@ class VQVAEPatch(Autoencoder):
         patches = x.permute(0, 2, 1).reshape(-1, pe.patch_size)                       # (B*T, P)
         # (the patch embedding stays an fp32 PyTorch GEMM: K = 25 is 0.3 % of the FLOPs, and feeding the raw signal
         # as bf16 through vqb_token_linear mode 2 was measured to cost index matches -- 99.86 % -> 99.59 %)
-        h = F.linear(patches, pe.proj.weight[:, 0, :], pe.proj.bias).contiguous()     # (B*T, H) fp32
-        a = F.gelu(h).to(torch.bfloat16)
+        h = torch.matmul(patches, pe.proj.weight[:, 0, :].t())                        # (B*T, H) fp32, bias added below
+        a = ops.token_bias_gelu(h, pe.proj.bias)                                       # h += b; a = bf16(gelu(h)), one pass
         u = torch.empty_like(a)
         blocks = self._fused_weights()
         for i, (w1, b1, w2, b2) in enumerate(blocks):

@@ -283,3 +283,19 @@ def token_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Option
                                   t_rows, k, n, int(mode), torch.cuda.current_stream(a.device).cuda_stream)
     _lib.check(rc, "vqb_token_linear")
     return out
+
+
+def token_bias_gelu(h: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """h += bias (in place, fp32 (T, N)); returns bf16(gelu(h)) -- vqb_token_bias_gelu."""
+    if not h.is_cuda or h.dtype != torch.float32 or not h.is_contiguous() or h.dim() != 2:
+        raise RuntimeError("token_bias_gelu: h must be a contiguous CUDA fp32 (T, N) tensor (no CPU fallback)")
+    if not bias.is_cuda or bias.dtype != torch.float32 or bias.numel() != h.shape[1]:
+        raise RuntimeError("token_bias_gelu: bias must be a CUDA fp32 (N,) tensor")
+    if out is None:
+        out = torch.empty(h.shape, dtype=torch.bfloat16, device=h.device)
+    lib = _lib.load()
+    with torch.cuda.device(h.device):
+        rc = lib.vqb_token_bias_gelu(h.device.index, h.data_ptr(), bias.contiguous().data_ptr(), out.data_ptr(),
+                                     h.shape[0], h.shape[1], torch.cuda.current_stream(h.device).cuda_stream)
+    _lib.check(rc, "vqb_token_bias_gelu")
+    return out
