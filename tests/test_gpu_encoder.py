@@ -63,7 +63,9 @@ def test_token_linear_gelu_is_the_erf_form():
     K, N, T = 64, 256, 256
     a = torch.zeros(T, K, device=dev, dtype=torch.bfloat16)
     w = torch.zeros(N, K, device=dev, dtype=torch.bfloat16)
-    x = torch.linspace(-6, 6, N, device=dev)
+    x = torch.cat([torch.linspace(-6, 6, N - 32, device=dev),
+                   torch.tensor([-1e4, -300., -40., -12., -9., -8., -7., -6.5, 6.5, 7., 8., 9., 12., 40., 300., 1e4] * 2,
+                                device=dev)])
     h = x.repeat(T, 1).contiguous()
     out = torch.empty(T, N, dtype=torch.bfloat16, device=dev)
     ops.token_linear(a, w, torch.zeros(N, device=dev), h=h, out=out, mode=1)
@@ -115,7 +117,7 @@ def test_fused_bf16_encoder_tracks_the_fp32_encoder():
 def test_token_bias_gelu():
     dev = _dev()
     g = torch.Generator(device=dev).manual_seed(3)
-    h = torch.randn(1000, 512, device=dev, generator=g) * 2
+    h = torch.randn(1000, 512, device=dev, generator=g) * 4      # pre-activations out to |x| ~ 20
     b = torch.randn(512, device=dev, generator=g)
     ref_h = h + b
     out = ops.token_bias_gelu(h, b)
@@ -123,3 +125,25 @@ def test_token_bias_gelu():
     ref = torch.nn.functional.gelu(ref_h)
     bound = 5e-5 + 3e-4 * ref_h.abs() + 2.0 ** -8 * ref.abs()     # MUFU.TANH (2^-11 on the tanh) + bf16 rounding
     assert bool(((out.float() - ref).abs() <= bound).all())
+
+
+def test_fused_bf16_encoder_folds_eval_batchnorm():
+    """The module's constructor default is batch_norm=True: in eval mode the fused path folds the BatchNorm affine maps
+    into the layer weights and still tracks the fp32 encoder."""
+    dev = _dev()
+    torch.manual_seed(1)
+    model = vqb200.VQVAEPatch(hidden_dim=256, input_dim=2, num_embeddings=64, embedding_dim=32, n_resblocks=2,
+                              learning_rate=1e-3, patch_size=25, batch_norm=True).to(dev)
+    with torch.no_grad():                      # non-trivial running statistics and affine parameters
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.8, 1.2); m.bias.normal_(0, 0.1)
+    model.eval()
+    x = torch.randn(200, 200, 2, device=dev)
+    with torch.no_grad():
+        z_ref = model.encode(x)
+        model.encoder_mode = "fused_bf16"
+        assert model._fused_ok(x)
+        z_fused = model.encode(x)
+    assert (z_fused - z_ref).abs().max().item() <= 0.05 * z_ref.abs().max().item()

@@ -40,11 +40,12 @@ constexpr int SMEM_BYTES = OFF_BARS + 256;
 // GELU(x) = x Phi(x) as 0.5 x (1 + tanh(x (c1 + c3 x^2 + c5 x^4))): the odd polynomial is a minimax fit of
 // atanh(erf(x / sqrt 2)) (max |error| of the formula 2.5e-5, against 4.7e-4 for the textbook two-term "tanh GELU");
 // MUFU.TANH adds up to 2^-11 relative on the tanh, i.e. <= 2.5e-4 |x| on the result -- below a tenth of the bf16
-// spacing of the value it is rounded to.  7 FMA-pipe instructions + 1 MUFU per element: the A&S erf form (2 MUFU, ~30
+// spacing of the value it is rounded to; x^2 is clamped to 36 because the fitted polynomial turns over beyond |x| ~ 10
+// (tanh is +-1 there to fp32 accuracy).  7 FMA-pipe instructions + 1 FMNMX + 1 MUFU per element: the A&S erf form (2 MUFU, ~30
 // instructions with IEEE reciprocal / exp) made the epilogue 2.6x longer than the tile's MMAs (profiles/README.md).
 __device__ __forceinline__ float gelu_fast(float x)
 {
-    const float u = x * x;
+    const float u = fminf(x * x, 36.0f);                 // the fit covers |x| <= 6; beyond, tanh(1.67 x) is +-1 anyway
     float p = fmaf(-3.51517534e-4f, u, 3.70056510e-2f);
     p = fmaf(p, u, 7.97507878e-1f);
     float t;

@@ -191,21 +191,32 @@ class VQVAEPatch(Autoencoder):
 
     def _fused_ok(self, x) -> bool:
         cnn = self.encoder[0]
+        # (BatchNorm layers are fine in eval mode: a per-channel affine map, folded into the layer's weights below)
         return (x.is_cuda and x.dtype == torch.float32 and not self.training and not torch.is_grad_enabled()
-                and cnn.seperate and not cnn._has_bn and all(b._centre_tap_ok() for b in cnn.shared_conv)
+                and cnn.seperate and all(b._centre_tap_ok() for b in cnn.shared_conv)
                 and self.patch_embed.proj.out_channels % 256 == 0)
 
     def _fused_weights(self):
-        """bf16 centre-tap weights of the residual blocks, rebuilt when a parameter changes."""
-        params = [p for blk in self.encoder[0].shared_conv for p in (blk.block[1].weight, blk.block[4].weight)]
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        """bf16 centre-tap weights of the residual blocks (eval-mode BatchNorm folded in: y = (W x + b - mean) *
+        gamma / sqrt(var + eps) + beta is again a linear layer), rebuilt when a parameter or running statistic changes."""
+        blocks = list(self.encoder[0].shared_conv)
+        tracked = [t for blk in blocks for m in (blk.block[1], blk.block[2], blk.block[4], blk.block[5])
+                   for t in list(m.parameters()) + list(m.buffers())]
+        key = tuple((t.data_ptr(), t._version) for t in tracked)
         cache = getattr(self, "_fused_cache", None)
         if cache is None or cache[0] != key:
+            def fold(conv, norm, c):
+                w, b = conv.weight[:, :, c].float(), conv.bias.float()
+                if isinstance(norm, nn.BatchNorm1d):
+                    scale = norm.weight.float() / torch.sqrt(norm.running_var.float() + norm.eps)
+                    w, b = w * scale[:, None], (b - norm.running_mean.float()) * scale + norm.bias.float()
+                return w.to(torch.bfloat16).contiguous(), b.contiguous()
             ws = []
-            for blk in self.encoder[0].shared_conv:
-                c = blk.padding
-                ws.append((blk.block[1].weight[:, :, c].to(torch.bfloat16).contiguous(), blk.block[1].bias.float().contiguous(),
-                           blk.block[4].weight[:, :, c].to(torch.bfloat16).contiguous(), blk.block[4].bias.float().contiguous()))
+            with torch.no_grad():
+                for blk in blocks:
+                    w1, b1 = fold(blk.block[1], blk.block[2], blk.padding)
+                    w2, b2 = fold(blk.block[4], blk.block[5], blk.padding)
+                    ws.append((w1, b1, w2, b2))
             cache = (key, ws)
             object.__setattr__(self, "_fused_cache", cache)
         return cache[1]
