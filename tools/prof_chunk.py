@@ -1,5 +1,6 @@
+"""GPU box: torch-profiler kernel table of one 65536-cycle bulk-encode chunk in fused_bf16 mode."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, vqb200
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
