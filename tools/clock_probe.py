@@ -1,4 +1,5 @@
-"""GPU box: SM clock / power while the tcgen05 forward runs back to back for a few seconds."""
+"""GPU box: SM clock / power while a kernel runs back to back for a few seconds
+(python tools/clock_probe.py [tc] [fma] [bwd] [bwdz] [copy])."""
 import os, sys, time, threading
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, pynvml, vqb200
@@ -13,12 +14,19 @@ def sampler():
         samples.append((time.time(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
                         pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
         time.sleep(0.05)
+idx = ops.forward(z, w, 0.25)[3]
+g = torch.randn(n, 32, device=dev); gl = torch.tensor(1.7, device=dev); dst = torch.empty_like(z)
+def work(path):
+    if path == "bwd": return ops.backward(g, gl, z, idx, w, 0.25)
+    if path == "bwdz": return ops.backward(g, gl, z, idx, w, 0.25, need_e=False)
+    if path == "copy": return dst.copy_(z)
+    return ops.forward(z, w, 0.25, path=path)
 for path in (sys.argv[1:] or ["tc", "fma"]):
     samples.clear(); stop = False
     t = threading.Thread(target=sampler); t.start()
     torch.cuda.synchronize(); t0 = time.time(); it = 0
     while time.time() - t0 < 3.0:
-        for _ in range(50): ops.forward(z, w, 0.25, path=path)
+        for _ in range(50): work(path)
         torch.cuda.synchronize(); it += 50
     dt = time.time() - t0; stop = True; t.join()
     mid = samples[len(samples)//4:]

@@ -39,3 +39,7 @@ for cta in range(2):
         print(f"  {name:12s} p10 {np.percentile(v,10):7.0f} p50 {np.percentile(v,50):7.0f} p90 {np.percentile(v,90):7.0f} p99 {np.percentile(v,99):7.0f} mean {v.mean():7.0f}")
     per = np.diff(d[:, 5])
     print(f"  filter-done period: p50 {np.percentile(per,50):.0f} mean {per.mean():.0f}; span per tile {(a[200,7]-a[20,0])/180:.0f}")
+    h2 = a[22:200, 3] - a[20:198, 5]      # accumulator released by tile i (last warp) -> MMA of tile i + 2 issued
+    print(f"  accumulator hand-back (flt_out(i) -> mma(i+2)): p10 {np.percentile(h2,10):.0f} p50 {np.percentile(h2,50):.0f} p90 {np.percentile(h2,90):.0f}")
+    cyc = a[22:200, 3] - a[20:198, 3]
+    print(f"  TMEM buffer cycle (mma(i) -> mma(i+2)): p50 {np.percentile(cyc,50):.0f} = mma->ep_in {np.median(d[:,4]-d[:,3]):.0f} + filter(last warp) {np.median(d[:,5]-d[:,4]):.0f} + hand-back {np.percentile(h2,50):.0f}")

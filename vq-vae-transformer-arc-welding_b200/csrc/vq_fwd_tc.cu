@@ -668,7 +668,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
             tc_fence_before();
             mbar_arrive(bar(T_EMPTY + b));        // accumulator drained: the next MMA may overwrite it
-            if (r == 0) stamp(i, 5);
+            if (TRACE && lane == 0 && blockIdx.x < kTraceCtas && i < kTraceTiles)    // the last of the group's four warps
+                atomicMax(&trace[((size_t)blockIdx.x * kTraceTiles + i) * kTraceEvents + 5], (unsigned long long)clock64());
             // packed (value | group id) top-2 of each grouping -- off the accumulator's critical path
             float a1 = inf, a2 = inf, b1 = inf, b2 = inf;
 #pragma unroll
