@@ -1,4 +1,5 @@
-"""GPU box: clock64 timeline of the TMA-ring backward kernel (CTA 0, tiles 40..103) from a -DBW_TRACE=1 build:\n    python tools/ab_build.py trace:-DBW_TRACE=1 && gpurun -- python tools/bwd_trace.py"""
+"""GPU box: clock64 timeline of the TMA-ring backward kernel (CTA 0, tiles 40..103) from a -DBW_TRACE=1 build:
+    python tools/ab_build.py trace:-DBW_TRACE=1 && gpurun -- python tools/bwd_trace.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("VQB_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vq-vae-transformer-arc-welding_b200", "ab_trace.so"))

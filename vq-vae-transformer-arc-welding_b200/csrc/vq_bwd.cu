@@ -203,15 +203,28 @@ __global__ void __launch_bounds__(256) vq_bwd32_kernel(const float *__restrict__
 // D = 32, K <= 256, contiguous z / g_zq, all outputs wanted: the TMA-ring kernel (persistent, one CTA per SM).
 // The kernel above keeps loads in flight only while a CTA is in its phase 1; here the data movement is decoupled
 // from both phases the way the forward kernel does it:
-//   warp 0      ring owner (one thread): TMA loads of a 128-vector tile of z and of g_zq into a 4-deep ring
-//               (2 x 16 KB per slot), refill of a slot as soon as phase 2 is done with it
+//   warp 0      ring owner (one thread): TMA loads of a 128-vector tile of z and of g_zq plus a 1-D bulk copy of the
+//               tile's ids into a 4-deep ring (2 x 16 KB + 1 KB per slot), refill of a slot as soon as phase 2 is
+//               done with it
 //   warps 1-8   phase 1: eight threads per vector; residual E[idx] - z written IN PLACE over the z tile,
 //               grad_z = g_zq - cz * residual stored to global memory (16 bytes per thread, 512 contiguous bytes
-//               per warp; the codebook is resident in shared memory; the tile's ids are fetched one tile ahead,
-//               straight from global memory)
+//               per warp; the codebook is resident in shared memory)
 //   warps 9-24  phase 2: warp w owns the codes c with c % 16 == w and adds the residual rows of its vectors
 //               into the CTA's K x 32 accumulator (accumulate_rows), while phase 1 works on the next slot
 //   flush       one global atomicAdd per accumulator entry per CTA.
+// Measured at N = 2^24, K = 256 (tools/bwd_time.py, tools/bwd_trace.py; profiles/README.md): 1.32 ms = 77 % of the HBM
+// roofline (the kernel above: 1.57 ms).  What the clock64 timeline of a -DBW_TRACE=1 build shows: phase 1 takes ~2800
+// clocks per tile and phase 2 ~2200 per warp against a tile period of ~2700 -- both phases run one dependent
+// instruction per ~12 clocks and warp, so it is their instruction COUNT per tile that bounds the kernel now, not the
+// ring (3 stages 1.42 ms, 4 stages 1.32 ms, 5 stages 1.55 ms: no L1 left).  Measured and rejected on the way:
+//   * grad_z through a TMA store out of the slot (refill waits for the store to have read it: 1.55 ms);
+//   * ids fetched by the phase-1 threads one tile ahead with ordinary loads (the __syncwarp behind the barrier wait
+//     then waits for those loads as well, 3.5 us under load: 1.51 ms) -- they travel through the ring now;
+//   * phase 2 sums in registers behind a warp-uniform switch over the code (divergence-safe code: 1.98 ms);
+//   * two / four vectors per phase-2 step with equal codes chained in registers (1.39 / 1.59 ms: more instructions);
+//   * phase 1 handing every vector to its owner's list with shared-memory atomics instead of phase 2 scanning the
+//     tile's codes (2.8 ms); a bounds-check-free phase 1 for full tiles (phase 1 2800 -> 2100 clocks, kernel 1.34 ms:
+//     the faster phase 1 only takes issue slots from phase 2).
 // ---------------------------------------------------------------------------------------
 #ifdef BW_TRACE   // debug build (tools/ab_build.py trace:-DBW_TRACE=1): clock64 stamps of CTA 0, tiles 40..103
 __device__ long long bw_trace_buf[6 * 64];
