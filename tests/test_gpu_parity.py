@@ -474,3 +474,59 @@ def test_tc_wide_vectors(D, K):
                 assert torch.isnan(out[0])
             else:
                 assert out[0].item() == pytest.approx(float(ora.loss), rel=REL)
+
+
+@pytest.mark.parametrize("K", [256, 100, 1])
+@pytest.mark.parametrize("n", [128, 129, 255, 1000, 128 * 148 * 2 + 77])
+def test_backward_tma_ring_kernel(K, n):
+    """D = 32, K <= 256, contiguous rows, both gradients wanted: the TMA-ring kernel (csrc/vq_bwd.cu).  Ragged and
+    odd-length last tiles (the ids travel as 16-byte granules; an odd last row is fetched separately), fewer codes
+    than the shared-memory accumulator holds, and the same call on a strided view of z (generic kernel) as a
+    cross-check.  fp64 closed form of the oracle; grad_z 1e-5 relative, grad_E 1e-5 of its largest entry."""
+    dev = _dev()
+    rng = np.random.default_rng(n * 1000 + K)
+    D = 32
+    z_np = (0.1 * rng.standard_normal((n, D))).astype(np.float32)
+    E = (0.1 * rng.standard_normal((K, D))).astype(np.float32)
+    g_np = rng.standard_normal((n, D)).astype(np.float32)
+    z = torch.from_numpy(z_np).to(dev)
+    w = torch.from_numpy(E).to(dev)
+    g = torch.from_numpy(g_np).to(dev)
+    gl = torch.tensor(1.7, device=dev)
+    idx = ops.forward(z, w, 0.25, path="fma")[3]
+    gz, gE = ops.backward(g, gl, z, idx, w, 0.25)
+    torch.cuda.synchronize()
+    ogz, ogE = O.backward(g_np, 1.7, z_np, idx.cpu().numpy().reshape(-1), E, 0.25)
+    np.testing.assert_allclose(gz.cpu().numpy(), ogz, rtol=REL, atol=1e-7)
+    scale = np.abs(ogE).max() + 1e-30
+    np.testing.assert_allclose(gE.cpu().numpy(), ogE, rtol=1e-4, atol=REL * scale)
+    # the generic kernel on a strided view of the same vectors
+    wide = torch.zeros(n, 2 * D, device=dev)
+    wide[:, :D] = z
+    gz2, gE2 = ops.backward(g, gl, wide[:, :D], idx, w, 0.25)
+    assert torch.equal(gz, gz2)
+    np.testing.assert_allclose(gE2.cpu().numpy(), gE.cpu().numpy(), rtol=1e-4, atol=REL * scale)
+
+
+def test_backward_tma_ring_ignores_out_of_range_ids():
+    """Ids outside [0, K) contribute a zero residual (grad_z = g_zq, nothing added to grad_E) in every backward
+    kernel; the TMA-ring kernel and the generic one agree on it."""
+    dev = _dev()
+    torch.manual_seed(11)
+    n, D, K = 1000, 32, 64
+    z = 0.1 * torch.randn(n, D, device=dev)
+    w = 0.1 * torch.randn(K, D, device=dev)
+    g = torch.randn(n, D, device=dev)
+    gl = torch.tensor(0.9, device=dev)
+    idx = ops.forward(z, w, 0.25)[3].clone()
+    idx[5] = -3
+    idx[77] = K
+    idx[999] = 1 << 40
+    gz, gE = ops.backward(g, gl, z, idx, w, 0.25)
+    wide = torch.zeros(n, 2 * D, device=dev)
+    wide[:, :D] = z
+    gz2, gE2 = ops.backward(g, gl, wide[:, :D], idx, w, 0.25)
+    assert torch.equal(gz, gz2)
+    for r in (5, 77, 999):
+        assert torch.equal(gz[r], g[r])
+    torch.testing.assert_close(gE, gE2, rtol=1e-4, atol=1e-9)
