@@ -68,7 +68,7 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------
 class ClockSampler:
     def __init__(self, index: int, period: float = 0.02):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
         self._stop = threading.Event()
         self._thread = None
         self._index, self._period = index, period
@@ -97,6 +97,7 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
                 getter = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                     nv.nvmlDeviceGetCurrentClocksThrottleReasons
                 self.reasons.update(self._reason_names(int(getter(self._h))))
@@ -114,7 +115,9 @@ class ClockSampler:
         if self._thread is not None:
             self._thread.join()
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w": statistics.median(self.power) if self.power else None,
+                "power_w_max": max(self.power) if self.power else None}
 
 
 # ---------------------------------------------------------------------------------------
@@ -291,6 +294,27 @@ def run_ours(args) -> None:
         del z_host, zq_host, idx_host
     clocks = sampler.stop()
 
+    # ---- straight-through backward on the same batch (reported beside the headline, not part of it) ----
+    bwd = None
+    if not args.no_bwd:
+        gq = torch.randn(n, DIM, device=dev, generator=g)
+        gl = torch.tensor(1.0, device=dev)
+        for _ in range(3):
+            ops.backward(gq, gl, z, idx, weight, BETA)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(args.steps, 10))
+        b0.record()
+        for _ in range(reps):
+            ops.backward(gq, gl, z, idx, weight, BETA)
+        b1.record()
+        barrier()
+        tb = torch.tensor([b0.elapsed_time(b1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        bwd_ms = float(tb.item())
+        del gq
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -318,6 +342,14 @@ def run_ours(args) -> None:
                 "kernel_share_of_step": k_ms * kn.value / ms_total if ms_total > 0 else None,
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src}
 
+    if not args.no_bwd:
+        bwd_bytes = n * (12 * DIM + 8)                 # read g_zq, z, idx; write grad_z
+        bwd = {"ms_per_call": bwd_ms, "patches_per_s": world * n / (bwd_ms * 1e-3),
+               "roofline": {"bound": "hbm", "achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak if peak else None,
+                            "algorithmic_bytes_per_call": bwd_bytes},
+               "what": "vqb_backward (grad_z + dense grad_E), whole call timed with CUDA events: memset + kernel + scale kernel"}
+
     cpu = None
     if not args.no_cpu:
         # bounded sample of the same workload: 2^18-vector chunks for about 10-20 s of CPU work
@@ -334,7 +366,7 @@ def run_ours(args) -> None:
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(world, n), "path": args.path,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "backward": bwd,
         "index_match": {"vs": "oracle (oracle/vq_oracle.c)", "rows": sample_rows, "rate": match},
         "check": {"loss": float(loss.item()), "perplexity": float(ppl.item()), "histogram_total": int(counts.sum().item())},
     }
@@ -354,6 +386,7 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=1 << 20, help="host-path pipeline chunk")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-bwd", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world > 1:

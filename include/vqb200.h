@@ -147,6 +147,15 @@ int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const f
  * embedding (model/vq_vae_patch_embedd.py:13-17) and the first fused layer, in one pass.  n a multiple of 4. */
 int vqb_token_bias_gelu(int device, float *h, const float *bias, void *out_bf16, int64_t n_tokens, int n, void *stream);
 
+/* Patch embedding fused with the first block's leading GELU (model/vq_vae_patch_embedd.py:7-17, the
+ * PatchEmbedding.forward the reference calls at :158 and dataloader/latentspace_dataloader.py:147,157):
+ * x (n_cycles, seq_len, channels) fp32 contiguous -> tokens in the reference's channel-major order (all patches of
+ * channel 0 first), h (n_cycles * T, hidden) fp32 = patches @ w^T + bias with T = channels * seq_len / patch,
+ * out = bf16(gelu(h)) (may be NULL).  w: (hidden, patch) fp32 row-major = Conv1d weight[:, 0, :].  fp32 FMA arithmetic.
+ * hidden == 512, patch <= 64, seq_len a multiple of patch; h 16-byte aligned. */
+int vqb_patch_embed(int device, const float *x, int64_t n_cycles, int seq_len, int channels, int patch, const float *w,
+                    const float *bias, float *h, void *out_bf16, int hidden, void *stream);
+
 /* out[i] = codebook[idx[i]] (n, d).  Out-of-range indices yield NaN rows and set
  * *bad_index (device int, may be NULL) to 1. */
 int vqb_gather(int device, const int64_t *idx, int64_t n, const float *codebook, int k, int d,

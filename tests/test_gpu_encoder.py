@@ -147,3 +147,25 @@ def test_fused_bf16_encoder_folds_eval_batchnorm():
         assert model._fused_ok(x)
         z_fused = model.encode(x)
     assert (z_fused - z_ref).abs().max().item() <= 0.05 * z_ref.abs().max().item()
+
+
+@pytest.mark.parametrize("B,L,C,P", [(37, 200, 2, 25), (64, 200, 2, 10), (5, 200, 2, 50), (3, 64, 3, 64)])
+def test_patch_embed_kernel(B, L, C, P):
+    """vqb_patch_embed against the reference's PatchEmbedding arithmetic (model/vq_vae_patch_embedd.py:13-17:
+    permute, reshape, stride-P conv == linear per patch): h within 1e-5 relative (fp32, different summation order),
+    the bf16 activation within the fused GELU's stated bound; ragged token tiles (B * T not a multiple of 32)."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(B * 1000 + P)
+    x = torch.randn(B, L, C, device=dev, generator=g)
+    conv = torch.nn.Conv1d(1, 512, kernel_size=P, stride=P)
+    with torch.no_grad():        # the reference's own ops on the CPU in fp32 (cuDNN would run the conv in TF32 by default)
+        ref = conv(x.cpu().permute(0, 2, 1).reshape(B, 1, -1)).permute(0, 2, 1).reshape(-1, 512).to(dev)   # (B*T, H)
+    conv = conv.to(dev)
+    h, a = ops.patch_embed(x, conv.weight, conv.bias, P)
+    assert h.shape == ref.shape and a.shape == ref.shape and a.dtype == torch.bfloat16
+    torch.testing.assert_close(h, ref, rtol=1e-5, atol=2e-6)
+    act = torch.nn.functional.gelu(h)
+    bound = 5e-5 + 3e-4 * h.abs() + 2.0 ** -8 * act.abs()
+    assert bool(((a.float() - act).abs() <= bound).all())
+    h2, a2 = ops.patch_embed(x, conv.weight, conv.bias, P, want_act=False)
+    assert a2 is None and torch.equal(h, h2)

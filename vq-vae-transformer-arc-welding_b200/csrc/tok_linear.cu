@@ -295,6 +295,127 @@ cudaError_t launch_tok_bias_gelu(float *h, const float *bias, void *out, int64_t
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// Patch embedding (model/vq_vae_patch_embedd.py:13-17): channel-major patchify + linear P -> H + bias, fused with the
+// first residual block's leading GELU / bf16 cast.  fp32 FMA arithmetic (K = P = 25 is 0.3 % of the encoder's FLOPs
+// and the raw signal in bf16 costs index matches, see encode_fused_bf16): the point is the memory traffic -- the
+// stock sequence (permute copy, SGEMM, bias, GELU, cast) moves ~9 KB per token, this kernel reads 4P bytes and
+// writes 4H + 2H.
+//   x   (n_cycles, L, C) fp32 contiguous; token t of cycle b is channel c = t / (L/P), patch p = t % (L/P):
+//       components x[b][p*P + k][c], k = 0..P-1
+//   w   (H, P) fp32 row-major (Conv1d weight[:, 0, :]), bias (H)
+//   h   (n_cycles * T, H) fp32, T = C * L / P;   a = bf16(gelu(h)) (same shape, may be NULL)
+// CTA: 256 threads, 32 tokens x H = 512 outputs per step, W^T and the bias resident in shared memory; thread
+// (tx = tid % 64, ty = tid / 64) owns tokens 8 ty .. 8 ty + 7 and columns 4 tx .. 4 tx + 3, 256 + 4 tx .. + 3.
+// ---------------------------------------------------------------------------------------
+namespace pe {
+constexpr int TOK = 32, H = 512, PMAX = 64;
+}
+
+__global__ void __launch_bounds__(256) patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                          const float *__restrict__ bias, float *__restrict__ h,
+                                                          __nv_bfloat16 *__restrict__ a, int64_t n_tokens, int L, int C, int P)
+{
+    using namespace pe;
+    extern __shared__ __align__(16) float pe_smem[];
+    float *wt = pe_smem;                       // [P][H]   W transposed
+    float *bs = wt + P * H;                    // [H]
+    float *xt = bs + H;                        // [P][TOK] the tile's patches, component-major
+    const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+    for (int i = tid; i < H * P; i += 256) {
+        const int col = i / P, k = i - col * P;
+        wt[k * H + col] = __ldg(w + i);
+    }
+    for (int i = tid; i < H; i += 256)
+        bs[i] = __ldg(bias + i);
+    const int ppc = L / P;                     // patches per channel
+    const int T = ppc * C;                     // tokens per cycle
+    const int64_t n_tiles = (n_tokens + TOK - 1) / TOK;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * TOK;
+        __syncthreads();                       // previous tile's xt is no longer read (also orders the W^T fill)
+        for (int i = tid; i < TOK * P; i += 256) {
+            const int tok = i / P, k = i - tok * P;
+            const int64_t t = t0 + tok;
+            float v = 0.0f;
+            if (t < n_tokens) {
+                const int64_t b = t / T;
+                const int ct = (int)(t - b * T), c = ct / ppc, pp = ct - c * ppc;
+                v = __ldg(x + (b * L + (int64_t)pp * P + k) * C + c);
+            }
+            xt[k * TOK + tok] = v;
+        }
+        __syncthreads();
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                acc[i][j] = 0.0f;
+        for (int k = 0; k < P; ++k) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(xt + k * TOK + 8 * ty);
+            const float4 x1 = *reinterpret_cast<const float4 *>(xt + k * TOK + 8 * ty + 4);
+            const float4 w0 = *reinterpret_cast<const float4 *>(wt + k * H + 4 * tx);
+            const float4 w1 = *reinterpret_cast<const float4 *>(wt + k * H + 256 + 4 * tx);
+            const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    acc[i][j] = fmaf(xs[i], ws[j], acc[i][j]);
+        }
+        const float4 b0 = *reinterpret_cast<const float4 *>(bs + 4 * tx);
+        const float4 b1 = *reinterpret_cast<const float4 *>(bs + 256 + 4 * tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t t = t0 + 8 * ty + i;
+            if (t >= n_tokens)
+                break;
+            const float4 o0 = make_float4(acc[i][0] + b0.x, acc[i][1] + b0.y, acc[i][2] + b0.z, acc[i][3] + b0.w);
+            const float4 o1 = make_float4(acc[i][4] + b1.x, acc[i][5] + b1.y, acc[i][6] + b1.z, acc[i][7] + b1.w);
+            __stcs(reinterpret_cast<float4 *>(h + t * H + 4 * tx), o0);
+            __stcs(reinterpret_cast<float4 *>(h + t * H + 256 + 4 * tx), o1);
+            if (a) {
+                const __nv_bfloat162 p0 = __floats2bfloat162_rn(tl::gelu_fast(o0.x), tl::gelu_fast(o0.y));
+                const __nv_bfloat162 p1 = __floats2bfloat162_rn(tl::gelu_fast(o0.z), tl::gelu_fast(o0.w));
+                const __nv_bfloat162 p2 = __floats2bfloat162_rn(tl::gelu_fast(o1.x), tl::gelu_fast(o1.y));
+                const __nv_bfloat162 p3 = __floats2bfloat162_rn(tl::gelu_fast(o1.z), tl::gelu_fast(o1.w));
+                *reinterpret_cast<uint2 *>(a + t * H + 4 * tx) =
+                    make_uint2(*reinterpret_cast<const uint32_t *>(&p0), *reinterpret_cast<const uint32_t *>(&p1));
+                *reinterpret_cast<uint2 *>(a + t * H + 256 + 4 * tx) =
+                    make_uint2(*reinterpret_cast<const uint32_t *>(&p2), *reinterpret_cast<const uint32_t *>(&p3));
+            }
+        }
+    }
+}
+
+bool patch_embed_supported(int L, int C, int P, int H)
+{
+    return H == pe::H && P >= 1 && P <= pe::PMAX && C >= 1 && L >= P && L % P == 0;
+}
+
+cudaError_t launch_patch_embed(const float *x, const float *w, const float *bias, float *h, void *a, int64_t n_cycles,
+                               int L, int C, int P, int H, int sm_count, int max_smem, cudaStream_t st)
+{
+    if (!patch_embed_supported(L, C, P, H))
+        return cudaErrorNotSupported;
+    const int64_t n_tokens = n_cycles * (L / P) * C;
+    if (n_tokens == 0)
+        return cudaSuccess;
+    const int smem = (int)sizeof(float) * (P * pe::H + pe::H + P * pe::TOK);
+    if (smem > max_smem)
+        return cudaErrorNotSupported;
+    cudaError_t err = cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess)
+        return err;
+    const int64_t tiles = (n_tokens + pe::TOK - 1) / pe::TOK;
+    const int per_sm = max_smem / (smem + 1024) < 3 ? (max_smem / (smem + 1024) < 1 ? 1 : max_smem / (smem + 1024)) : 3;
+    const int grid = (int)(tiles < (int64_t)sm_count * per_sm ? tiles : (int64_t)sm_count * per_sm);
+    patch_embed_kernel<<<grid, 256, smem, st>>>(x, w, bias, h, (__nv_bfloat16 *)a, n_tokens, L, C, P);
+    return cudaGetLastError();
+}
+
 namespace {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,

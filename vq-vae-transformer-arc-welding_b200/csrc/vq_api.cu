@@ -298,6 +298,33 @@ int vqb_token_bias_gelu(int device, float *h, const float *bias, void *out_bf16,
     return VQB_OK;
 }
 
+int vqb_patch_embed(int device, const float *x, int64_t n_cycles, int seq_len, int channels, int patch, const float *w,
+                    const float *bias, float *h, void *out_bf16, int hidden, void *stream)
+{
+    if (!x || !w || !bias || !h || n_cycles < 0 || seq_len <= 0 || channels <= 0 || patch <= 0 || hidden <= 0)
+        return VQB_E_ARG;
+    if (!patch_embed_supported(seq_len, channels, patch, hidden) || !aligned(h, 16) || (out_bf16 && !aligned(out_bf16, 8)))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_patch_embed(x, w, bias, h, out_bf16, n_cycles, seq_len, channels, patch, hidden, info.sm_count,
+                             info.max_smem_per_block, (cudaStream_t)stream);
+    if (err == cudaErrorNotSupported)
+        return VQB_E_UNSUPPORTED;
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_cycles > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
 int vqb_backward(int device, const float *g_zq, const float *g_loss,
                  const float *z, int64_t n_outer, int64_t n_inner, int d,
                  int64_t stride_outer, int64_t stride_inner, int64_t stride_d,

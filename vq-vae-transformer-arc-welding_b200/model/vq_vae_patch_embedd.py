@@ -227,11 +227,15 @@ class VQVAEPatch(Autoencoder):
         from .. import ops
         b = x.shape[0]
         pe = self.patch_embed
-        patches = x.permute(0, 2, 1).reshape(-1, pe.patch_size)                       # (B*T, P)
-        # (the patch embedding stays an fp32 PyTorch GEMM: K = 25 is 0.3 % of the FLOPs, and feeding the raw signal
-        # as bf16 through vqb_token_linear mode 2 was measured to cost index matches -- 99.86 % -> 99.59 %)
-        h = torch.matmul(patches, pe.proj.weight[:, 0, :].t())                        # (B*T, H) fp32, bias added below
-        a = ops.token_bias_gelu(h, pe.proj.bias)                                       # h += b; a = bf16(gelu(h)), one pass
+        # (the patch embedding stays fp32 arithmetic: K = 25 is 0.3 % of the FLOPs, and feeding the raw signal as bf16
+        # through vqb_token_linear mode 2 was measured to cost index matches -- 99.86 % -> 99.59 %)
+        if pe.proj.out_channels == 512 and pe.patch_size <= 64 and x.is_contiguous():
+            # one kernel: patchify + linear + bias -> h fp32, a = bf16(gelu(h))  (vqb_patch_embed)
+            h, a = ops.patch_embed(x, pe.proj.weight, pe.proj.bias, pe.patch_size)
+        else:
+            patches = x.permute(0, 2, 1).reshape(-1, pe.patch_size)                   # (B*T, P)
+            h = torch.matmul(patches, pe.proj.weight[:, 0, :].t())                    # (B*T, H) fp32, bias added below
+            a = ops.token_bias_gelu(h, pe.proj.bias)                                   # h += b; a = bf16(gelu(h)), one pass
         u = torch.empty_like(a)
         blocks = self._fused_weights()
         for i, (w1, b1, w2, b2) in enumerate(blocks):

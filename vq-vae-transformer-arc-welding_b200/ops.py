@@ -299,3 +299,30 @@ def token_bias_gelu(h: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Ten
                                      h.shape[0], h.shape[1], torch.cuda.current_stream(h.device).cuda_stream)
     _lib.check(rc, "vqb_token_bias_gelu")
     return out
+
+
+def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, patch: int, want_act: bool = True):
+    """PatchEmbedding.forward (model/vq_vae_patch_embedd.py:13-17) on token rows, fused with the first residual block's
+    leading GELU: x (B, L, C) fp32 contiguous -> (h (B*T, H) fp32, a = bf16(gelu(h)) or None) -- vqb_patch_embed.
+    weight: the Conv1d weight (H, 1, P) or its (H, P) slice; tokens come out channel-major like the reference's."""
+    _require_cuda_fp32(x, "x")
+    _require_cuda_fp32(weight, "patch_embed weight")
+    _require_cuda_fp32(bias, "patch_embed bias")
+    if x.dim() != 3 or not x.is_contiguous():
+        raise RuntimeError("patch_embed: x must be a contiguous (B, L, C) tensor")
+    b, l, c = x.shape
+    w = weight.detach().reshape(weight.shape[0], -1).contiguous()
+    hdim = w.shape[0]
+    if w.shape[1] != patch or l % patch:
+        raise RuntimeError("patch_embed: weight / patch size / sequence length mismatch")
+    n_tokens = b * (l // patch) * c
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        h = torch.empty((n_tokens, hdim), dtype=torch.float32, device=x.device)
+        a = torch.empty((n_tokens, hdim), dtype=torch.bfloat16, device=x.device) if want_act else None
+        rc = lib.vqb_patch_embed(x.device.index, x.data_ptr(), b, l, c, int(patch), w.data_ptr(),
+                                 bias.detach().contiguous().data_ptr(), h.data_ptr(),
+                                 a.data_ptr() if a is not None else None, hdim,
+                                 torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "vqb_patch_embed")
+    return h, a
