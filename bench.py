@@ -41,6 +41,7 @@ N_VECTORS = 1 << 24
 METRIC = "vq_encoded_patches_per_sec"
 UNIT = "patches/s"
 FALLBACK_HBM_GBS = 6650.0
+_emit = None      # set by main(): writes the JSON line to the real stdout
 
 
 def workload_config(n_gpus: int, n_rows: int) -> dict:
@@ -173,7 +174,7 @@ def run_reference(args) -> None:
         "note": "reference's op sequence (model/vector_quantizer.py:88-119) as torch CPU ops on all host threads; "
                 "the reference's own files are not present on the GPU box (oracle port, DESIGN.md)",
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------
@@ -370,7 +371,7 @@ def run_ours(args) -> None:
         "index_match": {"vs": "oracle (oracle/vq_oracle.c)", "rows": sample_rows, "rate": match},
         "check": {"loss": float(loss.item()), "perplexity": float(ppl.item()), "histogram_total": int(counts.sum().item())},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -391,6 +392,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    # stdout carries the ONE JSON line and nothing else: libraries that write to fd 1 (NCCL prints its version banner
+    # there) are pointed at stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(line: dict) -> None:
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:
