@@ -102,3 +102,24 @@ def test_bulk_loops_equal_per_cycle_reference_loop(patch_golden):
     assert zq.shape == (n_windows, seq_len, model.embedding_dim * model.enc_out_len) and zq.dtype == np.float64
     E = model.vector_quantization.embedding.weight.detach().cpu().numpy()
     np.testing.assert_allclose(zq.reshape(n_windows, seq_len, model.enc_out_len, -1), E[ids], rtol=0, atol=1e-6)
+
+
+def test_bulk_builder_dedupe_gives_identical_ids(patch_golden):
+    """Overlapping windows (stride of one cycle): with `dedupe = True` every distinct cycle is encoded once and the ids
+    array is identical to the plain loop's (SURVEY.md section 8(f) row 2)."""
+    case = C.PATCH_CASES[0]
+    model = _load(case, patch_golden).eval()
+    enc = LatentSpaceEncoder(model, window_size=200, device=DEV)
+    rs = np.random.RandomState(9)
+    seq_len, n_windows = 5, 24
+    stream = torch.from_numpy(rs.standard_normal((n_windows + seq_len - 1, 200, 2)).astype(np.float32))
+    data = torch.stack([stream[i:i + seq_len].reshape(seq_len * 200, 2) for i in range(n_windows)])
+    loader = [data[i:i + 8] for i in range(0, n_windows, 8)]
+    plain, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
+    calls = []
+    inner = enc.get_latent_space_IDs
+    enc.get_latent_space_IDs = lambda x, p=False: (calls.append(x.shape[0]), inner(x, p))[1]
+    enc.dedupe = True
+    fast, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
+    assert np.array_equal(plain, fast)
+    assert calls == [12, 12, 12]            # 8 windows x 5 cycles = 40 rows hold 12 distinct cycles per batch

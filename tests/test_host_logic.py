@@ -88,3 +88,44 @@ def test_lightning_hook_surface():
     with pytest.raises(NotImplementedError):
         vqb200.VQVAEPatch(hidden_dim=16, input_dim=2, num_embeddings=8, embedding_dim=4, n_resblocks=1,
                           learning_rate=1e-3, use_improved_vq=True)
+
+
+def test_dedupe_rows_and_encode_unique():
+    """Distinct cycles are found on bit patterns: windows with a stride of one cycle."""
+    import torch
+    from vqb200.dataloader import latentspace_dataloader as L
+    g = torch.Generator().manual_seed(5)
+    base = torch.randn(40, 200, 2, generator=g)
+    base[7] = base[3]                                   # a genuine duplicate among the distinct cycles
+    base[9, 0, 0] = 0.0
+    base[11] = base[9]
+    base[11, 0, 0] = -0.0                               # -0.0 != +0.0 bitwise: kept apart (never merged wrongly)
+    windows = torch.stack([base[i:i + 20] for i in range(20)])          # (20 windows, 20 cycles, 200, 2)
+    cycles = windows.reshape(-1, 200, 2)
+    rep, inv = L.dedupe_rows(cycles)
+    assert rep.numel() == 38                            # 39 cycles are touched, one pair is identical
+    assert torch.equal(cycles[rep[inv]].view(torch.int32), cycles.view(torch.int32))
+    calls = []
+    def encode(c):                                      # a per-cycle function with T = 3 "tokens"
+        calls.append(c.shape[0])
+        return torch.stack([c.sum(dim=(1, 2)), c[:, 0, 0], c[:, -1, 1]], dim=1)
+    out = L.encode_unique(encode, cycles)
+    assert calls == [38] and torch.equal(out, encode(cycles))
+    # no duplicates: one plain call
+    calls.clear()
+    L.encode_unique(encode, base[[0, 1, 2]])
+    assert calls == [3]
+    assert L.dedupe_rows(cycles[:0])[0].numel() == 0
+
+
+def test_dedupe_rows_survives_hash_collisions(monkeypatch):
+    """With useless hashes every row lands in one group; the word-for-word check must split it again."""
+    import torch
+    from vqb200.dataloader import latentspace_dataloader as L
+    monkeypatch.setattr(L, "_hash_weights", lambda width, device, seed: torch.zeros(width, dtype=torch.int64, device=device))
+    g = torch.Generator().manual_seed(6)
+    rows = torch.randn(10, 8, generator=g)
+    rows[4] = rows[0]
+    rep, inv = L.dedupe_rows(rows)
+    assert torch.equal(rows[rep[inv]], rows)
+    assert rep.numel() == 9                             # rows 0 and 4 share the first group, the other eight stand alone

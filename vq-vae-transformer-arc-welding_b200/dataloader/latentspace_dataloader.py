@@ -14,6 +14,8 @@ What changes underneath:
     (O(n^2) host copying, :238).  Here all cycles of a batch go through the encoder and the
     fused VQ kernel in ONE call (cycles are independent: every op before the decoder is
     per token), results land in preallocated arrays, and only ids cross PCIe for the id tasks;
+  * overlapping windows repeat cycles: with `dedupe = True` every distinct cycle of a batch is encoded once and its
+    ids are scattered to all its windows (encode_unique; identical arrays, up to 20x less encoder work);
   * multi-GPU: batches are sharded across ranks (one process per GPU), the codebook and
     encoder weights are replicated, the only collectives are an optional gather of the ids and
     one K-element all-reduce of the code-usage histogram (bulk_encode_ids / gather_sharded).
@@ -25,6 +27,55 @@ from typing import Callable, Iterable, Optional, Tuple
 import numpy as np
 import torch
 from torch import distributed as dist
+
+
+# ---------------------------------------------------------------------------------------
+# duplicate cycles
+# ---------------------------------------------------------------------------------------
+# The reference's windows overlap: with a stride of one cycle, a batch of 512 windows x 20 cycles holds ~531 distinct
+# cycles, and the loops above :171-263 encode every one of the 10 240.  Every op before the decoder is per cycle, so the
+# ids of a cycle do not depend on the window it is seen in: encode each distinct cycle once and scatter.  Distinct is
+# decided on the BIT PATTERN of the samples: two 64-bit multiplicative hashes group the rows, and every row is then
+# compared word for word with its group's representative, so a hash collision costs a second pass, never a wrong id.
+_HASH_SEEDS = (0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F)
+
+
+def _hash_weights(width: int, device, seed: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed & 0x7FFFFFFF)
+    w = torch.randint(-(1 << 62), 1 << 62, (width,), generator=g, dtype=torch.int64)
+    return (w | 1).to(device)                 # odd multipliers; int64 arithmetic wraps
+
+
+def dedupe_rows(rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """rows (n, ...) float32 -> (rep, inverse): rep (u,) int64 indices of one representative per group of bit-identical
+    rows (the first occurrence), inverse (n,) int64 with rows[i] bit-identical to rows[rep[inverse[i]]].  Rows that a
+    hash collision put into a foreign group come back as their own representatives."""
+    n = rows.shape[0]
+    if n == 0:
+        e = torch.empty(0, dtype=torch.int64, device=rows.device)
+        return e, e
+    bits = rows.reshape(n, -1).contiguous().view(torch.int32)
+    wide = bits.to(torch.int64)
+    keys = torch.stack([(wide * _hash_weights(bits.shape[1], rows.device, s)).sum(dim=1) for s in _HASH_SEEDS], dim=1)
+    _, inverse = torch.unique(keys, dim=0, return_inverse=True)
+    u = int(inverse.max().item()) + 1
+    ar = torch.arange(n, device=rows.device)
+    rep = torch.full((u,), n, dtype=torch.int64, device=rows.device).scatter_reduce_(0, inverse, ar, reduce="amin")
+    same = (bits == bits[rep[inverse]]).all(dim=1)            # word-for-word check against the representative
+    if not bool(same.all()):
+        stray = (~same).nonzero().view(-1)                    # collided rows: each becomes its own group
+        inverse = inverse.clone()
+        inverse[stray] = u + torch.arange(stray.numel(), device=rows.device)
+        rep = torch.cat([rep, stray])
+    return rep, inverse
+
+
+def encode_unique(encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: torch.Tensor) -> torch.Tensor:
+    """encode_fn(cycles) for a per-cycle encode_fn ((b, ...) -> (b, T)), evaluated once per distinct cycle."""
+    rep, inverse = dedupe_rows(cycles)
+    if rep.numel() == cycles.shape[0]:
+        return encode_fn(cycles)
+    return encode_fn(cycles[rep])[inverse]
 
 
 class LatentSpaceEncoder:
@@ -39,6 +90,10 @@ class LatentSpaceEncoder:
         self.latent_space_model = latent_space_model.to(self.device)
         self.window_size = window_size
         self.code_counts = None
+        #: encode every distinct cycle of a batch once (overlapping windows repeat cycles; see encode_unique).  The ids
+        #: are the same whenever the encoder is row-wise deterministic (eval mode; the fused encoder always is).  The
+        #: code-usage histogram then counts distinct cycles.
+        self.dedupe = False
 
     # ---- single encode calls (:144-161) -------------------------------------------------
     def _encode(self, x, has_patch_embed: bool):
@@ -95,7 +150,10 @@ class LatentSpaceEncoder:
                 x, y = (item, None) if no_labels else item
                 b = x.shape[0]
                 cyc = self._cycles(x, seq_len).to(self.device, non_blocking=True)
-                ids = self.get_latent_space_IDs(cyc, has_patch_embed)
+                if self.dedupe:
+                    ids = encode_unique(lambda c: self.get_latent_space_IDs(c, has_patch_embed).view(c.shape[0], -1), cyc)
+                else:
+                    ids = self.get_latent_space_IDs(cyc, has_patch_embed)
                 c = getattr(model.vector_quantization, "code_counts", None)
                 if c is not None:
                     counts = c.clone() if counts is None else counts + c
