@@ -20,7 +20,7 @@ e0.record(); ops.forward(z, w, 0.25, path="tc"); e1.record()
 torch.cuda.synchronize()
 print(f"traced call: {e0.elapsed_time(e1):.3f} ms for {n // 128} tiles on 148 CTAs = {e0.elapsed_time(e1) * 1e6 / (n / 128 / 148):.0f} ns per tile and CTA")
 lib.vqb_debug_set_tc_trace(None)
-t = buf.cpu().numpy().reshape(4, 256, 8).astype(np.int64)
+t = buf.cpu().numpy().reshape(4, -1, 8).astype(np.int64)
 names = ["tma", "cv_in", "cv_out", "mma", "ep_in", "flt_out", "out_done", "slot_free"]
 for cta in range(2):
     a = t[cta]
@@ -45,5 +45,7 @@ for cta in range(2):
     print(f"  accumulator hand-back (flt_out(i) -> mma(i+2)): p10 {np.percentile(h2,10):.0f} p50 {np.percentile(h2,50):.0f} p90 {np.percentile(h2,90):.0f}")
     cyc = a[22:200, 3] - a[20:198, 3]
     print(f"  TMEM buffer cycle (mma(i) -> mma(i+2)): p50 {np.percentile(cyc,50):.0f} = mma->ep_in {np.median(d[:,4]-d[:,3]):.0f} + filter(last warp) {np.median(d[:,5]-d[:,4]):.0f} + hand-back {np.percentile(h2,50):.0f}")
-    for lo, hi in ((10, 60), (60, 120), (120, 180), (180, 250)):
+    last = int((a[:, 7] > 0).sum()) - 1
+    print(f"  whole kernel, CTA {cta}: {last + 1} tiles, first TMA -> last slot free {a[last, 7] - a[0, 0]} clocks = {(a[last, 7] - a[0, 0]) / (last + 1):.0f} per tile")
+    for lo, hi in ((10, 60), (60, 120), (120, 180), (180, 250), (250, 450), (450, 650), (650, last)):
         print(f"  tiles {lo}-{hi}: mma period {np.median(np.diff(a[lo:hi, 3])):.0f}  slot_free period {np.median(np.diff(a[lo:hi, 7])):.0f}  mean {(a[hi, 7] - a[lo, 7]) / (hi - lo):.0f}")

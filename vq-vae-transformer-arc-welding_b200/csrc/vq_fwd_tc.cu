@@ -407,7 +407,7 @@ __device__ __forceinline__ void merge_running(unsigned long long *run, int64_t r
 // ---------------------------------------------------------------------------------------
 // TRACE: debug build of the same kernel that records clock64() of eight pipeline events per tile
 // (first kTraceTiles tiles of the first kTraceCtas CTAs) -- tools/tc_trace.py turns them into a timeline.
-constexpr int kTraceCtas = 4, kTraceTiles = 256, kTraceEvents = 8;
+constexpr int kTraceCtas = 4, kTraceTiles = 1024, kTraceEvents = 8;
 // WIDE: 32 < D <= 64 (two pipeline items per tile); a separate instantiation keeps the D <= 32 kernel's hot loops free
 // of the wide-vector code.
 template <bool TRACE, bool WIDE>
