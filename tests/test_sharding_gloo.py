@@ -42,6 +42,10 @@ def _worker(rank, world, port, n, out_dir):
         ids = bulk_encode_ids(_fake_encode, cycles, batch=5)
         local, (lo, hi) = bulk_encode_ids(_fake_encode, cycles, batch=5, gather=False)
         counts = reduce_counts(torch.bincount(local.reshape(-1), minlength=16))
+        again = torch.bincount(local.reshape(-1), minlength=16)
+        work = reduce_counts(again, async_op=True)          # same sum through the asynchronous form
+        work.wait()
+        assert torch.equal(again, counts)
         assert vqb200.get_world_size() == world
         t = torch.ones(3)
         assert vqb200.all_reduce(t) is t and torch.equal(t, torch.full((3,), float(world)))
@@ -74,3 +78,4 @@ def test_single_process_paths():
     assert gather_sharded(ids, 10) is ids
     c = torch.ones(4, dtype=torch.int64)
     assert reduce_counts(c) is c
+    assert reduce_counts(c, async_op=True) is None

@@ -209,11 +209,15 @@ def gather_sharded(local: torch.Tensor, n_total: int) -> torch.Tensor:
     return torch.cat(out, dim=0)
 
 
-def reduce_counts(counts: torch.Tensor) -> torch.Tensor:
-    """Sum of the per-rank code-usage histograms (the one collective bulk encoding needs)."""
+def reduce_counts(counts: torch.Tensor, async_op: bool = False):
+    """Sum of the per-rank code-usage histograms (the one collective bulk encoding needs), in place.  async_op=True
+    returns the work handle instead (None on a single rank): the 2 KB all-reduce then overlaps whatever the caller
+    launches next, and `handle.wait()` orders the current stream behind it."""
     if _dist_ready():
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    return counts
+        work = dist.all_reduce(counts, op=dist.ReduceOp.SUM, async_op=async_op)
+        if async_op:
+            return work
+    return None if async_op else counts
 
 
 def bulk_encode_ids(encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: torch.Tensor, batch: int = 65536,
