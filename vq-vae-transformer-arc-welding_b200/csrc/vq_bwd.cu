@@ -398,32 +398,11 @@ vq_bwd32_tma_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_cons
 
 namespace {
 
-typedef CUresult (*BwEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 // (N, 32) fp32 row-major tensor under 128-row boxes, no swizzle: eight threads per row read / write 16-byte chunks
 bool bw_make_map(CUtensorMap *map, const float *base, int64_t n_rows)
 {
-    static BwEncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<BwEncodeTiledFn>(ptr);
-    }
-    if (!fn)
-        return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)bw::D, (cuuint64_t)n_rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)bw::D * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)bw::D, (cuuint32_t)bw::ROWS};
-    const cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return tc::make_tensor_map_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, n_rows, bw::D, bw::ROWS, bw::D,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
 }  // namespace

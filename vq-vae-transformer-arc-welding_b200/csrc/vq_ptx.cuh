@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda.h>
+#include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
 
@@ -184,6 +185,44 @@ __device__ __forceinline__ void tmem_wait_ld_fence(uint32_t (&v)[32])
                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                  :
                  : "memory");
+}
+
+
+// ---- host side: 2-D tiled tensor maps (the driver entry point is fetched once through the runtime, no -lcuda) ----
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                           const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline TensorMapEncodeTiledFn tensor_map_encoder()
+{
+    static TensorMapEncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TensorMapEncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// (rows, cols) row-major tensor of `elem_bytes`-wide elements under boxes of box_rows x box_cols; out-of-range parts of a
+// box are zero-filled on load and clipped on store
+inline bool make_tensor_map_2d(CUtensorMap *map, CUtensorMapDataType dtype, int elem_bytes, const void *base, int64_t rows,
+                               int64_t cols, int box_rows, int box_cols, CUtensorMapSwizzle swizzle,
+                               CUtensorMapL2promotion l2)
+{
+    TensorMapEncodeTiledFn enc = tensor_map_encoder();
+    if (!enc)
+        return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * (cuuint64_t)elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, dtype, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, l2,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace tc
