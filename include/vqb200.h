@@ -156,6 +156,14 @@ int vqb_token_bias_gelu(int device, float *h, const float *bias, void *out_bf16,
 int vqb_patch_embed(int device, const float *x, int64_t n_cycles, int seq_len, int channels, int patch, const float *w,
                     const float *bias, float *h, void *out_bf16, int hidden, void *stream);
 
+/* Packing copy for the reference encoder's output layout (model/vq_vae_patch_embedd.py:91 returns z_e as a permuted
+ * view, logical (B, T, D) over physical (B, D, T); model/vector_quantizer.py:88 reshapes it into rows): vector (b, t),
+ * component j at z[b * stride_outer + t * stride_inner + j * stride_d] -> out (n_outer * n_inner, d) contiguous.
+ * Supported: stride_inner == 1, stride_d == n_inner (<= 64), d <= 128; anything else returns VQB_E_UNSUPPORTED and the
+ * caller makes the copy itself. */
+int vqb_pack_rows(int device, const float *z, int64_t n_outer, int64_t n_inner, int d, int64_t stride_outer,
+                  int64_t stride_inner, int64_t stride_d, float *out, void *stream);
+
 /* out[i] = codebook[idx[i]] (n, d).  Out-of-range indices yield NaN rows and set
  * *bad_index (device int, may be NULL) to 1. */
 int vqb_gather(int device, const int64_t *idx, int64_t n, const float *codebook, int k, int d,

@@ -530,3 +530,19 @@ def test_backward_tma_ring_ignores_out_of_range_ids():
     for r in (5, 77, 999):
         assert torch.equal(gz[r], g[r])
     torch.testing.assert_close(gE, gE2, rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("B,T,D", [(1000, 16, 32), (37, 16, 32), (5, 8, 64), (300, 3, 8), (64, 64, 128)])
+def test_pack_rows_kernel(B, T, D):
+    """vqb_pack_rows: the reference encoder's permuted view (logical (B, T, D) over physical (B, D, T)) -> contiguous rows,
+    bit-equal to torch's strided copy; other layouts fall back to that copy."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(B + T + D)
+    phys = torch.randn(B, D, T, device=dev, generator=g)
+    view = phys.permute(0, 2, 1)
+    packed = ops.pack_rows(view, D)
+    assert packed.is_contiguous() and torch.equal(packed, view.contiguous())
+    wide = torch.randn(B, D + 3, T, device=dev, generator=g)[:, :D, :].permute(0, 2, 1)   # gap between the blocks
+    assert torch.equal(ops.pack_rows(wide, D), wide.contiguous())
+    other = torch.randn(B, T, 2 * D, device=dev, generator=g)[:, :, :D]                   # not the encoder's layout
+    assert torch.equal(ops.pack_rows(other, D), other.contiguous())

@@ -35,3 +35,11 @@ ms = timeit(lambda: ops.backward(g, gl, zc, idx, w, 0.25, need_e=False))
 print(f"bwd grad_z only     : {ms:.3f} ms -> {n * (12 * D + 8) / ms / 1e6:.0f} GB/s algorithmic (phase 1 alone)")
 ms = timeit(lambda: ops.backward(g, gl, zc, idx, w, 0.25, need_z=False))
 print(f"bwd grad_E only     : {ms:.3f} ms (reads z, idx; no g_zq read? no grad_z write)")
+# through autograd (VQStraightThrough): forward + backward on the reference encoder's permuted layout vs contiguous rows
+def fb(zin):
+    zr = zin.detach().requires_grad_(True)
+    wr = w.detach().requires_grad_(True)
+    loss, zq, ppl, _i, _c = ops.VQStraightThrough.apply(zr, wr, 0.25, "auto")
+    torch.autograd.backward([loss, zq], [gl, g.view_as(zq)])
+print(f"autograd fwd+bwd contiguous : {timeit(lambda: fb(zc)):.3f} ms")
+print(f"autograd fwd+bwd permuted z : {timeit(lambda: fb(zperm)):.3f} ms (one packing copy shared by forward and backward)")

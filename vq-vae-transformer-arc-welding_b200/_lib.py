@@ -38,6 +38,7 @@ SIGNATURES = {
                           _vp, _vp, _vp, _sz, _vp]),
     "vqb_token_linear": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _u, _vp]),
     "vqb_token_bias_gelu": (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp]),
+    "vqb_pack_rows": (_i, [_i, _vp, _i64, _i64, _i, _i64, _i64, _i64, _vp, _vp]),
     "vqb_patch_embed": (_i, [_i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "vqb_gather": (_i, [_i, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     "vqb_one_hot": (_i, [_i, _vp, _i64, _i, _vp, _vp]),
@@ -52,6 +53,8 @@ SIGNATURES = {
     "vqb_host_set_codebook": (_i, [_vp, _vp]),
     "vqb_encode_host": (_i, [_vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp, _u, ctypes.POINTER(_i)]),
 }
+
+E_UNSUPPORTED = -3      # VQB_E_UNSUPPORTED (include/vqb200.h)
 
 
 def load():

@@ -325,6 +325,33 @@ int vqb_patch_embed(int device, const float *x, int64_t n_cycles, int seq_len, i
     return VQB_OK;
 }
 
+int vqb_pack_rows(int device, const float *z, int64_t n_outer, int64_t n_inner, int d, int64_t stride_outer,
+                  int64_t stride_inner, int64_t stride_d, float *out, void *stream)
+{
+    if (!z || !out || n_outer < 0 || n_inner <= 0 || d <= 0)
+        return VQB_E_ARG;
+    if (!pack_rows_supported(n_inner, d, stride_outer, stride_inner, stride_d))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_pack_rows(z, out, n_outer, n_inner, d, stride_outer, stride_inner, stride_d, info.sm_count,
+                           (cudaStream_t)stream);
+    if (err == cudaErrorNotSupported)
+        return VQB_E_UNSUPPORTED;
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_outer > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
 int vqb_backward(int device, const float *g_zq, const float *g_loss,
                  const float *z, int64_t n_outer, int64_t n_inner, int d,
                  int64_t stride_outer, int64_t stride_inner, int64_t stride_d,

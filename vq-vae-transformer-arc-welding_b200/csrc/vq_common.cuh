@@ -137,6 +137,9 @@ cudaError_t launch_tok_bias_gelu(float *h, const float *bias, void *out, int64_t
 bool patch_embed_supported(int L, int C, int P, int H);
 cudaError_t launch_patch_embed(const float *x, const float *w, const float *bias, float *h, void *a, int64_t n_cycles,
                                int L, int C, int P, int H, int sm_count, int max_smem, cudaStream_t st);
+bool pack_rows_supported(int64_t n_inner, int d, int64_t s_outer, int64_t s_inner, int64_t s_d);
+cudaError_t launch_pack_rows(const float *src, float *dst, int64_t n_outer, int64_t n_inner, int d, int64_t s_outer,
+                             int64_t s_inner, int64_t s_d, int sm_count, cudaStream_t st);
 void count_launches(int n);
 void set_tc_trace(unsigned long long *buf);
 size_t tc_trace_words();
