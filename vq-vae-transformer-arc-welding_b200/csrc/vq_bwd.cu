@@ -233,6 +233,8 @@ __device__ long long bw_trace_buf[6 * 64];
 #define BW_STAMP(ev, it) do {} while (0)
 #endif
 namespace bw {
+// Experiment knobs (tools/ab_build.py name:-DBW_STAGES=3 ...; tools/ab_bwd.py): ring depth, and two ablations whose results
+// are wrong by construction -- BW_SKIP_ACC (phase 2 arrives without accumulating), BW_SKIP_STORE (no grad_z stores).
 #ifndef BW_STAGES
 #define BW_STAGES 4
 #endif
