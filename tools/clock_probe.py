@@ -1,5 +1,5 @@
 """GPU box: SM clock / power while a kernel runs back to back for a few seconds
-(python tools/clock_probe.py [tc] [fma] [bwd] [bwdz] [copy])."""
+(python tools/clock_probe.py [tc] [fma] [bwd] [bwdz] [copy] [tl0] [tl1]; tl0 / tl1 = the fused encoder layer, modes 0 / 1)."""
 import os, sys, time, threading
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, pynvml, vqb200
@@ -16,7 +16,12 @@ def sampler():
         time.sleep(0.05)
 idx = ops.forward(z, w, 0.25)[3]
 g = torch.randn(n, 32, device=dev); gl = torch.tensor(1.7, device=dev); dst = torch.empty_like(z)
+T = 1 << 20
+a_t = torch.randn(T, 512, device=dev).to(torch.bfloat16); w_t = (torch.randn(512, 512, device=dev) * 0.06).to(torch.bfloat16)
+b_t = torch.zeros(512, device=dev); h_t = torch.randn(T, 512, device=dev); o_t = torch.empty(T, 512, dtype=torch.bfloat16, device=dev)
 def work(path):
+    if path == "tl0": return ops.token_linear(a_t, w_t, b_t, out=o_t, mode=0)
+    if path == "tl1": return ops.token_linear(a_t, w_t, b_t, h=h_t, out=o_t, mode=1)
     if path == "bwd": return ops.backward(g, gl, z, idx, w, 0.25)
     if path == "bwdz": return ops.backward(g, gl, z, idx, w, 0.25, need_e=False)
     if path == "copy": return dst.copy_(z)
