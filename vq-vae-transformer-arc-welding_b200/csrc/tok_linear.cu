@@ -312,15 +312,20 @@ namespace pe {
 constexpr int TOK = 32, H = 512, PMAX = 64;
 }
 
+// PT: patch size fixed at compile time (the repo's 25: the k loop unrolls and the operand loads of the next steps are
+// issued ahead of the FMAs), 0 = run-time P.  The next tile's samples are fetched into registers before the FMA loop and
+// parked in the other half of a double-buffered tile afterwards: one __syncthreads per tile, global latency hidden.
+template <int PT>
 __global__ void __launch_bounds__(256) patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                           const float *__restrict__ bias, float *__restrict__ h,
-                                                          __nv_bfloat16 *__restrict__ a, int64_t n_tokens, int L, int C, int P)
+                                                          __nv_bfloat16 *__restrict__ a, int64_t n_tokens, int L, int C, int p_rt)
 {
     using namespace pe;
+    const int P = PT ? PT : p_rt;
     extern __shared__ __align__(16) float pe_smem[];
     float *wt = pe_smem;                       // [P][H]   W transposed
     float *bs = wt + P * H;                    // [H]
-    float *xt = bs + H;                        // [P][TOK] the tile's patches, component-major
+    float *xt = bs + H;                        // 2 x [P][TOK] the tile's patches, component-major (double-buffered)
     const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
     for (int i = tid; i < H * P; i += 256) {
         const int col = i / P, k = i - col * P;
@@ -331,40 +336,72 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float *__restric
     const int ppc = L / P;                     // patches per channel
     const int T = ppc * C;                     // tokens per cycle
     const int64_t n_tiles = (n_tokens + TOK - 1) / TOK;
+    constexpr int XPT = (TOK * PMAX + 255) / 256;            // samples a thread fetches per tile, at most
+    float xr[XPT];
+    auto fetch = [&](int64_t tile) {           // this thread's samples of `tile` (zeros beyond the tensor)
+        const int64_t t0 = tile * TOK;
+#pragma unroll
+        for (int q = 0; q < XPT; ++q) {
+            const int i = tid + 256 * q;
+            float v = 0.0f;
+            if (i < TOK * P) {
+                const int tok = i / P, k = i - tok * P;
+                const int64_t t = t0 + tok;
+                if (t < n_tokens) {
+                    const int64_t b = t / T;
+                    const int ct = (int)(t - b * T), c = ct / ppc, pp = ct - c * ppc;
+                    v = __ldg(x + (b * L + (int64_t)pp * P + k) * C + c);
+                }
+            }
+            xr[q] = v;
+        }
+    };
+    auto park = [&](float *dst) {
+#pragma unroll
+        for (int q = 0; q < XPT; ++q) {
+            const int i = tid + 256 * q;
+            if (i < TOK * P) {
+                const int tok = i / P, k = i - tok * P;
+                dst[k * TOK + tok] = xr[q];
+            }
+        }
+    };
+    int buf = 0;
+    if ((int64_t)blockIdx.x < n_tiles) {
+        fetch(blockIdx.x);
+        park(xt);
+    }
+    __syncthreads();
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t t0 = tile * TOK;
-        __syncthreads();                       // previous tile's xt is no longer read (also orders the W^T fill)
-        for (int i = tid; i < TOK * P; i += 256) {
-            const int tok = i / P, k = i - tok * P;
-            const int64_t t = t0 + tok;
-            float v = 0.0f;
-            if (t < n_tokens) {
-                const int64_t b = t / T;
-                const int ct = (int)(t - b * T), c = ct / ppc, pp = ct - c * ppc;
-                v = __ldg(x + (b * L + (int64_t)pp * P + k) * C + c);
-            }
-            xt[k * TOK + tok] = v;
-        }
-        __syncthreads();
+        const float *xc = xt + buf * (PMAX * TOK);
+        const bool more = tile + gridDim.x < n_tiles;
+        if (more)
+            fetch(tile + gridDim.x);           // in flight during the FMA loop
         float acc[8][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 acc[i][j] = 0.0f;
-        for (int k = 0; k < P; ++k) {
-            const float4 x0 = *reinterpret_cast<const float4 *>(xt + k * TOK + 8 * ty);
-            const float4 x1 = *reinterpret_cast<const float4 *>(xt + k * TOK + 8 * ty + 4);
-            const float4 w0 = *reinterpret_cast<const float4 *>(wt + k * H + 4 * tx);
-            const float4 w1 = *reinterpret_cast<const float4 *>(wt + k * H + 256 + 4 * tx);
-            const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-            const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+        for (int k = 0; k < (PT ? PT : 1); ++k) {
+            for (int kk = PT ? k : 0; kk < (PT ? k + 1 : P); ++kk) {
+                const float4 x0 = *reinterpret_cast<const float4 *>(xc + kk * TOK + 8 * ty);
+                const float4 x1 = *reinterpret_cast<const float4 *>(xc + kk * TOK + 8 * ty + 4);
+                const float4 w0 = *reinterpret_cast<const float4 *>(wt + kk * H + 4 * tx);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wt + kk * H + 256 + 4 * tx);
+                const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    acc[i][j] = fmaf(xs[i], ws[j], acc[i][j]);
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        acc[i][j] = fmaf(xs[i], ws[j], acc[i][j]);
+            }
         }
+        if (more)
+            park(xt + (buf ^ 1) * (PMAX * TOK));
         const float4 b0 = *reinterpret_cast<const float4 *>(bs + 4 * tx);
         const float4 b1 = *reinterpret_cast<const float4 *>(bs + 256 + 4 * tx);
 #pragma unroll
@@ -387,6 +424,8 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float *__restric
                     make_uint2(*reinterpret_cast<const uint32_t *>(&p2), *reinterpret_cast<const uint32_t *>(&p3));
             }
         }
+        __syncthreads();                       // the other half is complete, this one may be overwritten next time round
+        buf ^= 1;
     }
 }
 
@@ -403,16 +442,17 @@ cudaError_t launch_patch_embed(const float *x, const float *w, const float *bias
     const int64_t n_tokens = n_cycles * (L / P) * C;
     if (n_tokens == 0)
         return cudaSuccess;
-    const int smem = (int)sizeof(float) * (P * pe::H + pe::H + P * pe::TOK);
+    const int smem = (int)sizeof(float) * (P * pe::H + pe::H + 2 * pe::PMAX * pe::TOK);
     if (smem > max_smem)
         return cudaErrorNotSupported;
-    cudaError_t err = cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    auto kern = P == 25 ? patch_embed_kernel<25> : patch_embed_kernel<0>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess)
         return err;
     const int64_t tiles = (n_tokens + pe::TOK - 1) / pe::TOK;
     const int per_sm = max_smem / (smem + 1024) < 3 ? (max_smem / (smem + 1024) < 1 ? 1 : max_smem / (smem + 1024)) : 3;
     const int grid = (int)(tiles < (int64_t)sm_count * per_sm ? tiles : (int64_t)sm_count * per_sm);
-    patch_embed_kernel<<<grid, 256, smem, st>>>(x, w, bias, h, (__nv_bfloat16 *)a, n_tokens, L, C, P);
+    kern<<<grid, 256, smem, st>>>(x, w, bias, h, (__nv_bfloat16 *)a, n_tokens, L, C, P);
     return cudaGetLastError();
 }
 
