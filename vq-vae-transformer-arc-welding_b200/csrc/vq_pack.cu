@@ -11,6 +11,8 @@ namespace vqb {
 
 // src: element (b, t, j) at src[b * s_outer + j * T + t]  (block of D x T floats per b, T contiguous)
 // dst: (B * T, D) contiguous rows
+// VEC: 16-byte global accesses (T and D multiples of 4, 16-byte aligned blocks), else 4-byte ones
+template <bool VEC>
 __global__ void __launch_bounds__(256) vq_pack_rows_kernel(const float *__restrict__ src, float *__restrict__ dst,
                                                            int64_t n_outer, int T, int D, int64_t s_outer)
 {
@@ -20,15 +22,30 @@ __global__ void __launch_bounds__(256) vq_pack_rows_kernel(const float *__restri
     float *t = tile + warp * D * pitch;
     for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < n_outer; b += (int64_t)gridDim.x * 8) {
         const float *s = src + b * s_outer;
-        for (int i = lane; i < block; i += 32) {    // i = j * T + tt, consecutive in memory
-            const int j = i / T, tt = i - j * T;
-            t[j * pitch + tt] = __ldg(s + i);
-        }
-        __syncwarp();
         float *o = dst + b * block;
-        for (int i = lane; i < block; i += 32) {    // i = tt * D + j, consecutive in memory
-            const int tt = i / D, j = i - tt * D;
-            __stcs(o + i, t[j * pitch + tt]);
+        if (VEC) {
+            for (int i = 4 * lane; i < block; i += 128) {    // i = j * T + tt, four consecutive tt of one j
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(s + i));
+                const int j = i / T, tt = i - j * T;
+                float *p = t + j * pitch + tt;
+                p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+            }
+            __syncwarp();
+            for (int i = 4 * lane; i < block; i += 128) {    // i = tt * D + j, four consecutive j of one tt
+                const int tt = i / D, j = i - tt * D;
+                const float *p = t + j * pitch + tt;
+                __stcs(reinterpret_cast<float4 *>(o + i), make_float4(p[0], p[pitch], p[2 * pitch], p[3 * pitch]));
+            }
+        } else {
+            for (int i = lane; i < block; i += 32) {         // i = j * T + tt, consecutive in memory
+                const int j = i / T, tt = i - j * T;
+                t[j * pitch + tt] = __ldg(s + i);
+            }
+            __syncwarp();
+            for (int i = lane; i < block; i += 32) {         // i = tt * D + j, consecutive in memory
+                const int tt = i / D, j = i - tt * D;
+                __stcs(o + i, t[j * pitch + tt]);
+            }
         }
         __syncwarp();
     }
@@ -48,12 +65,15 @@ cudaError_t launch_pack_rows(const float *src, float *dst, int64_t n_outer, int6
     if (n_outer == 0)
         return cudaSuccess;
     const int smem = (int)(sizeof(float) * d * (n_inner + 1) * 8);
-    cudaError_t err = cudaFuncSetAttribute(vq_pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const bool vec = n_inner % 4 == 0 && d % 4 == 0 && s_outer % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    auto kern = vec ? vq_pack_rows_kernel<true> : vq_pack_rows_kernel<false>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess)
         return err;
     const int64_t blocks = (n_outer + 7) / 8;
     const int grid = (int)(blocks < (int64_t)sm_count * 8 ? blocks : (int64_t)sm_count * 8);
-    vq_pack_rows_kernel<<<grid, 256, smem, st>>>(src, dst, n_outer, (int)n_inner, d, s_outer);
+    kern<<<grid, 256, smem, st>>>(src, dst, n_outer, (int)n_inner, d, s_outer);
     return cudaGetLastError();
 }
 
