@@ -79,7 +79,10 @@ constexpr int WL_CTAS = 192;                              // >= number of CTAs (
 constexpr int WL_CAP = 2048;                              // vectors a CTA can queue for the fix-up kernel
 constexpr int IMG_WL = IMG_WLCOUNT + WL_CTAS * 4;         // uint2 [WL_CTAS][WL_CAP]: row, A-mask | B-mask << 16
 constexpr int IMG_BYTES = IMG_WL + WL_CTAS * WL_CAP * 8;
-constexpr int FIX_SPLIT = 4;                              // fix-up CTAs per queue
+#ifndef VQB_FIX_SPLIT
+#define VQB_FIX_SPLIT 8
+#endif
+constexpr int FIX_SPLIT = VQB_FIX_SPLIT;                  // fix-up CTAs per queue (8 x 148 CTAs of 256 threads = one resident wave)
 
 struct Consts {
     unsigned emax2_bits;   // max_k ee_k (finite ones), as float bits
