@@ -17,8 +17,8 @@
 // (same operand precision as the reference under its own torch.set_float32_matmul_precision('medium'));
 // the quantiser behind it stays exact.
 //
-// Tile 128 tokens x 256 outputs, K streamed in 64-element chunks through a 4-stage TMA ring (A 16 KB + W 32 KB per
-// stage, SWIZZLE_128B), 4 tcgen05.mma (128 x 256 x 16) per chunk into one of two 256-column TMEM accumulators,
+// Tile 128 tokens x 256 outputs, K streamed in 64-element chunks through a 3-stage TMA ring (A 16 KB + W 32 KB per
+// stage, SWIZZLE_128B; tl::Plan), 4 tcgen05.mma (128 x 256 x 16) per chunk into one of two 256-column TMEM accumulators,
 // eight epilogue warps (TMEM lane quarter x column half) that overlap with the next tile's MMAs.
 #include "vq_common.cuh"
 #include "vq_ptx.cuh"
@@ -28,14 +28,20 @@ namespace vqb {
 namespace tl {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 3;                               // (the fourth stage made room for the residual prefetch buffers)
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
 constexpr int THREADS = 128 + 256;                       // 4 service warps + 8 epilogue warps
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
-constexpr int OFF_XPOSE = OFF_B + STAGES * B_BYTES;      // 8 x 2 x 4096: per epilogue warp, two 32 x 128-byte transposing buffers
-constexpr int OFF_BARS = OFF_XPOSE + 8 * 8192;
-constexpr int SMEM_BYTES = OFF_BARS + 256;
+// Shared-memory plan per mode: three operand stages; modes 1 / 2 give every epilogue warp two 4 KB transposing buffers
+// (residual slab prefetch), mode 0 needs one.  (A fourth stage for mode 0 fits in 227 KB and was measured: 0.63 ms against
+// 0.58-0.61 ms -- with all of the SM's memory carved out as shared memory there is no L1 left for the bias / descriptor loads.)
+template <int MODE> struct Plan {
+    static constexpr int STAGES = 3;
+    static constexpr int XPOSE_PER_WARP = MODE == 0 ? 4096 : 8192;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
+    static constexpr int OFF_XPOSE = OFF_B + STAGES * B_BYTES;
+    static constexpr int OFF_BARS = OFF_XPOSE + 8 * XPOSE_PER_WARP;
+    static constexpr int SMEM_BYTES = OFF_BARS + 256;
+};
 
 // GELU(x) = x Phi(x) as 0.5 x (1 + tanh(x (c1 + c3 x^2 + c5 x^4))): the odd polynomial is a minimax fit of
 // atanh(erf(x / sqrt 2)) (max |error| of the formula 2.5e-5, against 4.7e-4 for the textbook two-term "tanh GELU");
@@ -64,6 +70,8 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 {
     using namespace tc;
     using namespace tl;
+    constexpr int STAGES = Plan<MODE>::STAGES, OFF_A = Plan<MODE>::OFF_A, OFF_B = Plan<MODE>::OFF_B,
+                  OFF_XPOSE = Plan<MODE>::OFF_XPOSE, OFF_BARS = Plan<MODE>::OFF_BARS;
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     if ((sbase & 1023u) != 0)
@@ -144,7 +152,7 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ================= epilogue: TMEM -> bias (+ residual) -> GELU -> bf16 =================
         const int q = warp & 3;                           // TMEM lane quarter
         const int ch = (warp - 4) >> 2;                   // column half of the 256-column accumulator
-        unsigned char *xp0 = smem + OFF_XPOSE + (warp - 4) * 8192;
+        unsigned char *xp0 = smem + OFF_XPOSE + (warp - 4) * Plan<MODE>::XPOSE_PER_WARP;
         // cp.async of the residual slab `sl` of the current item into buffer `buf` (lane -> row 4i + lane/8, chunk lane%8;
         // rows beyond the tensor are zero-filled): in flight while the tile's MMAs / the previous slab are worked on
         auto prefetch_h = [&](int64_t row0, int col0, int buf) {
@@ -473,7 +481,8 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
                               int K, int N, int mode, int sm_count, int max_smem, cudaStream_t st)
 {
     using namespace tl;
-    if (!tok_linear_supported(K, N) || SMEM_BYTES > max_smem || (mode != 0 && !h) || (mode == 0 && !out))
+    const int smem_bytes = mode == 0 ? Plan<0>::SMEM_BYTES : Plan<1>::SMEM_BYTES;
+    if (!tok_linear_supported(K, N) || smem_bytes > max_smem || (mode != 0 && !h) || (mode == 0 && !out))
         return cudaErrorNotSupported;
     if (n_tokens == 0)
         return cudaSuccess;
@@ -483,10 +492,10 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
     const int64_t items = (n_tokens + BM - 1) / BM * (N / BN);
     const int grid = (int)(items < sm_count ? items : sm_count);
     auto kern = mode == 0 ? tok_linear_kernel<0> : mode == 1 ? tok_linear_kernel<1> : tok_linear_kernel<2>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (err != cudaSuccess)
         return err;
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, K, N);
+    kern<<<grid, THREADS, smem_bytes, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, K, N);
     return cudaGetLastError();
 }
 
