@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(256) vq_bwd32_kernel(const float *__restrict__
 //   * two / four vectors per phase-2 step with equal codes chained in registers (1.39 / 1.59 ms: more instructions);
 //   * phase 1 handing every vector to its owner's list with shared-memory atomics instead of phase 2 scanning the
 //     tile's codes (2.8 ms); a bounds-check-free phase 1 for full tiles (phase 1 2800 -> 2100 clocks, kernel 1.34 ms:
-//     the faster phase 1 only takes issue slots from phase 2).
+//     the faster phase 1 only takes issue slots from phase 2);
+//   * codes and owners as bytes (two loads per tile instead of four + compares) with 16 / 20 / 23 phase-2 warps:
+//     1.50 / 1.77 / 1.84 ms -- the byte stores of phase 1 serialise and more warps only add contention.
 // ---------------------------------------------------------------------------------------
 #ifdef BW_TRACE   // debug build (tools/ab_build.py trace:-DBW_TRACE=1): clock64 stamps of CTA 0, tiles 40..103
 __device__ long long bw_trace_buf[6 * 64];
