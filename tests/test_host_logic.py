@@ -148,3 +148,21 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "vq_encoded_patches_per_sec" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_encoder_side_ops_refuse_cpu_tensors():
+    """The patch-embedding and encoder-layer entry points have no CPU path either."""
+    import torch
+    from vqb200 import ops
+    x = torch.randn(2, 200, 2)
+    w = torch.randn(512, 1, 25)
+    b = torch.randn(512)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.patch_embed(x, w, b, 25)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.token_bias_gelu(torch.randn(4, 512), b)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.token_linear(torch.randn(256, 512).to(torch.bfloat16), torch.randn(512, 512).to(torch.bfloat16), b)
+    # a layout-only helper: on CPU tensors it is torch's own copy, the quantiser behind it still refuses them
+    v = torch.randn(3, 32, 16).permute(0, 2, 1)
+    assert torch.equal(ops.pack_rows(v, 32), v.contiguous())
