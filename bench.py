@@ -117,8 +117,10 @@ class ClockSampler:
             self._thread.join()
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
-                "power_w": statistics.median(self.power) if self.power else None,
-                "power_w_max": max(self.power) if self.power else None}
+                # NVML's board power is a ~1 s moving average: over a 22 ms device loop plus the PCIe-bound e2e leg it
+                # stays far below what the kernels draw back to back (tools/clock_probe.py: 990 W, sw_power_cap)
+                "power_w_nvml_avg": statistics.median(self.power) if self.power else None,
+                "power_w_nvml_avg_max": max(self.power) if self.power else None}
 
 
 # ---------------------------------------------------------------------------------------
