@@ -62,6 +62,18 @@ extern "C" {
 #define VQB_PATH_FMA 1u    /* force the CUDA-core FMA kernel (exact, any K/D/strides) */
 #define VQB_PATH_TC 2u     /* force the tcgen05 kernel; VQB_E_UNSUPPORTED if not possible */
 #define VQB_PATH_MASK 3u
+/* The caller vouches that `workspace` still holds what an earlier vqb_forward call prepared from THIS codebook
+ * (same contents, same k and d): the per-call codebook kernels are skipped.  VQB_KEEP_CODEBOOK covers the code norms
+ * and the non-finite census (every path), VQB_KEEP_TC_IMAGE additionally the tcgen05 operand image (only meaningful
+ * after a call that took the tcgen05 path with k <= 256; ignored for larger codebooks).  The PyTorch binding sets them
+ * from (data_ptr, _version) of the weight tensor. */
+/* id width of vqb_encode_host's idx_host (default: int64) */
+#define VQB_IDS_I64 0u
+#define VQB_IDS_U8 16u
+#define VQB_IDS_U16 32u
+#define VQB_IDS_MASK 48u
+#define VQB_KEEP_CODEBOOK 4u
+#define VQB_KEEP_TC_IMAGE 8u
 
 typedef struct vqb_device_info {
     int device;
@@ -104,7 +116,8 @@ int vqb_select_path(int device, int64_t n, int k, int d, int64_t stride_row, int
  *   counts      (k)    uint64          -- code-usage histogram of this call
  *   stats       (4)    uint64 or NULL  -- [0] rows decided by the tcgen05 filter alone,
  *                                         [1] rows re-evaluated exactly, [2] rows on the
- *                                         non-finite path, [3] reserved
+ *                                         non-finite path, [3] SM clocks (clock64) of the
+ *                                         longest-running CTA of the tcgen05 kernel
  */
 int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, int d,
                 int64_t stride_outer, int64_t stride_inner, int64_t stride_d,
@@ -201,11 +214,15 @@ int vqb_host_set_codebook(vqb_host_ctx *ctx, const float *codebook_host);
  * Quantise n host vectors (contiguous (n, d) fp32; pinned memory gives async copies).
  * H2D copy, kernels and D2H copy of successive chunks overlap.  zq_host / idx_host may
  * be NULL (ids-only is what dataloader/latentspace_dataloader.py:160-161 consumes).
- * Scalars are written to host on return (the call synchronises its own streams).
+ * idx_host receives int64 ids (what the reference's loop stores, :220) unless flags carry VQB_IDS_U8 (k <= 256) or
+ * VQB_IDS_U16 (k <= 65536): the same ids narrowed on the device, 8x / 4x fewer bytes over PCIe.
+ * flags = VQB_PATH_* | VQB_IDS_*.  The codebook kernels run once per vqb_host_set_codebook, not once per call.
+ * Scalars are written to host on return (the call synchronises its own streams; on an error return all of its
+ * streams have been drained, so no copy still targets the caller's buffers).
  * launches_out (optional) receives the number of kernels launched.
  */
 int vqb_encode_host(vqb_host_ctx *ctx, const float *z_host, int64_t n, float beta,
-                    float *zq_host, int64_t *idx_host, float *loss_host, float *perplexity_host,
+                    float *zq_host, void *idx_host, float *loss_host, float *perplexity_host,
                     unsigned long long *counts_host, unsigned flags, int *launches_out);
 /* Device-timed duration (CUDA events, first H2D to last D2H) of the last vqb_encode_host. */
 int vqb_host_last_ms(vqb_host_ctx *ctx, float *ms);

@@ -130,6 +130,86 @@ def run_patch_cases(VQVAEPatch):
     return out, meta
 
 
+def build_ref_model(VQVAEPatch, case):
+    torch.manual_seed(case["seed"])
+    model = VQVAEPatch(hidden_dim=case["hidden_dim"], input_dim=case["input_dim"],
+                       num_embeddings=case["num_embeddings"], embedding_dim=case["embedding_dim"],
+                       n_resblocks=case["n_resblocks"], learning_rate=1e-3, dropout_p=0.0,
+                       patch_size=case["patch_size"], seq_len=case["seq_len"],
+                       batch_norm=case["batch_norm"], beta=case["beta"])
+    with torch.no_grad():  # spread the codebook so that several codes are used
+        model.vector_quantization.embedding.weight.mul_(case["num_embeddings"] * 0.5)
+    return model
+
+
+def run_wide_case(VQVAEPatch):
+    """A model the fused tcgen05 encoder layers accept (hidden_dim = 256): the reference's z_e and ids, stored with
+    only the tensors its encode path reads (tests/golden/cases.py: PATCH_WIDE_CASE)."""
+    case = C.PATCH_WIDE_CASE
+    name = case["name"]
+    model = build_ref_model(VQVAEPatch, case).eval()
+    x = torch.from_numpy(C.make_cycles(case))
+    with torch.no_grad():
+        tokens = model.patch_embed(x)
+        z_e = model.encoder(tokens)
+        _loss, _zq, ppl, _, idx = model.vector_quantization(z_e)
+    sd = model.state_dict()
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("patch_embed.") or k.startswith("encoder.1.") or k.startswith("vector_quantization."):
+            out[f"{name}/sd/{k}"] = v.numpy().copy()
+        elif k.startswith("encoder.0.") and k.endswith(".bias"):
+            out[f"{name}/sd/{k}"] = v.numpy().copy()
+        elif k.startswith("encoder.0.") and k.endswith(".weight"):
+            assert v.shape[2] == 3
+            out[f"{name}/centre/{k}"] = v[:, :, 1].numpy().copy()
+    out[f"{name}/z_e"] = z_e.contiguous().numpy()
+    out[f"{name}/idx"] = idx.numpy().reshape(-1).astype(np.int32)
+    out[f"{name}/perplexity"] = np.float32(ppl.item())
+    meta = dict(z_e_shape=list(z_e.shape), used_codes=len(set(idx.reshape(-1).tolist())))
+    print(f"{name:18s} tokens={idx.numel()} used_codes={meta['used_codes']} ppl={ppl.item():.3f}")
+    return out, meta
+
+
+def run_bulk_case(VQVAEPatch):
+    """The reference's own bulk loops (dataloader/latentspace_dataloader.py:171-263) run as unbound functions on a
+    stand-in `self` (the constructor wants the ASIMoW CSV data set): the three arrays they build from overlapping
+    windows."""
+    import types
+    from dataloader.latentspace_dataloader import LatentSpaceDataLoader as L  # type: ignore
+    case = C.BULK_CASE
+    name = case["name"]
+    mcase = next(c for c in C.PATCH_CASES if c["name"] == case["model"])
+    model = build_ref_model(VQVAEPatch, mcase)
+    win, labels, slices = C.make_windows(case)
+    win_t, lab_t = torch.from_numpy(win), torch.from_numpy(labels)
+    loader = [(win_t[lo:hi], lab_t[lo:hi]) for lo, hi in slices]
+    me = types.SimpleNamespace(latent_space_model=model, device="cpu", window_size=200, task="classification_ids")
+    me.get_latent_space = types.MethodType(L.get_latent_space, me)
+    me.get_latent_space_IDs = types.MethodType(L.get_latent_space_IDs, me)
+    me.create_latent_space_dataset_VQ_VAE_IDs = types.MethodType(L.create_latent_space_dataset_VQ_VAE_IDs, me)
+    ids, y = L.create_latent_space_dataset_VQ_VAE_IDs(me, loader, seq_len=case["seq_len"], has_patch_embed=True)
+    zq, y2 = L.create_latent_space_dataset_VQ_VAE(me, loader, seq_len=case["seq_len"], has_patch_embed=True)
+    me.task = "autoregressive_ids"
+    ar, y3 = L.create_latent_space_dataset_VQ_VAE_autoreggressive(me, [w for w, _ in loader], seq_len=case["seq_len"],
+                                                                 has_patch_embed=True)
+    me.task = "autoregressive_ids_classification"
+    ar2, y4 = L.create_latent_space_dataset_VQ_VAE_autoreggressive(me, loader, seq_len=case["seq_len"],
+                                                                  has_patch_embed=True)
+    assert np.array_equal(ar2, ar) and np.array_equal(y4, y)
+    # the encoder outputs behind those ids (same reference modules, same per-cycle slices): what a near-tie is judged on
+    model.eval()
+    with torch.no_grad():
+        z_e = np.stack([np.stack([model.encoder(model.patch_embed(w[:, i * 200:(i + 1) * 200, :].clone())).contiguous().numpy()
+                                  for i in range(case["seq_len"])], axis=1) for w, _ in loader])
+    z_e = z_e.reshape((-1,) + z_e.shape[2:]) if z_e.ndim == 6 else np.concatenate(list(z_e), axis=0)
+    out = {f"{name}/ids": ids, f"{name}/labels": y, f"{name}/zq": zq, f"{name}/labels_zq": y2,
+           f"{name}/ar_ids": ar, f"{name}/ar_labels": y3, f"{name}/z_e": z_e.astype(np.float32)}
+    meta = {k.split("/")[1]: dict(shape=list(v.shape), dtype=str(v.dtype)) for k, v in out.items()}
+    print(f"{name:18s} ids {ids.shape} {ids.dtype}  zq {zq.shape} {zq.dtype}  ar {ar.shape}")
+    return out, meta
+
+
 def default_config_keys(VQVAEPatch):
     """State-dict layout of the repo-default model (train_reconstruction_embedding.py:220-230)."""
     res = {}
@@ -152,6 +232,10 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "vq_golden.npz"), **vq_out)
     p_out, p_meta = run_patch_cases(VQVAEPatch)
     np.savez_compressed(os.path.join(GOLDEN, "patch_golden.npz"), **p_out)
+    w_out, w_meta = run_wide_case(VQVAEPatch)
+    np.savez_compressed(os.path.join(GOLDEN, "patch_wide_golden.npz"), **w_out)
+    b_out, b_meta = run_bulk_case(VQVAEPatch)
+    np.savez_compressed(os.path.join(GOLDEN, "bulk_golden.npz"), **b_out)
     manifest = dict(
         generator="oracle/make_golden.py",
         reference_root=REF,
@@ -161,11 +245,13 @@ def main():
         matmul_precision=torch.get_float32_matmul_precision(),
         vq=vq_meta,
         patch=p_meta,
+        patch_wide=w_meta,
+        bulk=b_meta,
         default_config_state_dict=default_config_keys(VQVAEPatch),
     )
     with open(os.path.join(GOLDEN, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
-    for fn in ("vq_golden.npz", "patch_golden.npz", "manifest.json"):
+    for fn in ("vq_golden.npz", "patch_golden.npz", "patch_wide_golden.npz", "bulk_golden.npz", "manifest.json"):
         print(fn, os.path.getsize(os.path.join(GOLDEN, fn)), "bytes")
 
 

@@ -26,6 +26,18 @@ def patch_golden():
 
 
 @pytest.fixture(scope="session")
+def patch_wide_golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "patch_wide_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def bulk_golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "bulk_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def manifest():
     import json
     with open(os.path.join(ROOT, "tests", "golden", "manifest.json")) as f:

@@ -136,3 +136,47 @@ def make_cycles(case: dict) -> np.ndarray:
     rs = np.random.RandomState(case["seed"])
     return np.ascontiguousarray(rs.standard_normal((case["batch"], case["seq_len"], case["input_dim"])),
                                 dtype=np.float32)
+
+
+# ---- a patch model wide enough for the fused tcgen05 encoder layers (hidden_dim a multiple of 256) ----
+# Only the tensors the ENCODE path reads are stored with the fixture (patch projection, centre taps of the residual
+# blocks' k=3 convolutions -- the outer taps only ever meet zero padding, SURVEY.md appendix A.7 --, the 1x1
+# projection and the codebook), together with the reference's z_e and ids.
+PATCH_WIDE_CASE = dict(name="patch_wide", hidden_dim=256, input_dim=2, num_embeddings=64, embedding_dim=32,
+                       n_resblocks=2, patch_size=25, seq_len=200, batch_norm=False, beta=0.25, batch=256, seed=104)
+
+
+# ---- the reference's bulk loops over overlapping windows (dataloader/latentspace_dataloader.py:171-263) ----
+# A stream of `n_stream` cycles is cut into windows of `seq_len` cycles with a stride of one cycle (the layout
+# dataloader/asimow_dataloader.py:185-206 produces), batched like a DataLoader would; the model is PATCH_CASES[0].
+BULK_CASE = dict(name="bulk_overlap", model="patch_small", seq_len=4, n_stream=15, batch=4, seed=105)
+
+
+def make_windows(case: dict):
+    """-> (windows (n, seq_len*200, 2) float32, labels (n,) float32, list of (lo, hi) batch slices)."""
+    rs = np.random.RandomState(case["seed"])
+    stream = rs.standard_normal((case["n_stream"], 200, 2)).astype(np.float32)
+    n = case["n_stream"] - case["seq_len"] + 1
+    win = np.stack([stream[i:i + case["seq_len"]].reshape(case["seq_len"] * 200, 2) for i in range(n)])
+    labels = rs.randint(0, 2, n).astype(np.float32)
+    slices = [(lo, min(lo + case["batch"], n)) for lo in range(0, n, case["batch"])]
+    return np.ascontiguousarray(win), labels, slices
+
+
+def unexplained_mismatches(z_e: np.ndarray, codebook: np.ndarray, got: np.ndarray, ref: np.ndarray, rel: float) -> int:
+    """Ids may differ from the reference's only where the reference's own z_e puts the two codes at (nearly) the same
+    distance: |d(z, E[got]) - d(z, E[ref])| <= rel * (|z|^2 + |e|^2), evaluated in float64 on the REFERENCE z_e.
+    `rel` is the relative accuracy of the encoder that produced `got` (about 1e-5 for an fp32 encoder with another
+    summation order; 2^-8-ish for bf16 operands).  Returns the number of mismatches this does not explain."""
+    z = np.asarray(z_e, dtype=np.float64).reshape(-1, codebook.shape[1])
+    E = np.asarray(codebook, dtype=np.float64)
+    got = np.asarray(got).reshape(-1)
+    ref = np.asarray(ref).reshape(-1)
+    bad = np.nonzero(got != ref)[0]
+    if bad.size == 0:
+        return 0
+    zb = z[bad]
+    dg = ((zb - E[got[bad]]) ** 2).sum(1)
+    dr = ((zb - E[ref[bad]]) ** 2).sum(1)
+    scale = (zb ** 2).sum(1) + np.maximum((E[got[bad]] ** 2).sum(1), (E[ref[bad]] ** 2).sum(1))
+    return int((np.abs(dg - dr) > rel * scale).sum())

@@ -260,11 +260,75 @@ def test_host_buffer_path_matches_oracle(K, D, n):
     assert np.array_equal(counts.astype(np.int64), ora.counts)
     assert loss == pytest.approx(float(ora.loss), rel=REL)
     assert ppl == pytest.approx(float(ora.perplexity), rel=REL)
-    # ids-only mode (what the latent-dataset builder consumes)
+    # ids-only mode (what the latent-dataset builder consumes); the second call re-uses the prepared codebook
     idx2 = torch.empty(n, dtype=torch.int64).pin_memory()
     enc.encode(z, 0.25, idx_out=idx2)
     assert torch.equal(idx, idx2)
+    # compact ids: the same ids in 1 (K <= 256) or 2 bytes each
+    small = torch.empty(n, dtype=torch.uint8 if K <= 256 else torch.uint16).pin_memory()
+    enc.encode(z, 0.25, idx_out=small)
+    assert np.array_equal(small.numpy().astype(np.int64), idx.numpy())
+    if K > 256:
+        with pytest.raises(RuntimeError):
+            enc.encode(z, 0.25, idx_out=torch.empty(n, dtype=torch.uint8))
     enc.close()
+
+
+def test_host_buffer_path_validates_its_arguments():
+    """Raw host pointers cross the C ABI: wrong dtypes, strided views, short buffers and device tensors raise instead of
+    being misread or overrun (round-1 advisor finding)."""
+    rs = np.random.RandomState(3)
+    E = rs.uniform(-0.01, 0.01, (64, 32)).astype(np.float32)
+    enc = ops.HostEncoder(E, device=0, chunk_rows=4096, depth=2)
+    z = (0.1 * rs.standard_normal((1000, 32))).astype(np.float32)
+    idx = np.empty(1000, np.int64)
+    enc.encode(z, idx_out=idx)                                        # baseline: fine
+    enc.encode(torch.from_numpy(z).reshape(10, 100, 32), idx_out=idx)  # any shape with numel % d == 0
+    for bad_z in (z.astype(np.float64), z[:, ::2], z.reshape(-1)[:31999], torch.from_numpy(z).cuda(), list(z[:2])):
+        with pytest.raises((RuntimeError, TypeError)):
+            enc.encode(bad_z, idx_out=idx)
+    for kw in (dict(idx_out=np.empty(1000, np.int32)), dict(idx_out=np.empty(999, np.int64)),
+               dict(zq_out=np.empty((1000, 16), np.float32)), dict(counts_out=np.zeros(63, np.uint64)),
+               dict(counts_out=np.zeros(64, np.float64)), dict(idx_out=np.empty(2000, np.int64)[::2])):
+        with pytest.raises(RuntimeError):
+            enc.encode(z, **kw)
+    enc.close()
+
+
+def test_codebook_cache_follows_the_weight_version():
+    """The binding re-uses the prepared codebook (norms, census, tcgen05 image) while (data_ptr, _version) of the weight
+    stay the same, and re-prepares after an in-place update; a write through .data needs clear_workspaces()."""
+    dev = _dev()
+    rs = np.random.RandomState(11)
+    z_np = (0.1 * rs.standard_normal((5000, 32))).astype(np.float32)
+    E = rs.uniform(-1 / 256, 1 / 256, (256, 32)).astype(np.float32)
+    z = torch.from_numpy(z_np).to(dev)
+    w = torch.nn.Parameter(torch.from_numpy(E).to(dev))
+    for path in ("tc", "fma", "auto"):
+        a = ops.forward(z, w, 0.25, path=path)
+        b = ops.forward(z, w, 0.25, path=path)                        # cached
+        ora = O.forward(z_np, E, 0.25)
+        for out in (a, b):
+            assert np.array_equal(out[3].cpu().numpy().reshape(-1), ora.indices.reshape(-1))
+            assert np.array_equal(out[1].cpu().numpy(), ora.z_q)
+            assert out[0].item() == pytest.approx(float(ora.loss), rel=REL)
+    with torch.no_grad():
+        w.mul_(-3.0)                                                  # in place: bumps _version
+    E2 = w.detach().cpu().numpy()
+    ora2 = O.forward(z_np, E2, 0.25)
+    for path in ("auto", "fma"):
+        out = ops.forward(z, w, 0.25, path=path)
+        assert np.array_equal(out[3].cpu().numpy().reshape(-1), ora2.indices.reshape(-1))
+    w.data.add_(0.001)                                                # invisible to _version
+    ops.clear_workspaces()
+    ora3 = O.forward(z_np, w.detach().cpu().numpy(), 0.25)
+    out = ops.forward(z, w, 0.25)
+    assert np.array_equal(out[3].cpu().numpy().reshape(-1), ora3.indices.reshape(-1))
+    # a small call (FMA path) followed by a large one (tcgen05 path) on the same workspace: the image is built then
+    ops.clear_workspaces()
+    ops.forward(z[:64], w, 0.25)
+    out = ops.forward(z, w, 0.25)
+    assert np.array_equal(out[3].cpu().numpy().reshape(-1), ora3.indices.reshape(-1))
 
 
 # ---------------------------------------------------------------------------------------

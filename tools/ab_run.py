@@ -43,7 +43,8 @@ if os.environ.get("VQB_SUSTAINED"):
     lib.vqb_profile_collect(ctypes.byref(ms), ctypes.byref(k))
     stop = True; th.join(); mid = samples[len(samples) // 3:]
     sus = f" | sustained kernel {ms.value / k.value:.4f} ms, clk {sorted(s[0] for s in mid)[len(mid)//2]} MHz, {sorted(s[1] for s in mid)[len(mid)//2]:.0f} W"
-print(f"{os.environ.get('VQB_NAME'):24s} exact={ok} slow_rows={int(out[5][1])}  mean {tot/3:.4f} ms best {best:.4f} ms -> {n*264/(tot/3)/1e6/6448.4*100:.1f}%% of HBM roofline" + sus)
+st = ops.forward(z, w, 0.25, path="tc", want_stats=True)[5]; clk = int(st[3]); tiles = n // 128 / 148
+print(f"{os.environ.get('VQB_NAME'):24s} exact={ok} slow_rows={int(out[5][1])} clk/tile {clk / tiles:.0f} ({clk / (best * 1e-3) / 1e9:.2f} GHz at best)  mean {tot/3:.4f} ms best {best:.4f} ms -> {n*264/(tot/3)/1e6/6448.4*100:.1f}%% of HBM roofline" + sus)
 ''' % ROOT
 for name in sys.argv[1:]:
     env = dict(os.environ, VQB_NAME=name)

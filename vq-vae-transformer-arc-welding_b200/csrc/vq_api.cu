@@ -147,7 +147,8 @@ int vqb_select_path(int device, int64_t n, int k, int d, int64_t stride_row, int
     if (n <= 0 || k <= 0 || d <= 0)
         return VQB_E_ARG;
     const bool contiguous = stride_d == 1 && stride_row == d;
-    if (info.cc_major == 10 && contiguous && (tc_shape_supported(k, d) || tc_chunked_supported(k, d)) && n >= 128)
+    if (info.cc_major == 10 && contiguous && (tc_shape_supported(k, d) || tc_chunked_supported(k, d)) && n >= 128 &&
+        n < (1ll << 31))
         return (int)VQB_PATH_TC;
     return (int)VQB_PATH_FMA;
 }
@@ -183,17 +184,18 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
     WsHeader *hdr = (WsHeader *)ws;
     unsigned long long *cnt = counts ? counts : (unsigned long long *)(ws + L.off_counts);
 
-    // zero: header, colcnt, colwhich (contiguous prefix of the workspace) and the histogram
-    if ((err = cudaMemsetAsync(ws, 0, kHeaderBytes, st)) != cudaSuccess) return (int)err;
-    if ((err = cudaMemsetAsync(ws + L.off_colcnt, 0, L.off_counts - L.off_colcnt, st)) != cudaSuccess) return (int)err;
-    if ((err = cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * k, st)) != cudaSuccess) return (int)err;
-    if (stats && (err = cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 4, st)) != cudaSuccess) return (int)err;
-
     float *ee = (float *)(ws + L.off_ee);
     int *colcnt = (int *)(ws + L.off_colcnt);
     int *colwhich = (int *)(ws + L.off_colwhich);
-    if ((err = launch_prep(codebook, k, d, L.kpad, ee, colcnt, colwhich, hdr, st)) != cudaSuccess) return (int)err;
-    count_launches(1);
+    const bool keep = (flags & VQB_KEEP_CODEBOOK) != 0;
+    if (!keep) {
+        // zero: header, (ee), colcnt, colwhich -- one contiguous prefix of the workspace -- then the codebook prep
+        if ((err = cudaMemsetAsync(ws, 0, L.off_counts, st)) != cudaSuccess) return (int)err;
+        if ((err = launch_prep(codebook, k, d, L.kpad, ee, colcnt, colwhich, hdr, st)) != cudaSuccess) return (int)err;
+        count_launches(1);
+    }
+    if ((err = cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * k, st)) != cudaSuccess) return (int)err;
+    if (stats && (err = cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 4, st)) != cudaSuccess) return (int)err;
 
     int n_ctas = 1;
     double *partials = (double *)(ws + L.off_partials);
@@ -209,7 +211,9 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
         unsigned path = flags & VQB_PATH_MASK;
         // K > 256 runs as one tcgen05 pass per 256-code chunk; the running best lives in the idx buffer
         const bool tc_chunked = tc_chunked_supported(k, d) && idx != nullptr;
-        const bool tc_ok = p.z.rows_contiguous(d) && (tc_shape_supported(k, d) || tc_chunked) && aligned(z, 16);
+        // (the tcgen05 kernels address rows with 32-bit TMA coordinates: 2^31 rows and more take the FMA path)
+        const bool tc_ok = p.z.rows_contiguous(d) && (tc_shape_supported(k, d) || tc_chunked) && aligned(z, 16) &&
+                           n < (1ll << 31);
         if (path == VQB_PATH_TC && !tc_ok)
             return VQB_E_UNSUPPORTED;
         if (path == VQB_PATH_AUTO)
@@ -223,8 +227,12 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
         if (path == VQB_PATH_TC) {
             launches = 0;
             // the tcgen05 launcher brackets only its main kernel (after its own codebook prep)
-            err = (tc_shape_supported(k, d) ? launch_fwd_tc : launch_fwd_tc_chunked)(
-                p, (float *)(ws + L.off_tc), info.sm_count, info.max_smem_per_block, &n_ctas, &launches, st, ev0, ev1);
+            if (tc_shape_supported(k, d))
+                err = launch_fwd_tc(p, (float *)(ws + L.off_tc), info.sm_count, info.max_smem_per_block, &n_ctas,
+                                    &launches, st, ev0, ev1, keep && (flags & VQB_KEEP_TC_IMAGE) != 0);
+            else
+                err = launch_fwd_tc_chunked(p, (float *)(ws + L.off_tc), info.sm_count, info.max_smem_per_block, &n_ctas,
+                                            &launches, st, ev0, ev1);
         } else {
             if (ev0) cudaEventRecord(ev0, st);
             err = launch_fwd_fma(p, info.sm_count, info.max_smem_per_block, &n_ctas, st);

@@ -124,7 +124,7 @@ cudaError_t launch_bwd(const float *g_zq, const float *g_loss, const ZView &z, c
 bool tc_shape_supported(int K, int D);
 cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas,
                           int *n_launches, cudaStream_t st, cudaEvent_t ev_begin = nullptr,
-                          cudaEvent_t ev_end = nullptr);
+                          cudaEvent_t ev_end = nullptr, bool image_ready = false);
 bool tc_chunked_supported(int K, int D);
 cudaError_t launch_fwd_tc_chunked(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas,
                                   int *n_launches, cudaStream_t st, cudaEvent_t ev_begin = nullptr,

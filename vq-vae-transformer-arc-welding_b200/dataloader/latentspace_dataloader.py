@@ -98,6 +98,10 @@ class LatentSpaceEncoder:
     # ---- single encode calls (:144-161) -------------------------------------------------
     def _encode(self, x, has_patch_embed: bool):
         model = self.latent_space_model
+        if has_patch_embed and hasattr(model, "encode"):
+            # VQVAEPatch.encode = patch_embed -> encoder, in the model's `encoder_mode` (the fused tcgen05 layers when
+            # selected); a reference model without that method takes the reference's own two calls below (:145-149)
+            return model.encode(x)
         x = model.patch_embed(x) if has_patch_embed else x.permute(0, 2, 1)
         return model.encoder(x)
 

@@ -5,6 +5,7 @@ stream, autograd bookkeeping); all arithmetic happens inside libvqb200.so.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 from typing import Optional, Tuple
 
@@ -13,8 +14,26 @@ import torch
 from . import _lib
 
 PATHS = {"auto": _lib.PATH_AUTO, "fma": _lib.PATH_FMA, "tc": _lib.PATH_TC}
+KEEP_CODEBOOK, KEEP_TC_IMAGE = 4, 8            # VQB_KEEP_* (include/vqb200.h)
+IDS_FLAGS = {"int64": 0, "uint8": 16, "uint16": 32}   # VQB_IDS_*
 
-_workspaces = {}
+#: reuse what the workspace holds about a codebook (code norms, census, tcgen05 operand image) while the weight tensor's
+#: (data_ptr, _version) stay the same -- in inference the codebook kernels then run once, not once per call.  In-place
+#: updates through autograd-visible ops (optimizers, copy_, load_state_dict) bump _version; writing through `.data`
+#: does not: call clear_workspaces() after such a write, or switch this off.
+CACHE_CODEBOOK = True
+
+# (device, k, d, stream handle) -> workspace tensor; least recently used entries are dropped beyond _WS_MAX (one entry
+# holds ~3.2 MB, mostly the fix-up queues), clear_workspaces() empties it
+_workspaces: "collections.OrderedDict" = collections.OrderedDict()
+_ws_state = {}          # id(workspace tensor) -> (weight data_ptr, weight _version, tcgen05 image valid)
+_WS_MAX = 16
+
+
+def clear_workspaces() -> None:
+    """Drop every cached kernel workspace (their memory returns to the caching allocator)."""
+    _workspaces.clear()
+    _ws_state.clear()
 
 
 def _require_cuda_fp32(t: torch.Tensor, name: str) -> None:
@@ -37,6 +56,11 @@ def _workspace(device: torch.device, k: int, d: int) -> torch.Tensor:
         nbytes = _lib.load().vqb_workspace_bytes(k, d)
         ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
+        while len(_workspaces) > _WS_MAX:
+            _, old = _workspaces.popitem(last=False)
+            _ws_state.pop(id(old), None)
+    else:
+        _workspaces.move_to_end(key)
     return ws
 
 
@@ -122,14 +146,26 @@ def forward(z: torch.Tensor, weight: torch.Tensor, beta: float, path: str = "aut
         ws = _workspace(dev, k, d)
         ws_ptr, ws_bytes = _ws_ptr(ws)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        # what this workspace already holds about this very codebook (see CACHE_CODEBOOK)
+        flags = PATHS[path]
+        tag = (w.data_ptr(), w._version)
+        state = _ws_state.get(id(ws)) if CACHE_CODEBOOK else None
+        if state is not None and state[:2] == tag:
+            flags |= KEEP_CODEBOOK | (KEEP_TC_IMAGE if state[2] else 0)
+        contiguous_rows = s_d == 1 and n_inner == 1 and s_outer == d
+        takes_tc = (path != "fma" and contiguous_rows and k <= 256 and _tc_eligible(n, k, d) and n < (1 << 31)
+                    and zsrc.data_ptr() % 16 == 0)
+        _ws_state.pop(id(ws), None)            # nothing is vouched for if the call below fails
         rc = lib.vqb_forward(
             dev.index, zsrc.data_ptr(), n_outer, n_inner, d, s_outer, s_inner, s_d,
             w.data_ptr(), k, float(beta),
             zq.data_ptr() if zq is not None else None, idx.data_ptr(),
             scal.data_ptr() if want_loss else None, scal.data_ptr() + 4, counts.data_ptr(),
             stats.data_ptr() if stats is not None else None,
-            ws_ptr, ws_bytes, PATHS[path], stream)
+            ws_ptr, ws_bytes, flags, stream)
     _lib.check(rc, "vqb_forward")
+    if CACHE_CODEBOOK:
+        _ws_state[id(ws)] = tag + (takes_tc or bool(flags & KEEP_TC_IMAGE),)
     out = (scal[0] if want_loss else None, zq, scal[1], idx, counts)
     return out + (stats,) if want_stats else out
 
@@ -169,8 +205,9 @@ def backward(g_zq: Optional[torch.Tensor], g_loss: Optional[torch.Tensor], z: to
     return grad_z, grad_e
 
 
-def gather(indices: torch.Tensor, weight: torch.Tensor, target_shape=None) -> torch.Tensor:
-    """E[indices] (model/vector_quantizer.py:121-131)."""
+def gather(indices: torch.Tensor, weight: torch.Tensor, target_shape=None, check_range: bool = False) -> torch.Tensor:
+    """E[indices] (model/vector_quantizer.py:121-131).  Out-of-range ids give NaN rows and set the kernel's flag;
+    check_range=True reads that flag (one device synchronisation) and raises like the reference's scatter_ does."""
     _require_cuda_fp32(weight, "embedding.weight")
     if indices.dtype != torch.int64:
         raise RuntimeError(f"indices must be int64, got {indices.dtype}")
@@ -188,11 +225,19 @@ def gather(indices: torch.Tensor, weight: torch.Tensor, target_shape=None) -> to
         rc = lib.vqb_gather(dev.index, flat.data_ptr(), n, w.data_ptr(), k, d, out.data_ptr(),
                             bad.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "vqb_gather")
+    if check_range and int(bad.item()) != 0:
+        raise IndexError(f"gather: an index lies outside [0, {k})")
     return out.view(target_shape) if target_shape is not None else out
 
 
 def one_hot(indices: torch.Tensor, k: int) -> torch.Tensor:
     """(N, k) fp32 one-hot of (N, 1) int64 indices (model/vector_quantizer.py:98-100)."""
+    if not isinstance(indices, torch.Tensor) or indices.dtype != torch.int64:
+        raise RuntimeError(f"one_hot: indices must be an int64 tensor, got {getattr(indices, 'dtype', type(indices))}")
+    if not indices.is_cuda:
+        raise RuntimeError(f"one_hot: indices live on {indices.device}; there is no CPU fallback")
+    if k <= 0:
+        raise RuntimeError("one_hot: k must be positive")
     lib = _lib.load()
     dev = indices.device
     flat = indices.reshape(-1).contiguous()
@@ -252,19 +297,53 @@ class HostEncoder:
         self.last_launches = 0
 
     def encode(self, z_host, beta: float = 0.25, zq_out=None, idx_out=None, counts_out=None, path: str = "auto"):
-        """z_host: (n, d) fp32 contiguous numpy array or CPU tensor (pin it for async copies).
+        """z_host: (n, d) fp32 contiguous numpy array or CPU tensor (pin it for async copies).  idx_out: int64 (the
+        reference's id dtype), or uint8 (k <= 256) / uint16 (k <= 65536) for the same ids in 1 / 2 bytes each.
         Returns (loss, perplexity)."""
-        def ptr(a):
+        np = self._np
+
+        def ptr(a, name, kinds, min_elems):
+            """Raw host pointer of a C-contiguous numpy array / CPU tensor of the given dtype with >= min_elems
+            elements; anything else would be misread or overrun by the library, so it raises here."""
             if a is None:
                 return None
-            return a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data
-        n = z_host.shape[0] if z_host.ndim == 2 else z_host.size // self.d
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda:
+                    raise RuntimeError(f"{name} must live in host memory (got {a.device})")
+                dt, contiguous, elems, p = str(a.dtype).replace("torch.", ""), a.is_contiguous(), a.numel(), a.data_ptr()
+            elif isinstance(a, np.ndarray):
+                dt, contiguous, elems, p = a.dtype.name, a.flags["C_CONTIGUOUS"], a.size, a.ctypes.data
+            else:
+                raise TypeError(f"{name} must be a numpy array or a CPU torch tensor, got {type(a).__name__}")
+            if dt not in kinds:
+                raise RuntimeError(f"{name} must have dtype {' or '.join(kinds)}, got {dt}")
+            if not contiguous:
+                raise RuntimeError(f"{name} must be C-contiguous")
+            if elems < min_elems:
+                raise RuntimeError(f"{name} holds {elems} elements, the call needs {min_elems}")
+            return p
+
+        if not isinstance(z_host, (torch.Tensor, np.ndarray)):
+            raise TypeError("z_host must be a numpy array or a CPU torch tensor")
+        total = z_host.numel() if isinstance(z_host, torch.Tensor) else z_host.size
+        if total % self.d:
+            raise RuntimeError(f"z_host holds {total} elements, not a multiple of the vector width {self.d}")
+        n = total // self.d
+        z_ptr = ptr(z_host, "z_host", ("float32",), n * self.d)
+        zq_ptr = ptr(zq_out, "zq_out", ("float32",), n * self.d)
+        idx_ptr = ptr(idx_out, "idx_out", ("int64", "uint8", "uint16"), n)
+        id_kind = "int64"
+        if idx_out is not None:
+            id_kind = (str(idx_out.dtype).replace("torch.", "") if isinstance(idx_out, torch.Tensor) else idx_out.dtype.name)
+            if (id_kind == "uint8" and self.k > 256) or (id_kind == "uint16" and self.k > 65536):
+                raise RuntimeError(f"idx_out dtype {id_kind} cannot hold ids of a {self.k}-entry codebook")
+        cnt_ptr = ptr(counts_out, "counts_out", ("int64", "uint64"), self.k)
         loss = ctypes.c_float()
         ppl = ctypes.c_float()
         launches = ctypes.c_int()
-        rc = self._lib.vqb_encode_host(self._ctx, ptr(z_host), int(n), float(beta), ptr(zq_out), ptr(idx_out),
-                                       ctypes.addressof(loss), ctypes.addressof(ppl), ptr(counts_out),
-                                       PATHS[path], ctypes.byref(launches))
+        rc = self._lib.vqb_encode_host(self._ctx, z_ptr, int(n), float(beta), zq_ptr, idx_ptr,
+                                       ctypes.addressof(loss), ctypes.addressof(ppl), cnt_ptr,
+                                       PATHS[path] | IDS_FLAGS[id_kind], ctypes.byref(launches))
         _lib.check(rc, "vqb_encode_host")
         self.last_launches = launches.value
         return loss.value, ppl.value
