@@ -156,6 +156,23 @@ int vqb_backward(int device, const float *g_zq, const float *g_loss,
 int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const float *bias, float *h, void *out_bf16,
                      int64_t n_tokens, int k, int n, unsigned mode, void *stream);
 
+/*
+ * The whole residual-block chain of the patch encoder in one launch (model/vq_vae_patch_embedd.py:60-74 ResBlock,
+ * :103-111 CNNBlock with seperate=True; n_layers = 2 * n_resblocks dense layers, the centre taps of the k=3 convs):
+ *     for every block b:  h <- h + W[2b+1] gelu(W[2b] gelu(h) + bias[2b]) + bias[2b+1]
+ * A CTA keeps a 128-token tile on its SM for all layers (activations alternate between shared and tensor memory, the
+ * weights stream from L2), so HBM sees 1 read of a0 and h and 1 write of h per token.  Same arithmetic per layer as
+ * vqb_token_linear (bf16 operands, fp32 accumulation, fp32 residual stream).
+ *   a0_bf16 (n_tokens, hidden) bf16 = bf16(gelu(h)) of the incoming h (vqb_patch_embed writes both)
+ *   h       (n_tokens, hidden) fp32, updated in place
+ *   w_bf16  (n_layers, hidden, hidden) bf16 (out x in per layer), bias (n_layers, hidden) fp32
+ *   scratch vqb_encoder_chain_scratch_bytes(device, hidden) bytes of device memory (contents private)
+ * hidden in {256, 512}, n_layers even; all pointers 16-byte aligned.
+ */
+size_t vqb_encoder_chain_scratch_bytes(int device, int hidden);
+int vqb_encoder_chain(int device, const void *a0_bf16, float *h, const void *w_bf16, const float *bias, int64_t n_tokens,
+                      int hidden, int n_layers, void *scratch, size_t scratch_bytes, void *stream);
+
 /* h += bias (fp32 (n_tokens, n), in place); out = bf16(gelu(h)): the element-wise step between the fp32 patch
  * embedding (model/vq_vae_patch_embedd.py:13-17) and the first fused layer, in one pass.  n a multiple of 4. */
 int vqb_token_bias_gelu(int device, float *h, const float *bias, void *out_bf16, int64_t n_tokens, int n, void *stream);

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import torch
 
+import cases as C
 import vqb200
 from vqb200 import ops
 
@@ -107,7 +108,17 @@ def test_fused_bf16_encoder_tracks_the_fp32_encoder():
     assert z_fused.shape == z_ref.shape and z_fused.is_contiguous()
     err = (z_fused - z_ref).abs().max().item()
     assert err <= 0.05 * z_ref.abs().max().item(), err
-    assert (ids_fused == ids_ref).float().mean().item() > 0.97
+    # stated tolerance of the bf16-operand encoder: >= 99.5 % of the ids equal to the fp32 encoder's at the repo-default
+    # size (measured 99.86 % on 2^20 tokens; 4800 tokens here)
+    assert (ids_fused == ids_ref).float().mean().item() >= 0.995
+    # the one-launch chain and the layer-at-a-time kernels are the same arithmetic, layer for layer
+    with torch.no_grad():
+        model.encoder_mode = "fused_bf16"
+        model.fused_chain = False
+        z_layers = model.encode(x)
+        model.fused_chain = True
+        model.encoder_mode = "torch"
+    torch.testing.assert_close(z_fused, z_layers, rtol=1e-5, atol=1e-6)
     # training mode / autograd never takes the fused path
     model.train()
     model.encoder_mode = "fused_bf16"
@@ -169,3 +180,84 @@ def test_patch_embed_kernel(B, L, C, P):
     assert bool(((a.float() - act).abs() <= bound).all())
     h2, a2 = ops.patch_embed(x, conv.weight, conv.bias, P, want_act=False)
     assert a2 is None and torch.equal(h, h2)
+
+
+def _wide_model(patch_wide_golden, dev):
+    """The fused-eligible fixture model (hidden_dim = 256): only the tensors the encode path reads were stored."""
+    case = C.PATCH_WIDE_CASE
+    name = case["name"]
+    torch.manual_seed(1)
+    model = vqb200.VQVAEPatch(hidden_dim=case["hidden_dim"], input_dim=case["input_dim"],
+                              num_embeddings=case["num_embeddings"], embedding_dim=case["embedding_dim"],
+                              n_resblocks=case["n_resblocks"], learning_rate=1e-3, dropout_p=0.0,
+                              patch_size=case["patch_size"], seq_len=case["seq_len"],
+                              batch_norm=case["batch_norm"], beta=case["beta"])
+    sd = model.state_dict()
+    for k in patch_wide_golden.files:
+        if k.startswith(f"{name}/sd/"):
+            sd[k[len(name) + 4:]] = torch.from_numpy(patch_wide_golden[k])
+        elif k.startswith(f"{name}/centre/"):
+            key = k[len(name) + 8:]
+            wfull = sd[key].clone()
+            wfull[:, :, 1] = torch.from_numpy(patch_wide_golden[k])
+            sd[key] = wfull
+    model.load_state_dict(sd, strict=True)
+    return model.to(dev).eval()
+
+
+def test_encoder_modes_against_the_reference_fixture(patch_wide_golden):
+    """a1-a3 against the UNMODIFIED reference (tests/golden/patch_wide_golden.npz: z_e and ids of a hidden_dim = 256
+    model on 256 cycles).  fp32 encoder: ids equal except fp32 near-ties (1e-5 relative).  bf16-operand fused encoder
+    (one-launch chain and layer-at-a-time): stated tolerance >= 99.8 % of the ids, z_e within 2 % of its range."""
+    dev = _dev()
+    case = C.PATCH_WIDE_CASE
+    name = case["name"]
+    model = _wide_model(patch_wide_golden, dev)
+    x = torch.from_numpy(C.make_cycles(case)).to(dev)
+    ref_z, ref_ids = patch_wide_golden[f"{name}/z_e"], patch_wide_golden[f"{name}/idx"].astype(np.int64)
+    E = patch_wide_golden[f"{name}/sd/vector_quantization.embedding.weight"]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        z = model.encode(x)
+        ids = model.encode_ids(x).cpu().numpy().reshape(-1)
+    np.testing.assert_allclose(z.cpu().numpy(), ref_z, rtol=1e-4, atol=1e-5)
+    assert C.unexplained_mismatches(ref_z, E, ids, ref_ids, rel=1e-5) == 0
+    assert (ids == ref_ids).mean() >= 0.999
+    model.encoder_mode = "fused_bf16"
+    assert model._fused_ok(x)
+    for chain in (True, False):
+        model.fused_chain = chain
+        with torch.no_grad():
+            zf = model.encode(x)
+            idf = model.encode_ids(x).cpu().numpy().reshape(-1)
+        assert zf.shape == z.shape
+        assert np.abs(zf.cpu().numpy() - ref_z).max() <= 0.02 * np.abs(ref_z).max()
+        rate = (idf == ref_ids).mean()
+        assert rate >= 0.998, (chain, rate)
+
+
+@pytest.mark.parametrize("T,H,L", [(1, 512, 2), (127, 512, 4), (128 * 3 + 5, 512, 16), (128 * 150 + 77, 512, 16),
+                                   (1000, 256, 2), (128 * 149, 256, 6)])
+def test_encoder_chain_equals_layerwise(T, H, L):
+    """vqb_encoder_chain against the layer-at-a-time vqb_token_linear sequence on the same operands: same bf16 operands,
+    same accumulation order per layer, so the residual streams agree to fp32 rounding; ragged and multi-tile shapes."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(T + H + L)
+    h0 = torch.randn(T, H, device=dev, generator=g)
+    w = (torch.randn(L, H, H, device=dev, generator=g) * (1.0 / H) ** 0.5).to(torch.bfloat16)
+    b = 0.1 * torch.randn(L, H, device=dev, generator=g)
+    a0 = torch.nn.functional.gelu(h0).to(torch.bfloat16)
+    ref = h0.clone()
+    a, u = a0.clone(), torch.empty_like(a0)
+    for i in range(L // 2):
+        ops.token_linear(a, w[2 * i], b[2 * i], out=u, mode=0)
+        ops.token_linear(u, w[2 * i + 1], b[2 * i + 1], h=ref, out=a if 2 * i + 2 < L else None, mode=1)
+    out = ops.encoder_chain(a0, h0.clone(), w, b)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    # and against plain fp32 PyTorch on the same bf16-rounded operands (tolerance: bf16 rounding of the activations)
+    hh = h0.clone()
+    for i in range(L // 2):
+        t = torch.nn.functional.gelu(hh).to(torch.bfloat16).float() @ w[2 * i].float().t() + b[2 * i]
+        hh = hh + torch.nn.functional.gelu(t).to(torch.bfloat16).float() @ w[2 * i + 1].float().t() + b[2 * i + 1]
+    torch.testing.assert_close(out, hh, rtol=2e-2, atol=2e-2 * L ** 0.5)

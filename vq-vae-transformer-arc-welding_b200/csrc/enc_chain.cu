@@ -1,0 +1,372 @@
+// enc_chain.cu -- the whole residual-block chain of the patch encoder in ONE kernel (sm_100a, tcgen05 + TMA + TMEM).
+//
+// Reference: model/vq_vae_patch_embedd.py:60-74 (ResBlock), :103-111 (CNNBlock with seperate=True): to every token
+// independently, n_resblocks times   h <- h + W2 gelu(W1 gelu(h) + b1) + b2   with H x H weights (the centre tap of
+// Conv1d(k=3, pad=1) on a length-1 slice).  The layer-at-a-time kernel (tok_linear.cu) round-trips 6-8 KB per token
+// and block through HBM; here a CTA keeps a 128-token tile on the SM for all 2 * n_resblocks GEMMs:
+//
+//   * the bf16 activation tile (128 x H) ALTERNATES between shared memory and tensor memory: GEMM g reads its A
+//     operand from one of the two (tcgen05.mma with an smem descriptor, or with A in TMEM) while its epilogue writes
+//     the next GEMM's A operand into the other (st.shared in the UMMA K-major SW128 layout, or tcgen05.st of packed
+//     bf16 pairs).  One 128 KB activation buffer in shared memory therefore suffices, which leaves room for a
+//     6-stage weight ring (two smem buffers would not fit beside any ring at H = 512);
+//   * accumulators are N = 128 column quarters, two of them in flight (TMEM columns: H/2 for the activation operand,
+//     2 x 128 for the accumulators): the epilogue of quarter q overlaps the MMAs of quarter q + 1, and the next GEMM
+//     starts on the K-chunks the epilogue has already produced;
+//   * weights stream from L2 through a TMA ring that runs ahead across GEMM boundaries (they do not depend on the
+//     activations): 128 x 64 bf16 boxes of the stacked (L * H, H) weight tensor;
+//   * the fp32 residual stream lives in a per-CTA scratch tile (L2-resident: 148 x 256 KB) laid out so that the
+//     epilogue's thread-per-row accesses coalesce; the first block reads it from, the last block writes it to the
+//     caller's row-major h.
+//
+// bf16 operands, fp32 accumulation, fp32 residual stream, GELU as in tok_linear.cu (gelu_fast): the same arithmetic
+// as the layer-at-a-time path, layer for layer.
+#include "vq_common.cuh"
+#include "vq_ptx.cuh"
+
+namespace vqb {
+
+namespace ec {
+
+constexpr int BM = 128;                    // tokens per tile (TMEM lanes)
+constexpr int NQ = 128;                    // accumulator width (columns of one MMA)
+constexpr int BK = 64;                     // K-chunk of a weight stage (128 bytes of bf16: one SW128 row)
+constexpr int W_STAGE = NQ * BK * 2;       // 16 KB
+constexpr int W_STAGES = 6;
+constexpr int THREADS = 128 + 256;         // 4 service warps + 8 epilogue warps
+
+template <int H> struct Plan {
+    static constexpr int A_BYTES = BM * H * 2;                 // activation tile, H/64 K-chunks of 16 KB
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_W = OFF_A + A_BYTES;
+    static constexpr int OFF_BARS = OFF_W + W_STAGES * W_STAGE;
+    static constexpr int SMEM_BYTES = OFF_BARS + 512;
+    static constexpr int TMEM_A_COLS = H / 2;                  // packed bf16 pairs
+    static constexpr int TMEM_ACC0 = 256;                      // accumulators at columns 256 .. 511
+};
+
+__device__ __forceinline__ float gelu(float x)
+{   // identical to tl::gelu_fast (tok_linear.cu): 0.5 x (1 + tanh(x (c1 + c3 x^2 + c5 x^4))), minimax fit of the erf form
+    const float u = fminf(x * x, 36.0f);
+    float p = fmaf(-3.51517534e-4f, u, 3.70056510e-2f);
+    p = fmaf(p, u, 7.97507878e-1f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+}
+
+// tcgen05.mma with the A operand in tensor memory (lanes = rows, 32-bit columns = K pairs)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+}  // namespace ec
+
+// a0     : (n_tokens, H) bf16 row-major = bf16(gelu(h0)), the first GEMM's operand (TMA)
+// h      : (n_tokens, H) fp32 row-major, in: h0 (the patch embedding), out: the residual stream after the last block
+// w      : (L * H, H) bf16 row-major, layer l = rows [l*H, (l+1)*H) (out x in); bias (L * H) fp32
+// scratch: gridDim.x tiles of BM * H fp32 (the residual stream between the blocks)
+template <int H>
+__global__ void __launch_bounds__(ec::THREADS, 1)
+enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_w,
+                 const float *__restrict__ bias, float *__restrict__ h, float *__restrict__ scratch,
+                 int64_t n_tokens, int L)
+{
+    using namespace tc;
+    using namespace ec;
+    using P = Plan<H>;
+    constexpr int NQT = H / NQ;                // accumulator quarters per GEMM (4 at H = 512)
+    constexpr int NKC = H / BK;                // K-chunks per GEMM (8 at H = 512)
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    if ((sbase & 1023u) != 0)
+        __trap();
+    enum { W_FULL = 0, W_EMPTY = W_FULL + W_STAGES, ACC_FULL = W_EMPTY + W_STAGES, ACC_EMPTY = ACC_FULL + 2,
+           A_RDY = ACC_EMPTY + 2, A0_FULL = A_RDY + 4, A_FREE = A0_FULL + 1, N_BARS = A_FREE + 1 };
+    static_assert(8 * N_BARS + 8 <= 512, "barrier area");
+    auto bar = [&](int i) { return sbase + P::OFF_BARS + 8 * i; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + P::OFF_BARS + 8 * N_BARS);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const int64_t n_tiles = (n_tokens + BM - 1) / BM;
+    const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < W_STAGES; ++s) {
+            mbar_init(bar(W_FULL + s), 1);
+            mbar_init(bar(W_EMPTY + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar(ACC_FULL + b), 1);
+            mbar_init(bar(ACC_EMPTY + b), 256);
+        }
+        for (int q = 0; q < 4; ++q)
+            mbar_init(bar(A_RDY + q), 256);
+        mbar_init(bar(A0_FULL), 1);
+        mbar_init(bar(A_FREE), 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= weight producer: runs ahead of the MMAs across GEMM and tile boundaries =================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < my_tiles; ++t)
+                for (int g = 0; g < L; ++g)
+                    for (int q = 0; q < NQT; ++q)
+                        for (int kc = 0; kc < NKC; ++kc) {
+                            mbar_wait<32>(bar(W_EMPTY + s), ph ^ 1u);
+                            mbar_expect_tx(bar(W_FULL + s), W_STAGE);
+                            tma_load_2d(sbase + P::OFF_W + s * W_STAGE, &map_w, bar(W_FULL + s), kc * BK, g * H + q * NQ);
+                            if (++s == W_STAGES) {
+                                s = 0;
+                                ph ^= 1u;
+                            }
+                        }
+        }
+    } else if (warp == 3) {
+        // ================= first operand of every tile: bf16(gelu(h0)) rows by TMA =================
+        if (lane == 0) {
+            for (int t = 0; t < my_tiles; ++t) {
+                if (t > 0)
+                    mbar_wait<64>(bar(A_FREE), (uint32_t)((t - 1) & 1));    // the last GEMM that read the smem tile is done
+                const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
+                mbar_expect_tx(bar(A0_FULL), P::A_BYTES);
+#pragma unroll
+                for (int kc = 0; kc < NKC; ++kc)
+                    tma_load_2d(sbase + P::OFF_A + kc * (BM * BK * 2), &map_a0, bar(A0_FULL), kc * BK, (int)(tile * BM));
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_bf16(NQ);
+            int s = 0;
+            uint32_t wph = 0;
+            uint32_t acc_n = 0;                                  // accumulator quarters issued so far
+            uint32_t ardy_n = 0;                                 // completed A_RDY phases (per quarter barrier) so far
+            for (int t = 0; t < my_tiles; ++t) {
+                mbar_wait<32>(bar(A0_FULL), (uint32_t)(t & 1));
+                for (int g = 0; g < L; ++g) {
+                    const bool from_tmem = (g & 1) != 0;         // even GEMMs read shared memory, odd ones tensor memory
+                    for (int q = 0; q < NQT; ++q, ++acc_n) {
+                        const int ab = (int)(acc_n & 1u);
+                        mbar_wait<32>(bar(ACC_EMPTY + ab), ((acc_n >> 1) & 1u) ^ 1u);
+                        const uint32_t d = tmem_base + P::TMEM_ACC0 + ab * NQ;
+                        for (int kc = 0; kc < NKC; ++kc) {
+                            if (g > 0 && q == 0 && (kc & 1) == 0)    // K-chunks 2j, 2j+1 = quarter j of the previous epilogue
+                                mbar_wait<32>(bar(A_RDY + (kc >> 1)), ardy_n & 1u);
+                            mbar_wait<32>(bar(W_FULL + s), wph);
+                            tc_fence_after();
+                            const uint64_t wd = desc_sw128(sbase + P::OFF_W + s * W_STAGE);
+                            if (!from_tmem) {
+                                const uint64_t ad = desc_sw128(sbase + P::OFF_A + kc * (BM * BK * 2));
+#pragma unroll
+                                for (int j = 0; j < BK / 16; ++j)
+                                    umma_bf16(d, ad + 2 * j, wd + 2 * j, idesc, (kc | j) != 0);
+                            } else {
+                                const uint32_t at = tmem_base + kc * (BK / 2);
+#pragma unroll
+                                for (int j = 0; j < BK / 16; ++j)
+                                    umma_bf16_ts(d, at + 8 * j, wd + 2 * j, idesc, (kc | j) != 0);
+                            }
+                            umma_commit(bar(W_EMPTY + s));
+                            if (++s == W_STAGES) {
+                                s = 0;
+                                wph ^= 1u;
+                            }
+                        }
+                        umma_commit(bar(ACC_FULL + ab));
+                    }
+                    if (g > 0)
+                        ++ardy_n;
+                    if (g == L - 2)
+                        umma_commit(bar(A_FREE));                // every MMA that reads the smem tile has been issued
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: TMEM -> bias (+ residual) -> GELU -> bf16 -> next operand =================
+        const int q4 = warp & 3;                                 // TMEM lane quarter
+        const int ch = (warp - 4) >> 2;                          // column half of the 128-column accumulator
+        const int r = q4 * 32 + lane;                            // row of the tile
+        float *scr = scratch + (size_t)blockIdx.x * (BM * H);
+        uint32_t acc_n = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t row = tile * BM + r;
+            const bool row_ok = row < n_tokens;
+            for (int g = 0; g < L; ++g) {
+                const bool odd = (g & 1) != 0, last = g == L - 1;
+                const bool h_in_std = g == 1, h_out_std = last;   // first block reads, last block writes the caller's h
+                for (int q = 0; q < NQT; ++q, ++acc_n) {
+                    const int ab = (int)(acc_n & 1u);
+                    const int colq = q * NQ + ch * 64;           // this thread's 64 columns of the GEMM's output
+                    // residual slab 0 is fetched before the accumulator is waited for
+                    float hv[32];
+                    auto load_h = [&](int col0) {
+                        if (h_in_std) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 v = row_ok ? __ldcs(reinterpret_cast<const float4 *>(h + row * H + col0) + c)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                                hv[4 * c] = v.x; hv[4 * c + 1] = v.y; hv[4 * c + 2] = v.z; hv[4 * c + 3] = v.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 v = *reinterpret_cast<const float4 *>(scr + ((size_t)((col0 >> 2) + c) * BM + r) * 4);
+                                hv[4 * c] = v.x; hv[4 * c + 1] = v.y; hv[4 * c + 2] = v.z; hv[4 * c + 3] = v.w;
+                            }
+                        }
+                    };
+                    if (odd)
+                        load_h(colq);
+                    if (warp == 4)
+                        mbar_wait<32>(bar(ACC_FULL + ab), (acc_n >> 1) & 1u);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + P::TMEM_ACC0 + ab * NQ + ch * 64 + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll
+                    for (int sl = 0; sl < 2; ++sl) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + sl * 32, v);
+                        tmem_wait_ld_fence(v);
+                        if (sl == 1) {
+                            tc_fence_before();
+                            mbar_arrive(bar(ACC_EMPTY + ab));    // the last slab sits in registers: the accumulator is free
+                        }
+                        const int col0 = colq + sl * 32;
+                        if (odd && sl == 1)
+                            load_h(col0);
+                        float x[32];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + (size_t)g * H + col0) + c);
+                            x[4 * c] = __uint_as_float(v[4 * c]) + b.x;
+                            x[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + b.y;
+                            x[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + b.z;
+                            x[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + b.w;
+                        }
+                        if (odd) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c)
+                                x[c] += hv[c];
+                            if (h_out_std) {
+                                if (row_ok) {
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c)
+                                        __stcs(reinterpret_cast<float4 *>(h + row * H + col0) + c,
+                                               make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
+                                }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    *reinterpret_cast<float4 *>(scr + ((size_t)((col0 >> 2) + c) * BM + r) * 4) =
+                                        make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                            }
+                        }
+                        if (!last) {
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                const __nv_bfloat162 p2 = __floats2bfloat162_rn(gelu(x[2 * c]), gelu(x[2 * c + 1]));
+                                pk[c] = *reinterpret_cast<const uint32_t *>(&p2);
+                            }
+                            if (!odd) {
+                                // even GEMM: the next operand goes to tensor memory, 16 columns of packed pairs
+                                tmem_st16(tmem_base + (col0 >> 1) + ((uint32_t)(q4 * 32) << 16), pk);
+                            } else {
+                                // odd GEMM: the next operand goes to the smem tile (K-chunk col0 / 64, SW128 rows)
+                                unsigned char *arow = smem + P::OFF_A + (col0 >> 6) * (BM * BK * 2) + r * 128;
+                                const int c16 = (col0 & 63) >> 3;        // first 16-byte chunk of the 128-byte row
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    *reinterpret_cast<uint4 *>(arow + (((c16 + c) ^ (r & 7)) << 4)) =
+                                        make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                            }
+                        }
+                    }
+                    if (!last) {
+                        if (!odd) {
+                            tmem_wait_st();
+                            tc_fence_before();
+                        } else {
+                            fence_proxy_async();
+                        }
+                        mbar_arrive(bar(A_RDY + q));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+bool enc_chain_supported(int H, int L) { return (H == 512 || H == 256) && L >= 2 && L % 2 == 0 && L <= 64; }
+
+size_t enc_chain_scratch_bytes(int H, int sm_count) { return (size_t)sm_count * ec::BM * H * sizeof(float); }
+
+cudaError_t launch_enc_chain(const void *a0, float *h, const void *w, const float *bias, int64_t n_tokens, int H, int L,
+                             float *scratch, size_t scratch_bytes, int sm_count, int max_smem, cudaStream_t st)
+{
+    using namespace ec;
+    if (!enc_chain_supported(H, L))
+        return cudaErrorNotSupported;
+    if (n_tokens == 0)
+        return cudaSuccess;
+    if (n_tokens >= (1ll << 31))
+        return cudaErrorNotSupported;
+    const int64_t tiles = (n_tokens + BM - 1) / BM;
+    const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    if (scratch_bytes < (size_t)grid * BM * H * sizeof(float))
+        return cudaErrorInvalidValue;
+    const int smem_bytes = H == 512 ? Plan<512>::SMEM_BYTES : Plan<256>::SMEM_BYTES;
+    if (smem_bytes > max_smem)
+        return cudaErrorNotSupported;
+    CUtensorMap map_a0, map_w;
+    if (!tc::make_tensor_map_2d(&map_a0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a0, n_tokens, H, BM, BK,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
+        !tc::make_tensor_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, (int64_t)L * H, H, NQ, BK,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
+        return cudaErrorNotSupported;
+    auto kern = H == 512 ? enc_chain_kernel<512> : enc_chain_kernel<256>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (err != cudaSuccess)
+        return err;
+    kern<<<grid, THREADS, smem_bytes, st>>>(map_a0, map_w, bias, h, scratch, n_tokens, L);
+    return cudaGetLastError();
+}
+
+}  // namespace vqb

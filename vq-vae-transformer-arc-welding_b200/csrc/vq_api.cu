@@ -283,6 +283,44 @@ int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const f
     return VQB_OK;
 }
 
+size_t vqb_encoder_chain_scratch_bytes(int device, int hidden)
+{
+    vqb_device_info info;
+    if (device_info(device, &info) != VQB_OK || hidden <= 0)
+        return 0;
+    return enc_chain_scratch_bytes(hidden, info.sm_count);
+}
+
+int vqb_encoder_chain(int device, const void *a0_bf16, float *h, const void *w_bf16, const float *bias, int64_t n_tokens,
+                      int hidden, int n_layers, void *scratch, size_t scratch_bytes, void *stream)
+{
+    if (!a0_bf16 || !h || !w_bf16 || !bias || !scratch || n_tokens < 0 || hidden <= 0 || n_layers <= 0)
+        return VQB_E_ARG;
+    if (!enc_chain_supported(hidden, n_layers) || !aligned(a0_bf16, 16) || !aligned(w_bf16, 16) || !aligned(bias, 16) ||
+        !aligned(h, 16) || !aligned(scratch, 16))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    if (scratch_bytes < enc_chain_scratch_bytes(hidden, info.sm_count))
+        return VQB_E_WORKSPACE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_enc_chain(a0_bf16, h, w_bf16, bias, n_tokens, hidden, n_layers, (float *)scratch, scratch_bytes,
+                           info.sm_count, info.max_smem_per_block, (cudaStream_t)stream);
+    if (err == cudaErrorNotSupported)
+        return VQB_E_UNSUPPORTED;
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_tokens > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
 int vqb_token_bias_gelu(int device, float *h, const float *bias, void *out_bf16, int64_t n_tokens, int n, void *stream)
 {
     if (!h || !bias || !out_bf16 || n_tokens < 0 || n <= 0)

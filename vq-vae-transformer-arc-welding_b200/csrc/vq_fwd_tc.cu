@@ -68,6 +68,9 @@ constexpr int W_SVC = VQB_ROLEMAP ? 4 * GROUPS + 4 : 0;      // service warpgrou
 #ifndef VQB_LDPIPE
 #define VQB_LDPIPE 1
 #endif
+#ifndef VQB_MMA_ORDER
+#define VQB_MMA_ORDER 0
+#endif
 // Register pool of the CTA = THREADS x (registers at launch); setmaxnreg moves it between the warpgroups:
 // 4 groups: 768 x 80 = 61440 = 128 x (40 + 56 + 4 x 96);  3 groups: 640 x 96 = 61440 = 128 x (40 + 56 + 3 x 128).
 // (An increase beyond what the other warpgroups released blocks forever.)
@@ -549,12 +552,21 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 const uint32_t d = tmem_base + b * KMAX;
                 const bool wide = p.D - 32 * dc > 16;                  // else components 16..31 of this chunk are padding
                 // K-slices of 16 bf16 = 32 bytes = +2 in the descriptor's address field
+#if VQB_MMA_ORDER == 0
                 umma_bf16(d, a + 0, bm + 0, idesc, dc);                // z1[0:16]  . E1[0:16]
                 if (wide) umma_bf16(d, a + 2, bm + 2, idesc, 1);       // z1[16:32] . E1[16:32]
                 umma_bf16(d, a + 0, bm + 4, idesc, 1);                 // z1[0:16]  . E2[0:16]
                 if (wide) umma_bf16(d, a + 2, bm + 6, idesc, 1);       // z1[16:32] . E2[16:32]
                 umma_bf16(d, a + 4, bm + 0, idesc, 1);                 // z2[0:16]  . E1[0:16]
                 if (wide) umma_bf16(d, a + 6, bm + 2, idesc, 1);       // z2[16:32] . E1[16:32]
+#else       // consecutive MMAs share their B operand slice
+                umma_bf16(d, a + 0, bm + 0, idesc, dc);                // z1[0:16]  . E1[0:16]
+                umma_bf16(d, a + 4, bm + 0, idesc, 1);                 // z2[0:16]  . E1[0:16]
+                if (wide) umma_bf16(d, a + 2, bm + 2, idesc, 1);       // z1[16:32] . E1[16:32]
+                if (wide) umma_bf16(d, a + 6, bm + 2, idesc, 1);       // z2[16:32] . E1[16:32]
+                umma_bf16(d, a + 0, bm + 4, idesc, 1);                 // z1[0:16]  . E2[0:16]
+                if (wide) umma_bf16(d, a + 2, bm + 6, idesc, 1);       // z1[16:32] . E2[16:32]
+#endif
                 umma_commit(bar(A_EMPTY + ba));
                 if (dc == nd - 1) {
                     umma_bf16(d, aaug, baug, idesc, 1);                // + ee_k

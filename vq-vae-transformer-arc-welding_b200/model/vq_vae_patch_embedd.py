@@ -182,6 +182,8 @@ class VQVAEPatch(Autoencoder):
     #: operands / fp32 accumulation -- the operand precision the reference itself selects with
     #: torch.set_float32_matmul_precision('medium') (train_*.py), without the element-wise passes.
     encoder_mode = "torch"
+    #: in "fused_bf16" mode: all residual blocks in one launch (csrc/enc_chain.cu) instead of one launch per layer
+    fused_chain = True
 
     def encode(self, x):
         """x (B, seq_len, input_dim) -> z_e (B, T, D)."""
@@ -217,9 +219,16 @@ class VQVAEPatch(Autoencoder):
                     w1, b1 = fold(blk.block[1], blk.block[2], blk.padding)
                     w2, b2 = fold(blk.block[4], blk.block[5], blk.padding)
                     ws.append((w1, b1, w2, b2))
-            cache = (key, ws)
+            # the same layers stacked for the one-launch chain kernel: (L, H, H) bf16 and (L, H) fp32
+            stack_w = torch.stack([w for blk in ws for w in (blk[0], blk[2])]).contiguous()
+            stack_b = torch.stack([b for blk in ws for b in (blk[1], blk[3])]).contiguous()
+            cache = (key, ws, stack_w, stack_b)
             object.__setattr__(self, "_fused_cache", cache)
         return cache[1]
+
+    def _fused_stack(self):
+        self._fused_weights()
+        return self._fused_cache[2], self._fused_cache[3]
 
     def encode_fused_bf16(self, x):
         """The encoder with its 16 hidden x hidden layers on the fused kernel: tokens (B*T, H) stay row-major,
@@ -236,6 +245,13 @@ class VQVAEPatch(Autoencoder):
             patches = x.permute(0, 2, 1).reshape(-1, pe.patch_size)                   # (B*T, P)
             h = torch.matmul(patches, pe.proj.weight[:, 0, :].t())                    # (B*T, H) fp32, bias added below
             a = ops.token_bias_gelu(h, pe.proj.bias)                                   # h += b; a = bf16(gelu(h)), one pass
+        if self.fused_chain and h.shape[1] in (256, 512) and len(self.encoder[0].shared_conv) >= 1:
+            # every residual block in ONE launch: the token tile never leaves the SM between the layers (vqb_encoder_chain)
+            stack_w, stack_b = self._fused_stack()
+            ops.encoder_chain(a, h, stack_w, stack_b)
+            proj = self.encoder[1].shared_conv
+            z_e = F.linear(h, proj.weight[:, :, 0], proj.bias)
+            return z_e.view(b, -1, z_e.shape[-1])
         u = torch.empty_like(a)
         blocks = self._fused_weights()
         for i, (w1, b1, w2, b2) in enumerate(blocks):

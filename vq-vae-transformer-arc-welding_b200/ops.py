@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import collections
 import ctypes
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -17,8 +18,8 @@ PATHS = {"auto": _lib.PATH_AUTO, "fma": _lib.PATH_FMA, "tc": _lib.PATH_TC}
 KEEP_CODEBOOK, KEEP_TC_IMAGE = 4, 8            # VQB_KEEP_* (include/vqb200.h)
 IDS_FLAGS = {"int64": 0, "uint8": 16, "uint16": 32}   # VQB_IDS_*
 
-#: reuse what the workspace holds about a codebook (code norms, census, tcgen05 operand image) while the weight tensor's
-#: (data_ptr, _version) stay the same -- in inference the codebook kernels then run once, not once per call.  In-place
+#: reuse what the workspace holds about a codebook (code norms, census, tcgen05 operand image) while the caller passes the
+#: SAME tensor object with the same (data_ptr, _version) -- in inference the codebook kernels then run once, not once per call.  In-place
 #: updates through autograd-visible ops (optimizers, copy_, load_state_dict) bump _version; writing through `.data`
 #: does not: call clear_workspaces() after such a write, or switch this off.
 CACHE_CODEBOOK = True
@@ -26,7 +27,7 @@ CACHE_CODEBOOK = True
 # (device, k, d, stream handle) -> workspace tensor; least recently used entries are dropped beyond _WS_MAX (one entry
 # holds ~3.2 MB, mostly the fix-up queues), clear_workspaces() empties it
 _workspaces: "collections.OrderedDict" = collections.OrderedDict()
-_ws_state = {}          # id(workspace tensor) -> (weight data_ptr, weight _version, tcgen05 image valid)
+_ws_state = {}          # id(workspace tensor) -> (weakref to the weight tensor, data_ptr, _version, tcgen05 image valid)
 _WS_MAX = 16
 
 
@@ -148,10 +149,12 @@ def forward(z: torch.Tensor, weight: torch.Tensor, beta: float, path: str = "aut
         stream = torch.cuda.current_stream(dev).cuda_stream
         # what this workspace already holds about this very codebook (see CACHE_CODEBOOK)
         flags = PATHS[path]
-        tag = (w.data_ptr(), w._version)
+        # (identity of the tensor OBJECT, not only of its address: the caching allocator hands a freed block to the next
+        # tensor of the same size, which would then look like the old codebook at version 0)
+        tag = (weight.data_ptr(), weight._version)
         state = _ws_state.get(id(ws)) if CACHE_CODEBOOK else None
-        if state is not None and state[:2] == tag:
-            flags |= KEEP_CODEBOOK | (KEEP_TC_IMAGE if state[2] else 0)
+        if state is not None and state[0]() is weight and state[1:3] == tag and w.data_ptr() == tag[0]:
+            flags |= KEEP_CODEBOOK | (KEEP_TC_IMAGE if state[3] else 0)
         contiguous_rows = s_d == 1 and n_inner == 1 and s_outer == d
         takes_tc = (path != "fma" and contiguous_rows and k <= 256 and _tc_eligible(n, k, d) and n < (1 << 31)
                     and zsrc.data_ptr() % 16 == 0)
@@ -165,7 +168,7 @@ def forward(z: torch.Tensor, weight: torch.Tensor, beta: float, path: str = "aut
             ws_ptr, ws_bytes, flags, stream)
     _lib.check(rc, "vqb_forward")
     if CACHE_CODEBOOK:
-        _ws_state[id(ws)] = tag + (takes_tc or bool(flags & KEEP_TC_IMAGE),)
+        _ws_state[id(ws)] = (weakref.ref(weight),) + tag + (takes_tc or bool(flags & KEEP_TC_IMAGE),)
     out = (scal[0] if want_loss else None, zq, scal[1], idx, counts)
     return out + (stats,) if want_stats else out
 
@@ -430,3 +433,36 @@ def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, patch
                                  torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(rc, "vqb_patch_embed")
     return h, a
+
+
+_chain_scratch = {}
+
+
+def encoder_chain(a0: torch.Tensor, h: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """All residual blocks of the patch encoder in one launch (vqb_encoder_chain, csrc/enc_chain.cu):
+    for every block b:  h <- h + w[2b+1] gelu(w[2b] gelu(h) + bias[2b]) + bias[2b+1], h updated in place and returned.
+    a0 (T, H) bf16 = bf16(gelu(h)); h (T, H) fp32; w (L, H, H) bf16 (out x in per layer); bias (L, H) fp32; H in {256, 512}."""
+    for t, name, dt in ((a0, "a0", torch.bfloat16), (h, "h", torch.float32), (w, "w", torch.bfloat16),
+                        (bias, "bias", torch.float32)):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != dt or not t.is_contiguous():
+            raise RuntimeError(f"encoder_chain: {name} must be a contiguous CUDA {dt} tensor (no CPU fallback)")
+    if h.dim() != 2 or a0.shape != h.shape or w.dim() != 3 or w.shape[1] != h.shape[1] or w.shape[2] != h.shape[1] \
+            or tuple(bias.shape) != (w.shape[0], h.shape[1]):
+        raise RuntimeError("encoder_chain: shape mismatch")
+    lib = _lib.load()
+    dev = h.device
+    hidden, layers = h.shape[1], w.shape[0]
+    with torch.cuda.device(dev):
+        key = (dev.index, hidden, torch.cuda.current_stream(dev).cuda_stream)
+        scratch = _chain_scratch.get(key)
+        if scratch is None:
+            nbytes = lib.vqb_encoder_chain_scratch_bytes(dev.index, hidden)
+            if nbytes == 0:
+                raise RuntimeError("encoder_chain: unsupported device / hidden size")
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _chain_scratch[key] = scratch
+        rc = lib.vqb_encoder_chain(dev.index, a0.data_ptr(), h.data_ptr(), w.data_ptr(), bias.data_ptr(), h.shape[0],
+                                   hidden, layers, scratch.data_ptr(), scratch.numel(),
+                                   torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "vqb_encoder_chain")
+    return h
