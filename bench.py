@@ -18,6 +18,12 @@ z_q + ids + scalars back on the host, copies inside the timed region); `roofline
 dominant kernel against the measured HBM peak; `cpu_baseline` = the reference's op sequence
 on this box's host cores (oracle port, bounded sample).
 
+Further objects on the same line (each measured in this run, none part of `value`): `bulk_encode` = BASELINE
+configs[2], bulk latent-dataset encoding through LatentSpaceEncoder (synthetic cycles in, ids out, fused encoder chain
++ fused quantiser) with its tensor-roofline fraction, id match against the fp32 encoder and the reference's loop on
+host cores; `config1_forward` = BASELINE configs[0], the whole VQVAEPatch.forward at batch 256 on the GPU next to the
+reference's op sequence on host cores; `backward` = the straight-through backward call.
+
 --impl reference times that CPU port alone (the reference is a Python/PyTorch program whose
 own files cannot travel to the GPU box) on the same config and metric.
 """
@@ -180,6 +186,211 @@ def run_reference(args) -> None:
 
 
 # ---------------------------------------------------------------------------------------
+# host-side helpers of the e2e leg
+# ---------------------------------------------------------------------------------------
+def bind_to_gpu_numa(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so that the pinned staging buffers it
+    allocates next are first-touched on that GPU's NUMA node (eight ranks otherwise share one node's memory
+    controllers).  Returns (previous affinity, number of CPUs now used) or (None, None)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {i * 64 + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        before = os.sched_getaffinity(0)
+        cpus &= before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return before, len(cpus)
+    except Exception:
+        pass
+    return None, None
+
+
+def copy_roofline(torch, dev, z_host, zq_host, idx_host, reps: int = 3):
+    """Bare pinned copies of the e2e leg's buffers, no kernels: H2D alone, D2H alone, and both at once on two streams
+    (what vqb_encode_host overlaps).  The duplex time is the floor of the e2e step on this host."""
+    d_in = torch.empty(z_host.shape, dtype=z_host.dtype, device=dev)
+    d_zq = torch.empty(zq_host.shape, dtype=zq_host.dtype, device=dev)
+    d_idx = torch.empty(idx_host.shape, dtype=idx_host.dtype, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def timed(h2d: bool, d2h: bool) -> float:
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s1.wait_stream(torch.cuda.current_stream(dev))
+        s2.wait_stream(torch.cuda.current_stream(dev))
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(z_host, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    zq_host.copy_(d_zq, non_blocking=True)
+                    idx_host.copy_(d_idx, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(s1)
+        torch.cuda.current_stream(dev).wait_stream(s2)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    timed(True, True)
+    h2d_ms, d2h_ms, duplex_ms = timed(True, False), timed(False, True), timed(True, True)
+    in_b = z_host.numel() * 4
+    out_b = zq_host.numel() * 4 + idx_host.numel() * idx_host.element_size()
+    return {"h2d_gbs": in_b / h2d_ms / 1e6, "d2h_gbs": out_b / d2h_ms / 1e6, "duplex_ms": duplex_ms,
+            "h2d_ms": h2d_ms, "d2h_ms": d2h_ms}
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE configs[2]: bulk latent-dataset encoding (dataloader/latentspace_dataloader.py:205-243)
+# ---------------------------------------------------------------------------------------
+CYCLE_FLOP = 16 * 8_463_360        # SURVEY.md section 8(d): patchify 25.6 k + res blocks 8388.6 k + proj 32.8 k + VQ 16.4 k per token
+
+
+def default_model(torch, vqb200, dev):
+    torch.manual_seed(0)
+    return vqb200.VQVAEPatch(hidden_dim=512, input_dim=2, num_embeddings=K_CODES, embedding_dim=DIM, n_resblocks=8,
+                             learning_rate=1e-3, dropout_p=0.1, patch_size=25, batch_norm=False).to(dev).eval()
+
+
+def bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier):
+    from vqb200.dataloader import LatentSpaceEncoder
+    chunk, n_chunks = args.bulk_chunk, args.bulk_chunks
+    model = default_model(torch, vqb200, dev)
+    model.encoder_mode = "fused_bf16"
+    enc = LatentSpaceEncoder(model, window_size=200, device=str(dev))
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    pool = [torch.randn(chunk, 200, 2, device=dev, generator=g) for _ in range(2)]     # 2 x 105 MB: larger than L2
+    with torch.no_grad():
+        for i in range(2):
+            ids = enc.get_latent_space_IDs(pool[i & 1], has_patch_embed=True)
+        barrier()
+        l0 = lib.vqb_launch_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_chunks):
+            ids = enc.get_latent_space_IDs(pool[i & 1], has_patch_embed=True)
+        e1.record()
+        barrier()
+        launches = lib.vqb_launch_counter() - l0
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        # id match of the bf16-operand encoder against the fp32 encoder (TF32 off) on a sample of the same cycles
+        sample = pool[0][:4096]
+        got = enc.get_latent_space_IDs(sample, has_patch_embed=True).view(-1)
+        tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        model.encoder_mode = "torch"
+        ref = enc.get_latent_space_IDs(sample, has_patch_embed=True).view(-1)
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        match = float((got == ref).float().mean().item())
+    if rank != 0:
+        return None
+    cycles = world * chunk * n_chunks
+    patches = cycles * model.enc_out_len
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak_tf, peak_src = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+    achieved_tf = cycles * CYCLE_FLOP / (ms_max * 1e-3) / 1e12 / world       # per GPU
+    out = {
+        "workload": f"BASELINE configs[2]: LatentSpaceEncoder.get_latent_space_IDs on synthetic cycles randn(., 200, 2), "
+                    f"{n_chunks} chunks of {chunk} cycles per GPU resident in HBM, ids (int64) out; default model "
+                    f"(H=512, 8 res blocks, K={K_CODES}, D={DIM}), random-init weights seed 0",
+        "value": patches / (ms_max * 1e-3), "unit": UNIT, "per_gpu": patches / world / (ms_max * 1e-3),
+        "n_gpus": world, "ms_per_chunk": ms_max / n_chunks, "cycles_per_s": cycles / (ms_max * 1e-3),
+        "encoder_precision": "bf16 operands, fp32 accumulation and residual stream (encoder_mode='fused_bf16': "
+                             "vqb_patch_embed + vqb_encoder_chain), fp32 projection, exact quantiser",
+        "id_match_vs_fp32_encoder": {"rate": match, "rows": int(got.numel())},
+        "gpu_launches_per_chunk": launches / n_chunks,
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf, "flop_per_cycle": CYCLE_FLOP, "peak_source": peak_src,
+                     "traffic": None},
+    }
+    if not args.no_cpu:
+        # the reference's loop on host cores: per 512-window batch, cycle by cycle (one encode call per cycle slice)
+        from oracle import vq_oracle as O
+        torch.set_float32_matmul_precision("highest")
+        try:
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+        except Exception:
+            pass
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        xb = torch.randn(512, 200, 2, generator=torch.Generator().manual_seed(1000))
+        times = []
+        with torch.no_grad():
+            for i in range(4):
+                t0 = time.perf_counter()
+                z_e = O.torch_port_encode(sd, xb.clone(), 25)
+                O.torch_port_forward(z_e, sd["vector_quantization.embedding.weight"], BETA)[4].numpy().reshape(512, -1)
+                dt = time.perf_counter() - t0
+                if i:
+                    times.append(dt)
+                if sum(times) > 15.0:
+                    break
+        out["cpu_baseline"] = {"value": 512 * 16 * len(times) / sum(times), "unit": UNIT, "cores": torch.get_num_threads(),
+                               "kind": "port",
+                               "sample": f"{len(times)} encode calls of 512 cycles (the reference's per-cycle-slice call, "
+                                         f"dataloader/latentspace_dataloader.py:231-235) in {sum(times):.1f} s"}
+    return out
+
+
+def config1_leg(args, torch, vqb200, dev):
+    """BASELINE configs[0]: VQVAEPatch reconstruction forward, batch 256, fp32, eval."""
+    model = default_model(torch, vqb200, dev)
+    x = torch.randn(256, 200, 2, generator=torch.Generator().manual_seed(0))
+    xd = x.to(dev)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        for _ in range(2):
+            model(xd)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            model(xd)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    gpu_ms = e0.elapsed_time(e1) / 5
+    out = {"workload": "BASELINE configs[0]: VQVAEPatch.forward (encode + quantise + decode), batch 256, fp32 (TF32 off), eval",
+           "gpu_ms": gpu_ms, "gpu_patches_per_s": 256 * 16 / (gpu_ms * 1e-3)}
+    if not args.no_cpu:
+        from oracle import vq_oracle as O
+        torch.set_float32_matmul_precision("highest")
+        try:
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+        except Exception:
+            pass
+        cpu_model = default_model(torch, vqb200, torch.device("cpu"))     # stock PyTorch modules: the decoder half
+        sd = {k: v.detach() for k, v in cpu_model.state_dict().items()}
+        times = []
+        with torch.no_grad():
+            for i in range(4):
+                t0 = time.perf_counter()
+                z_e = O.torch_port_encode(sd, x, 25)                                         # :158-160
+                _, z_q, _, _, _ = O.torch_port_forward(z_e, sd["vector_quantization.embedding.weight"], BETA)   # :161
+                cpu_model.reverse_patch_embed(cpu_model.decoder(z_q.permute(0, 2, 1)))       # :164-165
+                dt = time.perf_counter() - t0
+                if i:
+                    times.append(dt)
+        cpu_ms = 1e3 * sum(times) / len(times)
+        out.update({"cpu_ms": cpu_ms, "cpu_patches_per_s": 256 * 16 / (cpu_ms * 1e-3), "cpu_cores": torch.get_num_threads(),
+                    "cpu_kind": "port (reference op sequence: encoder loop + VQ ops + stock decoder modules)"})
+    return out
+
+
+# ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
 def run_ours(args) -> None:
@@ -262,11 +473,14 @@ def run_ours(args) -> None:
     # ---- end to end through the host-buffer C-ABI call --------------------------------
     e2e = None
     if not args.no_e2e:
+        affinity_before, numa_cpus = bind_to_gpu_numa(local_rank)
         z_host = torch.empty((n, DIM), dtype=torch.float32).pin_memory()
         z_host.copy_(z)
         zq_host = torch.empty((n, DIM), dtype=torch.float32).pin_memory()
         idx_host = torch.empty((n,), dtype=torch.int64).pin_memory()
+        idx8_host = torch.empty((n,), dtype=torch.uint8).pin_memory()
         counts_host = np.zeros(K_CODES, np.uint64)
+        roof = copy_roofline(torch, dev, z_host, zq_host, idx_host)
         enc = ops.HostEncoder(weight, device=local_rank, chunk_rows=args.chunk_rows, depth=3)
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
@@ -290,11 +504,20 @@ def run_ours(args) -> None:
             lib.vqb_host_last_ms(enc._ctx, ctypes.byref(ms_buf))
             ids_ms += ms_buf.value
         barrier()
-        te = torch.tensor([dev_ms, wall * 1e3, ids_ms], device=dev, dtype=torch.float64)
+        # compact ids: the same ids as one byte each (K <= 256), what a tokeniser that keeps uint8 tokens reads back
+        ids8_ms = 0.0
+        for _ in range(e2e_steps):
+            enc.encode(z_host, BETA, idx_out=idx8_host, path=args.path)
+            lib.vqb_host_last_ms(enc._ctx, ctypes.byref(ms_buf))
+            ids8_ms += ms_buf.value
+        barrier()
+        te = torch.tensor([dev_ms, wall * 1e3, ids_ms, ids8_ms, roof["duplex_ms"], roof["h2d_ms"], roof["d2h_ms"]],
+                          device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms, ids_ms = (float(v) for v in te.tolist())
+        dev_ms, wall_ms, ids_ms, ids8_ms, duplex_ms, h2d_ms, d2h_ms = (float(v) for v in te.tolist())
         assert torch.equal(idx_host.to(dev), idx.view(-1)), "host path and device path disagree"
+        assert torch.equal(idx8_host.to(dev).to(torch.int64), idx.view(-1)), "compact ids disagree"
         e2e = {
             "value": world * n * e2e_steps / (max(dev_ms, 1e-9) * 1e-3), "unit": UNIT,
             "h2d_bytes_per_step": n * DIM * 4,
@@ -303,10 +526,25 @@ def run_ours(args) -> None:
             "timing": "CUDA events inside vqb_encode_host, first H2D to last D2H; wall clock alongside",
             "chunk_rows": args.chunk_rows, "gpu_launches_per_step": e2e_launches,
             "ids_only": {"value": world * n * e2e_steps / (max(ids_ms, 1e-9) * 1e-3), "unit": UNIT,
-                         "d2h_bytes_per_step": n * 8 + 8},
+                         "d2h_bytes_per_step": n * 8 + 8,
+                         "copy_floor_frac": h2d_ms / (ids_ms / e2e_steps) if ids_ms > 0 else None},
+            "ids_u8": {"value": world * n * e2e_steps / (max(ids8_ms, 1e-9) * 1e-3), "unit": UNIT,
+                       "d2h_bytes_per_step": n + 8,
+                       "copy_floor_frac": h2d_ms / (ids8_ms / e2e_steps) if ids8_ms > 0 else None},
+            # bare pinned copies of the same buffers on this host with all ranks copying at once (max over ranks): the
+            # floor of the step; frac = floor / measured step
+            "copy_roofline": {"h2d_ms": h2d_ms, "d2h_ms": d2h_ms, "duplex_ms": duplex_ms,
+                              "h2d_gbs_per_gpu": n * DIM * 4 / h2d_ms / 1e6,
+                              "d2h_gbs_per_gpu": (n * DIM * 4 + n * 8) / d2h_ms / 1e6,
+                              "frac": duplex_ms / (dev_ms / e2e_steps) if dev_ms > 0 else None,
+                              "what": "concurrent cudaMemcpyAsync H2D (z) + D2H (z_q, ids) of the step's pinned buffers, "
+                                      "no kernels, all ranks at once"},
+            "numa": {"bound_to_gpu_local_cpus": numa_cpus},
         }
         enc.close()
-        del z_host, zq_host, idx_host
+        del z_host, zq_host, idx_host, idx8_host
+        if affinity_before is not None:
+            os.sched_setaffinity(0, affinity_before)
     clocks = sampler.stop()
 
     # ---- straight-through backward on the same batch (reported beside the headline, not part of it) ----
@@ -330,16 +568,36 @@ def run_ours(args) -> None:
         bwd_ms = float(tb.item())
         del gq
 
+    # ---- BASELINE configs[2]: bulk latent-dataset encoding, every rank on its own shard ----
+    bulk = None
+    if not args.no_bulk:
+        idx_keep = idx[: 1 << 16].clone()
+        z_keep = z[: 1 << 16].clone()
+        del z, zq, idx, out            # make room: the encoder's activations want ~10 GB per chunk
+        torch.cuda.empty_cache()
+        bulk = bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier)
+        z, idx = z_keep, idx_keep
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- index match rate vs the oracle on a sample (outside every timed region) ------
+    cfg1 = config1_leg(args, torch, vqb200, dev) if not args.no_config1 else None
+
+    # ---- index match rate on a sample (outside every timed region): against the C oracle and against the
+    # reference's own torch op sequence (CPU), with the mismatches a near-tie explains counted separately ------
     from oracle import vq_oracle as O
     sample_rows = 1 << 16
-    ora = O.forward(z[:sample_rows].cpu().numpy(), weight.cpu().numpy(), BETA)
-    match = float((idx[:sample_rows].view(-1).cpu().numpy() == ora.indices.reshape(-1)).mean())
+    zs = z[:sample_rows].cpu()
+    ours = idx[:sample_rows].view(-1).cpu().numpy()
+    ora = O.forward(zs.numpy(), weight.cpu().numpy(), BETA)
+    match = float((ours == ora.indices.reshape(-1)).mean())
+    torch.set_float32_matmul_precision("highest")
+    with torch.no_grad():
+        port_idx = O.torch_port_forward(zs, weight.cpu(), BETA)[4].view(-1).numpy()
+    port_match = float((ours == port_idx).mean())
+    expl = O.explain_mismatches(zs.numpy(), weight.cpu().numpy(), ours, port_idx)
 
     peak, peak_src = measured_peaks()
     algo_bytes = n * (8 * DIM + 8)                     # read z, write z_q, int64 idx
@@ -382,7 +640,12 @@ def run_ours(args) -> None:
         "config": workload_config(world, n), "path": args.path,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "backward": bwd,
-        "index_match": {"vs": "oracle (oracle/vq_oracle.c)", "rows": sample_rows, "rate": match},
+        "index_match": {"vs": "oracle (oracle/vq_oracle.c)", "rows": sample_rows, "rate": match,
+                        "vs_torch_port": {"what": "the reference's op sequence (model/vector_quantizer.py:88-119) as torch CPU "
+                                                  "ops, matmul precision 'highest'", "rate": port_match,
+                                          "mismatches": expl["mismatch"], "explained_by_fp32_near_tie": expl["explained"],
+                                          "near_tie_explained_rate": (expl["explained"] / expl["mismatch"]) if expl["mismatch"] else 1.0}},
+        "bulk_encode": bulk, "config1_forward": cfg1,
         "check": {"loss": float(loss.item()), "perplexity": float(ppl.item()), "histogram_total": int(counts.sum().item())},
     }
     _emit(line)
@@ -402,6 +665,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bwd", action="store_true")
+    ap.add_argument("--no-bulk", action="store_true")
+    ap.add_argument("--no-config1", action="store_true")
+    ap.add_argument("--bulk-chunk", type=int, default=65536, help="cycles per encode call of the bulk-encode object")
+    ap.add_argument("--bulk-chunks", type=int, default=8, help="timed encode calls per GPU")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world > 1:

@@ -221,3 +221,31 @@ def torch_port_forward(z, weight, beta: float):
     usage = onehot.mean(dim=0)                                         # :114
     perplexity = torch.exp(-(usage * torch.log(usage + 1e-10)).sum())  # :115
     return loss, out.contiguous(), perplexity, onehot, nearest         # :118-119
+
+
+def torch_port_encode(sd: dict, x, patch_size: int = 25):
+    """The reference's encode call on torch CPU tensors, with its own loop structure: PatchEmbedding.forward
+    (model/vq_vae_patch_embedd.py:13-17), CNNBlock.forward with seperate=True (:103-111: a Python loop over the token
+    positions, every ResBlock (:60-74) applied to a LENGTH-1 slice through Conv1d(k=3, pad=1)), SepCNNBlock.forward
+    (:83-91: one 1x1 conv per position, cat, permute).  `sd` is a VQVAEPatch state dict (batch_norm=False, dropout in
+    eval mode = identity).  Returns z_e as the reference does: logical (B, T, D), a permuted view of (B, D, T)."""
+    import torch
+    import torch.nn.functional as F
+
+    b = x.shape[0]
+    t = x.permute(0, 2, 1).reshape(b, 1, -1)                                                    # :14-15
+    t = F.conv1d(t, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=patch_size)   # :16  (B, H, T)
+    n_blocks = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith("encoder.0.shared_conv."))
+    cols = []
+    for i in range(t.shape[2]):                                                                 # :106
+        h = t[:, :, i].unsqueeze(2)                                                             # :107
+        for j in range(n_blocks):                                                               # :109 (nn.Sequential of ResBlocks)
+            pre = f"encoder.0.shared_conv.{j}.block."
+            u = F.conv1d(F.gelu(h), sd[pre + "1.weight"], sd[pre + "1.bias"], padding=1)        # :64-65
+            u = F.conv1d(F.gelu(u), sd[pre + "4.weight"], sd[pre + "4.bias"], padding=1)        # :67-68
+            h = h + u                                                                           # :74
+        cols.append(h)
+    t = torch.cat(cols, dim=2)                                                                  # :111
+    outs = [F.conv1d(t[:, :, i].unsqueeze(2), sd["encoder.1.shared_conv.weight"], sd["encoder.1.shared_conv.bias"])
+            for i in range(t.shape[2])]                                                         # :86-89
+    return torch.cat(outs, dim=2).permute(0, 2, 1)                                              # :90-91

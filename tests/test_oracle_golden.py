@@ -114,3 +114,23 @@ def test_gather_restatement(golden):
     assert np.array_equal(out.reshape(-1, 32), E[idx])
     with pytest.raises(RuntimeError):
         O.gather(np.array([[256]]), E)
+
+
+def test_encoder_port_reproduces_the_reference_encoder(patch_golden):
+    """oracle.torch_port_encode (the CPU leg of bench.py's bulk-encode object) against z_e of the unmodified reference:
+    bit-equal, same permuted-view strides (model/vq_vae_patch_embedd.py:91)."""
+    import torch
+    import cases as C
+    from oracle import vq_oracle as O
+    for case in C.PATCH_CASES:
+        if case["batch_norm"]:
+            continue
+        pre = f"{case['name']}/sd/"
+        sd = {k[len(pre):]: torch.from_numpy(patch_golden[k]) for k in patch_golden.files if k.startswith(pre)}
+        x = torch.from_numpy(C.make_cycles(case))
+        with torch.no_grad():
+            z = O.torch_port_encode(sd, x, case["patch_size"])
+        assert not z.is_contiguous() and z.stride(1) == 1
+        assert np.array_equal(z.contiguous().numpy(), patch_golden[f"{case['name']}/z_e"])
+        ids = O.torch_port_forward(z, sd["vector_quantization.embedding.weight"], case["beta"])[4]
+        assert np.array_equal(ids.numpy().reshape(-1), patch_golden[f"{case['name']}/idx"])

@@ -49,7 +49,13 @@ def _worker(rank, world, port, n, out_dir):
         assert vqb200.get_world_size() == world
         t = torch.ones(3)
         assert vqb200.all_reduce(t) is t and torch.equal(t, torch.full((3,), float(world)))
-        torch.save(dict(ids=ids, counts=counts, lo=lo, hi=hi), os.path.join(out_dir, f"r{rank}.pt"))
+        # the training step's fused small all-reduce: [counts[K], loss * n, n] in one collective
+        from vqb200.model.vector_quantizer import fused_stats_all_reduce
+        my_counts = torch.bincount(local.reshape(-1), minlength=16)
+        my_loss = torch.tensor(0.5 + rank, dtype=torch.float32)
+        g_loss, g_ppl, g_counts = fused_stats_all_reduce(my_counts, my_loss, async_op=True).result()
+        torch.save(dict(ids=ids, counts=counts, lo=lo, hi=hi, my_n=int(my_counts.sum()), g_loss=g_loss, g_ppl=g_ppl,
+                        g_counts=g_counts), os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -69,6 +75,15 @@ def test_two_rank_bulk_encode_equals_single_process(tmp_path, n):
     assert r0["hi"] == r1["lo"] and r0["lo"] == 0 and r1["hi"] == n
     full = torch.bincount(want.reshape(-1), minlength=16)
     assert torch.equal(r0["counts"], full) and torch.equal(r1["counts"], full)
+    # fused statistics: exact counts, n-weighted mean of the per-rank losses, perplexity of the global histogram
+    n0, n1 = r0["my_n"], r1["my_n"]
+    want_loss = (0.5 * n0 + 1.5 * n1) / max(n0 + n1, 1)
+    p = full.float() / full.sum().float()
+    want_ppl = torch.exp(-torch.sum(p * torch.log(p + 1e-10)))
+    for r in (r0, r1):
+        assert torch.equal(r["g_counts"], full)
+        assert abs(float(r["g_loss"]) - want_loss) < 1e-6
+        assert abs(float(r["g_ppl"]) - float(want_ppl)) < 1e-5
 
 
 def test_single_process_paths():

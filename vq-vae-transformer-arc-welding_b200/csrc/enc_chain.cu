@@ -33,14 +33,20 @@ constexpr int NQ = 128;                    // accumulator width (columns of one 
 constexpr int BK = 64;                     // K-chunk of a weight stage (128 bytes of bf16: one SW128 row)
 constexpr int W_STAGE = NQ * BK * 2;       // 16 KB
 constexpr int W_STAGES = 6;
-constexpr int THREADS = 128 + 256;         // 4 service warps + 8 epilogue warps
+constexpr int EPI_WARPS = 16;              // lane quarter x 32-column slab of the 128-column accumulator
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 128 + EPI_THREADS; // 4 service warps + 16 epilogue warps (4 per SM sub-partition hide each other's latencies)
+#ifndef EC_ABLATE
+#define EC_ABLATE 0                        // timing experiments: 1 = epilogue without arithmetic / stores (results are wrong)
+#endif
 
 template <int H> struct Plan {
     static constexpr int A_BYTES = BM * H * 2;                 // activation tile, H/64 K-chunks of 16 KB
     static constexpr int OFF_A = 0;
     static constexpr int OFF_W = OFF_A + A_BYTES;
-    static constexpr int OFF_BARS = OFF_W + W_STAGES * W_STAGE;
-    static constexpr int SMEM_BYTES = OFF_BARS + 512;
+    static constexpr int OFF_BIAS = OFF_W + W_STAGES * W_STAGE;  // the current layer's bias (H floats)
+    static constexpr int OFF_BARS = OFF_BIAS + H * 4;
+    static constexpr int SMEM_BYTES = OFF_BARS + 256;
     static constexpr int TMEM_A_COLS = H / 2;                  // packed bf16 pairs
     static constexpr int TMEM_ACC0 = 256;                      // accumulators at columns 256 .. 511
 };
@@ -101,7 +107,8 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         __trap();
     enum { W_FULL = 0, W_EMPTY = W_FULL + W_STAGES, ACC_FULL = W_EMPTY + W_STAGES, ACC_EMPTY = ACC_FULL + 2,
            A_RDY = ACC_EMPTY + 2, A0_FULL = A_RDY + 4, A_FREE = A0_FULL + 1, N_BARS = A_FREE + 1 };
-    static_assert(8 * N_BARS + 8 <= 512, "barrier area");
+    static_assert(8 * N_BARS + 8 <= 256, "barrier area");
+    static_assert(P::SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KB");
     auto bar = [&](int i) { return sbase + P::OFF_BARS + 8 * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + P::OFF_BARS + 8 * N_BARS);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -116,10 +123,10 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar(ACC_FULL + b), 1);
-            mbar_init(bar(ACC_EMPTY + b), 256);
+            mbar_init(bar(ACC_EMPTY + b), EPI_THREADS);
         }
         for (int q = 0; q < 4; ++q)
-            mbar_init(bar(A_RDY + q), 256);
+            mbar_init(bar(A_RDY + q), EPI_THREADS);
         mbar_init(bar(A0_FULL), 1);
         mbar_init(bar(A_FREE), 1);
         fence_barrier_init();
@@ -214,10 +221,13 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         }
     } else if (warp >= 4) {
         // ================= epilogue: TMEM -> bias (+ residual) -> GELU -> bf16 -> next operand =================
+        // warp -> (TMEM lane quarter, 32-column slab of the accumulator): one slab per thread and accumulator quarter
         const int q4 = warp & 3;                                 // TMEM lane quarter
-        const int ch = (warp - 4) >> 2;                          // column half of the 128-column accumulator
+        const int sl = (warp - 4) >> 2;                          // slab 0..3 of the 128-column accumulator
         const int r = q4 * 32 + lane;                            // row of the tile
+        const int et = tid - 128;                                // 0 .. EPI_THREADS-1
         float *scr = scratch + (size_t)blockIdx.x * (BM * H);
+        float *bias_s = reinterpret_cast<float *>(smem + P::OFF_BIAS);
         uint32_t acc_n = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
@@ -226,12 +236,17 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             for (int g = 0; g < L; ++g) {
                 const bool odd = (g & 1) != 0, last = g == L - 1;
                 const bool h_in_std = g == 1, h_out_std = last;   // first block reads, last block writes the caller's h
+                // this layer's bias: fetched now, parked in shared memory behind the first quarter's barrier (every
+                // warp has then finished the previous layer), published by a second barrier
+                float bias_reg = 0.0f;
+                if (et < H)
+                    bias_reg = __ldg(bias + (size_t)g * H + et);
                 for (int q = 0; q < NQT; ++q, ++acc_n) {
                     const int ab = (int)(acc_n & 1u);
-                    const int colq = q * NQ + ch * 64;           // this thread's 64 columns of the GEMM's output
-                    // residual slab 0 is fetched before the accumulator is waited for
+                    const int col0 = q * NQ + sl * 32;           // this thread's 32 columns of the GEMM's output
+                    // the residual slab is requested before the accumulator is waited for
                     float hv[32];
-                    auto load_h = [&](int col0) {
+                    if (odd) {
                         if (h_in_std) {
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
@@ -246,79 +261,87 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                                 hv[4 * c] = v.x; hv[4 * c + 1] = v.y; hv[4 * c + 2] = v.z; hv[4 * c + 3] = v.w;
                             }
                         }
-                    };
-                    if (odd)
-                        load_h(colq);
+                    }
                     if (warp == 4)
                         mbar_wait<32>(bar(ACC_FULL + ab), (acc_n >> 1) & 1u);
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    tc_fence_after();
-                    const uint32_t taddr = tmem_base + P::TMEM_ACC0 + ab * NQ + ch * 64 + ((uint32_t)(q4 * 32) << 16);
-#pragma unroll
-                    for (int sl = 0; sl < 2; ++sl) {
-                        uint32_t v[32];
-                        tmem_ld32(taddr + sl * 32, v);
-                        tmem_wait_ld_fence(v);
-                        if (sl == 1) {
-                            tc_fence_before();
-                            mbar_arrive(bar(ACC_EMPTY + ab));    // the last slab sits in registers: the accumulator is free
-                        }
-                        const int col0 = colq + sl * 32;
-                        if (odd && sl == 1)
-                            load_h(col0);
-                        float x[32];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + (size_t)g * H + col0) + c);
-                            x[4 * c] = __uint_as_float(v[4 * c]) + b.x;
-                            x[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + b.y;
-                            x[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + b.z;
-                            x[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + b.w;
-                        }
-                        if (odd) {
-#pragma unroll
-                            for (int c = 0; c < 32; ++c)
-                                x[c] += hv[c];
-                            if (h_out_std) {
-                                if (row_ok) {
-#pragma unroll
-                                    for (int c = 0; c < 8; ++c)
-                                        __stcs(reinterpret_cast<float4 *>(h + row * H + col0) + c,
-                                               make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
-                                }
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < 8; ++c)
-                                    *reinterpret_cast<float4 *>(scr + ((size_t)((col0 >> 2) + c) * BM + r) * 4) =
-                                        make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
-                            }
-                        }
-                        if (!last) {
-                            uint32_t pk[16];
-#pragma unroll
-                            for (int c = 0; c < 16; ++c) {
-                                const __nv_bfloat162 p2 = __floats2bfloat162_rn(gelu(x[2 * c]), gelu(x[2 * c + 1]));
-                                pk[c] = *reinterpret_cast<const uint32_t *>(&p2);
-                            }
-                            if (!odd) {
-                                // even GEMM: the next operand goes to tensor memory, 16 columns of packed pairs
-                                tmem_st16(tmem_base + (col0 >> 1) + ((uint32_t)(q4 * 32) << 16), pk);
-                            } else {
-                                // odd GEMM: the next operand goes to the smem tile (K-chunk col0 / 64, SW128 rows)
-                                unsigned char *arow = smem + P::OFF_A + (col0 >> 6) * (BM * BK * 2) + r * 128;
-                                const int c16 = (col0 & 63) >> 3;        // first 16-byte chunk of the 128-byte row
-#pragma unroll
-                                for (int c = 0; c < 4; ++c)
-                                    *reinterpret_cast<uint4 *>(arow + (((c16 + c) ^ (r & 7)) << 4)) =
-                                        make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                            }
-                        }
+                    named_bar_sync(1, EPI_THREADS);
+                    if (q == 0) {
+                        if (et < H)
+                            bias_s[et] = bias_reg;
+                        named_bar_sync(2, EPI_THREADS);
                     }
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + P::TMEM_ACC0 + ab * NQ + sl * 32 + ((uint32_t)(q4 * 32) << 16);
+                    uint32_t v[32];
+                    tmem_ld32(taddr, v);
+                    tmem_wait_ld_fence(v);
+                    tc_fence_before();
+                    mbar_arrive(bar(ACC_EMPTY + ab));            // the slab sits in registers: this thread is done with the accumulator
+#if EC_ABLATE == 1
                     if (!last) {
                         if (!odd) {
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int c = 0; c < 16; ++c)
+                                pk[c] = v[c] ^ v[c + 16];
+                            tmem_st16(tmem_base + (col0 >> 1) + ((uint32_t)(q4 * 32) << 16), pk);
                             tmem_wait_st();
                             tc_fence_before();
                         } else {
+                            fence_proxy_async();
+                        }
+                        mbar_arrive(bar(A_RDY + q));
+                    }
+                    (void)hv; (void)bias_s; (void)scr; (void)h_out_std;
+                    continue;
+#endif
+                    float x[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 b = *reinterpret_cast<const float4 *>(bias_s + col0 + 4 * c);
+                        x[4 * c] = __uint_as_float(v[4 * c]) + b.x;
+                        x[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + b.y;
+                        x[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + b.z;
+                        x[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + b.w;
+                    }
+                    if (odd) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            x[c] += hv[c];
+                        if (h_out_std) {
+                            if (row_ok) {
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    __stcs(reinterpret_cast<float4 *>(h + row * H + col0) + c,
+                                           make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                *reinterpret_cast<float4 *>(scr + ((size_t)((col0 >> 2) + c) * BM + r) * 4) =
+                                    make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                        }
+                    }
+                    if (!last) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const __nv_bfloat162 p2 = __floats2bfloat162_rn(gelu(x[2 * c]), gelu(x[2 * c + 1]));
+                            pk[c] = *reinterpret_cast<const uint32_t *>(&p2);
+                        }
+                        if (!odd) {
+                            // even GEMM: the next operand goes to tensor memory, 16 columns of packed pairs
+                            tmem_st16(tmem_base + (col0 >> 1) + ((uint32_t)(q4 * 32) << 16), pk);
+                            tmem_wait_st();
+                            tc_fence_before();
+                        } else {
+                            // odd GEMM: the next operand goes to the smem tile (K-chunk col0 / 64, SW128 rows)
+                            unsigned char *arow = smem + P::OFF_A + (col0 >> 6) * (BM * BK * 2) + r * 128;
+                            const int c16 = (col0 & 63) >> 3;        // first 16-byte chunk of the 128-byte row
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                *reinterpret_cast<uint4 *>(arow + (((c16 + c) ^ (r & 7)) << 4)) =
+                                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                             fence_proxy_async();
                         }
                         mbar_arrive(bar(A_RDY + q));

@@ -72,6 +72,16 @@ class VectorQuantizer(LightningModule):
         """E[min_encoding_indices].view(target_shape), :121-131."""
         return ops.gather(min_encoding_indices, self.embedding.weight, target_shape)
 
+    def reduce_stats(self, loss, async_op: bool = True):
+        """Global loss and code usage of the last forward over all ranks in ONE small all-reduce of
+        [counts[K], loss * n, n], issued asynchronously by default so that it overlaps the
+        backward pass; `.result()` on the returned handle gives (global_loss, global_perplexity, global_counts).
+        The per-rank `loss` that drives autograd is untouched (the reference's semantics: per-rank mean, DDP averages
+        the gradients)."""
+        if self.code_counts is None:
+            raise RuntimeError("reduce_stats() needs a forward pass first")
+        return fused_stats_all_reduce(self.code_counts, loss, async_op=async_op)
+
     def global_perplexity(self):
         """Perplexity of the code usage summed over all ranks (opt-in; the reference never
         reduces it).  One K-element all-reduce over NCCL."""
@@ -81,6 +91,41 @@ class VectorQuantizer(LightningModule):
         all_reduce(counts)
         p = counts.to(torch.float32) / counts.sum().to(torch.float32)
         return torch.exp(-torch.sum(p * torch.log(p + 1e-10)))
+
+
+class StatsHandle:
+    """Pending fused all-reduce of [counts[K], loss * n, n] (fused_stats_all_reduce)."""
+
+    def __init__(self, buf, work, k):
+        self._buf, self._work, self._k = buf, work, k
+
+    def result(self):
+        """(global_loss, global_perplexity, global_counts int64 (K,)) -- waits for the collective if it is pending."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        k = self._k
+        counts, n = self._buf[:k], self._buf[k + 1]
+        p = (counts / n).to(torch.float32)
+        ppl = torch.exp(-torch.sum(p * torch.log(p + 1e-10)))
+        return (self._buf[k] / n).to(torch.float32), ppl, counts.round().to(torch.int64)
+
+
+def fused_stats_all_reduce(counts, loss, async_op: bool = True) -> StatsHandle:
+    """One all-reduce (SUM) of the float64 vector [counts[K], loss * n, n] with n = counts.sum(): counts stay exact up
+    to 2^53, the global loss is the n-weighted mean of the per-rank means.  Single-process runs skip the collective."""
+    k = counts.numel()
+    buf = torch.empty(k + 2, dtype=torch.float64, device=counts.device)
+    buf[:k] = counts
+    n = buf[:k].sum()
+    buf[k] = loss.detach().to(torch.float64) * n
+    buf[k + 1] = n
+    work = None
+    if get_world_size() > 1:
+        work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=async_op)
+        if not async_op:
+            work = None
+    return StatsHandle(buf, work, k)
 
 
 def get_world_size():
