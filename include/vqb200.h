@@ -167,11 +167,16 @@ int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const f
  *   h       (n_tokens, hidden) fp32, updated in place
  *   w_bf16  (n_layers, hidden, hidden) bf16 (out x in per layer), bias (n_layers, hidden) fp32
  *   scratch vqb_encoder_chain_scratch_bytes(device, hidden) bytes of device memory (contents private)
+ * proj_dim > 0 fuses the encoder's final per-token projection hidden -> proj_dim (SepCNNBlock, :83-91) as one more
+ * narrow GEMM on the resident tile: w_bf16 then holds 128 further rows behind the layers -- rows [0, proj_dim) =
+ * bf16(Wp), rows [64, 64 + proj_dim) = bf16(Wp - bf16(Wp)), zeros elsewhere -- and z_e (n_tokens, proj_dim) fp32 =
+ * bf16(h) Wp^T + proj_bias is written; h is then NOT written back.  proj_dim a multiple of 4, <= 64.
  * hidden in {256, 512}, n_layers even; all pointers 16-byte aligned.
  */
 size_t vqb_encoder_chain_scratch_bytes(int device, int hidden);
 int vqb_encoder_chain(int device, const void *a0_bf16, float *h, const void *w_bf16, const float *bias, int64_t n_tokens,
-                      int hidden, int n_layers, void *scratch, size_t scratch_bytes, void *stream);
+                      int hidden, int n_layers, void *scratch, size_t scratch_bytes, const float *proj_bias, float *z_e,
+                      int proj_dim, void *stream);
 
 /* h += bias (fp32 (n_tokens, n), in place); out = bf16(gelu(h)): the element-wise step between the fp32 patch
  * embedding (model/vq_vae_patch_embedd.py:13-17) and the first fused layer, in one pass.  n a multiple of 4. */

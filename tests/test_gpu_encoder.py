@@ -262,3 +262,27 @@ def test_encoder_chain_equals_layerwise(T, H, L):
         t = torch.nn.functional.gelu(hh).to(torch.bfloat16).float() @ w[2 * i].float().t() + b[2 * i]
         hh = hh + torch.nn.functional.gelu(t).to(torch.bfloat16).float() @ w[2 * i + 1].float().t() + b[2 * i + 1]
     torch.testing.assert_close(out, hh, rtol=2e-2, atol=2e-2 * L ** 0.5)
+
+
+@pytest.mark.parametrize("T,H,L,D", [(1000, 512, 4, 32), (128 * 149 + 3, 512, 16, 32), (777, 256, 2, 8), (300, 512, 2, 64)])
+def test_encoder_chain_fused_projection(T, H, L, D):
+    """The final H -> D projection fused into the chain launch: z_e = bf16(h_final) Wp^T + bp with Wp carried as an exact
+    bf16 hi + lo pair -- against the chain without projection followed by the same product in fp32 PyTorch."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(T + H + L + D)
+    h0 = torch.randn(T, H, device=dev, generator=g)
+    w = (torch.randn(L, H, H, device=dev, generator=g) * (1.0 / H) ** 0.5).to(torch.bfloat16)
+    b = 0.1 * torch.randn(L, H, device=dev, generator=g)
+    wp = torch.randn(D, H, device=dev, generator=g) * (1.0 / H) ** 0.5
+    bp = 0.1 * torch.randn(D, device=dev, generator=g)
+    a0 = torch.nn.functional.gelu(h0).to(torch.bfloat16)
+    h_final = ops.encoder_chain(a0, h0.clone(), w, b)
+    rows = ops.projection_rows(wp)
+    w_exact = rows[:D].float() + rows[64:64 + D].float()
+    assert (w_exact - wp).abs().max().item() <= 2.0 ** -16 * wp.abs().max().item()
+    ref = h_final.to(torch.bfloat16).float() @ w_exact.t() + bp
+    stack = torch.cat([w.reshape(-1, H), rows]).contiguous()
+    h_in = h0.clone()
+    z = ops.encoder_chain(a0, h_in, stack, b, proj_bias=bp)
+    assert z.shape == (T, D) and z.dtype == torch.float32
+    torch.testing.assert_close(z, ref, rtol=1e-4, atol=1e-4)

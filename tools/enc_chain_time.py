@@ -30,7 +30,15 @@ out = ops.encoder_chain(a0, h0.clone(), w, b)
 torch.cuda.synchronize()
 diff = (out - ref).abs().max().item()
 print(f"T={T} H={H} L={L}: max |chain - layerwise| = {diff:.3e} (scale {ref.abs().max().item():.3f}), equal={torch.equal(out, ref)}")
-for name, fn in (("chain", lambda: ops.encoder_chain(a0, hbuf, w, b)), ("layerwise", lambda: layerwise(hbuf))):
+wp = torch.randn(32, H, device=dev, generator=g) * (1.0 / H) ** 0.5
+bp = torch.zeros(32, device=dev)
+stack = torch.cat([w.reshape(-1, H), ops.projection_rows(wp)]).contiguous()
+zp = ops.encoder_chain(a0, h0.clone(), stack, b, proj_bias=bp)
+zr = out.to(torch.bfloat16).float() @ wp.t()
+print(f"  fused projection: max |z - ref| = {(zp - zr).abs().max().item():.3e} (scale {zr.abs().max().item():.3f})")
+for name, fn in (("chain", lambda: ops.encoder_chain(a0, hbuf, w, b)),
+                 ("chain+proj", lambda: ops.encoder_chain(a0, hbuf, stack, b, proj_bias=bp)),
+                 ("layerwise", lambda: layerwise(hbuf))):
     hbuf = h0.clone()
     for _ in range(2):
         fn()

@@ -19,6 +19,11 @@
 //     epilogue's thread-per-row accesses coalesce; the first block reads it from, the last block writes it to the
 //     caller's row-major h.
 //
+//   * optionally the encoder's final per-token projection H -> D (SepCNNBlock, model/vq_vae_patch_embedd.py:83-91) runs
+//     as one more, narrow GEMM on the same tile: operand bf16(h) (no GELU), weights as an exact bf16 hi + lo pair in two
+//     column groups of one N = 128 accumulator, z_e = acc_hi + acc_lo + bias written as fp32 rows -- the residual stream
+//     then never goes back to HBM at all.
+//
 // bf16 operands, fp32 accumulation, fp32 residual stream, GELU as in tok_linear.cu (gelu_fast): the same arithmetic
 // as the layer-at-a-time path, layer for layer.
 #include "vq_common.cuh"
@@ -30,9 +35,10 @@ namespace ec {
 
 constexpr int BM = 128;                    // tokens per tile (TMEM lanes)
 constexpr int NQ = 128;                    // accumulator width (columns of one MMA)
-constexpr int BK = 64;                     // K-chunk of a weight stage (128 bytes of bf16: one SW128 row)
-constexpr int W_STAGE = NQ * BK * 2;       // 16 KB
-constexpr int W_STAGES = 6;
+constexpr int BK = 64;                     // K-chunk of one TMA box (128 bytes of bf16: one SW128 row)
+constexpr int KS = 128;                    // K per weight stage = two boxes = one accumulator quarter of the previous GEMM
+constexpr int W_STAGE = NQ * KS * 2;       // 32 KB: eight MMAs per barrier round trip of the issuing warp
+constexpr int W_STAGES = 3;
 constexpr int EPI_WARPS = 16;              // lane quarter x 32-column slab of the 128-column accumulator
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 128 + EPI_THREADS; // 4 service warps + 16 epilogue warps (4 per SM sub-partition hide each other's latencies)
@@ -90,17 +96,21 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // h      : (n_tokens, H) fp32 row-major, in: h0 (the patch embedding), out: the residual stream after the last block
 // w      : (L * H, H) bf16 row-major, layer l = rows [l*H, (l+1)*H) (out x in); bias (L * H) fp32
 // scratch: gridDim.x tiles of BM * H fp32 (the residual stream between the blocks)
+// proj_d > 0: w holds 128 more rows after the L layers -- rows [0, proj_d) = bf16(Wp), rows [64, 64 + proj_d) =
+//          bf16(Wp - bf16(Wp)), zeros elsewhere -- and z_e (n_tokens, proj_d) fp32 = h_final Wp^T + proj_bias is written
+//          instead of h
 template <int H>
 __global__ void __launch_bounds__(ec::THREADS, 1)
 enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_w,
                  const float *__restrict__ bias, float *__restrict__ h, float *__restrict__ scratch,
-                 int64_t n_tokens, int L)
+                 int64_t n_tokens, int L, const float *__restrict__ proj_bias, float *__restrict__ z_e, int proj_d)
 {
     using namespace tc;
     using namespace ec;
     using P = Plan<H>;
     constexpr int NQT = H / NQ;                // accumulator quarters per GEMM (4 at H = 512)
-    constexpr int NKC = H / BK;                // K-chunks per GEMM (8 at H = 512)
+    constexpr int NKC = H / BK;                // 64-wide K-chunks of the activation tile (8 at H = 512)
+    constexpr int NKS = H / KS;                // weight stages per accumulator quarter (4 at H = 512)
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     if ((sbase & 1023u) != 0)
@@ -113,6 +123,9 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + P::OFF_BARS + 8 * N_BARS);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    // with a projection the chain has one more, single-quarter GEMM (index L, even: it reads the smem tile)
+    const bool proj = proj_d > 0;
+    const int LT = L + (proj ? 1 : 0);
     const int64_t n_tiles = (n_tokens + BM - 1) / BM;
     const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
@@ -142,16 +155,21 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 
     if (warp == 0) {
         // ================= weight producer: runs ahead of the MMAs across GEMM and tile boundaries =================
-        if (lane == 0) {
+        {
             int s = 0;
             uint32_t ph = 0;
             for (int t = 0; t < my_tiles; ++t)
-                for (int g = 0; g < L; ++g)
-                    for (int q = 0; q < NQT; ++q)
-                        for (int kc = 0; kc < NKC; ++kc) {
+                for (int g = 0; g < LT; ++g)
+                    for (int q = 0; q < (g == L ? 1 : NQT); ++q)
+                        for (int ks = 0; ks < NKS; ++ks) {
                             mbar_wait<32>(bar(W_EMPTY + s), ph ^ 1u);
-                            mbar_expect_tx(bar(W_FULL + s), W_STAGE);
-                            tma_load_2d(sbase + P::OFF_W + s * W_STAGE, &map_w, bar(W_FULL + s), kc * BK, g * H + q * NQ);
+                            if (elect_one()) {
+                                mbar_expect_tx(bar(W_FULL + s), W_STAGE);
+                                tma_load_2d(sbase + P::OFF_W + s * W_STAGE, &map_w, bar(W_FULL + s), ks * KS, g * H + q * NQ);
+                                tma_load_2d(sbase + P::OFF_W + s * W_STAGE + NQ * BK * 2, &map_w, bar(W_FULL + s), ks * KS + BK,
+                                            g * H + q * NQ);
+                            }
+                            __syncwarp();
                             if (++s == W_STAGES) {
                                 s = 0;
                                 ph ^= 1u;
@@ -160,62 +178,76 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         }
     } else if (warp == 3) {
         // ================= first operand of every tile: bf16(gelu(h0)) rows by TMA =================
-        if (lane == 0) {
-            for (int t = 0; t < my_tiles; ++t) {
-                if (t > 0)
-                    mbar_wait<64>(bar(A_FREE), (uint32_t)((t - 1) & 1));    // the last GEMM that read the smem tile is done
-                const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
+        for (int t = 0; t < my_tiles; ++t) {
+            if (t > 0)
+                mbar_wait<64>(bar(A_FREE), (uint32_t)((t - 1) & 1));    // the last GEMM that read the smem tile is done
+            const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
+            if (elect_one()) {
                 mbar_expect_tx(bar(A0_FULL), P::A_BYTES);
 #pragma unroll
                 for (int kc = 0; kc < NKC; ++kc)
                     tma_load_2d(sbase + P::OFF_A + kc * (BM * BK * 2), &map_a0, bar(A0_FULL), kc * BK, (int)(tile * BM));
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = idesc_bf16(NQ);
-            int s = 0;
-            uint32_t wph = 0;
-            uint32_t acc_n = 0;                                  // accumulator quarters issued so far
-            uint32_t ardy_n = 0;                                 // completed A_RDY phases (per quarter barrier) so far
-            for (int t = 0; t < my_tiles; ++t) {
-                mbar_wait<32>(bar(A0_FULL), (uint32_t)(t & 1));
-                for (int g = 0; g < L; ++g) {
-                    const bool from_tmem = (g & 1) != 0;         // even GEMMs read shared memory, odd ones tensor memory
-                    for (int q = 0; q < NQT; ++q, ++acc_n) {
-                        const int ab = (int)(acc_n & 1u);
-                        mbar_wait<32>(bar(ACC_EMPTY + ab), ((acc_n >> 1) & 1u) ^ 1u);
-                        const uint32_t d = tmem_base + P::TMEM_ACC0 + ab * NQ;
-                        for (int kc = 0; kc < NKC; ++kc) {
-                            if (g > 0 && q == 0 && (kc & 1) == 0)    // K-chunks 2j, 2j+1 = quarter j of the previous epilogue
-                                mbar_wait<32>(bar(A_RDY + (kc >> 1)), ardy_n & 1u);
-                            mbar_wait<32>(bar(W_FULL + s), wph);
-                            tc_fence_after();
-                            const uint64_t wd = desc_sw128(sbase + P::OFF_W + s * W_STAGE);
-                            if (!from_tmem) {
-                                const uint64_t ad = desc_sw128(sbase + P::OFF_A + kc * (BM * BK * 2));
+        // ================= MMA issuer: the whole warp runs the loop (uniform control flow), one elected lane issues =====
+        const uint32_t idesc = idesc_bf16(NQ);
+        const uint64_t a_base = desc_sw128(sbase + P::OFF_A);    // + kc * 1024 in the address field (16 KB K-chunks)
+        const uint64_t w_base = desc_sw128(sbase + P::OFF_W);    // + s * 2048 (32 KB stages), + 1024 for the second box
+        int s = 0;
+        uint32_t wph = 0;
+        uint32_t acc_n = 0;                                      // accumulator quarters issued so far
+        uint32_t ardy_n = 0;                                     // completed A_RDY phases (per quarter barrier) so far
+        for (int t = 0; t < my_tiles; ++t) {
+            mbar_wait<32>(bar(A0_FULL), (uint32_t)(t & 1));
+            for (int g = 0; g < LT; ++g) {
+                const bool from_tmem = (g & 1) != 0;             // even GEMMs read shared memory, odd ones tensor memory
+                for (int q = 0; q < (g == L ? 1 : NQT); ++q, ++acc_n) {
+                    const int ab = (int)(acc_n & 1u);
+                    mbar_wait<32>(bar(ACC_EMPTY + ab), ((acc_n >> 1) & 1u) ^ 1u);
+                    const uint32_t d = tmem_base + P::TMEM_ACC0 + ab * NQ;
 #pragma unroll
-                                for (int j = 0; j < BK / 16; ++j)
-                                    umma_bf16(d, ad + 2 * j, wd + 2 * j, idesc, (kc | j) != 0);
-                            } else {
-                                const uint32_t at = tmem_base + kc * (BK / 2);
+                    for (int ks = 0; ks < NKS; ++ks) {
+                        if (g > 0 && q == 0)                     // K range of stage ks = quarter ks of the previous epilogue
+                            mbar_wait<32>(bar(A_RDY + ks), ardy_n & 1u);
+                        mbar_wait<32>(bar(W_FULL + s), wph);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t wd = w_base + (uint64_t)(s * (W_STAGE >> 4));
 #pragma unroll
-                                for (int j = 0; j < BK / 16; ++j)
-                                    umma_bf16_ts(d, at + 8 * j, wd + 2 * j, idesc, (kc | j) != 0);
+                            for (int hk = 0; hk < KS / BK; ++hk) {           // the stage's two 64-wide boxes
+                                const int kc = ks * (KS / BK) + hk;
+                                if (!from_tmem) {
+                                    const uint64_t ad = a_base + (uint64_t)(kc * (BM * BK * 2 >> 4));
+#pragma unroll
+                                    for (int j = 0; j < BK / 16; ++j)
+                                        umma_bf16(d, ad + 2 * j, wd + hk * (NQ * BK * 2 >> 4) + 2 * j, idesc, (kc | j) != 0);
+                                } else {
+                                    const uint32_t at = tmem_base + kc * (BK / 2);
+#pragma unroll
+                                    for (int j = 0; j < BK / 16; ++j)
+                                        umma_bf16_ts(d, at + 8 * j, wd + hk * (NQ * BK * 2 >> 4) + 2 * j, idesc, (kc | j) != 0);
+                                }
                             }
                             umma_commit(bar(W_EMPTY + s));
-                            if (++s == W_STAGES) {
-                                s = 0;
-                                wph ^= 1u;
-                            }
                         }
-                        umma_commit(bar(ACC_FULL + ab));
+                        __syncwarp();
+                        if (++s == W_STAGES) {
+                            s = 0;
+                            wph ^= 1u;
+                        }
                     }
-                    if (g > 0)
-                        ++ardy_n;
-                    if (g == L - 2)
+                    if (elect_one())
+                        umma_commit(bar(ACC_FULL + ab));
+                    __syncwarp();
+                }
+                if (g > 0)
+                    ++ardy_n;
+                if (g == (proj ? L : L - 2)) {
+                    if (elect_one())
                         umma_commit(bar(A_FREE));                // every MMA that reads the smem tile has been issued
+                    __syncwarp();
                 }
             }
         }
@@ -233,15 +265,21 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
             const int64_t row = tile * BM + r;
             const bool row_ok = row < n_tokens;
-            for (int g = 0; g < L; ++g) {
-                const bool odd = (g & 1) != 0, last = g == L - 1;
-                const bool h_in_std = g == 1, h_out_std = last;   // first block reads, last block writes the caller's h
+            for (int g = 0; g < LT; ++g) {
+                const bool odd = (g & 1) != 0, last = g == LT - 1;
+                const bool is_proj = g == L;                      // the narrow projection GEMM (only when proj)
+                const bool plain = proj && g == L - 1;            // its operand is bf16(h), not bf16(gelu(h))
+                const bool h_in_std = g == 1, h_out_std = g == L - 1;   // first block reads, last block writes the caller's h
                 // this layer's bias: fetched now, parked in shared memory behind the first quarter's barrier (every
                 // warp has then finished the previous layer), published by a second barrier
                 float bias_reg = 0.0f;
-                if (et < H)
+                if (is_proj) {
+                    if (et < proj_d)
+                        bias_reg = __ldg(proj_bias + et);
+                } else if (et < H) {
                     bias_reg = __ldg(bias + (size_t)g * H + et);
-                for (int q = 0; q < NQT; ++q, ++acc_n) {
+                }
+                for (int q = 0; q < (is_proj ? 1 : NQT); ++q, ++acc_n) {
                     const int ab = (int)(acc_n & 1u);
                     const int col0 = q * NQ + sl * 32;           // this thread's 32 columns of the GEMM's output
                     // the residual slab is requested before the accumulator is waited for
@@ -272,6 +310,42 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     }
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + P::TMEM_ACC0 + ab * NQ + sl * 32 + ((uint32_t)(q4 * 32) << 16);
+                    if (is_proj) {
+                        // z_e = (operand . W_hi) + (operand . W_lo) + bias: accumulator columns [0, 64) and [64, 128);
+                        // slabs 0 and 1 own output columns [0, 32) and [32, 64), slabs 2 and 3 only hand the buffer back
+                        if (sl < 2 && sl * 32 < proj_d) {
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {          // 16 output columns at a time keeps 32 registers live
+                                uint32_t vh[16], vl[16];
+                                tmem_ld16(taddr + 16 * hf, vh);
+                                tmem_ld16(taddr + 64 + 16 * hf, vl);
+                                tmem_wait_ld16(vh, vl);
+                                if (hf == 1) {
+                                    tc_fence_before();
+                                    mbar_arrive(bar(ACC_EMPTY + ab));
+                                }
+                                if (row_ok) {
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c) {
+                                        const int col = sl * 32 + 16 * hf + 4 * c;
+                                        if (col < proj_d) {              // proj_d is a multiple of 4
+                                            const float4 b = *reinterpret_cast<const float4 *>(bias_s + col);
+                                            float4 o;
+                                            o.x = (__uint_as_float(vh[4 * c]) + __uint_as_float(vl[4 * c])) + b.x;
+                                            o.y = (__uint_as_float(vh[4 * c + 1]) + __uint_as_float(vl[4 * c + 1])) + b.y;
+                                            o.z = (__uint_as_float(vh[4 * c + 2]) + __uint_as_float(vl[4 * c + 2])) + b.z;
+                                            o.w = (__uint_as_float(vh[4 * c + 3]) + __uint_as_float(vl[4 * c + 3])) + b.w;
+                                            *reinterpret_cast<float4 *>(z_e + row * proj_d + col) = o;
+                                        }
+                                    }
+                                }
+                            }
+                        } else {
+                            tc_fence_before();
+                            mbar_arrive(bar(ACC_EMPTY + ab));
+                        }
+                        continue;
+                    }
                     uint32_t v[32];
                     tmem_ld32(taddr, v);
                     tmem_wait_ld_fence(v);
@@ -309,7 +383,7 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                         for (int c = 0; c < 32; ++c)
                             x[c] += hv[c];
                         if (h_out_std) {
-                            if (row_ok) {
+                            if (row_ok && !proj) {                // (with the projection fused the residual stream stays on chip)
 #pragma unroll
                                 for (int c = 0; c < 8; ++c)
                                     __stcs(reinterpret_cast<float4 *>(h + row * H + col0) + c,
@@ -326,7 +400,8 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                         uint32_t pk[16];
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {
-                            const __nv_bfloat162 p2 = __floats2bfloat162_rn(gelu(x[2 * c]), gelu(x[2 * c + 1]));
+                            const __nv_bfloat162 p2 = plain ? __floats2bfloat162_rn(x[2 * c], x[2 * c + 1])
+                                                            : __floats2bfloat162_rn(gelu(x[2 * c]), gelu(x[2 * c + 1]));
                             pk[c] = *reinterpret_cast<const uint32_t *>(&p2);
                         }
                         if (!odd) {
@@ -362,10 +437,13 @@ bool enc_chain_supported(int H, int L) { return (H == 512 || H == 256) && L >= 2
 size_t enc_chain_scratch_bytes(int H, int sm_count) { return (size_t)sm_count * ec::BM * H * sizeof(float); }
 
 cudaError_t launch_enc_chain(const void *a0, float *h, const void *w, const float *bias, int64_t n_tokens, int H, int L,
-                             float *scratch, size_t scratch_bytes, int sm_count, int max_smem, cudaStream_t st)
+                             float *scratch, size_t scratch_bytes, const float *proj_bias, float *z_e, int proj_d,
+                             int sm_count, int max_smem, cudaStream_t st)
 {
     using namespace ec;
     if (!enc_chain_supported(H, L))
+        return cudaErrorNotSupported;
+    if (proj_d != 0 && (proj_d < 4 || proj_d > 64 || proj_d % 4 != 0 || !proj_bias || !z_e))
         return cudaErrorNotSupported;
     if (n_tokens == 0)
         return cudaSuccess;
@@ -381,14 +459,14 @@ cudaError_t launch_enc_chain(const void *a0, float *h, const void *w, const floa
     CUtensorMap map_a0, map_w;
     if (!tc::make_tensor_map_2d(&map_a0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a0, n_tokens, H, BM, BK,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
-        !tc::make_tensor_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, (int64_t)L * H, H, NQ, BK,
+        !tc::make_tensor_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, (int64_t)L * H + (proj_d ? NQ : 0), H, NQ, BK,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
         return cudaErrorNotSupported;
     auto kern = H == 512 ? enc_chain_kernel<512> : enc_chain_kernel<256>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (err != cudaSuccess)
         return err;
-    kern<<<grid, THREADS, smem_bytes, st>>>(map_a0, map_w, bias, h, scratch, n_tokens, L);
+    kern<<<grid, THREADS, smem_bytes, st>>>(map_a0, map_w, bias, h, scratch, n_tokens, L, proj_bias, z_e, proj_d);
     return cudaGetLastError();
 }
 

@@ -108,8 +108,8 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (warp-uniform loop, the loads under elect_one) =================
+        {
             int64_t step = 0;
             for (int64_t it = 0; it < my_items; ++it) {
                 const int64_t item = blockIdx.x + it * gridDim.x;
@@ -118,16 +118,20 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int k = 0; k < n_k; ++k, ++step) {
                     const int s = (int)(step % STAGES);
                     mbar_wait<32>(bar(EMPTY + s), (uint32_t)(((step / STAGES) & 1) ^ 1));
-                    mbar_expect_tx(bar(FULL + s), A_BYTES + B_BYTES);
-                    tma_load_2d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), k * BK, (int)(mt * BM));
-                    tma_load_2d(sbase + OFF_B + s * B_BYTES, &map_w, bar(FULL + s), k * BK, nt * BN);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar(FULL + s), A_BYTES + B_BYTES);
+                        tma_load_2d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), k * BK, (int)(mt * BM));
+                        tma_load_2d(sbase + OFF_B + s * B_BYTES, &map_w, bar(FULL + s), k * BK, nt * BN);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp runs the loop, one elected lane issues (vq_ptx.cuh: elect_one) ====
+        {
             const uint32_t idesc = idesc_bf16(BN);
+            const uint64_t a_base = desc_sw128(sbase + OFF_A), w_base = desc_sw128(sbase + OFF_B);
             int64_t step = 0;
             for (int64_t it = 0; it < my_items; ++it) {
                 const int b = (int)(it & 1);
@@ -138,14 +142,19 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     const int s = (int)(step % STAGES);
                     mbar_wait<32>(bar(FULL + s), (uint32_t)((step / STAGES) & 1));
                     tc_fence_after();
-                    const uint64_t a = desc_sw128(sbase + OFF_A + s * A_BYTES);
-                    const uint64_t w = desc_sw128(sbase + OFF_B + s * B_BYTES);
+                    if (elect_one()) {
+                        const uint64_t a = a_base + (uint64_t)(s * (A_BYTES >> 4));
+                        const uint64_t w = w_base + (uint64_t)(s * (B_BYTES >> 4));
 #pragma unroll
-                    for (int j = 0; j < BK / 16; ++j)    // K-slices of 16 bf16 = 32 bytes = +2 in the address field
-                        umma_bf16(d, a + 2 * j, w + 2 * j, idesc, (k | j) != 0);
-                    umma_commit(bar(EMPTY + s));
+                        for (int j = 0; j < BK / 16; ++j)    // K-slices of 16 bf16 = 32 bytes = +2 in the address field
+                            umma_bf16(d, a + 2 * j, w + 2 * j, idesc, (k | j) != 0);
+                        umma_commit(bar(EMPTY + s));
+                    }
+                    __syncwarp();
                 }
-                umma_commit(bar(T_FULL + b));
+                if (elect_one())
+                    umma_commit(bar(T_FULL + b));
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {

@@ -292,10 +292,15 @@ size_t vqb_encoder_chain_scratch_bytes(int device, int hidden)
 }
 
 int vqb_encoder_chain(int device, const void *a0_bf16, float *h, const void *w_bf16, const float *bias, int64_t n_tokens,
-                      int hidden, int n_layers, void *scratch, size_t scratch_bytes, void *stream)
+                      int hidden, int n_layers, void *scratch, size_t scratch_bytes, const float *proj_bias, float *z_e,
+                      int proj_dim, void *stream)
 {
-    if (!a0_bf16 || !h || !w_bf16 || !bias || !scratch || n_tokens < 0 || hidden <= 0 || n_layers <= 0)
+    if (!a0_bf16 || !h || !w_bf16 || !bias || !scratch || n_tokens < 0 || hidden <= 0 || n_layers <= 0 || proj_dim < 0)
         return VQB_E_ARG;
+    if (proj_dim > 0 && (!proj_bias || !z_e))
+        return VQB_E_ARG;
+    if (proj_dim > 0 && (!aligned(proj_bias, 4) || !aligned(z_e, 16)))
+        return VQB_E_UNSUPPORTED;
     if (!enc_chain_supported(hidden, n_layers) || !aligned(a0_bf16, 16) || !aligned(w_bf16, 16) || !aligned(bias, 16) ||
         !aligned(h, 16) || !aligned(scratch, 16))
         return VQB_E_UNSUPPORTED;
@@ -311,7 +316,7 @@ int vqb_encoder_chain(int device, const void *a0_bf16, float *h, const void *w_b
     if (err != cudaSuccess)
         return (int)err;
     err = launch_enc_chain(a0_bf16, h, w_bf16, bias, n_tokens, hidden, n_layers, (float *)scratch, scratch_bytes,
-                           info.sm_count, info.max_smem_per_block, (cudaStream_t)stream);
+                           proj_bias, z_e, proj_dim, info.sm_count, info.max_smem_per_block, (cudaStream_t)stream);
     if (err == cudaErrorNotSupported)
         return VQB_E_UNSUPPORTED;
     if (err != cudaSuccess)

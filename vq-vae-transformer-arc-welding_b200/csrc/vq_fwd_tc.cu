@@ -68,9 +68,7 @@ constexpr int W_SVC = VQB_ROLEMAP ? 4 * GROUPS + 4 : 0;      // service warpgrou
 #ifndef VQB_LDPIPE
 #define VQB_LDPIPE 1
 #endif
-#ifndef VQB_MMA_ORDER
-#define VQB_MMA_ORDER 0
-#endif
+
 // Register pool of the CTA = THREADS x (registers at launch); setmaxnreg moves it between the warpgroups:
 // 4 groups: 768 x 80 = 61440 = 128 x (40 + 56 + 4 x 96);  3 groups: 640 x 96 = 61440 = 128 x (40 + 56 + 3 x 128).
 // (An increase beyond what the other warpgroups released blocks forever.)
@@ -525,8 +523,8 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     if (warp == W_SVC) {
         // (idle: the ring is refilled by the store warp the moment it has released a slot)
     } else if (warp == W_SVC + 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp runs the loop, one elected lane issues (vq_ptx.cuh: elect_one) ====
+        {
             // (Issuing the codebook as two N = kp/2 halves with an early commit was measured: the 14
             // half-width MMAs take ~2x the tensor time of 7 full-width ones, a net loss.)
             const uint32_t idesc = idesc_bf16(kp);
@@ -534,6 +532,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             const uint64_t baug = desc_sw32(sbase + OFF_BAUG);
             const uint64_t aaug = desc_sw32(sbase + OFF_AAUG);
             const uint64_t bmain1 = desc_sw128(sbase + OFF_EF32);      // second D-chunk of a wide codebook
+            const uint64_t a0 = desc_sw128(sbase + OFF_ARING);         // + ba * 1024 in the address field (16 KB buffers)
             // (32-bit counters throughout the per-tile loops: the tcgen05 path takes at most 2^31 - 1 rows)
             const int n_items = (int)my_items;
             int g = 0;                                                  // epilogue group of the tile: i % GROUPS
@@ -546,48 +545,48 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 if (dc == 0)
                     mbar_wait<32>(bar(T_EMPTY + b), (uint32_t)(((i >> 1) & 1) ^ 1));
                 tc_fence_after();
-                if (dc == 0) stamp(i, 3);
-                const uint64_t a = desc_sw128(sbase + OFF_ARING + ba * 16384);
-                const uint64_t bm = dc ? bmain1 : bmain;
-                const uint32_t d = tmem_base + b * KMAX;
+                if (dc == 0 && lane == 0) stamp(i, 3);
                 const bool wide = p.D - 32 * dc > 16;                  // else components 16..31 of this chunk are padding
-                // K-slices of 16 bf16 = 32 bytes = +2 in the descriptor's address field
-#if VQB_MMA_ORDER == 0
-                umma_bf16(d, a + 0, bm + 0, idesc, dc);                // z1[0:16]  . E1[0:16]
-                if (wide) umma_bf16(d, a + 2, bm + 2, idesc, 1);       // z1[16:32] . E1[16:32]
-                umma_bf16(d, a + 0, bm + 4, idesc, 1);                 // z1[0:16]  . E2[0:16]
-                if (wide) umma_bf16(d, a + 2, bm + 6, idesc, 1);       // z1[16:32] . E2[16:32]
-                umma_bf16(d, a + 4, bm + 0, idesc, 1);                 // z2[0:16]  . E1[0:16]
-                if (wide) umma_bf16(d, a + 6, bm + 2, idesc, 1);       // z2[16:32] . E1[16:32]
-#else       // consecutive MMAs share their B operand slice
-                umma_bf16(d, a + 0, bm + 0, idesc, dc);                // z1[0:16]  . E1[0:16]
-                umma_bf16(d, a + 4, bm + 0, idesc, 1);                 // z2[0:16]  . E1[0:16]
-                if (wide) umma_bf16(d, a + 2, bm + 2, idesc, 1);       // z1[16:32] . E1[16:32]
-                if (wide) umma_bf16(d, a + 6, bm + 2, idesc, 1);       // z2[16:32] . E1[16:32]
-                umma_bf16(d, a + 0, bm + 4, idesc, 1);                 // z1[0:16]  . E2[0:16]
-                if (wide) umma_bf16(d, a + 2, bm + 6, idesc, 1);       // z1[16:32] . E2[16:32]
-#endif
-                umma_commit(bar(A_EMPTY + ba));
-                if (dc == nd - 1) {
-                    umma_bf16(d, aaug, baug, idesc, 1);                // + ee_k
-                    umma_commit(bar(T_FULL + g));
-                    g = g + 1 == GROUPS ? 0 : g + 1;
+                if (elect_one()) {
+                    const uint64_t a = a0 + (uint64_t)(ba * (16384 >> 4));
+                    const uint64_t bm = dc ? bmain1 : bmain;
+                    const uint32_t d = tmem_base + b * KMAX;
+                    // K-slices of 16 bf16 = 32 bytes = +2 in the descriptor's address field
+                    umma_bf16(d, a + 0, bm + 0, idesc, dc);                // z1[0:16]  . E1[0:16]
+                    if (wide) umma_bf16(d, a + 2, bm + 2, idesc, 1);       // z1[16:32] . E1[16:32]
+                    umma_bf16(d, a + 0, bm + 4, idesc, 1);                 // z1[0:16]  . E2[0:16]
+                    if (wide) umma_bf16(d, a + 2, bm + 6, idesc, 1);       // z1[16:32] . E2[16:32]
+                    umma_bf16(d, a + 4, bm + 0, idesc, 1);                 // z2[0:16]  . E1[0:16]
+                    if (wide) umma_bf16(d, a + 6, bm + 2, idesc, 1);       // z2[16:32] . E1[16:32]
+                    umma_commit(bar(A_EMPTY + ba));
+                    if (dc == nd - 1) {
+                        umma_bf16(d, aaug, baug, idesc, 1);                // + ee_k
+                        umma_commit(bar(T_FULL + g));
+                    }
                 }
+                __syncwarp();
+                if (dc == nd - 1)
+                    g = g + 1 == GROUPS ? 0 : g + 1;
             }
         }
     } else if (warp == W_SVC + 3) {
         // ================= ring owner: z_q TMA store, slot release, TMA refill =================
         // (Keeping one store in flight and releasing slot i when store i+1 is issued was measured:
         // the extra tile period of slot hold time costs more than the wait it hides.)
-        if (lane == 0) {
+        // (warp-uniform loop, TMA instructions under elect_one: no election loops around UTMALDG / UTMASTG; bulk groups
+        // belong to the issuing thread -- elect.sync picks the same lane of a full warp every time)
+        {
             const int n_items = (int)my_items;
             auto load_item = [&](int it, int s) {
-                mbar_expect_tx(bar(Z_FULL + s), TILE_M * D * 4);
                 const int i = nd == 2 ? it >> 1 : it;
                 const int dc = nd == 2 ? (it & 1) : 0;
                 const uint32_t tile = blockIdx.x + (uint32_t)i * gridDim.x;
-                tma_load_2d(sbase + OFF_ZRING + s * 16384, &map_z, bar(Z_FULL + s), dc * D, (int)(tile * TILE_M));
-                if (dc == 0) stamp(i, 0);
+                if (elect_one()) {
+                    mbar_expect_tx(bar(Z_FULL + s), TILE_M * D * 4);
+                    tma_load_2d(sbase + OFF_ZRING + s * 16384, &map_z, bar(Z_FULL + s), dc * D, (int)(tile * TILE_M));
+                }
+                __syncwarp();
+                if (dc == 0 && lane == 0) stamp(i, 0);
             };
             for (int it = 0; it < n_items && it < STAGES; ++it)
                 load_item(it, it);
@@ -599,11 +598,14 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     const int i = nd == 2 ? it >> 1 : it;
                     const int dc = nd == 2 ? (it & 1) : 0;
                     const uint32_t tile = blockIdx.x + (uint32_t)i * gridDim.x;
-                    tma_store_2d(&map_zq, sbase + OFF_ZRING + s * 16384, dc * D, (int)(tile * TILE_M));
-                    tma_store_commit();
-                    tma_store_wait_read();     // the slot may be refilled once the store has read it
+                    if (elect_one()) {
+                        tma_store_2d(&map_zq, sbase + OFF_ZRING + s * 16384, dc * D, (int)(tile * TILE_M));
+                        tma_store_commit();
+                        tma_store_wait_read();     // the slot may be refilled once the store has read it
+                    }
+                    __syncwarp();
                 }
-                if (nd == 1 || (it & 1)) stamp(nd == 2 ? it >> 1 : it, 7);
+                if ((nd == 1 || (it & 1)) && lane == 0) stamp(nd == 2 ? it >> 1 : it, 7);
                 if (it + STAGES < n_items)
                     load_item(it + STAGES, s);
                 if (++s == STAGES) {
@@ -611,7 +613,9 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     qph ^= 1u;
                 }
             }
-            tma_store_wait_all();
+            if (elect_one())
+                tma_store_wait_all();
+            __syncwarp();
         }
     } else if (warp >= W_CONV && warp < W_CONV + 4) {
         // ================= converters: fp32 -> bf16 hi/lo, thread = row =================

@@ -184,6 +184,8 @@ class VQVAEPatch(Autoencoder):
     encoder_mode = "torch"
     #: in "fused_bf16" mode: all residual blocks in one launch (csrc/enc_chain.cu) instead of one launch per layer
     fused_chain = True
+    #: ... with the final H -> D projection fused into the same launch (operand bf16(h), weights exact to 2^-17)
+    fused_projection = True
 
     def encode(self, x):
         """x (B, seq_len, input_dim) -> z_e (B, T, D)."""
@@ -203,7 +205,7 @@ class VQVAEPatch(Autoencoder):
         gamma / sqrt(var + eps) + beta is again a linear layer), rebuilt when a parameter or running statistic changes."""
         blocks = list(self.encoder[0].shared_conv)
         tracked = [t for blk in blocks for m in (blk.block[1], blk.block[2], blk.block[4], blk.block[5])
-                   for t in list(m.parameters()) + list(m.buffers())]
+                   for t in list(m.parameters()) + list(m.buffers())] + list(self.encoder[1].shared_conv.parameters())
         key = tuple((t.data_ptr(), t._version) for t in tracked)
         cache = getattr(self, "_fused_cache", None)
         if cache is None or cache[0] != key:
@@ -222,13 +224,21 @@ class VQVAEPatch(Autoencoder):
             # the same layers stacked for the one-launch chain kernel: (L, H, H) bf16 and (L, H) fp32
             stack_w = torch.stack([w for blk in ws for w in (blk[0], blk[2])]).contiguous()
             stack_b = torch.stack([b for blk in ws for b in (blk[1], blk[3])]).contiguous()
-            cache = (key, ws, stack_w, stack_b)
+            # ... and, behind them, the final projection as an exact bf16 hi + lo pair (ops.projection_rows)
+            proj = self.encoder[1].shared_conv
+            with torch.no_grad():
+                wp = proj.weight[:, :, 0].float()
+                stack_wp = None
+                if wp.shape[0] <= 64 and wp.shape[0] % 4 == 0:
+                    from .. import ops
+                    stack_wp = torch.cat([stack_w.reshape(-1, stack_w.shape[-1]), ops.projection_rows(wp)]).contiguous()
+            cache = (key, ws, stack_w, stack_b, stack_wp)
             object.__setattr__(self, "_fused_cache", cache)
         return cache[1]
 
     def _fused_stack(self):
         self._fused_weights()
-        return self._fused_cache[2], self._fused_cache[3]
+        return self._fused_cache[2], self._fused_cache[3], self._fused_cache[4]
 
     def encode_fused_bf16(self, x):
         """The encoder with its 16 hidden x hidden layers on the fused kernel: tokens (B*T, H) stay row-major,
@@ -247,10 +257,14 @@ class VQVAEPatch(Autoencoder):
             a = ops.token_bias_gelu(h, pe.proj.bias)                                   # h += b; a = bf16(gelu(h)), one pass
         if self.fused_chain and h.shape[1] in (256, 512) and len(self.encoder[0].shared_conv) >= 1:
             # every residual block in ONE launch: the token tile never leaves the SM between the layers (vqb_encoder_chain)
-            stack_w, stack_b = self._fused_stack()
-            ops.encoder_chain(a, h, stack_w, stack_b)
+            stack_w, stack_b, stack_wp = self._fused_stack()
             proj = self.encoder[1].shared_conv
-            z_e = F.linear(h, proj.weight[:, :, 0], proj.bias)
+            if self.fused_projection and stack_wp is not None:
+                # ... and the final projection as one more GEMM on the resident tile: z_e comes straight out of the chain
+                z_e = ops.encoder_chain(a, h, stack_wp, stack_b, proj_bias=proj.bias.detach().float().contiguous())
+            else:
+                ops.encoder_chain(a, h, stack_w, stack_b)
+                z_e = F.linear(h, proj.weight[:, :, 0], proj.bias)
             return z_e.view(b, -1, z_e.shape[-1])
         u = torch.empty_like(a)
         blocks = self._fused_weights()

@@ -438,20 +438,41 @@ def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, patch
 _chain_scratch = {}
 
 
-def encoder_chain(a0: torch.Tensor, h: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+def projection_rows(wp: torch.Tensor) -> torch.Tensor:
+    """The 128 weight rows vqb_encoder_chain expects behind the layers for a fused projection: rows [0, D) = bf16(Wp),
+    rows [64, 64 + D) = bf16(Wp - bf16(Wp)) (together Wp to 2^-17 relative), zeros elsewhere.  wp: (D, H) fp32, D <= 64."""
+    d, hdim = wp.shape
+    rows = torch.zeros(128, hdim, dtype=torch.bfloat16, device=wp.device)
+    hi = wp.to(torch.bfloat16)
+    rows[:d] = hi
+    rows[64:64 + d] = (wp - hi.float()).to(torch.bfloat16)
+    return rows
+
+
+def encoder_chain(a0: torch.Tensor, h: torch.Tensor, w: torch.Tensor, bias: torch.Tensor,
+                  proj_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """All residual blocks of the patch encoder in one launch (vqb_encoder_chain, csrc/enc_chain.cu):
     for every block b:  h <- h + w[2b+1] gelu(w[2b] gelu(h) + bias[2b]) + bias[2b+1], h updated in place and returned.
-    a0 (T, H) bf16 = bf16(gelu(h)); h (T, H) fp32; w (L, H, H) bf16 (out x in per layer); bias (L, H) fp32; H in {256, 512}."""
+    a0 (T, H) bf16 = bf16(gelu(h)); h (T, H) fp32; w (L, H, H) bf16 (out x in per layer); bias (L, H) fp32; H in {256, 512}.
+    With proj_bias (D,) fp32 the final projection H -> D is fused: w is then (L * H + 128, H) -- the layers followed by
+    projection_rows(Wp) -- and z_e (T, D) fp32 is returned (h is not written back)."""
     for t, name, dt in ((a0, "a0", torch.bfloat16), (h, "h", torch.float32), (w, "w", torch.bfloat16),
                         (bias, "bias", torch.float32)):
         if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != dt or not t.is_contiguous():
             raise RuntimeError(f"encoder_chain: {name} must be a contiguous CUDA {dt} tensor (no CPU fallback)")
-    if h.dim() != 2 or a0.shape != h.shape or w.dim() != 3 or w.shape[1] != h.shape[1] or w.shape[2] != h.shape[1] \
-            or tuple(bias.shape) != (w.shape[0], h.shape[1]):
+    hidden = h.shape[1] if h.dim() == 2 else -1
+    if proj_bias is None:
+        ok = w.dim() == 3 and w.shape[1] == hidden and w.shape[2] == hidden
+        layers = w.shape[0] if ok else 0
+    else:
+        if not proj_bias.is_cuda or proj_bias.dtype != torch.float32 or not proj_bias.is_contiguous():
+            raise RuntimeError("encoder_chain: proj_bias must be a contiguous CUDA float32 tensor")
+        ok = w.dim() == 2 and w.shape[1] == hidden and (w.shape[0] - 128) % hidden == 0 and w.shape[0] > 128
+        layers = (w.shape[0] - 128) // hidden if ok else 0
+    if h.dim() != 2 or a0.shape != h.shape or not ok or tuple(bias.shape) != (layers, hidden):
         raise RuntimeError("encoder_chain: shape mismatch")
     lib = _lib.load()
     dev = h.device
-    hidden, layers = h.shape[1], w.shape[0]
     with torch.cuda.device(dev):
         key = (dev.index, hidden, torch.cuda.current_stream(dev).cuda_stream)
         scratch = _chain_scratch.get(key)
@@ -461,8 +482,14 @@ def encoder_chain(a0: torch.Tensor, h: torch.Tensor, w: torch.Tensor, bias: torc
                 raise RuntimeError("encoder_chain: unsupported device / hidden size")
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _chain_scratch[key] = scratch
+        z_e = None
+        if proj_bias is not None:
+            z_e = torch.empty((h.shape[0], proj_bias.numel()), dtype=torch.float32, device=dev)
         rc = lib.vqb_encoder_chain(dev.index, a0.data_ptr(), h.data_ptr(), w.data_ptr(), bias.data_ptr(), h.shape[0],
                                    hidden, layers, scratch.data_ptr(), scratch.numel(),
+                                   proj_bias.data_ptr() if proj_bias is not None else None,
+                                   z_e.data_ptr() if z_e is not None else None,
+                                   proj_bias.numel() if proj_bias is not None else 0,
                                    torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "vqb_encoder_chain")
-    return h
+    return z_e if z_e is not None else h
