@@ -1,6 +1,6 @@
 """GPU box, under compute-sanitizer (ONE tool per gpurun call):
-    compute-sanitizer --tool memcheck  --kernel-name regex:vqb python tools/sanitize_small.py
-    compute-sanitizer --tool racecheck --kernel-name regex:vqb python tools/sanitize_small.py
+    compute-sanitizer --tool memcheck  --kernel-name kns=3vqb python tools/sanitize_small.py
+    compute-sanitizer --tool racecheck --kernel-name kns=3vqb python tools/sanitize_small.py
 Small-N calls of every hand-written kernel of the path (all live in namespace vqb), each checked against its
 reference so that the run is also a functional test under the tool."""
 import os, sys

@@ -68,6 +68,24 @@ __device__ __forceinline__ float gelu(float x)
     return fmaf(hx, t, hx);
 }
 
+// The same GELU on two values at once with sm_100's packed fp32 instructions (FMUL2 / FFMA2: IEEE results per lane, so
+// bit-identical to the scalar form): 6 packed + 2 FMNMX + 2 MUFU per pair instead of 14 + 2 scalar instructions -- the
+// epilogue's issue slots, not the tensor pipe, bound the chain (profiles/README.md, round 2).
+__device__ __forceinline__ float2 gelu2(float2 x)
+{
+    float2 u = __fmul2_rn(x, x);
+    u.x = fminf(u.x, 36.0f);
+    u.y = fminf(u.y, 36.0f);
+    float2 p = __ffma2_rn(make_float2(-3.51517534e-4f, -3.51517534e-4f), u, make_float2(3.70056510e-2f, 3.70056510e-2f));
+    p = __ffma2_rn(p, u, make_float2(7.97507878e-1f, 7.97507878e-1f));
+    const float2 y = __fmul2_rn(x, p);
+    float2 t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(y.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(y.y));
+    const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    return __ffma2_rn(hx, t, hx);
+}
+
 // tcgen05.mma with the A operand in tensor memory (lanes = rows, 32-bit columns = K pairs)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -87,6 +105,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld16_one(uint32_t (&a)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -346,77 +378,81 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                         }
                         continue;
                     }
-                    uint32_t v[32];
-                    tmem_ld32(taddr, v);
-                    tmem_wait_ld_fence(v);
-                    tc_fence_before();
-                    mbar_arrive(bar(ACC_EMPTY + ab));            // the slab sits in registers: this thread is done with the accumulator
-#if EC_ABLATE == 1
-                    if (!last) {
-                        if (!odd) {
-                            uint32_t pk[16];
+                    // the slab in two halves of 16 columns (keeps the packed-pair registers within the 96 of a 640-thread CTA)
 #pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                pk[c] = v[c] ^ v[c + 16];
-                            tmem_st16(tmem_base + (col0 >> 1) + ((uint32_t)(q4 * 32) << 16), pk);
-                            tmem_wait_st();
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t v[16];
+                        tmem_ld16(taddr + 16 * hf, v);
+                        tmem_wait_ld16_one(v);
+                        if (hf == 1) {
                             tc_fence_before();
-                        } else {
-                            fence_proxy_async();
+                            mbar_arrive(bar(ACC_EMPTY + ab));    // the slab sits in registers: this thread is done with the accumulator
                         }
-                        mbar_arrive(bar(A_RDY + q));
-                    }
-                    (void)hv; (void)bias_s; (void)scr; (void)h_out_std;
-                    continue;
-#endif
-                    float x[32];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float4 b = *reinterpret_cast<const float4 *>(bias_s + col0 + 4 * c);
-                        x[4 * c] = __uint_as_float(v[4 * c]) + b.x;
-                        x[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + b.y;
-                        x[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + b.z;
-                        x[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + b.w;
-                    }
-                    if (odd) {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            x[c] += hv[c];
-                        if (h_out_std) {
-                            if (row_ok && !proj) {                // (with the projection fused the residual stream stays on chip)
-#pragma unroll
-                                for (int c = 0; c < 8; ++c)
-                                    __stcs(reinterpret_cast<float4 *>(h + row * H + col0) + c,
-                                           make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
-                            }
-                        } else {
+#if EC_ABLATE == 1
+                        if (!last && !odd) {
+                            uint32_t pk[8];
 #pragma unroll
                             for (int c = 0; c < 8; ++c)
-                                *reinterpret_cast<float4 *>(scr + ((size_t)((col0 >> 2) + c) * BM + r) * 4) =
-                                    make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                                pk[c] = v[c] ^ v[c + 8];
+                            tmem_st8(tmem_base + ((col0 + 16 * hf) >> 1) + ((uint32_t)(q4 * 32) << 16), pk);
+                        }
+                        continue;
+#endif
+                        const int colh = col0 + 16 * hf;
+                        float2 x[8];                             // 8 pairs (packed fp32 arithmetic)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 b = *reinterpret_cast<const float4 *>(bias_s + colh + 4 * c);
+                            x[2 * c] = __fadd2_rn(make_float2(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1])),
+                                                  make_float2(b.x, b.y));
+                            x[2 * c + 1] = __fadd2_rn(make_float2(__uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3])),
+                                                      make_float2(b.z, b.w));
+                        }
+                        if (odd) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                x[c] = __fadd2_rn(x[c], make_float2(hv[16 * hf + 2 * c], hv[16 * hf + 2 * c + 1]));
+                            if (h_out_std) {
+                                if (row_ok && !proj) {            // (with the projection fused the residual stream stays on chip)
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c)
+                                        __stcs(reinterpret_cast<float4 *>(h + row * H + colh) + c,
+                                               make_float4(x[2 * c].x, x[2 * c].y, x[2 * c + 1].x, x[2 * c + 1].y));
+                                }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    *reinterpret_cast<float4 *>(scr + ((size_t)((colh >> 2) + c) * BM + r) * 4) =
+                                        make_float4(x[2 * c].x, x[2 * c].y, x[2 * c + 1].x, x[2 * c + 1].y);
+                            }
+                        }
+                        if (!last) {
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float2 y = plain ? x[c] : gelu2(x[c]);
+                                const __nv_bfloat162 p2 = __floats2bfloat162_rn(y.x, y.y);
+                                pk[c] = *reinterpret_cast<const uint32_t *>(&p2);
+                            }
+                            if (!odd) {
+                                // even GEMM: the next operand goes to tensor memory, 8 columns of packed pairs
+                                tmem_st8(tmem_base + (colh >> 1) + ((uint32_t)(q4 * 32) << 16), pk);
+                            } else {
+                                // odd GEMM: the next operand goes to the smem tile (K-chunk colh / 64, SW128 rows)
+                                unsigned char *arow = smem + P::OFF_A + (colh >> 6) * (BM * BK * 2) + r * 128;
+                                const int c16 = (colh & 63) >> 3;        // first 16-byte chunk of the 128-byte row
+#pragma unroll
+                                for (int c = 0; c < 2; ++c)
+                                    *reinterpret_cast<uint4 *>(arow + (((c16 + c) ^ (r & 7)) << 4)) =
+                                        make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                            }
                         }
                     }
                     if (!last) {
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const __nv_bfloat162 p2 = plain ? __floats2bfloat162_rn(x[2 * c], x[2 * c + 1])
-                                                            : __floats2bfloat162_rn(gelu(x[2 * c]), gelu(x[2 * c + 1]));
-                            pk[c] = *reinterpret_cast<const uint32_t *>(&p2);
-                        }
                         if (!odd) {
-                            // even GEMM: the next operand goes to tensor memory, 16 columns of packed pairs
-                            tmem_st16(tmem_base + (col0 >> 1) + ((uint32_t)(q4 * 32) << 16), pk);
                             tmem_wait_st();
                             tc_fence_before();
                         } else {
-                            // odd GEMM: the next operand goes to the smem tile (K-chunk col0 / 64, SW128 rows)
-                            unsigned char *arow = smem + P::OFF_A + (col0 >> 6) * (BM * BK * 2) + r * 128;
-                            const int c16 = (col0 & 63) >> 3;        // first 16-byte chunk of the 128-byte row
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                *reinterpret_cast<uint4 *>(arow + (((c16 + c) ^ (r & 7)) << 4)) =
-                                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                             fence_proxy_async();
                         }
                         mbar_arrive(bar(A_RDY + q));

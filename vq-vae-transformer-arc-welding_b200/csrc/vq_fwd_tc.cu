@@ -276,7 +276,7 @@ __device__ __forceinline__ float emit_row(unsigned char *zrow, int x, const unsi
     // quarter-warp hit the same bank group: measured 2x slower.  Logical order is conflict-free.)
     const unsigned char *erow = ef32 + code * 128;
     const int xe = ((code ^ (code >> 3)) & 7) << 4;
-    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 rs01 = make_float2(0.f, 0.f), rs23 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         float4 *zp4 = reinterpret_cast<float4 *>(zrow + ((c << 4) ^ x));
@@ -291,16 +291,19 @@ __device__ __forceinline__ float emit_row(unsigned char *zrow, int x, const unsi
                     ev[t] = __int_as_float(0x7fc00000);
             }
         }
-        float4 o;
-        float dj;
-        dj = __fsub_rn(e.x, zv.x); rs[0] = fmaf(dj, dj, rs[0]); o.x = __fadd_rn(zv.x, dj);
-        dj = __fsub_rn(e.y, zv.y); rs[1] = fmaf(dj, dj, rs[1]); o.y = __fadd_rn(zv.y, dj);
-        dj = __fsub_rn(e.z, zv.z); rs[2] = fmaf(dj, dj, rs[2]); o.z = __fadd_rn(zv.z, dj);
-        dj = __fsub_rn(e.w, zv.w); rs[3] = fmaf(dj, dj, rs[3]); o.w = __fadd_rn(zv.w, dj);
-        if (write_zq)
-            *zp4 = o;
+        // packed fp32 pairs (FADD2 / FFMA2, IEEE per lane: the same values as the scalar form, half the instructions --
+        // the kernel's time tracks the energy of what it executes, profiles/README.md round 2)
+        const float2 d01 = __fadd2_rn(make_float2(e.x, e.y), make_float2(-zv.x, -zv.y));     // fl(e - z)
+        const float2 d23 = __fadd2_rn(make_float2(e.z, e.w), make_float2(-zv.z, -zv.w));
+        rs01 = __ffma2_rn(d01, d01, rs01);
+        rs23 = __ffma2_rn(d23, d23, rs23);
+        if (write_zq) {
+            const float2 o01 = __fadd2_rn(make_float2(zv.x, zv.y), d01);                     // fl(z + fl(e - z))
+            const float2 o23 = __fadd2_rn(make_float2(zv.z, zv.w), d23);
+            *zp4 = make_float4(o01.x, o01.y, o23.x, o23.y);
+        }
     }
-    return (rs[0] + rs[1]) + (rs[2] + rs[3]);
+    return (rs01.x + rs01.y) + (rs23.x + rs23.y);
 }
 
 
@@ -635,7 +638,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const unsigned char *zrow = smem + OFF_ZRING + s * 16384 + r * 128;
             unsigned char *arow = smem + OFF_ARING + b * 16384 + r * 128;
-            float zp[4] = {0.f, 0.f, 0.f, 0.f};     // ||z||^2 for the epilogue's filter radius (a bound, not the decision)
+            float2 zp[4];                            // ||z||^2 for the epilogue's filter radius (a bound, not the decision)
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                zp[h] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int cp = 0; cp < 4; ++cp) {        // two 16-byte chunks of z -> one chunk of z1 and one of z2
                 const float4 va = *reinterpret_cast<const float4 *>(zrow + (((2 * cp) << 4) ^ x));
@@ -645,8 +651,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                     const float x0 = xs[2 * h], x1 = xs[2 * h + 1];
-                    zp[h] = fmaf(x0, x0, zp[h]);
-                    zp[h] = fmaf(x1, x1, zp[h]);
+                    zp[h] = __ffma2_rn(make_float2(x0, x1), make_float2(x0, x1), zp[h]);
                     // z1 = rn_bf16(x), z2 = rn_bf16(x - z1).  (Measured alternatives: truncating instead of
                     // rounding saves two ALU ops per pair but widens the filter radius by 60 %; a Veltkamp split
                     // on the FMA pipe relieves the ALU pipe but issues four more instructions per pair, ~1 % slower.)
@@ -654,15 +659,19 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     // PRMT + shift pair each)
                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
                     const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2);
-                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16),
-                                                                    x1 - __uint_as_float(hb & 0xffff0000u));
+                    const float2 lo2 = __fadd2_rn(make_float2(x0, x1), make_float2(-__uint_as_float(hb << 16),
+                                                                                   -__uint_as_float(hb & 0xffff0000u)));
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(lo2.x, lo2.y);
                     hi[h] = hb;
                     lo[h] = *reinterpret_cast<const uint32_t *>(&l2);
                 }
                 *reinterpret_cast<uint4 *>(arow + ((cp << 4) ^ x)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4 *>(arow + (((cp + 4) << 4) ^ x)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            reinterpret_cast<float *>(smem + OFF_ZZ + s * 512)[r] = (zp[0] + zp[1]) + (zp[2] + zp[3]);
+            {
+                const float2 t = __fadd2_rn(__fadd2_rn(zp[0], zp[1]), __fadd2_rn(zp[2], zp[3]));
+                reinterpret_cast<float *>(smem + OFF_ZZ + s * 512)[r] = t.x + t.y;
+            }
             fence_proxy_async();
             mbar_arrive(bar(A_FULL + b));
             if (r == 0 && nd == 1) stamp(i, 2);
