@@ -168,15 +168,26 @@ int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const f
  *   w_bf16  (n_layers, hidden, hidden) bf16 (out x in per layer), bias (n_layers, hidden) fp32
  *   scratch vqb_encoder_chain_scratch_bytes(device, hidden) bytes of device memory (contents private)
  * proj_dim > 0 fuses the encoder's final per-token projection hidden -> proj_dim (SepCNNBlock, :83-91) as one more
- * narrow GEMM on the resident tile: w_bf16 then holds 128 further rows behind the layers -- rows [0, proj_dim) =
- * bf16(Wp), rows [64, 64 + proj_dim) = bf16(Wp - bf16(Wp)), zeros elsewhere -- and z_e (n_tokens, proj_dim) fp32 =
- * bf16(h) Wp^T + proj_bias is written; h is then NOT written back.  proj_dim a multiple of 4, <= 64.
+ * narrow GEMM on the resident tile, both operands as exact bf16 hi + lo pairs (fp32-accurate to 2^-16): w_bf16 then
+ * holds 128 further rows behind the layers -- rows [0, proj_dim) = bf16(Wp), rows [64, 64 + proj_dim) =
+ * bf16(Wp - bf16(Wp)), zeros elsewhere -- and z_e (n_tokens, proj_dim) fp32 = h Wp^T + proj_bias is written; h is
+ * then NOT written back.  proj_dim a multiple of 4, <= 64.
+ * pre_bias != NULL fuses the patch embedding (PatchEmbedding, :7-17) as a first short GEMM: a0_bf16 is then the
+ * (n_tokens, 64) operand vqb_patch_split writes, w_bf16 holds `hidden` further rows at its end (columns [0, 32) =
+ * bf16(Wpe), [32, 64) = bf16(Wpe - bf16(Wpe)), zero beyond the patch size; Wpe = Conv1d weight[:, 0, :]), pre_bias
+ * (hidden) is the Conv1d bias, and h is not read.  With both fusions h may be NULL: raw samples in, z_e out.
  * hidden in {256, 512}, n_layers even; all pointers 16-byte aligned.
  */
 size_t vqb_encoder_chain_scratch_bytes(int device, int hidden);
 int vqb_encoder_chain(int device, const void *a0_bf16, float *h, const void *w_bf16, const float *bias, int64_t n_tokens,
                       int hidden, int n_layers, void *scratch, size_t scratch_bytes, const float *proj_bias, float *z_e,
-                      int proj_dim, void *stream);
+                      int proj_dim, const float *pre_bias, void *stream);
+
+/* Operand of the fused patch embedding: x (n_cycles, seq_len, channels) fp32 contiguous -> out (n_tokens, 64) bf16,
+ * token order as in vqb_patch_embed (channel-major), row = [bf16(x_k), k < patch, zeros to 32 | bf16(x_k - bf16(x_k)),
+ * zeros to 32].  patch <= 32, seq_len a multiple of patch. */
+int vqb_patch_split(int device, const float *x, int64_t n_cycles, int seq_len, int channels, int patch, void *out_bf16,
+                    void *stream);
 
 /* h += bias (fp32 (n_tokens, n), in place); out = bf16(gelu(h)): the element-wise step between the fp32 patch
  * embedding (model/vq_vae_patch_embedd.py:13-17) and the first fused layer, in one pass.  n a multiple of 4. */

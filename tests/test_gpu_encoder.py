@@ -290,3 +290,31 @@ def test_encoder_chain_fused_projection(T, H, L, D):
     z = ops.encoder_chain(a0, h_in, stack, b, proj_bias=bp)
     assert z.shape == (T, D) and z.dtype == torch.float32
     torch.testing.assert_close(z, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("hidden,n_res,patch,B", [(512, 8, 25, 300), (256, 2, 10, 129), (512, 1, 25, 7)])
+def test_fully_fused_encoder_launch(hidden, n_res, patch, B):
+    """Raw samples in, z_e out in one launch (patch embedding as the first GEMM, projection as the last, both with bf16
+    hi + lo operand pairs) against the same chain fed by the fp32 patch-embedding kernel and followed by an fp32
+    projection: the two differ by 2^-16-relative operand errors only."""
+    dev = _dev()
+    torch.manual_seed(hidden + patch)
+    model = vqb200.VQVAEPatch(hidden_dim=hidden, input_dim=2, num_embeddings=64, embedding_dim=32, n_resblocks=n_res,
+                              learning_rate=1e-3, patch_size=patch, batch_norm=False).to(dev).eval()
+    x = torch.randn(B, 200, 2, device=dev)
+    model.encoder_mode = "fused_bf16"
+    with torch.no_grad():
+        assert model._fused_ok(x)
+        model.fused_patch_embed, model.fused_projection = False, False
+        z_ref = model.encode(x)
+        model.fused_projection = True
+        z_proj = model.encode(x)
+        model.fused_patch_embed = True
+        z_all = model.encode(x)
+    scale = z_ref.abs().max().item()
+    assert z_all.shape == z_ref.shape == (B, 16 if patch == 25 else 40, 32)
+    assert (z_proj - z_ref).abs().max().item() <= 2e-4 * scale       # hi + lo projection: fp32-faithful
+    # the fused patch embedding perturbs h0 by 2^-16 relative; the bf16 roundings of the 2 * n_res layers then differ
+    # on a few elements each, so the bound is the bf16-operand tolerance of the path, not 2^-16
+    assert (z_all - z_ref).abs().max().item() <= 0.02 * scale
+    assert ((z_all - z_ref).abs().mean() / z_ref.abs().mean()).item() <= 2e-3

@@ -34,7 +34,7 @@ wp = torch.randn(32, H, device=dev, generator=g) * (1.0 / H) ** 0.5
 bp = torch.zeros(32, device=dev)
 stack = torch.cat([w.reshape(-1, H), ops.projection_rows(wp)]).contiguous()
 zp = ops.encoder_chain(a0, h0.clone(), stack, b, proj_bias=bp)
-zr = out.to(torch.bfloat16).float() @ wp.t()
+zr = out @ wp.t()
 print(f"  fused projection: max |z - ref| = {(zp - zr).abs().max().item():.3e} (scale {zr.abs().max().item():.3f})")
 for name, fn in (("chain", lambda: ops.encoder_chain(a0, hbuf, w, b)),
                  ("chain+proj", lambda: ops.encoder_chain(a0, hbuf, stack, b, proj_bias=bp)),

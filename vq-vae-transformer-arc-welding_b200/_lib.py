@@ -39,7 +39,8 @@ SIGNATURES = {
     "vqb_token_linear": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _u, _vp]),
     "vqb_token_bias_gelu": (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp]),
     "vqb_encoder_chain_scratch_bytes": (_sz, [_i, _i]),
-    "vqb_encoder_chain": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _sz, _vp, _vp, _i, _vp]),
+    "vqb_encoder_chain": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _sz, _vp, _vp, _i, _vp, _vp]),
+    "vqb_patch_split": (_i, [_i, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "vqb_pack_rows": (_i, [_i, _vp, _i64, _i64, _i, _i64, _i64, _i64, _vp, _vp]),
     "vqb_patch_embed": (_i, [_i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "vqb_gather": (_i, [_i, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),

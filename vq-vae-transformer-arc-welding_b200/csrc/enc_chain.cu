@@ -20,9 +20,14 @@
 //     caller's row-major h.
 //
 //   * optionally the encoder's final per-token projection H -> D (SepCNNBlock, model/vq_vae_patch_embedd.py:83-91) runs
-//     as one more, narrow GEMM on the same tile: operand bf16(h) (no GELU), weights as an exact bf16 hi + lo pair in two
-//     column groups of one N = 128 accumulator, z_e = acc_hi + acc_lo + bias written as fp32 rows -- the residual stream
-//     then never goes back to HBM at all.
+//     as one more, narrow GEMM on the same tile.  Both of its operands are exact bf16 hi + lo pairs: the weights in two
+//     column groups of one N = 128 accumulator, the residual stream h as two K passes -- bf16(h) written by the last
+//     layer's epilogue, bf16(h - bf16(h)) written into the OTHER activation buffer once the last layer's MMAs are done
+//     (rounding h to a single bf16 costs ids: 99.70 % instead of 99.86 % of them equal to the fp32 encoder's).
+//     z_e = acc_hi + acc_lo + bias leaves as fp32 rows -- the residual stream then never goes back to HBM at all;
+//   * optionally the patch embedding (PatchEmbedding, :7-17) runs as a first, short GEMM on the tile (K = patch <= 32,
+//     samples and weights as bf16 hi + lo pairs, three products like the quantiser's filter: fp32-accurate to 2^-16),
+//     fed by a 128-byte-per-token operand the gather kernel below writes -- instead of 3 KB per token of h and a.
 //
 // bf16 operands, fp32 accumulation, fp32 residual stream, GELU as in tok_linear.cu (gelu_fast): the same arithmetic
 // as the layer-at-a-time path, layer for layer.
@@ -124,18 +129,25 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 }  // namespace ec
 
-// a0     : (n_tokens, H) bf16 row-major = bf16(gelu(h0)), the first GEMM's operand (TMA)
-// h      : (n_tokens, H) fp32 row-major, in: h0 (the patch embedding), out: the residual stream after the last block
-// w      : (L * H, H) bf16 row-major, layer l = rows [l*H, (l+1)*H) (out x in); bias (L * H) fp32
+// GEMM sequence of a tile: [PRE] LAYER x L [PROJ].  GEMM j reads its A operand from shared memory if j is even and from
+// tensor memory if j is odd; its epilogue writes the next operand into the other one.
+//
+// a0     : without PRE: (n_tokens, H) bf16 row-major = bf16(gelu(h0)), the first GEMM's operand (TMA);
+//          with PRE:    (n_tokens, 64) bf16 = [bf16(x) | bf16(x - bf16(x))] of the token's patch, 32 + 32 columns
+//                       (zero beyond the patch size) -- vq_patch_split_kernel
+// h      : (n_tokens, H) fp32 row-major.  Without PRE it holds h0 on entry; without PROJ it receives the residual
+//          stream after the last block; with both it is not touched (may be NULL)
+// w      : (L * H [+ 128] [+ H], H) bf16 row-major: layer l = rows [l*H, (l+1)*H) (out x in), then PROJ's 128 rows
+//          (rows [0, D) = bf16(Wp), rows [64, 64 + D) = bf16(Wp - bf16(Wp)), zeros elsewhere), then PRE's H rows
+//          (columns [0, 32) = bf16(Wpe), [32, 64) = bf16(Wpe - bf16(Wpe)), zero beyond the patch size)
+// bias   : (L * H) fp32;  proj_bias (D);  pre_bias (H)
 // scratch: gridDim.x tiles of BM * H fp32 (the residual stream between the blocks)
-// proj_d > 0: w holds 128 more rows after the L layers -- rows [0, proj_d) = bf16(Wp), rows [64, 64 + proj_d) =
-//          bf16(Wp - bf16(Wp)), zeros elsewhere -- and z_e (n_tokens, proj_d) fp32 = h_final Wp^T + proj_bias is written
-//          instead of h
 template <int H>
 __global__ void __launch_bounds__(ec::THREADS, 1)
 enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_w,
                  const float *__restrict__ bias, float *__restrict__ h, float *__restrict__ scratch,
-                 int64_t n_tokens, int L, const float *__restrict__ proj_bias, float *__restrict__ z_e, int proj_d)
+                 int64_t n_tokens, int L, const float *__restrict__ proj_bias, float *__restrict__ z_e, int proj_d,
+                 const float *__restrict__ pre_bias)
 {
     using namespace tc;
     using namespace ec;
@@ -148,16 +160,20 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     if ((sbase & 1023u) != 0)
         __trap();
     enum { W_FULL = 0, W_EMPTY = W_FULL + W_STAGES, ACC_FULL = W_EMPTY + W_STAGES, ACC_EMPTY = ACC_FULL + 2,
-           A_RDY = ACC_EMPTY + 2, A0_FULL = A_RDY + 4, A_FREE = A0_FULL + 1, N_BARS = A_FREE + 1 };
+           A_RDY = ACC_EMPTY + 2, A0_FULL = A_RDY + 4, A_FREE = A0_FULL + 1, LO_RDY = A_FREE + 1, N_BARS = LO_RDY + 1 };
     static_assert(8 * N_BARS + 8 <= 256, "barrier area");
     static_assert(P::SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KB");
     auto bar = [&](int i) { return sbase + P::OFF_BARS + 8 * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + P::OFF_BARS + 8 * N_BARS);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // with a projection the chain has one more, single-quarter GEMM (index L, even: it reads the smem tile)
-    const bool proj = proj_d > 0;
-    const int LT = L + (proj ? 1 : 0);
+    const bool pre = pre_bias != nullptr, proj = proj_d > 0;
+    const int j_layer0 = pre ? 1 : 0;          // first LAYER GEMM
+    const int j_proj = j_layer0 + L;           // PROJ GEMM (if any)
+    const int NG = j_proj + (proj ? 1 : 0);    // GEMMs per tile
+    const int w_row_proj = L * H, w_row_pre = L * H + (proj ? NQ : 0);
+    // the last GEMM that READS the smem tile (A_FREE follows it): PROJ reads both buffers; else the last even GEMM
+    const int j_free = proj ? j_proj : ((NG - 1) & 1 ? NG - 2 : NG - 1);
     const int64_t n_tiles = (n_tokens + BM - 1) / BM;
     const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
@@ -174,6 +190,7 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             mbar_init(bar(A_RDY + q), EPI_THREADS);
         mbar_init(bar(A0_FULL), 1);
         mbar_init(bar(A_FREE), 1);
+        mbar_init(bar(LO_RDY), EPI_THREADS);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -187,38 +204,53 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 
     if (warp == 0) {
         // ================= weight producer: runs ahead of the MMAs across GEMM and tile boundaries =================
-        {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int t = 0; t < my_tiles; ++t)
-                for (int g = 0; g < LT; ++g)
-                    for (int q = 0; q < (g == L ? 1 : NQT); ++q)
-                        for (int ks = 0; ks < NKS; ++ks) {
-                            mbar_wait<32>(bar(W_EMPTY + s), ph ^ 1u);
-                            if (elect_one()) {
-                                mbar_expect_tx(bar(W_FULL + s), W_STAGE);
-                                tma_load_2d(sbase + P::OFF_W + s * W_STAGE, &map_w, bar(W_FULL + s), ks * KS, g * H + q * NQ);
-                                tma_load_2d(sbase + P::OFF_W + s * W_STAGE + NQ * BK * 2, &map_w, bar(W_FULL + s), ks * KS + BK,
-                                            g * H + q * NQ);
-                            }
-                            __syncwarp();
-                            if (++s == W_STAGES) {
-                                s = 0;
-                                ph ^= 1u;
-                            }
-                        }
-        }
+        int s = 0;
+        uint32_t ph = 0;
+        auto stage = [&](int row, int col, bool two_boxes) {
+            mbar_wait<32>(bar(W_EMPTY + s), ph ^ 1u);
+            if (elect_one()) {
+                mbar_expect_tx(bar(W_FULL + s), two_boxes ? W_STAGE : W_STAGE / 2);
+                tma_load_2d(sbase + P::OFF_W + s * W_STAGE, &map_w, bar(W_FULL + s), col, row);
+                if (two_boxes)
+                    tma_load_2d(sbase + P::OFF_W + s * W_STAGE + NQ * BK * 2, &map_w, bar(W_FULL + s), col + BK, row);
+            }
+            __syncwarp();
+            if (++s == W_STAGES) {
+                s = 0;
+                ph ^= 1u;
+            }
+        };
+        for (int t = 0; t < my_tiles; ++t)
+            for (int j = 0; j < NG; ++j) {
+                if (pre && j == 0) {
+                    for (int q = 0; q < NQT; ++q)
+                        stage(w_row_pre + q * NQ, 0, false);              // one 64-column box: [Wpe_hi | Wpe_lo]
+                } else if (proj && j == j_proj) {
+                    for (int pass = 0; pass < 2; ++pass)                  // the hi and the lo pass use the same rows
+                        for (int ks = 0; ks < NKS; ++ks)
+                            stage(w_row_proj, ks * KS, true);
+                } else {
+                    for (int q = 0; q < NQT; ++q)
+                        for (int ks = 0; ks < NKS; ++ks)
+                            stage((j - j_layer0) * H + q * NQ, ks * KS, true);
+                }
+            }
     } else if (warp == 3) {
-        // ================= first operand of every tile: bf16(gelu(h0)) rows by TMA =================
+        // ================= first operand of every tile by TMA: bf16(gelu(h0)) rows, or the split patches =================
         for (int t = 0; t < my_tiles; ++t) {
             if (t > 0)
                 mbar_wait<64>(bar(A_FREE), (uint32_t)((t - 1) & 1));    // the last GEMM that read the smem tile is done
             const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
             if (elect_one()) {
-                mbar_expect_tx(bar(A0_FULL), P::A_BYTES);
+                if (pre) {
+                    mbar_expect_tx(bar(A0_FULL), BM * BK * 2);
+                    tma_load_2d(sbase + P::OFF_A, &map_a0, bar(A0_FULL), 0, (int)(tile * BM));
+                } else {
+                    mbar_expect_tx(bar(A0_FULL), P::A_BYTES);
 #pragma unroll
-                for (int kc = 0; kc < NKC; ++kc)
-                    tma_load_2d(sbase + P::OFF_A + kc * (BM * BK * 2), &map_a0, bar(A0_FULL), kc * BK, (int)(tile * BM));
+                    for (int kc = 0; kc < NKC; ++kc)
+                        tma_load_2d(sbase + P::OFF_A + kc * (BM * BK * 2), &map_a0, bar(A0_FULL), kc * BK, (int)(tile * BM));
+                }
             }
             __syncwarp();
         }
@@ -229,54 +261,85 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         const uint64_t w_base = desc_sw128(sbase + P::OFF_W);    // + s * 2048 (32 KB stages), + 1024 for the second box
         int s = 0;
         uint32_t wph = 0;
-        uint32_t acc_n = 0;                                      // accumulator quarters issued so far
+        uint32_t acc_n = 0;                                      // accumulators issued so far
         uint32_t ardy_n = 0;                                     // completed A_RDY phases (per quarter barrier) so far
+        auto next_stage = [&]() {
+            if (++s == W_STAGES) {
+                s = 0;
+                wph ^= 1u;
+            }
+        };
+        // one K pass (H wide) of an accumulator: operand from shared memory (K-chunks of the tile) or tensor memory
+        auto k_pass = [&](uint32_t d, bool from_tmem, bool wait_a, bool fresh) {
+#pragma unroll
+            for (int ks = 0; ks < NKS; ++ks) {
+                if (wait_a)                                      // K range of stage ks = quarter ks of the previous epilogue
+                    mbar_wait<32>(bar(A_RDY + ks), ardy_n & 1u);
+                mbar_wait<32>(bar(W_FULL + s), wph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t wd = w_base + (uint64_t)(s * (W_STAGE >> 4));
+#pragma unroll
+                    for (int hk = 0; hk < KS / BK; ++hk) {       // the stage's two 64-wide boxes
+                        const int kc = ks * (KS / BK) + hk;
+                        if (!from_tmem) {
+                            const uint64_t ad = a_base + (uint64_t)(kc * (BM * BK * 2 >> 4));
+#pragma unroll
+                            for (int i = 0; i < BK / 16; ++i)
+                                umma_bf16(d, ad + 2 * i, wd + hk * (NQ * BK * 2 >> 4) + 2 * i, idesc, !fresh || (kc | i) != 0);
+                        } else {
+                            const uint32_t at = tmem_base + kc * (BK / 2);
+#pragma unroll
+                            for (int i = 0; i < BK / 16; ++i)
+                                umma_bf16_ts(d, at + 8 * i, wd + hk * (NQ * BK * 2 >> 4) + 2 * i, idesc, !fresh || (kc | i) != 0);
+                        }
+                    }
+                    umma_commit(bar(W_EMPTY + s));
+                }
+                __syncwarp();
+                next_stage();
+            }
+        };
         for (int t = 0; t < my_tiles; ++t) {
             mbar_wait<32>(bar(A0_FULL), (uint32_t)(t & 1));
-            for (int g = 0; g < LT; ++g) {
-                const bool from_tmem = (g & 1) != 0;             // even GEMMs read shared memory, odd ones tensor memory
-                for (int q = 0; q < (g == L ? 1 : NQT); ++q, ++acc_n) {
+            for (int j = 0; j < NG; ++j) {
+                const bool from_tmem = (j & 1) != 0;             // even GEMMs read shared memory, odd ones tensor memory
+                const bool is_pre = pre && j == 0, is_proj = proj && j == j_proj;
+                const int nq = is_proj ? 1 : NQT;
+                for (int q = 0; q < nq; ++q, ++acc_n) {
                     const int ab = (int)(acc_n & 1u);
                     mbar_wait<32>(bar(ACC_EMPTY + ab), ((acc_n >> 1) & 1u) ^ 1u);
                     const uint32_t d = tmem_base + P::TMEM_ACC0 + ab * NQ;
-#pragma unroll
-                    for (int ks = 0; ks < NKS; ++ks) {
-                        if (g > 0 && q == 0)                     // K range of stage ks = quarter ks of the previous epilogue
-                            mbar_wait<32>(bar(A_RDY + ks), ardy_n & 1u);
+                    if (is_pre) {
+                        // h0 = x_hi Wpe_hi + x_hi Wpe_lo + x_lo Wpe_hi: K-slices 0, 1 = hi and 2, 3 = lo of the 64-column chunk
                         mbar_wait<32>(bar(W_FULL + s), wph);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint64_t wd = w_base + (uint64_t)(s * (W_STAGE >> 4));
-#pragma unroll
-                            for (int hk = 0; hk < KS / BK; ++hk) {           // the stage's two 64-wide boxes
-                                const int kc = ks * (KS / BK) + hk;
-                                if (!from_tmem) {
-                                    const uint64_t ad = a_base + (uint64_t)(kc * (BM * BK * 2 >> 4));
-#pragma unroll
-                                    for (int j = 0; j < BK / 16; ++j)
-                                        umma_bf16(d, ad + 2 * j, wd + hk * (NQ * BK * 2 >> 4) + 2 * j, idesc, (kc | j) != 0);
-                                } else {
-                                    const uint32_t at = tmem_base + kc * (BK / 2);
-#pragma unroll
-                                    for (int j = 0; j < BK / 16; ++j)
-                                        umma_bf16_ts(d, at + 8 * j, wd + hk * (NQ * BK * 2 >> 4) + 2 * j, idesc, (kc | j) != 0);
-                                }
-                            }
+                            umma_bf16(d, a_base + 0, wd + 0, idesc, 0);
+                            umma_bf16(d, a_base + 2, wd + 2, idesc, 1);
+                            umma_bf16(d, a_base + 0, wd + 4, idesc, 1);
+                            umma_bf16(d, a_base + 2, wd + 6, idesc, 1);
+                            umma_bf16(d, a_base + 4, wd + 0, idesc, 1);
+                            umma_bf16(d, a_base + 6, wd + 2, idesc, 1);
                             umma_commit(bar(W_EMPTY + s));
                         }
                         __syncwarp();
-                        if (++s == W_STAGES) {
-                            s = 0;
-                            wph ^= 1u;
-                        }
+                        next_stage();
+                    } else if (is_proj) {
+                        k_pass(d, from_tmem, true, true);        // bf16(h) against [Wp_hi | Wp_lo]
+                        mbar_wait<32>(bar(LO_RDY), (uint32_t)(t & 1));
+                        k_pass(d, !from_tmem, false, false);     // bf16(h - bf16(h)) from the other buffer, same accumulator
+                    } else {
+                        k_pass(d, from_tmem, j > 0 && q == 0, true);
                     }
                     if (elect_one())
                         umma_commit(bar(ACC_FULL + ab));
                     __syncwarp();
                 }
-                if (g > 0)
+                if (j > 0)
                     ++ardy_n;
-                if (g == (proj ? L : L - 2)) {
+                if (j == j_free) {
                     if (elect_one())
                         umma_commit(bar(A_FREE));                // every MMA that reads the smem tile has been issued
                     __syncwarp();
@@ -290,33 +353,60 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         const int sl = (warp - 4) >> 2;                          // slab 0..3 of the 128-column accumulator
         const int r = q4 * 32 + lane;                            // row of the tile
         const int et = tid - 128;                                // 0 .. EPI_THREADS-1
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         float *scr = scratch + (size_t)blockIdx.x * (BM * H);
         float *bias_s = reinterpret_cast<float *>(smem + P::OFF_BIAS);
+        // 16 packed bf16 pairs of this thread's row, columns [col, col + 16), into the operand buffer GEMM j + 1 reads
+        auto put_operand = [&](bool to_tmem, int col, const uint32_t (&pk)[8]) {
+            if (to_tmem) {
+                tmem_st8(tmem_base + (col >> 1) + lane_addr, pk);
+            } else {
+                unsigned char *arow = smem + P::OFF_A + (col >> 6) * (BM * BK * 2) + r * 128;
+                const int c16 = (col & 63) >> 3;                 // first 16-byte chunk of the 128-byte row
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    *reinterpret_cast<uint4 *>(arow + (((c16 + c) ^ (r & 7)) << 4)) =
+                        make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+        };
+        auto publish = [&](bool to_tmem, int bar_id) {           // make the operand visible to the MMAs, then arrive
+            if (to_tmem) {
+                tmem_wait_st();
+                tc_fence_before();
+            } else {
+                fence_proxy_async();
+            }
+            mbar_arrive(bar(bar_id));
+        };
         uint32_t acc_n = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
             const int64_t row = tile * BM + r;
             const bool row_ok = row < n_tokens;
-            for (int g = 0; g < LT; ++g) {
-                const bool odd = (g & 1) != 0, last = g == LT - 1;
-                const bool is_proj = g == L;                      // the narrow projection GEMM (only when proj)
-                const bool plain = proj && g == L - 1;            // its operand is bf16(h), not bf16(gelu(h))
-                const bool h_in_std = g == 1, h_out_std = g == L - 1;   // first block reads, last block writes the caller's h
-                // this layer's bias: fetched now, parked in shared memory behind the first quarter's barrier (every
-                // warp has then finished the previous layer), published by a second barrier
+            for (int j = 0; j < NG; ++j) {
+                const bool is_pre = pre && j == 0, is_proj = proj && j == j_proj;
+                const int l = j - j_layer0;                      // layer index of a LAYER GEMM
+                const bool resid = !is_pre && !is_proj && (l & 1) != 0;      // second GEMM of a block: + residual
+                const bool last = j == NG - 1;
+                const bool to_tmem = (j & 1) == 0;               // where the NEXT operand goes
+                const bool plain = proj && j == j_proj - 1;      // PROJ's operand is bf16(h), not bf16(gelu(h))
+                const bool h_in_std = !pre && l == 1;            // without PRE the caller's h holds h0
+                const bool h_out_std = !proj && l == L - 1;      // without PROJ the caller's h receives the result
+                // this GEMM's bias: fetched now, parked in shared memory behind the first quarter's barrier (every warp
+                // has then finished the previous GEMM), published by a second barrier
                 float bias_reg = 0.0f;
                 if (is_proj) {
                     if (et < proj_d)
                         bias_reg = __ldg(proj_bias + et);
                 } else if (et < H) {
-                    bias_reg = __ldg(bias + (size_t)g * H + et);
+                    bias_reg = __ldg((is_pre ? pre_bias : bias + (size_t)l * H) + et);
                 }
                 for (int q = 0; q < (is_proj ? 1 : NQT); ++q, ++acc_n) {
                     const int ab = (int)(acc_n & 1u);
                     const int col0 = q * NQ + sl * 32;           // this thread's 32 columns of the GEMM's output
                     // the residual slab is requested before the accumulator is waited for
                     float hv[32];
-                    if (odd) {
+                    if (resid) {
                         if (h_in_std) {
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
@@ -341,9 +431,9 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                         named_bar_sync(2, EPI_THREADS);
                     }
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + P::TMEM_ACC0 + ab * NQ + sl * 32 + ((uint32_t)(q4 * 32) << 16);
+                    const uint32_t taddr = tmem_base + P::TMEM_ACC0 + ab * NQ + sl * 32 + lane_addr;
                     if (is_proj) {
-                        // z_e = (operand . W_hi) + (operand . W_lo) + bias: accumulator columns [0, 64) and [64, 128);
+                        // z_e = (h . Wp_hi) + (h . Wp_lo) + bias: accumulator columns [0, 64) and [64, 128);
                         // slabs 0 and 1 own output columns [0, 32) and [32, 64), slabs 2 and 3 only hand the buffer back
                         if (sl < 2 && sl * 32 < proj_d) {
 #pragma unroll
@@ -388,17 +478,17 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                             tc_fence_before();
                             mbar_arrive(bar(ACC_EMPTY + ab));    // the slab sits in registers: this thread is done with the accumulator
                         }
+                        const int colh = col0 + 16 * hf;
 #if EC_ABLATE == 1
-                        if (!last && !odd) {
+                        if (!last) {
                             uint32_t pk[8];
 #pragma unroll
                             for (int c = 0; c < 8; ++c)
                                 pk[c] = v[c] ^ v[c + 8];
-                            tmem_st8(tmem_base + ((col0 + 16 * hf) >> 1) + ((uint32_t)(q4 * 32) << 16), pk);
+                            put_operand(to_tmem, colh, pk);
                         }
                         continue;
 #endif
-                        const int colh = col0 + 16 * hf;
                         float2 x[8];                             // 8 pairs (packed fp32 arithmetic)
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
@@ -408,12 +498,14 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                             x[2 * c + 1] = __fadd2_rn(make_float2(__uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3])),
                                                       make_float2(b.z, b.w));
                         }
-                        if (odd) {
+                        if (resid) {
 #pragma unroll
                             for (int c = 0; c < 8; ++c)
                                 x[c] = __fadd2_rn(x[c], make_float2(hv[16 * hf + 2 * c], hv[16 * hf + 2 * c + 1]));
+                        }
+                        if (resid || is_pre) {                   // the residual stream: h0 after PRE, h after every block
                             if (h_out_std) {
-                                if (row_ok && !proj) {            // (with the projection fused the residual stream stays on chip)
+                                if (row_ok) {
 #pragma unroll
                                     for (int c = 0; c < 4; ++c)
                                         __stcs(reinterpret_cast<float4 *>(h + row * H + colh) + c,
@@ -434,29 +526,34 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                                 const __nv_bfloat162 p2 = __floats2bfloat162_rn(y.x, y.y);
                                 pk[c] = *reinterpret_cast<const uint32_t *>(&p2);
                             }
-                            if (!odd) {
-                                // even GEMM: the next operand goes to tensor memory, 8 columns of packed pairs
-                                tmem_st8(tmem_base + (colh >> 1) + ((uint32_t)(q4 * 32) << 16), pk);
-                            } else {
-                                // odd GEMM: the next operand goes to the smem tile (K-chunk colh / 64, SW128 rows)
-                                unsigned char *arow = smem + P::OFF_A + (colh >> 6) * (BM * BK * 2) + r * 128;
-                                const int c16 = (colh & 63) >> 3;        // first 16-byte chunk of the 128-byte row
+                            put_operand(to_tmem, colh, pk);
+                        }
+                    }
+                    if (!last)
+                        publish(to_tmem, A_RDY + q);
+                }
+                if (plain) {
+                    // ---- PROJ's second operand: bf16(h - bf16(h)) of the whole row into the buffer the last layer's MMAs
+                    // have finished reading (its last accumulator was waited for above), h from the scratch tile
+#pragma unroll 1
+                    for (int q = 0; q < NQT; ++q) {
 #pragma unroll
-                                for (int c = 0; c < 2; ++c)
-                                    *reinterpret_cast<uint4 *>(arow + (((c16 + c) ^ (r & 7)) << 4)) =
-                                        make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int colh = q * NQ + sl * 32 + 16 * hf;
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float4 v = *reinterpret_cast<const float4 *>(scr + ((size_t)((colh >> 2) + c) * BM + r) * 4);
+                                const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+                                const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
+                                const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
+                                pk[2 * c] = *reinterpret_cast<const uint32_t *>(&l01);
+                                pk[2 * c + 1] = *reinterpret_cast<const uint32_t *>(&l23);
                             }
+                            put_operand(!to_tmem, colh, pk);
                         }
                     }
-                    if (!last) {
-                        if (!odd) {
-                            tmem_wait_st();
-                            tc_fence_before();
-                        } else {
-                            fence_proxy_async();
-                        }
-                        mbar_arrive(bar(A_RDY + q));
-                    }
+                    publish(!to_tmem, LO_RDY);
                 }
             }
         }
@@ -468,19 +565,60 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------
+// Operand of the PRE GEMM: token t of cycle b is channel c = t / (L/P), patch p = t % (L/P) (the reference's
+// channel-major order, model/vq_vae_patch_embedd.py:14-15) with samples x[b][p*P + k][c]; out[token] =
+// [bf16(x_k) k < P, 0 ... | bf16(x_k - bf16(x_k)), 0 ...] as 32 + 32 bf16 (128 bytes per token).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vq_patch_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out,
+                                                             int64_t n_tokens, int L, int C, int P)
+{
+    const int ppc = L / P, T = ppc * C;
+    // one thread per (token, k): 32 threads per token write the hi and the lo half of one row
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_tokens * 32; i += (int64_t)gridDim.x * 256) {
+        const int64_t t = i >> 5;
+        const int k = (int)(i & 31);
+        float v = 0.0f;
+        if (k < P) {
+            const int64_t b = t / T;
+            const int ct = (int)(t - b * T), c = ct / ppc, pp = ct - c * ppc;
+            v = __ldg(x + (b * L + (int64_t)pp * P + k) * C + c);
+        }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        out[t * 64 + k] = hi;
+        out[t * 64 + 32 + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
 bool enc_chain_supported(int H, int L) { return (H == 512 || H == 256) && L >= 2 && L % 2 == 0 && L <= 64; }
+bool patch_split_supported(int L, int C, int P) { return P >= 1 && P <= 32 && C >= 1 && L >= P && L % P == 0; }
 
 size_t enc_chain_scratch_bytes(int H, int sm_count) { return (size_t)sm_count * ec::BM * H * sizeof(float); }
 
+cudaError_t launch_patch_split(const float *x, void *out, int64_t n_cycles, int L, int C, int P, int sm_count, cudaStream_t st)
+{
+    if (!patch_split_supported(L, C, P))
+        return cudaErrorNotSupported;
+    const int64_t n_tokens = n_cycles * (L / P) * C;
+    if (n_tokens == 0)
+        return cudaSuccess;
+    const int64_t blocks = (n_tokens * 32 + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)sm_count * 16 ? blocks : (int64_t)sm_count * 16);
+    vq_patch_split_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16 *)out, n_tokens, L, C, P);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_enc_chain(const void *a0, float *h, const void *w, const float *bias, int64_t n_tokens, int H, int L,
                              float *scratch, size_t scratch_bytes, const float *proj_bias, float *z_e, int proj_d,
-                             int sm_count, int max_smem, cudaStream_t st)
+                             const float *pre_bias, int sm_count, int max_smem, cudaStream_t st)
 {
     using namespace ec;
     if (!enc_chain_supported(H, L))
         return cudaErrorNotSupported;
     if (proj_d != 0 && (proj_d < 4 || proj_d > 64 || proj_d % 4 != 0 || !proj_bias || !z_e))
         return cudaErrorNotSupported;
+    if ((!pre_bias || !proj_d) && !h)
+        return cudaErrorInvalidValue;
     if (n_tokens == 0)
         return cudaSuccess;
     if (n_tokens >= (1ll << 31))
@@ -493,16 +631,17 @@ cudaError_t launch_enc_chain(const void *a0, float *h, const void *w, const floa
     if (smem_bytes > max_smem)
         return cudaErrorNotSupported;
     CUtensorMap map_a0, map_w;
-    if (!tc::make_tensor_map_2d(&map_a0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a0, n_tokens, H, BM, BK,
+    const int64_t w_rows = (int64_t)L * H + (proj_d ? NQ : 0) + (pre_bias ? H : 0);
+    if (!tc::make_tensor_map_2d(&map_a0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a0, n_tokens, pre_bias ? BK : H, BM, BK,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
-        !tc::make_tensor_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, (int64_t)L * H + (proj_d ? NQ : 0), H, NQ, BK,
+        !tc::make_tensor_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, w_rows, H, NQ, BK,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
         return cudaErrorNotSupported;
     auto kern = H == 512 ? enc_chain_kernel<512> : enc_chain_kernel<256>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (err != cudaSuccess)
         return err;
-    kern<<<grid, THREADS, smem_bytes, st>>>(map_a0, map_w, bias, h, scratch, n_tokens, L, proj_bias, z_e, proj_d);
+    kern<<<grid, THREADS, smem_bytes, st>>>(map_a0, map_w, bias, h, scratch, n_tokens, L, proj_bias, z_e, proj_d, pre_bias);
     return cudaGetLastError();
 }
 

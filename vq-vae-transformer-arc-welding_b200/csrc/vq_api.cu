@@ -293,16 +293,17 @@ size_t vqb_encoder_chain_scratch_bytes(int device, int hidden)
 
 int vqb_encoder_chain(int device, const void *a0_bf16, float *h, const void *w_bf16, const float *bias, int64_t n_tokens,
                       int hidden, int n_layers, void *scratch, size_t scratch_bytes, const float *proj_bias, float *z_e,
-                      int proj_dim, void *stream)
+                      int proj_dim, const float *pre_bias, void *stream)
 {
-    if (!a0_bf16 || !h || !w_bf16 || !bias || !scratch || n_tokens < 0 || hidden <= 0 || n_layers <= 0 || proj_dim < 0)
+    if (!a0_bf16 || !w_bf16 || !bias || !scratch || n_tokens < 0 || hidden <= 0 || n_layers <= 0 || proj_dim < 0)
         return VQB_E_ARG;
     if (proj_dim > 0 && (!proj_bias || !z_e))
         return VQB_E_ARG;
-    if (proj_dim > 0 && (!aligned(proj_bias, 4) || !aligned(z_e, 16)))
-        return VQB_E_UNSUPPORTED;
+    if (!(pre_bias && proj_dim > 0) && !h)          // h is the input without PRE and the output without PROJ
+        return VQB_E_ARG;
     if (!enc_chain_supported(hidden, n_layers) || !aligned(a0_bf16, 16) || !aligned(w_bf16, 16) || !aligned(bias, 16) ||
-        !aligned(h, 16) || !aligned(scratch, 16))
+        (h && !aligned(h, 16)) || !aligned(scratch, 16) || (proj_dim > 0 && (!aligned(proj_bias, 4) || !aligned(z_e, 16))) ||
+        (pre_bias && !aligned(pre_bias, 4)))
         return VQB_E_UNSUPPORTED;
     vqb_device_info info;
     int rc = device_info(device, &info);
@@ -316,12 +317,38 @@ int vqb_encoder_chain(int device, const void *a0_bf16, float *h, const void *w_b
     if (err != cudaSuccess)
         return (int)err;
     err = launch_enc_chain(a0_bf16, h, w_bf16, bias, n_tokens, hidden, n_layers, (float *)scratch, scratch_bytes,
-                           proj_bias, z_e, proj_dim, info.sm_count, info.max_smem_per_block, (cudaStream_t)stream);
+                           proj_bias, z_e, proj_dim, pre_bias, info.sm_count, info.max_smem_per_block, (cudaStream_t)stream);
     if (err == cudaErrorNotSupported)
         return VQB_E_UNSUPPORTED;
     if (err != cudaSuccess)
         return (int)err;
     if (n_tokens > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
+int vqb_patch_split(int device, const float *x, int64_t n_cycles, int seq_len, int channels, int patch, void *out_bf16,
+                    void *stream)
+{
+    if (!x || !out_bf16 || n_cycles < 0 || seq_len <= 0 || channels <= 0 || patch <= 0)
+        return VQB_E_ARG;
+    if (!patch_split_supported(seq_len, channels, patch))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_patch_split(x, out_bf16, n_cycles, seq_len, channels, patch, info.sm_count, (cudaStream_t)stream);
+    if (err == cudaErrorNotSupported)
+        return VQB_E_UNSUPPORTED;
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_cycles > 0)
         count_launches(1);
     return VQB_OK;
 }

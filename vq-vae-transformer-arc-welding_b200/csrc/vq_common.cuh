@@ -138,7 +138,9 @@ bool enc_chain_supported(int H, int L);
 size_t enc_chain_scratch_bytes(int H, int sm_count);
 cudaError_t launch_enc_chain(const void *a0, float *h, const void *w, const float *bias, int64_t n_tokens, int H, int L,
                              float *scratch, size_t scratch_bytes, const float *proj_bias, float *z_e, int proj_d,
-                             int sm_count, int max_smem, cudaStream_t st);
+                             const float *pre_bias, int sm_count, int max_smem, cudaStream_t st);
+bool patch_split_supported(int L, int C, int P);
+cudaError_t launch_patch_split(const float *x, void *out, int64_t n_cycles, int L, int C, int P, int sm_count, cudaStream_t st);
 bool patch_embed_supported(int L, int C, int P, int H);
 cudaError_t launch_patch_embed(const float *x, const float *w, const float *bias, float *h, void *a, int64_t n_cycles,
                                int L, int C, int P, int H, int sm_count, int max_smem, cudaStream_t st);

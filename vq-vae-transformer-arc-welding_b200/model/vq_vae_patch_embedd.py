@@ -186,6 +186,8 @@ class VQVAEPatch(Autoencoder):
     fused_chain = True
     #: ... with the final H -> D projection fused into the same launch (operand bf16(h), weights exact to 2^-17)
     fused_projection = True
+    #: ... and the patch embedding as its first GEMM (samples and weights as bf16 hi + lo pairs: fp32-accurate to 2^-16)
+    fused_patch_embed = True
 
     def encode(self, x):
         """x (B, seq_len, input_dim) -> z_e (B, T, D)."""
@@ -205,7 +207,8 @@ class VQVAEPatch(Autoencoder):
         gamma / sqrt(var + eps) + beta is again a linear layer), rebuilt when a parameter or running statistic changes."""
         blocks = list(self.encoder[0].shared_conv)
         tracked = [t for blk in blocks for m in (blk.block[1], blk.block[2], blk.block[4], blk.block[5])
-                   for t in list(m.parameters()) + list(m.buffers())] + list(self.encoder[1].shared_conv.parameters())
+                   for t in list(m.parameters()) + list(m.buffers())] + list(self.encoder[1].shared_conv.parameters()) \
+            + list(self.patch_embed.proj.parameters())
         key = tuple((t.data_ptr(), t._version) for t in tracked)
         cache = getattr(self, "_fused_cache", None)
         if cache is None or cache[0] != key:
@@ -225,20 +228,25 @@ class VQVAEPatch(Autoencoder):
             stack_w = torch.stack([w for blk in ws for w in (blk[0], blk[2])]).contiguous()
             stack_b = torch.stack([b for blk in ws for b in (blk[1], blk[3])]).contiguous()
             # ... and, behind them, the final projection as an exact bf16 hi + lo pair (ops.projection_rows)
+            from .. import ops
             proj = self.encoder[1].shared_conv
             with torch.no_grad():
                 wp = proj.weight[:, :, 0].float()
                 stack_wp = None
                 if wp.shape[0] <= 64 and wp.shape[0] % 4 == 0:
-                    from .. import ops
                     stack_wp = torch.cat([stack_w.reshape(-1, stack_w.shape[-1]), ops.projection_rows(wp)]).contiguous()
-            cache = (key, ws, stack_w, stack_b, stack_wp)
+                # ... and, last, the patch embedding as a bf16 hi + lo pair (ops.patch_rows) for the fully fused launch
+                stack_all = None
+                pe = self.patch_embed.proj
+                if stack_wp is not None and pe.kernel_size[0] <= 32:
+                    stack_all = torch.cat([stack_wp, ops.patch_rows(pe.weight[:, 0, :].float(), stack_w.shape[-1])]).contiguous()
+            cache = (key, ws, stack_w, stack_b, stack_wp, stack_all)
             object.__setattr__(self, "_fused_cache", cache)
         return cache[1]
 
     def _fused_stack(self):
         self._fused_weights()
-        return self._fused_cache[2], self._fused_cache[3], self._fused_cache[4]
+        return self._fused_cache[2], self._fused_cache[3], self._fused_cache[4], self._fused_cache[5]
 
     def encode_fused_bf16(self, x):
         """The encoder with its 16 hidden x hidden layers on the fused kernel: tokens (B*T, H) stay row-major,
@@ -246,6 +254,18 @@ class VQVAEPatch(Autoencoder):
         from .. import ops
         b = x.shape[0]
         pe = self.patch_embed
+        hidden = pe.proj.out_channels
+        chain_ok = self.fused_chain and hidden in (256, 512) and len(self.encoder[0].shared_conv) >= 1
+        if chain_ok and self.fused_projection and self.fused_patch_embed and x.is_contiguous():
+            stack_all = self._fused_stack()[3]
+            if stack_all is not None:
+                # raw samples in, z_e out: patch embedding, every residual block and the projection in ONE launch
+                # (vqb_patch_split writes the 128-byte-per-token operand of the first GEMM)
+                proj = self.encoder[1].shared_conv
+                z_e = ops.encoder_chain(ops.patch_split(x, pe.patch_size), None, stack_all, self._fused_stack()[1],
+                                        proj_bias=proj.bias.detach().float().contiguous(),
+                                        pre_bias=pe.proj.bias.detach().float().contiguous())
+                return z_e.view(b, -1, z_e.shape[-1])
         # (the patch embedding stays fp32 arithmetic: K = 25 is 0.3 % of the FLOPs, and feeding the raw signal as bf16
         # through vqb_token_linear mode 2 was measured to cost index matches -- 99.86 % -> 99.59 %)
         if pe.proj.out_channels == 512 and pe.patch_size <= 64 and x.is_contiguous():
@@ -255,9 +275,9 @@ class VQVAEPatch(Autoencoder):
             patches = x.permute(0, 2, 1).reshape(-1, pe.patch_size)                   # (B*T, P)
             h = torch.matmul(patches, pe.proj.weight[:, 0, :].t())                    # (B*T, H) fp32, bias added below
             a = ops.token_bias_gelu(h, pe.proj.bias)                                   # h += b; a = bf16(gelu(h)), one pass
-        if self.fused_chain and h.shape[1] in (256, 512) and len(self.encoder[0].shared_conv) >= 1:
+        if chain_ok:
             # every residual block in ONE launch: the token tile never leaves the SM between the layers (vqb_encoder_chain)
-            stack_w, stack_b, stack_wp = self._fused_stack()
+            stack_w, stack_b, stack_wp, _ = self._fused_stack()
             proj = self.encoder[1].shared_conv
             if self.fused_projection and stack_wp is not None:
                 # ... and the final projection as one more GEMM on the resident tile: z_e comes straight out of the chain

@@ -449,30 +449,67 @@ def projection_rows(wp: torch.Tensor) -> torch.Tensor:
     return rows
 
 
-def encoder_chain(a0: torch.Tensor, h: torch.Tensor, w: torch.Tensor, bias: torch.Tensor,
-                  proj_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+def patch_rows(wpe: torch.Tensor, hidden: int) -> torch.Tensor:
+    """The `hidden` weight rows vqb_encoder_chain expects at the end of its weight stack for a fused patch embedding:
+    columns [0, 32) = bf16(Wpe), [32, 64) = bf16(Wpe - bf16(Wpe)), zero elsewhere.  wpe: (hidden, P) fp32, P <= 32."""
+    hdim, p = wpe.shape
+    rows = torch.zeros(hdim, hidden, dtype=torch.bfloat16, device=wpe.device)
+    hi = wpe.to(torch.bfloat16)
+    rows[:, :p] = hi
+    rows[:, 32:32 + p] = (wpe - hi.float()).to(torch.bfloat16)
+    return rows
+
+
+def patch_split(x: torch.Tensor, patch: int) -> torch.Tensor:
+    """x (B, L, C) fp32 contiguous -> (B * T, 64) bf16 operand of the fused patch embedding (vqb_patch_split): per token
+    the patch's samples as a bf16 hi + lo pair, 32 + 32 columns, tokens in the reference's channel-major order."""
+    _require_cuda_fp32(x, "x")
+    if x.dim() != 3 or not x.is_contiguous():
+        raise RuntimeError("patch_split: x must be a contiguous (B, L, C) tensor")
+    b, l, c = x.shape
+    if patch > 32 or l % patch:
+        raise RuntimeError("patch_split: patch size must divide the sequence length and be <= 32")
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        out = torch.empty((b * (l // patch) * c, 64), dtype=torch.bfloat16, device=x.device)
+        rc = lib.vqb_patch_split(x.device.index, x.data_ptr(), b, l, c, int(patch), out.data_ptr(),
+                                 torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "vqb_patch_split")
+    return out
+
+
+def encoder_chain(a0: torch.Tensor, h: Optional[torch.Tensor], w: torch.Tensor, bias: torch.Tensor,
+                  proj_bias: Optional[torch.Tensor] = None, pre_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """All residual blocks of the patch encoder in one launch (vqb_encoder_chain, csrc/enc_chain.cu):
     for every block b:  h <- h + w[2b+1] gelu(w[2b] gelu(h) + bias[2b]) + bias[2b+1], h updated in place and returned.
     a0 (T, H) bf16 = bf16(gelu(h)); h (T, H) fp32; w (L, H, H) bf16 (out x in per layer); bias (L, H) fp32; H in {256, 512}.
-    With proj_bias (D,) fp32 the final projection H -> D is fused: w is then (L * H + 128, H) -- the layers followed by
-    projection_rows(Wp) -- and z_e (T, D) fp32 is returned (h is not written back)."""
-    for t, name, dt in ((a0, "a0", torch.bfloat16), (h, "h", torch.float32), (w, "w", torch.bfloat16),
-                        (bias, "bias", torch.float32)):
+    With proj_bias (D,) fp32 the final projection H -> D is fused: w is then 2-D, the L * H layer rows followed by
+    projection_rows(Wp), and z_e (T, D) fp32 is returned (h is not written back).
+    With pre_bias (H,) fp32 the patch embedding is fused too: a0 is then patch_split(x) (T, 64), w ends with
+    patch_rows(Wpe, H), and h is not read (it may be None when proj_bias is given as well)."""
+    hidden = bias.shape[1] if bias.dim() == 2 else -1
+    checks = [(a0, "a0", torch.bfloat16), (w, "w", torch.bfloat16), (bias, "bias", torch.float32)]
+    if h is not None:
+        checks.append((h, "h", torch.float32))
+    if proj_bias is not None:
+        checks.append((proj_bias, "proj_bias", torch.float32))
+    if pre_bias is not None:
+        checks.append((pre_bias, "pre_bias", torch.float32))
+    for t, name, dt in checks:
         if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != dt or not t.is_contiguous():
             raise RuntimeError(f"encoder_chain: {name} must be a contiguous CUDA {dt} tensor (no CPU fallback)")
-    hidden = h.shape[1] if h.dim() == 2 else -1
-    if proj_bias is None:
-        ok = w.dim() == 3 and w.shape[1] == hidden and w.shape[2] == hidden
-        layers = w.shape[0] if ok else 0
-    else:
-        if not proj_bias.is_cuda or proj_bias.dtype != torch.float32 or not proj_bias.is_contiguous():
-            raise RuntimeError("encoder_chain: proj_bias must be a contiguous CUDA float32 tensor")
-        ok = w.dim() == 2 and w.shape[1] == hidden and (w.shape[0] - 128) % hidden == 0 and w.shape[0] > 128
-        layers = (w.shape[0] - 128) // hidden if ok else 0
-    if h.dim() != 2 or a0.shape != h.shape or not ok or tuple(bias.shape) != (layers, hidden):
+    layers = bias.shape[0]
+    extra = (128 if proj_bias is not None else 0) + (hidden if pre_bias is not None else 0)
+    n_tokens = a0.shape[0]
+    ok = (a0.dim() == 2 and a0.shape[1] == (64 if pre_bias is not None else hidden)
+          and w.numel() == (layers * hidden + extra) * hidden and (extra == 0 or w.dim() == 2)
+          and (h is None or tuple(h.shape) == (n_tokens, hidden))
+          and (h is not None or (proj_bias is not None and pre_bias is not None))
+          and (pre_bias is None or pre_bias.numel() == hidden))
+    if not ok:
         raise RuntimeError("encoder_chain: shape mismatch")
     lib = _lib.load()
-    dev = h.device
+    dev = a0.device
     with torch.cuda.device(dev):
         key = (dev.index, hidden, torch.cuda.current_stream(dev).cuda_stream)
         scratch = _chain_scratch.get(key)
@@ -484,12 +521,13 @@ def encoder_chain(a0: torch.Tensor, h: torch.Tensor, w: torch.Tensor, bias: torc
             _chain_scratch[key] = scratch
         z_e = None
         if proj_bias is not None:
-            z_e = torch.empty((h.shape[0], proj_bias.numel()), dtype=torch.float32, device=dev)
-        rc = lib.vqb_encoder_chain(dev.index, a0.data_ptr(), h.data_ptr(), w.data_ptr(), bias.data_ptr(), h.shape[0],
-                                   hidden, layers, scratch.data_ptr(), scratch.numel(),
+            z_e = torch.empty((n_tokens, proj_bias.numel()), dtype=torch.float32, device=dev)
+        rc = lib.vqb_encoder_chain(dev.index, a0.data_ptr(), h.data_ptr() if h is not None else None, w.data_ptr(),
+                                   bias.data_ptr(), n_tokens, hidden, layers, scratch.data_ptr(), scratch.numel(),
                                    proj_bias.data_ptr() if proj_bias is not None else None,
                                    z_e.data_ptr() if z_e is not None else None,
                                    proj_bias.numel() if proj_bias is not None else 0,
+                                   pre_bias.data_ptr() if pre_bias is not None else None,
                                    torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "vqb_encoder_chain")
     return z_e if z_e is not None else h
