@@ -308,8 +308,9 @@ def bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier):
                     f"(H=512, 8 res blocks, K={K_CODES}, D={DIM}), random-init weights seed 0",
         "value": patches / (ms_max * 1e-3), "unit": UNIT, "per_gpu": patches / world / (ms_max * 1e-3),
         "n_gpus": world, "ms_per_chunk": ms_max / n_chunks, "cycles_per_s": cycles / (ms_max * 1e-3),
-        "encoder_precision": "bf16 operands, fp32 accumulation and residual stream (encoder_mode='fused_bf16': "
-                             "vqb_patch_embed + vqb_encoder_chain), fp32 projection, exact quantiser",
+        "encoder_precision": "encoder_mode='fused_bf16': vqb_patch_split + vqb_encoder_chain (one launch: patch embedding "
+                             "and projection with bf16 hi+lo operand pairs = fp32-accurate to 2^-16, the 16 hidden layers "
+                             "with bf16 operands, fp32 accumulation and fp32 residual stream), exact quantiser",
         "id_match_vs_fp32_encoder": {"rate": match, "rows": int(got.numel())},
         "gpu_launches_per_chunk": launches / n_chunks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",

@@ -36,11 +36,18 @@ for mode in ("fp32", "tf32"):
         pairs.append((a, b))
         return out
     vq.forward = timed_forward
-    def step():
+    import contextlib
+    stats = {}
+    def step(sync=True):
         opt.zero_grad(set_to_none=True)
-        emb_loss, x_hat, ppl = net(x)
-        loss = torch.nn.functional.mse_loss(x_hat, x) + emb_loss
-        loss.backward()
+        with (contextlib.nullcontext() if sync or world == 1 else net.no_sync()):
+            emb_loss, x_hat, ppl = net(x)
+            # global loss / perplexity / code counts: ONE fused small all-reduce, issued now, collected after backward
+            handle = vq.reduce_stats(emb_loss) if sync else None
+            loss = torch.nn.functional.mse_loss(x_hat, x) + emb_loss
+            loss.backward()
+        if handle is not None:
+            stats["global"] = handle.result()
         torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
         opt.step()
         return loss
@@ -60,8 +67,28 @@ for mode in ("fp32", "tf32"):
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item() / steps
     vq_fwd_ms = sum(a.elapsed_time(b) for a, b in pairs) / steps
+    # the same step without the gradient all-reduce (DDP no_sync) and without the statistics all-reduce: what NCCL
+    # adds to the step as exposed (non-overlapped) time
+    ms_nosync = ms
+    if world > 1:
+        for _ in range(2):
+            step(sync=False)
+        torch.cuda.synchronize(); dist.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(steps):
+            step(sync=False)
+        f1.record(); torch.cuda.synchronize()
+        t2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms_nosync = t2.item() / steps
     res[mode] = {"ms_per_step": ms, "patches_per_s": world * B * model.enc_out_len / (ms * 1e-3),
-                 "vq_forward_ms": vq_fwd_ms, "vq_forward_share": vq_fwd_ms / ms, "loss": float(loss.item())}
+                 "vq_forward_ms": vq_fwd_ms, "vq_forward_share": vq_fwd_ms / ms, "loss": float(loss.item()),
+                 "ms_per_step_without_nccl": ms_nosync, "nccl_exposed_ms": ms - ms_nosync,
+                 "nccl_exposed_share": (ms - ms_nosync) / ms,
+                 "grad_bytes_all_reduced": int(sum(p.numel() for p in model.parameters()) * 4),
+                 "global_stats": ({"loss": float(stats["global"][0]), "perplexity": float(stats["global"][1]),
+                                   "codes_used": int((stats["global"][2] > 0).sum())} if "global" in stats else None)}
     vq.forward = orig
 if rank == 0:
     print(json.dumps({"workload": f"VQ-VAE-Patch train step, B={B} cycles/GPU, H=512, 8 resblocks, K=256, D=32, RAdam, "
