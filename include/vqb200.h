@@ -210,6 +210,12 @@ int vqb_patch_embed(int device, const float *x, int64_t n_cycles, int seq_len, i
 int vqb_pack_rows(int device, const float *z, int64_t n_outer, int64_t n_inner, int d, int64_t stride_outer,
                   int64_t stride_inner, int64_t stride_d, float *out, void *stream);
 
+/* Input / target rows of the transformer's next-token task from token ids (dataloader/base_dataloader.py:74-110,
+ * MyLatentAutoregressiveDataset): ids (n_windows, n_tokens) int64 -> x = [start_token, ids...], y = [ids..., end_token],
+ * both (n_windows, n_tokens + 1) int64.  The reference takes start / end = max id of the data set + 1 / + 2. */
+int vqb_ar_pairs(int device, const int64_t *ids, int64_t n_windows, int n_tokens, int64_t start_token, int64_t end_token,
+                 int64_t *x, int64_t *y, void *stream);
+
 /* out[i] = codebook[idx[i]] (n, d).  Out-of-range indices yield NaN rows and set
  * *bad_index (device int, may be NULL) to 1. */
 int vqb_gather(int device, const int64_t *idx, int64_t n, const float *codebook, int k, int d,

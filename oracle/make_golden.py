@@ -197,6 +197,13 @@ def run_bulk_case(VQVAEPatch):
     ar2, y4 = L.create_latent_space_dataset_VQ_VAE_autoreggressive(me, loader, seq_len=case["seq_len"],
                                                                   has_patch_embed=True)
     assert np.array_equal(ar2, ar) and np.array_equal(y4, y)
+    # the transformer's data set built from those ids by the reference's own class (dataloader/base_dataloader.py:74-110)
+    from dataloader.base_dataloader import MyLatentAutoregressiveDataset  # type: ignore
+    ds = MyLatentAutoregressiveDataset(ar, y)
+    items = [ds[i] for i in range(len(ds))]
+    ar_x = np.stack([it[0].numpy() for it in items])
+    ar_cond = np.stack([it[1].numpy() for it in items])
+    ar_y = np.stack([it[2].numpy() for it in items])
     # the encoder outputs behind those ids (same reference modules, same per-cycle slices): what a near-tie is judged on
     model.eval()
     with torch.no_grad():
@@ -204,7 +211,9 @@ def run_bulk_case(VQVAEPatch):
                                   for i in range(case["seq_len"])], axis=1) for w, _ in loader])
     z_e = z_e.reshape((-1,) + z_e.shape[2:]) if z_e.ndim == 6 else np.concatenate(list(z_e), axis=0)
     out = {f"{name}/ids": ids, f"{name}/labels": y, f"{name}/zq": zq, f"{name}/labels_zq": y2,
-           f"{name}/ar_ids": ar, f"{name}/ar_labels": y3, f"{name}/z_e": z_e.astype(np.float32)}
+           f"{name}/ar_ids": ar, f"{name}/ar_labels": y3, f"{name}/z_e": z_e.astype(np.float32),
+           f"{name}/ar_ds_x": ar_x, f"{name}/ar_ds_cond": ar_cond, f"{name}/ar_ds_y": ar_y,
+           f"{name}/ar_ds_num_classes": np.int64(ds.num_classes)}
     meta = {k.split("/")[1]: dict(shape=list(v.shape), dtype=str(v.dtype)) for k, v in out.items()}
     print(f"{name:18s} ids {ids.shape} {ids.dtype}  zq {zq.shape} {zq.dtype}  ar {ar.shape}")
     return out, meta

@@ -156,3 +156,35 @@ def test_bulk_builder_dedupe_gives_identical_ids(patch_golden):
     fast, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
     assert np.array_equal(plain, fast)
     assert calls == [12, 12, 12]            # 8 windows x 5 cycles = 40 rows hold 12 distinct cycles per batch
+
+
+def test_on_the_fly_tokenizer_matches_the_reference_dataset(patch_golden, bulk_golden):
+    """f4: windows -> (x, cond, y) in one call against MyLatentAutoregressiveDataset of the UNMODIFIED reference
+    (dataloader/base_dataloader.py:74-110) built from the ids its own bulk loop produced (tests/golden/bulk_golden.npz)."""
+    from vqb200.dataloader import OnTheFlyTokenizer
+    from vqb200 import ops
+    case = C.BULK_CASE
+    name = case["name"]
+    mcase = next(c for c in C.PATCH_CASES if c["name"] == case["model"])
+    model = _load(mcase, patch_golden).eval()
+    win, labels, _ = C.make_windows(case)
+    ref_x, ref_y = bulk_golden[f"{name}/ar_ds_x"], bulk_golden[f"{name}/ar_ds_y"]
+    # the reference's start / end tokens follow the largest id present in ITS data set
+    max_token = int(bulk_golden[f"{name}/ar_ids"].max())
+    tok = OnTheFlyTokenizer(model, window_size=200, device=DEV, max_token=max_token)
+    assert tok.num_classes == int(bulk_golden[f"{name}/ar_ds_num_classes"])
+    x, cond, y = tok(torch.from_numpy(win), torch.from_numpy(labels), n_cycles=case["seq_len"])
+    assert x.dtype == torch.int64 and y.dtype == torch.int64 and cond.dtype == torch.int64
+    assert np.array_equal(x.cpu().numpy(), ref_x) and np.array_equal(y.cpu().numpy(), ref_y)
+    assert np.array_equal(cond.cpu().numpy(), bulk_golden[f"{name}/ar_ds_cond"])
+    # default: num_embeddings + 2 classes, the transformer's own assumption (train_transformer_mtasks.py:146)
+    tok2 = OnTheFlyTokenizer(model, window_size=200, device=DEV)
+    assert (tok2.start_token, tok2.end_token, tok2.num_classes) == (model.num_embeddings, model.num_embeddings + 1,
+                                                                    model.num_embeddings + 2)
+    # the kernel alone, ragged sizes
+    ids = torch.randint(0, 50, (7, 33), device=DEV)
+    xx, yy = ops.ar_pairs(ids, 50, 51)
+    assert torch.equal(xx[:, 1:], ids) and torch.equal(yy[:, :-1], ids)
+    assert bool((xx[:, 0] == 50).all()) and bool((yy[:, -1] == 51).all())
+    with pytest.raises(RuntimeError):
+        ops.ar_pairs(ids.cpu(), 50, 51)

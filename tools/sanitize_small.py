@@ -44,8 +44,20 @@ assert torch.allclose(hc, href, rtol=1e-5, atol=1e-5)
 wp = torch.randn(32, H, device=dev) * (1.0 / H) ** 0.5
 zp = ops.encoder_chain(a0, h0.clone(), torch.cat([wl.reshape(-1, H), ops.projection_rows(wp)]).contiguous(), bl,
                        proj_bias=torch.zeros(32, device=dev))
-assert torch.allclose(zp, hc.to(torch.bfloat16).float() @ wp.t(), rtol=1e-3, atol=1e-3)
+assert torch.allclose(zp, hc @ wp.t(), rtol=1e-3, atol=1e-3)
 print("token_linear / encoder_chain ok")
+torch.manual_seed(1)
+model = vqb200.VQVAEPatch(hidden_dim=512, input_dim=2, num_embeddings=64, embedding_dim=32, n_resblocks=2,
+                          learning_rate=1e-3, patch_size=25, batch_norm=False).to(dev).eval()
+xm = torch.randn(19, 200, 2, device=dev)
+with torch.no_grad():
+    model.encoder_mode = "fused_bf16"
+    model.fused_patch_embed = False
+    z1 = model.encode(xm)
+    model.fused_patch_embed = True
+    z2 = model.encode(xm)                      # vqb_patch_split + the fully fused chain launch
+assert (z1 - z2).abs().max().item() <= 0.02 * z1.abs().max().item()
+print("fully fused encoder launch ok")
 x = torch.randn(5, 200, 2, device=dev)
 conv = torch.nn.Conv1d(1, 512, 25, stride=25).to(dev)
 hh, act = ops.patch_embed(x, conv.weight, conv.bias, 25)

@@ -43,6 +43,7 @@ SIGNATURES = {
     "vqb_patch_split": (_i, [_i, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "vqb_pack_rows": (_i, [_i, _vp, _i64, _i64, _i, _i64, _i64, _i64, _vp, _vp]),
     "vqb_patch_embed": (_i, [_i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "vqb_ar_pairs": (_i, [_i, _vp, _i64, _i, _i64, _i64, _vp, _vp, _vp]),
     "vqb_gather": (_i, [_i, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     "vqb_one_hot": (_i, [_i, _vp, _i64, _i, _vp, _vp]),
     "vqb_launch_counter": (ctypes.c_longlong, []),

@@ -430,6 +430,25 @@ int vqb_pack_rows(int device, const float *z, int64_t n_outer, int64_t n_inner, 
     return VQB_OK;
 }
 
+int vqb_ar_pairs(int device, const int64_t *ids, int64_t n_windows, int n_tokens, int64_t start_token, int64_t end_token,
+                 int64_t *x, int64_t *y, void *stream)
+{
+    if (n_windows < 0 || n_tokens <= 0 || (n_windows > 0 && (!ids || !x || !y)))
+        return VQB_E_ARG;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_ar_pairs(ids, n_windows, n_tokens, start_token, end_token, x, y, info.sm_count, (cudaStream_t)stream);
+    if (err != cudaSuccess)
+        return (int)err;
+    count_launches(n_windows > 0 ? 1 : 0);
+    return VQB_OK;
+}
+
 int vqb_backward(int device, const float *g_zq, const float *g_loss,
                  const float *z, int64_t n_outer, int64_t n_inner, int d,
                  int64_t stride_outer, int64_t stride_inner, int64_t stride_d,

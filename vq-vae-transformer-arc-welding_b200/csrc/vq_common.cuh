@@ -147,6 +147,8 @@ cudaError_t launch_patch_embed(const float *x, const float *w, const float *bias
 bool pack_rows_supported(int64_t n_inner, int d, int64_t s_outer, int64_t s_inner, int64_t s_d);
 cudaError_t launch_pack_rows(const float *src, float *dst, int64_t n_outer, int64_t n_inner, int d, int64_t s_outer,
                              int64_t s_inner, int64_t s_d, int sm_count, cudaStream_t st);
+cudaError_t launch_ar_pairs(const int64_t *ids, int64_t n_windows, int n, int64_t start_token, int64_t end_token, int64_t *x,
+                            int64_t *y, int sm_count, cudaStream_t st);
 void count_launches(int n);
 void set_tc_trace(unsigned long long *buf);
 size_t tc_trace_words();

@@ -77,4 +77,34 @@ cudaError_t launch_pack_rows(const float *src, float *dst, int64_t n_outer, int6
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// Autoregressive pairs for the transformer (dataloader/base_dataloader.py:74-110, MyLatentAutoregressiveDataset):
+//   x[w] = [start, ids[w][0 .. n-1]],   y[w] = [ids[w][0 .. n-1], end]     (both n + 1 long)
+// One pass, ids read once: thread i of a window handles position i of both rows.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vq_ar_pairs_kernel(const int64_t *__restrict__ ids, int64_t n_windows, int n,
+                                                          int64_t start_token, int64_t end_token, int64_t *__restrict__ x,
+                                                          int64_t *__restrict__ y)
+{
+    const int64_t total = n_windows * (int64_t)(n + 1);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t w = i / (n + 1);
+        const int pos = (int)(i - w * (n + 1));
+        const int64_t *row = ids + w * n;
+        x[i] = pos == 0 ? start_token : row[pos - 1];
+        y[i] = pos == n ? end_token : row[pos];
+    }
+}
+
+cudaError_t launch_ar_pairs(const int64_t *ids, int64_t n_windows, int n, int64_t start_token, int64_t end_token, int64_t *x,
+                            int64_t *y, int sm_count, cudaStream_t st)
+{
+    if (n_windows == 0)
+        return cudaSuccess;
+    const int64_t blocks = (n_windows * (int64_t)(n + 1) + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)sm_count * 8 ? blocks : (int64_t)sm_count * 8);
+    vq_ar_pairs_kernel<<<grid, 256, 0, st>>>(ids, n_windows, n, start_token, end_token, x, y);
+    return cudaGetLastError();
+}
+
 }  // namespace vqb

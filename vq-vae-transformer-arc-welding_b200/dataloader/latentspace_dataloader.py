@@ -82,12 +82,19 @@ class LatentSpaceEncoder:
     """Encode-side of ``LatentSpaceDataLoader`` (reference :16-39 for the constructor fields
     that matter here: the model, ``window_size`` and the device)."""
 
-    def __init__(self, latent_space_model, window_size: int = 200, device: Optional[str] = None):
+    def __init__(self, latent_space_model, window_size: int = 200, device: Optional[str] = None,
+                 encoder_mode: Optional[str] = "auto"):
+        """encoder_mode: "auto" (default) selects the model's fused tcgen05 encoder ("fused_bf16": bf16 operands for the
+        hidden layers, fp32 accumulation and residual stream) when the model offers it -- the reference builds its latent
+        data sets under torch.set_float32_matmul_precision('medium') (train_transformer_mtasks.py:245), i.e. with bf16
+        matmuls too; "torch" keeps the fp32 PyTorch layers; None leaves the model's setting alone."""
         if device is None:
             # the reference hard-codes cuda:0 (:34); one process per GPU uses its own device
             device = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"
         self.device = device
         self.latent_space_model = latent_space_model.to(self.device)
+        if encoder_mode is not None and hasattr(self.latent_space_model, "encoder_mode"):
+            self.latent_space_model.encoder_mode = "fused_bf16" if encoder_mode == "auto" else encoder_mode
         self.window_size = window_size
         self.code_counts = None
         #: encode every distinct cycle of a batch once (overlapping windows repeat cycles; see encode_unique).  The ids
@@ -175,6 +182,45 @@ class LatentSpaceEncoder:
         new_x, new_y = self.create_latent_space_dataset_VQ_VAE_IDs(
             loader, seq_len=seq_len, has_patch_embed=has_patch_embed, no_labels=(task == "autoregressive_ids"))
         return new_x.reshape((new_x.shape[0], -1)), new_y
+
+
+class OnTheFlyTokenizer:
+    """Windows of raw cycles -> the transformer's training batch, on the GPU, per step:
+    what the reference prepares offline as a pickled data set -- the id loop of dataloader/latentspace_dataloader.py:
+    205-263 followed by MyLatentAutoregressiveDataset (dataloader/base_dataloader.py:74-110) -- as one call:
+        (x, cond, y) = tok(windows, labels)
+    windows (B, n_cycles * window, C) fp32, labels (B,) or None;  x = [start, ids...], y = [ids..., end] int64
+    (B, n_cycles * enc_out_len + 1), cond = labels as int64 (zeros without labels), like the data set's __getitem__.
+
+    start / end tokens: the reference derives them from the largest id PRESENT in its pickled data set (max_id + 1 / + 2,
+    :85-90) while the model is built with num_embeddings + 2 classes (train_transformer_mtasks.py:146); a stream has no
+    "whole data set", so `max_token` defaults to num_embeddings - 1 (the two agree whenever the last code is used)."""
+
+    def __init__(self, latent_space_model, window_size: int = 200, device: Optional[str] = None,
+                 encoder_mode: Optional[str] = "auto", max_token: Optional[int] = None):
+        self.encoder = LatentSpaceEncoder(latent_space_model, window_size=window_size, device=device,
+                                          encoder_mode=encoder_mode)
+        model = self.encoder.latent_space_model
+        model.eval()
+        self.max_token = int(model.num_embeddings - 1 if max_token is None else max_token)
+        self.start_token, self.end_token = self.max_token + 1, self.max_token + 2
+        self.num_classes = self.max_token + 3
+
+    def __call__(self, windows: torch.Tensor, labels: Optional[torch.Tensor] = None, n_cycles: Optional[int] = None):
+        from .. import ops
+        enc = self.encoder
+        b = windows.shape[0]
+        if n_cycles is None:
+            n_cycles = windows.shape[1] // enc.window_size
+        with torch.no_grad():
+            cyc = enc._cycles(windows, n_cycles).to(enc.device, non_blocking=True)
+            ids = enc.get_latent_space_IDs(cyc, has_patch_embed=True).view(b, -1)
+            x, y = ops.ar_pairs(ids, self.start_token, self.end_token)
+        if labels is None:
+            cond = torch.zeros((b, 1), dtype=torch.long, device=x.device)
+        else:
+            cond = torch.as_tensor(labels).to(x.device).to(torch.long)
+        return x, cond, y
 
 
 # ---------------------------------------------------------------------------------------

@@ -233,6 +233,25 @@ def gather(indices: torch.Tensor, weight: torch.Tensor, target_shape=None, check
     return out.view(target_shape) if target_shape is not None else out
 
 
+def ar_pairs(ids: torch.Tensor, start_token: int, end_token: int):
+    """(x, y) of the transformer's next-token task (dataloader/base_dataloader.py:85-95): ids (W, n) int64 CUDA ->
+    x = [start, ids...], y = [ids..., end], both (W, n + 1) int64 -- vqb_ar_pairs, one pass."""
+    if not isinstance(ids, torch.Tensor) or ids.dtype != torch.int64 or ids.dim() != 2:
+        raise RuntimeError("ar_pairs: ids must be a 2-D int64 tensor")
+    if not ids.is_cuda:
+        raise RuntimeError(f"ar_pairs: ids live on {ids.device}; there is no CPU fallback")
+    ids = ids.contiguous()
+    w, n = ids.shape
+    lib = _lib.load()
+    with torch.cuda.device(ids.device):
+        x = torch.empty((w, n + 1), dtype=torch.int64, device=ids.device)
+        y = torch.empty((w, n + 1), dtype=torch.int64, device=ids.device)
+        rc = lib.vqb_ar_pairs(ids.device.index, ids.data_ptr(), w, n, int(start_token), int(end_token), x.data_ptr(),
+                              y.data_ptr(), torch.cuda.current_stream(ids.device).cuda_stream)
+    _lib.check(rc, "vqb_ar_pairs")
+    return x, y
+
+
 def one_hot(indices: torch.Tensor, k: int) -> torch.Tensor:
     """(N, k) fp32 one-hot of (N, 1) int64 indices (model/vector_quantizer.py:98-100)."""
     if not isinstance(indices, torch.Tensor) or indices.dtype != torch.int64:
