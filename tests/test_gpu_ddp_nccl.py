@@ -24,7 +24,10 @@ def _build(patch_sd, case, dev):
                               patch_size=case["patch_size"], seq_len=case["seq_len"],
                               batch_norm=case["batch_norm"], beta=case["beta"])
     model.load_state_dict(patch_sd, strict=True)
-    return model.to(dev).train()
+    # eval mode with gradients: the decoder's BatchNorm1d (PatchEmbeddingInverse, model/vq_vae_patch_embedd.py:19-57) then
+    # uses its running statistics -- in training mode each rank would normalise with the statistics of its own shard
+    # (the reference does not use SyncBatchNorm), which no single-GPU run on the whole batch reproduces
+    return model.to(dev).eval()
 
 
 def _worker(rank, world, port, patch_sd, case, x_all, out_dir):

@@ -59,10 +59,11 @@ with torch.no_grad():
 assert (z1 - z2).abs().max().item() <= 0.02 * z1.abs().max().item()
 print("fully fused encoder launch ok")
 x = torch.randn(5, 200, 2, device=dev)
-conv = torch.nn.Conv1d(1, 512, 25, stride=25).to(dev)
+conv = torch.nn.Conv1d(1, 512, 25, stride=25)
+with torch.no_grad():      # fp32 reference on the CPU (cuDNN would run the conv in TF32)
+    r = conv(x.cpu().permute(0, 2, 1).reshape(5, 1, -1)).permute(0, 2, 1).reshape(-1, 512).to(dev)
+conv = conv.to(dev)
 hh, act = ops.patch_embed(x, conv.weight, conv.bias, 25)
-with torch.no_grad():
-    r = conv(x.permute(0, 2, 1).reshape(5, 1, -1)).permute(0, 2, 1).reshape(-1, 512)
 assert torch.allclose(hh, r, rtol=1e-4, atol=1e-5)
 print("patch_embed ok")
 torch.cuda.synchronize()
