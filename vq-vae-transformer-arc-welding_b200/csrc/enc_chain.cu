@@ -206,13 +206,17 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         // ================= weight producer: runs ahead of the MMAs across GEMM and tile boundaries =================
         int s = 0;
         uint32_t ph = 0;
-        auto stage = [&](int row, int col, bool two_boxes) {
+        // a stage = two 16 KB boxes: weights [row, row + 128) x [col, col + 128); for PRE the second box is the tile's
+        // patch operand instead (tok_row >= 0), so that the first GEMM of the NEXT tile never waits for the smem tile
+        auto stage = [&](int row, int col, int64_t tok_row) {
             mbar_wait<32>(bar(W_EMPTY + s), ph ^ 1u);
             if (elect_one()) {
-                mbar_expect_tx(bar(W_FULL + s), two_boxes ? W_STAGE : W_STAGE / 2);
+                mbar_expect_tx(bar(W_FULL + s), W_STAGE);
                 tma_load_2d(sbase + P::OFF_W + s * W_STAGE, &map_w, bar(W_FULL + s), col, row);
-                if (two_boxes)
+                if (tok_row < 0)
                     tma_load_2d(sbase + P::OFF_W + s * W_STAGE + NQ * BK * 2, &map_w, bar(W_FULL + s), col + BK, row);
+                else
+                    tma_load_2d(sbase + P::OFF_W + s * W_STAGE + NQ * BK * 2, &map_a0, bar(W_FULL + s), 0, (int)tok_row);
             }
             __syncwarp();
             if (++s == W_STAGES) {
@@ -223,34 +227,30 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         for (int t = 0; t < my_tiles; ++t)
             for (int j = 0; j < NG; ++j) {
                 if (pre && j == 0) {
-                    for (int q = 0; q < NQT; ++q)
-                        stage(w_row_pre + q * NQ, 0, false);              // one 64-column box: [Wpe_hi | Wpe_lo]
+                    const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
+                    for (int q = 0; q < NQT; ++q)                         // [Wpe_hi | Wpe_lo] rows of the quarter + the patches
+                        stage(w_row_pre + q * NQ, 0, tile * BM);
                 } else if (proj && j == j_proj) {
                     for (int pass = 0; pass < 2; ++pass)                  // the hi and the lo pass use the same rows
                         for (int ks = 0; ks < NKS; ++ks)
-                            stage(w_row_proj, ks * KS, true);
+                            stage(w_row_proj, ks * KS, -1);
                 } else {
                     for (int q = 0; q < NQT; ++q)
                         for (int ks = 0; ks < NKS; ++ks)
-                            stage((j - j_layer0) * H + q * NQ, ks * KS, true);
+                            stage((j - j_layer0) * H + q * NQ, ks * KS, -1);
                 }
             }
     } else if (warp == 3) {
-        // ================= first operand of every tile by TMA: bf16(gelu(h0)) rows, or the split patches =================
-        for (int t = 0; t < my_tiles; ++t) {
+        // ================= without PRE: the first operand of every tile, bf16(gelu(h0)) rows, by TMA =================
+        for (int t = 0; t < my_tiles && !pre; ++t) {
             if (t > 0)
                 mbar_wait<64>(bar(A_FREE), (uint32_t)((t - 1) & 1));    // the last GEMM that read the smem tile is done
             const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
             if (elect_one()) {
-                if (pre) {
-                    mbar_expect_tx(bar(A0_FULL), BM * BK * 2);
-                    tma_load_2d(sbase + P::OFF_A, &map_a0, bar(A0_FULL), 0, (int)(tile * BM));
-                } else {
-                    mbar_expect_tx(bar(A0_FULL), P::A_BYTES);
+                mbar_expect_tx(bar(A0_FULL), P::A_BYTES);
 #pragma unroll
-                    for (int kc = 0; kc < NKC; ++kc)
-                        tma_load_2d(sbase + P::OFF_A + kc * (BM * BK * 2), &map_a0, bar(A0_FULL), kc * BK, (int)(tile * BM));
-                }
+                for (int kc = 0; kc < NKC; ++kc)
+                    tma_load_2d(sbase + P::OFF_A + kc * (BM * BK * 2), &map_a0, bar(A0_FULL), kc * BK, (int)(tile * BM));
             }
             __syncwarp();
         }
@@ -301,7 +301,8 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             }
         };
         for (int t = 0; t < my_tiles; ++t) {
-            mbar_wait<32>(bar(A0_FULL), (uint32_t)(t & 1));
+            if (!pre)
+                mbar_wait<32>(bar(A0_FULL), (uint32_t)(t & 1));
             for (int j = 0; j < NG; ++j) {
                 const bool from_tmem = (j & 1) != 0;             // even GEMMs read shared memory, odd ones tensor memory
                 const bool is_pre = pre && j == 0, is_proj = proj && j == j_proj;
@@ -316,12 +317,13 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                         tc_fence_after();
                         if (elect_one()) {
                             const uint64_t wd = w_base + (uint64_t)(s * (W_STAGE >> 4));
-                            umma_bf16(d, a_base + 0, wd + 0, idesc, 0);
-                            umma_bf16(d, a_base + 2, wd + 2, idesc, 1);
-                            umma_bf16(d, a_base + 0, wd + 4, idesc, 1);
-                            umma_bf16(d, a_base + 2, wd + 6, idesc, 1);
-                            umma_bf16(d, a_base + 4, wd + 0, idesc, 1);
-                            umma_bf16(d, a_base + 6, wd + 2, idesc, 1);
+                            const uint64_t pd = wd + (NQ * BK * 2 >> 4);    // the patch operand: second box of the stage
+                            umma_bf16(d, pd + 0, wd + 0, idesc, 0);
+                            umma_bf16(d, pd + 2, wd + 2, idesc, 1);
+                            umma_bf16(d, pd + 0, wd + 4, idesc, 1);
+                            umma_bf16(d, pd + 2, wd + 6, idesc, 1);
+                            umma_bf16(d, pd + 4, wd + 0, idesc, 1);
+                            umma_bf16(d, pd + 6, wd + 2, idesc, 1);
                             umma_commit(bar(W_EMPTY + s));
                         }
                         __syncwarp();
@@ -339,7 +341,7 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                 }
                 if (j > 0)
                     ++ardy_n;
-                if (j == j_free) {
+                if (j == j_free && !pre) {
                     if (elect_one())
                         umma_commit(bar(A_FREE));                // every MMA that reads the smem tile has been issued
                     __syncwarp();
