@@ -1,17 +1,17 @@
-"""GPU box, for ncu: a few launches of vqb_encoder_chain on T tokens (default 2^18), nothing else."""
+"""GPU box, for ncu: a few fully fused encode calls (vqb_patch_split + vqb_encoder_chain with the patch embedding as its
+first and the projection as its last GEMM) of the default model on `n` cycles (default 16384 = 2^18 tokens)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, vqb200
-from vqb200 import ops
 dev = torch.device("cuda:0")
-T = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
-H, L = 512, 16
-g = torch.Generator(device=dev).manual_seed(0)
-h0 = torch.randn(T, H, device=dev, generator=g)
-w = (torch.randn(L, H, H, device=dev, generator=g) * (1.0 / H) ** 0.5).to(torch.bfloat16)
-b = 0.1 * torch.randn(L, H, device=dev, generator=g)
-a0 = torch.nn.functional.gelu(h0).to(torch.bfloat16)
-for _ in range(4):
-    ops.encoder_chain(a0, h0.clone(), w, b)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+torch.manual_seed(0)
+model = vqb200.VQVAEPatch(hidden_dim=512, input_dim=2, num_embeddings=256, embedding_dim=32, n_resblocks=8,
+                          learning_rate=1e-3, dropout_p=0.1, patch_size=25, batch_norm=False).to(dev).eval()
+model.encoder_mode = "fused_bf16"
+x = torch.randn(n, 200, 2, device=dev)
+with torch.no_grad():
+    for _ in range(4):
+        z = model.encode(x)
 torch.cuda.synchronize()
-print("done")
+print("done", tuple(z.shape))
