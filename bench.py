@@ -302,6 +302,12 @@ def bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier):
     except Exception:
         peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
     achieved_tf = cycles * CYCLE_FLOP / (ms_max * 1e-3) / 1e12 / world       # per GPU
+    chain_traffic = None
+    try:        # DRAM bytes of the dominant kernel (the fused encoder launch) per launch, from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            chain_traffic = float(json.load(f)["enc_chain_bytes_per_token"]) * chunk * model.enc_out_len
+    except Exception:
+        pass
     out = {
         "workload": f"BASELINE configs[2]: LatentSpaceEncoder.get_latent_space_IDs on synthetic cycles randn(., 200, 2), "
                     f"{n_chunks} chunks of {chunk} cycles per GPU resident in HBM, ids (int64) out; default model "
@@ -315,7 +321,7 @@ def bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier):
         "gpu_launches_per_chunk": launches / n_chunks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "flop_per_cycle": CYCLE_FLOP, "peak_source": peak_src,
-                     "traffic": None},
+                     "traffic": chain_traffic, "kernel": "enc_chain_kernel<512> (vqb_encoder_chain: one launch per chunk)"},
     }
     if not args.no_cpu:
         # the reference's loop on host cores: per 512-window batch, cycle by cycle (one encode call per cycle slice)
