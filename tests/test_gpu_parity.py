@@ -540,6 +540,75 @@ def test_tc_wide_vectors(D, K):
                 assert out[0].item() == pytest.approx(float(ora.loss), rel=REL)
 
 
+def _check_against_oracle(z, E, out, n, D):
+    ora = O.forward(z, E, 0.25)
+    assert np.array_equal(out[3].cpu().numpy().reshape(-1), ora.indices.reshape(-1))
+    assert np.array_equal(out[1].cpu().numpy(), ora.z_q.reshape(n, D), equal_nan=True)
+    assert np.array_equal(out[4].cpu().numpy(), ora.counts)
+    if np.isnan(ora.loss):
+        assert torch.isnan(out[0])
+    else:
+        assert out[0].item() == pytest.approx(float(ora.loss), rel=REL)
+    assert out[2].item() == pytest.approx(float(ora.perplexity), rel=REL)
+
+
+@pytest.mark.parametrize("K,D", [(7, 68), (256, 96), (256, 128), (300, 100), (700, 128), (1024, 64), (2100, 32), (4096, 128)])
+def test_tcs_wide_vectors_and_large_codebooks(K, D):
+    """The tile-stationary kernel (csrc/vq_fwd_tcs.cu): 64 < D <= 128 (three / four D-chunks per tile, operand blocks
+    streamed through the ring) and K > 256 with D > 32, histogram in shared memory (K <= 2048) and in global memory;
+    ties across chunks and column halves, NaN / inf rows, poisoned codebook columns."""
+    rs = np.random.RandomState(K * 3 + D)
+    E = (0.1 * rs.standard_normal((K, D))).astype(np.float32)
+    E[K - 1] = E[0]                                           # exact tie, first against last code
+    if K > 200:
+        E[130] = E[5]                                         # ... and across the two column halves of a chunk
+    dev = _dev()
+    for n in (128, 1500, 128 * 148 + 300):
+        z = (0.1 * rs.standard_normal((n, D))).astype(np.float32)
+        z[0] = E[0]; z[1] = (E[1] + E[2]) / 2; z[2] = E[5 % K]; z[5, D - 1] = np.nan; z[6, D // 2 + 1] = np.inf
+        assert ops._tc_eligible(n, K, D)
+        for Eb in (E, None):
+            if Eb is None:
+                if n != 1500:
+                    continue
+                Eb = E.copy(); Eb[min(3, K - 1), D - 2] = np.nan; Eb[K // 2, 0] = np.inf
+            out = ops.forward(torch.from_numpy(z).to(dev), torch.from_numpy(Eb).to(dev), 0.25, path="tc")
+            _check_against_oracle(z, Eb, out, n, D)
+
+
+@pytest.mark.parametrize("K,D,tiles_per_cta", [(512, 32, 5), (1024, 32, 4), (768, 16, 7), (300, 64, 3), (256, 128, 5)])
+def test_tcs_many_tiles_per_cta(K, D, tiles_per_cta):
+    """Several tiles (odd and even counts: pairs and a lone last tile) per CTA, so every ring wraps and both TMEM
+    buffers / epilogue groups see many chunk items; ids-only calls take no finish pass."""
+    rs = np.random.RandomState(K + 7 * D + tiles_per_cta)
+    n = 128 * 148 * tiles_per_cta - 61
+    E = (0.1 * rs.standard_normal((K, D))).astype(np.float32)
+    z = (0.1 * rs.standard_normal((n, D))).astype(np.float32)
+    dev = _dev()
+    zt, Et = torch.from_numpy(z).to(dev), torch.from_numpy(E).to(dev)
+    out = ops.forward(zt, Et, 0.25, path="tc")
+    _check_against_oracle(z, E, out, n, D)
+    ids = ops.forward(zt, Et, 0.25, path="tc", want_zq=False, want_loss=False)
+    assert np.array_equal(ids[3].cpu().numpy(), out[3].cpu().numpy())
+    assert np.array_equal(ids[4].cpu().numpy(), out[4].cpu().numpy())
+
+
+def test_tcs_degenerate_codebook_overflows_the_queue():
+    """Every code duplicated: no vector can be certified, the per-CTA queues (2048 entries) overflow and the rest is
+    decided by the exact scan inside the main loop -- slow, but still the oracle's ids (lowest index of each pair)."""
+    rs = np.random.RandomState(11)
+    K, D = 512, 32
+    n = 148 * 2048 + 148 * 128 * 2
+    E = (0.1 * rs.standard_normal((K, D))).astype(np.float32)
+    E[256:] = E[:256]
+    z = (0.1 * rs.standard_normal((n, D))).astype(np.float32)
+    dev = _dev()
+    out = ops.forward(torch.from_numpy(z).to(dev), torch.from_numpy(E).to(dev), 0.25, path="tc", want_stats=True)
+    _check_against_oracle(z, E, out, n, D)
+    assert int(out[5][1].item()) == n                         # every vector went through an exact scan
+    assert int(out[3].max().item()) < 256
+
+
 @pytest.mark.parametrize("K", [256, 100, 1])
 @pytest.mark.parametrize("n", [128, 129, 255, 1000, 128 * 148 * 2 + 77])
 def test_backward_tma_ring_kernel(K, n):

@@ -39,6 +39,7 @@
 //               decision -> z_q written in place into the ring slot -> TMA store; idx, loss, histogram
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "vq_common.cuh"
 #include "vq_ptx.cuh"
@@ -1139,38 +1140,42 @@ bool make_map(CUtensorMap *map, const float *base, int64_t n_rows, int d)
 // histogram and the int64 index are produced in one streaming pass (eight threads per vector).
 // ---------------------------------------------------------------------------------------
 constexpr int kFinishMaxK = 16384;     // shared-memory histogram (u32 per code)
+// NF: float4 columns per thread (columns sub, sub + 8, ...: rows of up to 32 * NF components); U vectors per thread and step
+template <int NF>
 __global__ void __launch_bounds__(256) vq_tc_finish_kernel(const FwdParams p, double *__restrict__ partial_out)
 {
+    constexpr int U = NF > 2 ? 2 : 4;
     extern __shared__ unsigned fhist[];
     const int tid = threadIdx.x, sub = tid & 7, d = p.D;
-    for (int t = tid; t < p.K; t += 256)
+    const int hist_k = p.chunk_mode == 3 ? 0 : p.K;
+    for (int t = tid; t < hist_k; t += 256)
         fhist[t] = 0u;
     __syncthreads();
     const bool poisoned = p.hdr_in->poisoned_columns != 0;
     double sq = 0.0;
     // four vectors per thread and step, all of a step's loads issued before anything depends on them
     // (code -> E[code] is a dependent chain: one vector at a time is latency-bound, measured 1.48 ms -> see profiles)
-    const int nf = d > 32 ? 2 : 1;                    // float4 columns per thread: sub (and sub + 8 for wide rows)
-    for (int64_t row0 = (int64_t)blockIdx.x * 128 + (tid >> 3); row0 < p.z.n_rows; row0 += (int64_t)gridDim.x * 128) {
-        int code[4];
-        float4 zv[4][2];
+    const int nf = (d + 31) / 32;                     // float4 columns per thread: sub, sub + 8, ... (wide rows)
+    for (int64_t row0 = (int64_t)blockIdx.x * (32 * U) + (tid >> 3); row0 < p.z.n_rows; row0 += (int64_t)gridDim.x * (32 * U)) {
+        int code[U];
+        float4 zv[U][NF];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t row = row0 + 32 * u;
             code[u] = row < p.z.n_rows ? (int)(unsigned)(p.run[row] & 0xffffffffull) : -1;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < NF; ++h) {
                 const int f = sub + 8 * h;
                 zv[u][h] = (row < p.z.n_rows && h < nf && 4 * f < d)
                                ? __ldg(reinterpret_cast<const float4 *>(p.z.base + row * d) + f)
                                : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        float4 ev[4][2];
+        float4 ev[U][NF];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < NF; ++h) {
                 const int f = sub + 8 * h;
                 ev[u][h] = (code[u] >= 0 && h < nf && 4 * f < d)
                                ? __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)code[u] * d) + f)
@@ -1178,12 +1183,12 @@ __global__ void __launch_bounds__(256) vq_tc_finish_kernel(const FwdParams p, do
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t row = row0 + 32 * u;
             if (code[u] < 0)
                 continue;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < NF; ++h) {
                 const int f = sub + 8 * h;
                 if (h >= nf || 4 * f >= d)
                     continue;
@@ -1207,14 +1212,14 @@ __global__ void __launch_bounds__(256) vq_tc_finish_kernel(const FwdParams p, do
                     __stcs(reinterpret_cast<float4 *>(p.zq + row * d) + f, o);
                 sq += (double)rs;
             }
-            if (sub == 0) {
+            if (sub == 0 && p.chunk_mode != 3) {      // (chunk_mode 3: ids and histogram are final already, vq_fwd_tcs.cu)
                 p.idx[row] = code[u];     // same 8 bytes the running best lived in
                 atomicAdd(fhist + code[u], 1u);
             }
         }
     }
     __syncthreads();
-    for (int t = tid; t < p.K; t += 256) {
+    for (int t = tid; t < hist_k; t += 256) {
         const unsigned c = fhist[t];
         if (c)
             atomicAdd(p.counts + t, (unsigned long long)c);
@@ -1230,6 +1235,29 @@ __global__ void __launch_bounds__(256) vq_tc_finish_kernel(const FwdParams p, do
             t += red[w];
         partial_out[blockIdx.x] = p.accumulate ? partial_out[blockIdx.x] + t : t;
     }
+}
+
+// z_q and the loss for ids that are already final in p.idx (the tile-stationary kernel of vq_fwd_tcs.cu)
+cudaError_t launch_tc_finish_ids(const FwdParams &p, int sm_count, int *n_ctas, cudaStream_t st)
+{
+    FwdParams pf = p;
+    pf.run = reinterpret_cast<unsigned long long *>(p.idx);
+    pf.chunk_mode = 3;
+    const int64_t groups = (p.z.n_rows + 127) / 128;
+    int grid = (int)(groups < (int64_t)sm_count * 6 ? groups : (int64_t)sm_count * 6);
+    if (grid < 1)
+        grid = 1;
+    if (grid > kMaxPartials)
+        grid = kMaxPartials;
+    // (no histogram in this mode: one word of dynamic shared memory)
+    if (p.D <= 32)
+        vq_tc_finish_kernel<1><<<grid, 256, sizeof(unsigned), st>>>(pf, p.partials);
+    else if (p.D <= 64)
+        vq_tc_finish_kernel<2><<<grid, 256, sizeof(unsigned), st>>>(pf, p.partials);
+    else
+        vq_tc_finish_kernel<4><<<grid, 256, sizeof(unsigned), st>>>(pf, p.partials);
+    *n_ctas = grid;
+    return cudaGetLastError();
 }
 
 static unsigned long long *g_trace_buf = nullptr;   // debug only, see vqb_debug_set_tc_trace
@@ -1301,9 +1329,21 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
 // finish kernel.  Exactness carries over: every chunk winner is the oracle's argmin within its chunk, and
 // the chunks are compared by oracle-order distances with the lower chunk winning ties.
 // ---------------------------------------------------------------------------------------
+// Shapes beyond the resident-codebook kernel (K > 256, or 64 < D <= 128) run on the tile-stationary kernel of
+// vq_fwd_tcs.cu; the pass-per-chunk schedule below is kept for A/B runs (VQB_CHUNK_PASSES=1 in the environment).
+bool tcs_shape_supported(int K, int D);
+cudaError_t launch_fwd_tcs(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas, int *n_launches,
+                           cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end, bool image_ready);
+
+static bool chunk_passes_requested()
+{
+    static const bool v = [] { const char *e = getenv("VQB_CHUNK_PASSES"); return e && e[0] == '1'; }();
+    return v;
+}
+
 bool tc_chunked_supported(int K, int D)
 {
-    return tc_shape_supported(tc::KMAX, D) && K > tc::KMAX && K <= kFinishMaxK;
+    return !tc_shape_supported(K, D) && tcs_shape_supported(K, D);
 }
 
 cudaError_t launch_fwd_tc_chunked(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas,
@@ -1312,6 +1352,8 @@ cudaError_t launch_fwd_tc_chunked(const FwdParams &p, float *tc_scratch, int sm_
     using namespace tc;
     if (!tc_chunked_supported(p.K, p.D) || !p.idx)
         return cudaErrorNotSupported;
+    if (!(chunk_passes_requested() && tc_shape_supported(KMAX, p.D) && p.K <= kFinishMaxK))
+        return launch_fwd_tcs(p, tc_scratch, sm_count, max_smem, n_ctas, n_launches, st, ev_begin, ev_end, false);
     if (ev_begin)
         cudaEventRecord(ev_begin, st);
     int launches = 0, pass_ctas = 1;
@@ -1341,11 +1383,11 @@ cudaError_t launch_fwd_tc_chunked(const FwdParams &p, float *tc_scratch, int sm_
         grid = 1;
     if (grid > kMaxPartials)
         grid = kMaxPartials;
-    cudaError_t err = cudaFuncSetAttribute(vq_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(sizeof(unsigned) * kFinishMaxK));
+    auto fin = p.D <= 32 ? vq_tc_finish_kernel<1> : vq_tc_finish_kernel<2>;
+    cudaError_t err = cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned) * kFinishMaxK));
     if (err != cudaSuccess)
         return err;
-    vq_tc_finish_kernel<<<grid, 256, sizeof(unsigned) * (size_t)p.K, st>>>(pf, p.partials);
+    fin<<<grid, 256, sizeof(unsigned) * (size_t)p.K, st>>>(pf, p.partials);
     err = cudaGetLastError();
     if (ev_end)
         cudaEventRecord(ev_end, st);

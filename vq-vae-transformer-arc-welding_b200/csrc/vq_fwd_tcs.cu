@@ -1,0 +1,836 @@
+// vq_fwd_tcs.cu -- tile-stationary tcgen05 forward kernel for LARGE codebooks (K > 256) and WIDE vectors (D <= 128).
+//
+// Replaces model/vector_quantizer.py:88-119 for the corners of BASELINE configs[1]'s K x D sweep.  The K <= 256 kernel
+// (vq_fwd_tc.cu) keeps the codebook operand resident and streams vectors past it; round 1 ran a large codebook as one
+// full pass of that kernel per 256-code chunk, i.e. every chunk re-read z from HBM, re-converted it to bf16 hi/lo,
+// evaluated one exact distance per vector and went through the 8-byte running best in global memory.  Here a
+// 128-vector tile is converted ONCE and stays in shared memory while the codebook's operand image streams past it:
+//
+//   * the image (built once per codebook by vq_tcs_prep_kernel, L2-resident) is a sequence of 40 KB blocks, one per
+//     (256-code chunk c, 32-component D-chunk dc):  -2*[E1|E2] as a SW128 K-major B operand (32 KB) + the chunk's
+//     ee_k as an exact three-way bf16 split (8 KB, SW32; multiplied by a ones tile);  blocks travel through an
+//     NB-deep ring by 1-D bulk copies (when all blocks fit in the ring they are loaded once and stay);
+//   * per (tile, chunk) the issuer runs 6 MMAs per D-chunk + the norm slice into one of two 256-column TMEM
+//     accumulators -- the same  s~ = ee - 2(z1.E1 + z1.E2 + z2.E1)  as vq_fwd_tc.cu, same error bound;
+//   * the epilogue reduces the chunk's 256 approximate scores to A-group / B-group minima (two warps per TMEM lane
+//     quarter, 128 columns each) and keeps, per vector and in REGISTERS across all chunks,
+//         m1   the smallest approximate score so far,   code  its code,
+//         cert whether the unit (128 codes) that holds it has exactly one code within delta of its own minimum,
+//         m2   the smallest minimum of every OTHER unit;
+//     after the last chunk the two half-states are merged and the vector is certified iff  cert and m2 > m1 + delta:
+//     then every other code is more than delta above the winner, which is the oracle's argmin.
+//     No exact distance is evaluated for certified vectors at all (the chunked path paid one per vector and chunk);
+//   * uncertified vectors (~0.3 %) are queued per CTA and decided by vq_tcs_fixup_kernel with the oracle-order
+//     expression over ALL K codes (first NaN wins, lowest index on ties); a full queue falls back to the same scan
+//     inside the main loop, so degenerate codebooks (duplicate rows, non-finite entries) stay exact, only slow;
+//   * ids and the histogram are written here; z_q and the loss come from vq_tc_finish_kernel (one streaming pass)
+//     when the caller asks for them.
+//
+// Two schedules (template ND = D-chunks per tile):
+//   ND == 1 (D <= 32): tiles are processed in PAIRS -- for every codebook chunk the B block is used by both tiles, so
+//     L2 -> shared traffic is 20 KB per 7 MMAs, and tile j of the pair owns TMEM buffer j and epilogue group j (8 warps);
+//   ND >= 2: one tile at a time, TMEM buffers alternate per (tile, chunk) item, one epilogue group.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "vq_common.cuh"
+#include "vq_ptx.cuh"
+
+namespace vqb {
+
+namespace tcs {
+
+using tc::TILE_M;
+// byte offset of 16-byte chunk `c` of row `r` in a 128-byte-row SW128 tile
+__device__ __forceinline__ int sw128(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+
+constexpr int CH = 256;                   // codes per chunk (= MMA N)
+constexpr int NA = 4;                     // bf16 [z1|z2] operand slots of 16 KB
+constexpr int MAIN_B = 32768, AUG_B = 8192, STAGE_B = MAIN_B + AUG_B;
+constexpr int ZZ_SLOTS = 8;               // ||z||^2 per row for the last 8 tiles (see the converter)
+constexpr int HIST_MAXK = 2048;           // shared-memory histogram up to this K, global atomics beyond
+constexpr int WL_CTAS = 192, WL_CAP = 2048;
+constexpr int FIX_SPLIT = 8;
+
+template <int ND> struct Cfg {
+    static constexpr int G = ND == 1 ? 2 : 1;         // tiles that share a B block
+    static constexpr int NG = G;                      // epilogue groups (4 warps each)
+    static constexpr int THREADS = 128 * NG + 256;    // epilogue groups, 4 converter warps, 4 service warps
+    static constexpr int NZ = 3;                      // fp32 z slots (TMA targets, freed by the converters)
+    static constexpr int NB = 2;                      // B ring stages of 40 KB
+    static constexpr int OFF_Z = 0;
+    static constexpr int OFF_A = OFF_Z + NZ * 16384;
+    static constexpr int OFF_B = OFF_A + NA * 16384;
+    static constexpr int OFF_AAUG = OFF_B + NB * STAGE_B;
+    static constexpr int OFF_ZZ = OFF_AAUG + 4096;
+    static constexpr int OFF_CODES = OFF_ZZ + ZZ_SLOTS * 512;        // int [2 groups][128]: the tile's codes for the z_q walk
+    static constexpr int OFF_HIST = OFF_CODES + 2 * 128 * 4;
+    static constexpr int OFF_BARS = OFF_HIST + HIST_MAXK * 4;
+    static constexpr int SMEM = OFF_BARS + 512;
+};
+
+struct Consts {
+    unsigned emax2_bits;   // max_k ee_k over the finite ones, as float bits
+    unsigned nonfinite;    // some ee_k is not finite
+    unsigned pad[14];
+};
+
+__host__ __device__ inline size_t img_const_off(int nc, int nd) { return (size_t)nc * nd * STAGE_B; }
+__host__ __device__ inline size_t img_wlcount_off(int nc, int nd) { return img_const_off(nc, nd) + 64; }
+__host__ __device__ inline size_t img_wl_off(int nc, int nd) { return img_wlcount_off(nc, nd) + WL_CTAS * 4 + 192; }   // 16-byte aligned
+__host__ __device__ inline size_t img_bytes(int nc, int nd) { return img_wl_off(nc, nd) + (size_t)WL_CTAS * WL_CAP * 16; }
+
+// Oracle-order argmin over ALL K codes for one vector, by one warp (rare path: uncertified vectors).  z row and
+// codebook come from global memory / L2; lowest index on ties, first NaN wins (torch.argmin).  Every lane returns
+// the same code.  D is a multiple of 4, rows are 16-byte aligned.
+__device__ __noinline__ int warp_exact_scan(const float *__restrict__ zrow, int D, const float *__restrict__ E,
+                                            const float *__restrict__ ee, int K)
+{
+    const int lane = threadIdx.x & 31;
+    const float4 *z4 = reinterpret_cast<const float4 *>(zrow);
+    float zz = 0.0f;
+    for (int j = 0; j < D / 4; ++j) {
+        const float4 v = __ldg(z4 + j);
+        zz = fmaf(v.x, v.x, zz); zz = fmaf(v.y, v.y, zz); zz = fmaf(v.z, v.z, zz); zz = fmaf(v.w, v.w, zz);
+    }
+    float best = __int_as_float(0x7f800000);
+    int bidx = 0x7fffffff;
+    unsigned first_nan = 0xffffffffu;
+    for (int k = lane; k < K; k += 32) {
+        const float4 *e4 = reinterpret_cast<const float4 *>(E + (size_t)k * D);
+        float acc = 0.0f;
+        for (int j = 0; j < D / 4; ++j) {
+            const float4 v = __ldg(z4 + j);
+            const float4 e = __ldg(e4 + j);
+            acc = fmaf(v.x, e.x, acc); acc = fmaf(v.y, e.y, acc); acc = fmaf(v.z, e.z, acc); acc = fmaf(v.w, e.w, acc);
+        }
+        const float dist = ref_distance(zz, ee[k], acc);
+        if (dist != dist)
+            first_nan = min(first_nan, (unsigned)k);
+        if (dist < best) {                  // k ascends per lane: strict < keeps the lowest index
+            best = dist;
+            bidx = k;
+        }
+    }
+    const unsigned nan_k = __reduce_min_sync(0xffffffffu, first_nan);
+    if (nan_k != 0xffffffffu)
+        return (int)nan_k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob < best || (ob == best && oi < bidx)) {
+            best = ob;
+            bidx = oi;
+        }
+    }
+    return bidx == 0x7fffffff ? 0 : bidx;
+}
+
+__device__ __forceinline__ float min16u(const uint32_t *v)
+{
+    using tc::min3;
+    const float t0 = min3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+    const float t1 = min3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+    const float t2 = min3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+    const float t3 = min3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+    const float t4 = min3(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]));
+    return fminf(min3(__uint_as_float(v[15]), t0, t1), min3(t2, t3, t4));
+}
+
+}  // namespace tcs
+
+// ---------------------------------------------------------------------------------------
+// prep: one thread per (padded) code writes its rows of every (chunk, D-chunk) block of the operand image
+// ---------------------------------------------------------------------------------------
+__global__ void vq_tcs_prep_kernel(const float *__restrict__ E, const float *__restrict__ ee, int K, int d, int nc, int nd,
+                                   unsigned char *__restrict__ img)
+{
+    using namespace tcs;
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= nc * CH)
+        return;
+    const int c = kk / CH, k = kk % CH;
+    const bool real = kk < K;
+    Consts *cst = reinterpret_cast<Consts *>(img + img_const_off(nc, nd));
+    // ee_k = a1 + a2 + a3 exactly (3 x 8 bits); pads and non-finite norms get a huge finite score
+    const float eek = real ? ee[kk] : 3.0e38f;
+    const bool fin = isfinite(eek);
+    const float eef = fin ? eek : 3.0e38f;
+    const __nv_bfloat16 a1 = __float2bfloat16_rn(eef);
+    const float r1 = eef - __bfloat162float(a1);
+    const __nv_bfloat16 a2 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+    for (int dc = 0; dc < nd; ++dc) {
+        unsigned char *blk = img + (size_t)(c * nd + dc) * STAGE_B;
+        float e[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            e[j] = (real && dc * 32 + j < d) ? __ldg(E + (size_t)kk * d + dc * 32 + j) : 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {   // row k = [-2*E1 (32 bf16) | -2*E2 (32 bf16)], SW128
+            __nv_bfloat16 out[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int j = (ch & 3) * 8 + t;
+                const __nv_bfloat16 hi = __float2bfloat16_rn(e[j]);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(e[j] - __bfloat162float(hi));
+                out[t] = __float2bfloat16_rn(-2.0f * __bfloat162float(ch < 4 ? hi : lo));   // exact scaling
+            }
+            *reinterpret_cast<uint4 *>(blk + sw128(k, ch)) = *reinterpret_cast<uint4 *>(out);
+        }
+        if (dc == nd - 1) {
+            __nv_bfloat16 out[8] = {a1, a2, a3, zero, zero, zero, zero, zero};
+            const int sw = (k >> 2) & 1;   // SW32: 16-byte chunk index ^= bit 7 of the byte offset
+            *reinterpret_cast<uint4 *>(blk + MAIN_B + k * 32 + ((0 ^ sw) << 4)) = *reinterpret_cast<uint4 *>(out);
+            *reinterpret_cast<uint4 *>(blk + MAIN_B + k * 32 + ((1 ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    if (real) {
+        if (fin)
+            atomicMax(&cst->emax2_bits, __float_as_uint(eek));   // non-negative floats order like uints
+        else
+            atomicOr(&cst->nonfinite, 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(tcs::Cfg<ND>::THREADS, 1)
+vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __grid_constant__ CUtensorMap map_z, int nc)
+{
+    using namespace tcs;
+    using namespace tc;
+    using C = Cfg<ND>;
+    constexpr int G = C::G, NG = C::NG, NZ = C::NZ, NB = C::NB;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    if ((sbase & 1023u) != 0)
+        __trap();
+    enum { Z_FULL = 0, Z_EMPTY = Z_FULL + NZ, A_FULL = Z_EMPTY + NZ, A_EMPTY = A_FULL + NA, B_FULL = A_EMPTY + NA,
+           B_EMPTY = B_FULL + NB, T_FULL = B_EMPTY + NB, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2 };
+    static_assert(8 * N_BARS + 16 <= 512, "barrier area");
+    auto bar = [&](int i) { return sbase + C::OFF_BARS + 8 * i; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::OFF_BARS + 8 * N_BARS);
+    unsigned *wl_count_s = reinterpret_cast<unsigned *>(smem + C::OFF_BARS + 8 * N_BARS + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long clk_begin = clock64();
+    const int64_t n_rows = p.z.n_rows;
+    const int n_tiles = (int)((n_rows + TILE_M - 1) / TILE_M);
+    const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int K = p.K, D = p.D;
+    const bool resident = nc * ND <= NB;              // every block of the image fits in the ring: load once
+    constexpr int W_CONV = 4 * NG, W_SVC = 4 * NG + 4, THREADS = C::THREADS;
+    double sq = 0.0;
+
+    if (warp == W_SVC && lane == 0) {
+        for (int s = 0; s < NZ; ++s) {
+            mbar_init(bar(Z_FULL + s), 1);
+            mbar_init(bar(Z_EMPTY + s), 128);
+        }
+        for (int s = 0; s < NA; ++s) {
+            mbar_init(bar(A_FULL + s), 128);
+            mbar_init(bar(A_EMPTY + s), 1);
+        }
+        for (int s = 0; s < NB; ++s) {
+            mbar_init(bar(B_FULL + s), 1);
+            mbar_init(bar(B_EMPTY + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar(T_FULL + b), 1);
+            mbar_init(bar(T_EMPTY + b), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == W_SVC + 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < TILE_M) {                               // ones tile of the norm slice (SW32)
+        const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
+        __nv_bfloat16 out[8] = {one, one, one, zero, zero, zero, zero, zero};
+        const int sw = (tid >> 2) & 1;
+        *reinterpret_cast<uint4 *>(smem + C::OFF_AAUG + tid * 32 + ((0 ^ sw) << 4)) = *reinterpret_cast<uint4 *>(out);
+        *reinterpret_cast<uint4 *>(smem + C::OFF_AAUG + tid * 32 + ((1 ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+    }
+    for (int t = tid; t < HIST_MAXK; t += THREADS)
+        reinterpret_cast<unsigned *>(smem + C::OFF_HIST)[t] = 0u;
+    if (tid == 0)
+        *wl_count_s = 0u;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const Consts *cst = reinterpret_cast<const Consts *>(img + img_const_off(nc, ND));
+
+    if (warp >= W_SVC)
+        reg_dec<56>();      // (register pool: 128 x (56 + 56) + 128 * NG x 200 <= THREADS x registers at launch)
+    if (warp == W_SVC) {
+        // ================= z loader: one 128 x 32 fp32 box per (tile, D-chunk) item =================
+        const int n_items = my_tiles * ND;
+        int s = 0;
+        uint32_t ph = 1;                                         // Z_EMPTY parity: the first round passes
+        for (int it = 0; it < n_items; ++it) {
+            const int i = ND == 1 ? it : it / ND, dc = ND == 1 ? 0 : it % ND;
+            const uint32_t tile = blockIdx.x + (uint32_t)i * gridDim.x;
+            mbar_wait<64>(bar(Z_EMPTY + s), ph);
+            if (elect_one()) {
+                mbar_expect_tx(bar(Z_FULL + s), TILE_M * 32 * 4);
+                tma_load_2d(sbase + C::OFF_Z + s * 16384, &map_z, bar(Z_FULL + s), dc * 32, (int)(tile * TILE_M));
+            }
+            __syncwarp();
+            if (++s == NZ) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+    } else if (warp == W_SVC + 2) {
+        // ================= B loader: operand blocks of the image through the ring =================
+        const int n_groups = (my_tiles + G - 1) / G;
+        const int per_group = nc * ND;
+        const long long n_uses = resident ? (my_tiles > 0 ? per_group : 0) : (long long)n_groups * per_group;
+        int s = 0, blk = 0;
+        uint32_t ph = 1;
+        for (long long u = 0; u < n_uses; ++u) {
+            mbar_wait<64>(bar(B_EMPTY + s), ph);
+            const uint32_t bytes = (blk % ND) == ND - 1 ? (uint32_t)STAGE_B : (uint32_t)MAIN_B;
+            if (elect_one()) {
+                mbar_expect_tx(bar(B_FULL + s), bytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sbase + C::OFF_B + s * STAGE_B), "l"(img + (size_t)blk * STAGE_B), "r"(bytes), "r"(bar(B_FULL + s))
+                             : "memory");
+            }
+            __syncwarp();
+            if (++blk == per_group)
+                blk = 0;
+            if (++s == NB) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+    } else if (warp == W_SVC + 1) {
+        // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
+        const uint32_t idesc = idesc_bf16(CH);
+        const uint64_t aaug = desc_sw32(sbase + C::OFF_AAUG);
+        const uint64_t a0 = desc_sw128(sbase + C::OFF_A);
+        const uint64_t b0 = desc_sw128(sbase + C::OFF_B);
+        const uint64_t baug0 = desc_sw32(sbase + C::OFF_B + MAIN_B);
+        unsigned a_cnt = 0;                      // A items consumed so far (slot = a_cnt % NA at the group's start)
+        unsigned b_cnt = 0;                      // B uses so far
+        unsigned t_cnt0 = 0u, t_cnt1 = 0u;       // accumulations started per TMEM buffer
+        unsigned item = 0;                       // (tile, chunk) items so far (ND >= 2: buffer = item & 1)
+        for (int g0 = 0; g0 < my_tiles; g0 += G) {
+            const int gt = my_tiles - g0 < G ? my_tiles - g0 : G;
+            for (int c = 0; c < nc; ++c) {
+                for (int dc = 0; dc < ND; ++dc) {
+                    const int bs = resident ? (c * ND + dc) : (int)(b_cnt % NB);
+                    mbar_wait<32>(bar(B_FULL + bs), resident ? 0u : (uint32_t)((b_cnt / NB) & 1));
+                    const bool wide = D - 32 * dc > 16;          // else components 16..31 of this D-chunk are padding
+                    for (int j = 0; j < gt; ++j) {
+                        const unsigned ai = a_cnt + (unsigned)(j * ND + dc);
+                        const int as = (int)(ai % NA);
+                        const int buf = G == 2 ? j : (int)(item & 1u);
+                        if (c == 0)
+                            mbar_wait<32>(bar(A_FULL + as), (uint32_t)((ai / NA) & 1));
+                        if (dc == 0) {
+                            mbar_wait<32>(bar(T_EMPTY + buf), (uint32_t)(((buf ? t_cnt1 : t_cnt0) & 1) ^ 1));
+                            if (buf) ++t_cnt1; else ++t_cnt0;
+                        }
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t a = a0 + (uint64_t)(as * (16384 >> 4));
+                            const uint64_t bm = b0 + (uint64_t)(bs * (STAGE_B >> 4));
+                            const uint32_t d = tmem_base + buf * CH;
+                            umma_bf16(d, a + 0, bm + 0, idesc, dc);                // z1[0:16]  . E1[0:16]
+                            if (wide) umma_bf16(d, a + 2, bm + 2, idesc, 1);       // z1[16:32] . E1[16:32]
+                            umma_bf16(d, a + 0, bm + 4, idesc, 1);                 // z1[0:16]  . E2[0:16]
+                            if (wide) umma_bf16(d, a + 2, bm + 6, idesc, 1);       // z1[16:32] . E2[16:32]
+                            umma_bf16(d, a + 4, bm + 0, idesc, 1);                 // z2[0:16]  . E1[0:16]
+                            if (wide) umma_bf16(d, a + 6, bm + 2, idesc, 1);       // z2[16:32] . E1[16:32]
+                            if (c == nc - 1)
+                                umma_commit(bar(A_EMPTY + as));                    // the tile is done with this operand slot
+                            if (dc == ND - 1) {
+                                umma_bf16(d, aaug, baug0 + (uint64_t)(bs * (STAGE_B >> 4)), idesc, 1);   // + ee_k
+                                umma_commit(bar(T_FULL + buf));
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (!resident) {
+                        if (elect_one())
+                            umma_commit(bar(B_EMPTY + bs));
+                        __syncwarp();
+                    }
+                    ++b_cnt;
+                }
+                if (G == 1)
+                    ++item;
+            }
+            a_cnt += (unsigned)(gt * ND);
+        }
+    } else if (warp >= W_CONV && warp < W_CONV + 4) {
+        // ================= converters: fp32 -> bf16 hi/lo, thread = row (as in vq_fwd_tc.cu) =================
+        reg_dec<56>();
+        const int r = tid - W_CONV * 32;
+        const int x = (r & 7) << 4;
+        const int n_items = my_tiles * ND;
+        int zs = 0, as = 0;
+        uint32_t zph = 0, aph = 1;
+        float zz_acc = 0.0f;
+        for (int it = 0; it < n_items; ++it) {
+            const int i = ND == 1 ? it : it / ND, dc = ND == 1 ? 0 : it % ND;
+            if (warp == W_CONV) {
+                mbar_wait<64>(bar(Z_FULL + zs), zph);
+                mbar_wait<64>(bar(A_EMPTY + as), aph);
+            }
+            named_bar_sync(1, 128);
+            const unsigned char *zrow = smem + C::OFF_Z + zs * 16384 + r * 128;
+            unsigned char *arow = smem + C::OFF_A + as * 16384 + r * 128;
+            float2 zp[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                zp[h] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int cp = 0; cp < 4; ++cp) {
+                const float4 va = *reinterpret_cast<const float4 *>(zrow + (((2 * cp) << 4) ^ x));
+                const float4 vb = *reinterpret_cast<const float4 *>(zrow + (((2 * cp + 1) << 4) ^ x));
+                const float xs[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const float x0 = xs[2 * h], x1 = xs[2 * h + 1];
+                    zp[h] = __ffma2_rn(make_float2(x0, x1), make_float2(x0, x1), zp[h]);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2);
+                    const float2 lo2 = __fadd2_rn(make_float2(x0, x1), make_float2(-__uint_as_float(hb << 16),
+                                                                                   -__uint_as_float(hb & 0xffff0000u)));
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(lo2.x, lo2.y);
+                    hi[h] = hb;
+                    lo[h] = *reinterpret_cast<const uint32_t *>(&l2);
+                }
+                *reinterpret_cast<uint4 *>(arow + ((cp << 4) ^ x)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(arow + (((cp + 4) << 4) ^ x)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            {
+                const float2 t = __fadd2_rn(__fadd2_rn(zp[0], zp[1]), __fadd2_rn(zp[2], zp[3]));
+                zz_acc = dc == 0 ? t.x + t.y : zz_acc + (t.x + t.y);
+            }
+            // ||z||^2 of the whole row goes to the slot of the TILE (8 slots: the epilogue of tile i reads its slot before it
+            // hands back the accumulator of (i, chunk 0), and the MMAs of tile i + 6 cannot have been issued before that)
+            if (dc == ND - 1)
+                reinterpret_cast<float *>(smem + C::OFF_ZZ + (i & (ZZ_SLOTS - 1)) * 512)[r] = zz_acc;
+            fence_proxy_async();
+            mbar_arrive(bar(A_FULL + as));
+            mbar_arrive(bar(Z_EMPTY + zs));
+            if (++zs == NZ) {
+                zs = 0;
+                zph ^= 1u;
+            }
+            if (++as == NA) {
+                as = 0;
+                aph ^= 1u;
+            }
+        }
+    } else if (warp < 4 * NG) {
+        // ================= epilogue groups: 4 warps each, thread = row (TMEM lane), all 256 columns of the chunk ==========
+        reg_inc<200>();
+        const int e = warp >> 2;                  // group
+        const int q = warp & 3;                   // TMEM lane quarter
+        const int r = q * 32 + lane;              // row in tile
+        unsigned *hist = reinterpret_cast<unsigned *>(smem + C::OFF_HIST);
+        int *codes_s = reinterpret_cast<int *>(smem + C::OFF_CODES) + e * TILE_M;
+        const bool poisoned = p.hdr_in->poisoned_columns != 0;
+        const bool cb_bad = cst->nonfinite != 0 || poisoned || !(__uint_as_float(cst->emax2_bits) <= 1.0e37f);
+        uint4 *wl = reinterpret_cast<uint4 *>(img + img_wl_off(nc, ND)) + (size_t)blockIdx.x * WL_CAP;
+        const float big = 3.0e38f, inf = __int_as_float(0x7f800000);
+        const int q4 = D >> 2;                    // float4 per row
+        unsigned n_slow_total = 0;
+        unsigned t_cnt0 = 0u, t_cnt1 = 0u;        // accumulators consumed per TMEM buffer
+        unsigned item = 0;
+        float sqf = 0.0f;
+        int run = 0;
+        // tiles of this group: NG == 2: local tiles e, e + 2, ...; NG == 1: all
+        for (int i = e; i < my_tiles; i += NG) {
+            const uint32_t tile = blockIdx.x + (uint32_t)i * gridDim.x;
+            const uint32_t row = tile * TILE_M + r;
+            const bool ok = row < (uint32_t)n_rows;
+            // running state over the chunks: the two chunks with the smallest minima (minimum, chunk, its A/B-group masks)
+            // and the smallest minimum of all others
+            float m1 = inf, m2 = inf, m3 = inf, delta = 0.0f;
+            unsigned c1 = 0u, c2 = 0u, k1 = 0u, k2 = 0u;
+            for (int c = 0; c < nc; ++c) {
+                const int buf = G == 2 ? e : (int)(item & 1u);
+                group_wait<64>(q == 0, bar(T_FULL + buf), (uint32_t)((buf ? t_cnt1 : t_cnt0) & 1), 2 + e);
+                if (buf) ++t_cnt1; else ++t_cnt0;
+                ++item;
+                tc_fence_after();
+                if (c == 0) {
+                    const float eemax = __uint_as_float(cst->emax2_bits);
+                    const float emax = sqrt_approx(eemax) * 1.00001f;
+                    const float zz = reinterpret_cast<const float *>(smem + C::OFF_ZZ + (i & (ZZ_SLOTS - 1)) * 512)[r];
+                    const float zn = sqrt_approx(fmaxf(zz, 7.52316385e-37f)) * 1.00001f;
+                    // filter radius: vq_fwd_tc.cu's bound, with the D-proportional terms scaled by the number of D-chunks;
+                    // rows whose exact distances could overflow (or are not finite) get an infinite radius: never certified,
+                    // never queued with candidates
+                    delta = (2.1e-4f + 3.0e-5f * (ND - 1)) * zn * emax + 8.0e-6f * eemax + 3.0e-7f * (zn + emax) * (zn + emax) +
+                            (1.0e-35f + 1.0e-36f * emax);
+                    if (!(zz <= 1.0e37f))
+                        delta = inf;
+                }
+                const uint32_t taddr = tmem_base + buf * CH + ((uint32_t)(q * 32) << 16);
+                float amin[16], bmin[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                    bmin[t] = big;
+                auto reduce_slab = [&](const uint32_t (&v)[32], int sl) {
+                    amin[2 * sl] = min16u(&v[0]);
+                    amin[2 * sl + 1] = min16u(&v[16]);
+#pragma unroll
+                    for (int t = 0; t < 16; ++t)
+                        bmin[t] = min3(bmin[t], __uint_as_float(v[t]), __uint_as_float(v[t + 16]));
+                };
+                {   // two slabs in flight; the accumulator goes back the moment its last slab sits in registers
+                    uint32_t va[32], vb[32];
+                    tmem_ld32(taddr, va);
+#pragma unroll
+                    for (int sl = 0; sl < CH / 32; sl += 2) {
+                        tmem_wait_ld_fence(va);
+                        tmem_ld32(taddr + (sl + 1) * 32, vb);
+                        reduce_slab(va, sl);
+                        tmem_wait_ld_fence(vb);
+                        if (sl + 2 < CH / 32) {
+                            tmem_ld32(taddr + (sl + 2) * 32, va);
+                        } else {
+                            tc_fence_before();
+                            mbar_arrive(bar(T_EMPTY + buf));
+                        }
+                        reduce_slab(vb, sl + 1);
+                    }
+                }
+                float mt[6];
+#pragma unroll
+                for (int t = 0; t < 5; ++t)
+                    mt[t] = min3(amin[3 * t], amin[3 * t + 1], amin[3 * t + 2]);
+                const float m = fminf(min3(mt[0], mt[1], mt[2]), min3(mt[3], mt[4], amin[15]));
+                const float thr = m + delta;
+                float maf = 0.0f, mbf = 0.0f;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    maf = fmaf(amin[t] <= thr ? 1.0f : 0.0f, (float)(1 << t), maf);
+                    mbf = fmaf(bmin[t] <= thr ? 1.0f : 0.0f, (float)(1 << t), mbf);
+                }
+                const unsigned ma = __float_as_uint(maf + 8388608.0f) & 0xffffu;
+                const unsigned mb = __float_as_uint(mbf + 8388608.0f) & 0xffffu;
+                const unsigned kk = ma | (mb << 16);
+                // (a tie between two chunks leaves m2 == m1: not certified, both chunks' candidates are kept)
+                if (m < m1) {
+                    m3 = m2; m2 = m1; c2 = c1; k2 = k1;
+                    m1 = m; c1 = (unsigned)c; k1 = kk;
+                } else if (m < m2) {
+                    m3 = m2;
+                    m2 = m; c2 = (unsigned)c; k2 = kk;
+                } else {
+                    m3 = fminf(m3, m);
+                }
+            }
+            // ---- decision ----
+            const unsigned ma1 = k1 & 0xffffu, mb1 = k1 >> 16;
+            const bool single = ma1 != 0u && mb1 != 0u && (ma1 & (ma1 - 1u)) == 0u && (mb1 & (mb1 - 1u)) == 0u;
+            const float lim = m1 + delta;
+            int code = (int)(c1 * CH + ((31 - __clz(ma1 | 1u)) << 4 | (31 - __clz(mb1 | 1u))));
+            const bool certain = single && (m2 > lim) && !cb_bad && code < K;
+            bool slow = false;
+            if (!certain && ok) {
+                // the codes the filter could not rule out lie in the (at most two) chunks whose minimum is within delta of
+                // the best score, inside the A/B groups their masks name; otherwise (three close chunks, crowded masks,
+                // non-finite data) the fix-up kernel scans all K codes
+                const bool second = m2 <= lim;
+                const int ncand = __popc(ma1) * __popc(mb1) + (second ? __popc(k2 & 0xffffu) * __popc(k2 >> 16) : 0);
+                const bool listed = (m3 > lim) && !cb_bad && ncand >= 1 && ncand <= 32;
+                slow = true;
+                const unsigned pos = atomicAdd(wl_count_s, 1u);
+                if (pos < (unsigned)WL_CAP) {
+                    wl[pos] = listed ? make_uint4(row, c1 | (c2 << 16), k1, second ? k2 : 0u) : make_uint4(row, 0u, 0u, 0u);
+                    slow = false;
+                }
+            }
+            unsigned need = __ballot_sync(0xffffffffu, slow);
+            n_slow_total += __popc(__ballot_sync(0xffffffffu, !certain && ok));
+            while (need) {                        // queue full: the warp scans all K codes right here
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const uint32_t srow = tile * TILE_M + q * 32 + src;
+                const int res = warp_exact_scan(p.z.base + (size_t)srow * D, D, p.E, p.ee, K);
+                if (lane == src)
+                    code = res;
+            }
+            const bool emit = ok && (certain || slow);
+            if (emit) {
+                p.idx[row] = code;
+                if (K <= HIST_MAXK)
+                    atomicAdd(hist + code, 1u);
+                else
+                    atomicAdd(p.counts + code, 1ULL);
+            }
+            // ---- z_q and the squared residuals: the group walks the tile's rows with coalesced 16-byte accesses (the
+            // tile was read from HBM a few microseconds ago: these loads hit L2); queued rows are left to the fix-up ----
+            if (p.zq || p.need_sq) {
+                codes_s[r] = emit ? code : -1;
+                named_bar_sync(2 + e, 128);
+                const float4 *z4 = reinterpret_cast<const float4 *>(p.z.base) + (size_t)tile * TILE_M * q4;
+                float4 *o4 = p.zq ? reinterpret_cast<float4 *>(p.zq) + (size_t)tile * TILE_M * q4 : nullptr;
+                float rs = 0.0f;
+                // batches of 8 float4 per thread, every load of a batch issued before anything depends on it (one element
+                // at a time the walk is latency-bound: code -> codebook row is a dependent chain)
+                for (int f0 = r; f0 < TILE_M * q4; f0 += 8 * TILE_M) {
+                    int cd[8], cc[8];
+                    float4 zv[8], ev[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int f = f0 + u * TILE_M;
+                        const int rr = f / q4;
+                        cc[u] = f - rr * q4;
+                        cd[u] = f < TILE_M * q4 ? codes_s[rr] : -1;
+                        zv[u] = cd[u] >= 0 ? __ldg(z4 + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        ev[u] = cd[u] >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)cd[u] * D) + cc[u]) : zv[u];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (cd[u] < 0)
+                            continue;
+                        if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
+                            float *evp = reinterpret_cast<float *>(&ev[u]);
+                            for (int t = 0; t < 4; ++t) {
+                                const int j = 4 * cc[u] + t, cnt = p.colcnt[j];
+                                if (!(cnt == 0 || (cnt == 1 && p.colwhich[j] == cd[u] + 1)))
+                                    evp[t] = __int_as_float(0x7fc00000);
+                            }
+                        }
+                        float4 o;
+                        float dj;
+                        dj = __fsub_rn(ev[u].x, zv[u].x); rs = fmaf(dj, dj, rs); o.x = __fadd_rn(zv[u].x, dj);
+                        dj = __fsub_rn(ev[u].y, zv[u].y); rs = fmaf(dj, dj, rs); o.y = __fadd_rn(zv[u].y, dj);
+                        dj = __fsub_rn(ev[u].z, zv[u].z); rs = fmaf(dj, dj, rs); o.z = __fadd_rn(zv[u].z, dj);
+                        dj = __fsub_rn(ev[u].w, zv[u].w); rs = fmaf(dj, dj, rs); o.w = __fadd_rn(zv[u].w, dj);
+                        if (o4)
+                            __stcs(o4 + f0 + u * TILE_M, o);
+                    }
+                }
+                sqf += rs;
+                if (++run == 8) {                 // bounded fp32 run lengths, fp64 across them
+                    sq += (double)sqf;
+                    sqf = 0.0f;
+                    run = 0;
+                }
+            }
+        }
+        sq += (double)sqf;
+        if (p.stats && n_slow_total && lane == 0)
+            atomicAdd(p.stats + 1, (unsigned long long)n_slow_total);
+    }
+
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == W_SVC + 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (tid == 0) {
+        const unsigned n = *wl_count_s;
+        reinterpret_cast<unsigned *>(img + img_wlcount_off(nc, ND))[blockIdx.x] = n < (unsigned)WL_CAP ? n : (unsigned)WL_CAP;
+        if (p.stats)
+            atomicMax(p.stats + 3, (unsigned long long)(clock64() - clk_begin));
+    }
+    if (K <= HIST_MAXK) {
+        for (int t = tid; t < K; t += C::THREADS) {
+            const unsigned cnt = reinterpret_cast<unsigned *>(smem + C::OFF_HIST)[t];
+            if (cnt)
+                atomicAdd(p.counts + t, (unsigned long long)cnt);
+        }
+    }
+    // per-CTA sum of squared residuals (fixed order within the CTA)
+    __shared__ double red[C::THREADS / 32];
+    sq = warp_sum(sq);
+    if (lane == 0)
+        red[warp] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < C::THREADS / 32; ++w)
+            t += red[w];
+        p.partials[blockIdx.x] = p.accumulate ? p.partials[blockIdx.x] + t : t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// fix-up: one warp per queued vector.  Listed entries carry the (at most two) chunks and A/B-group masks that hold every
+// code the filter could not rule out: one lane per candidate evaluates the oracle-order distance, lowest index wins
+// (such rows and the codebook are finite: no NaN rule needed).  Unlisted entries (k1 == 0) scan all K codes.
+// The vector's idx / histogram / z_q / loss contributions are written here.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vq_tcs_fixup_kernel(const FwdParams p, const unsigned char *__restrict__ img, int nc, int nd,
+                                                            double *__restrict__ partial_out)
+{
+    using namespace tcs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int queue = blockIdx.x / FIX_SPLIT, part = blockIdx.x % FIX_SPLIT;
+    const unsigned count = reinterpret_cast<const unsigned *>(img + img_wlcount_off(nc, nd))[queue];
+    const uint4 *wl = reinterpret_cast<const uint4 *>(img + img_wl_off(nc, nd)) + (size_t)queue * WL_CAP;
+    const int K = p.K, D = p.D;
+    const bool poisoned = p.hdr_in->poisoned_columns != 0;
+    double sq = 0.0;
+    for (unsigned e = part * 8 + warp; e < count; e += 8 * FIX_SPLIT) {
+        const uint4 ent = wl[e];
+        const unsigned row = ent.x;
+        const float *zrow = p.z.base + (size_t)row * D;
+        int code;
+        if (ent.z == 0u) {
+            code = warp_exact_scan(zrow, D, p.E, p.ee, K);
+        } else {
+            const unsigned ma1 = ent.z & 0xffffu, mb1 = ent.z >> 16, ma2 = ent.w & 0xffffu, mb2 = ent.w >> 16;
+            const int nb1 = __popc(mb1), n1 = __popc(ma1) * nb1, nb2 = __popc(mb2), n2 = __popc(ma2) * nb2;
+            int k = -1;
+            if (lane < n1)
+                k = (int)(ent.y & 0xffffu) * CH + 16 * __fns(ma1, 0, lane / nb1 + 1) + __fns(mb1, 0, lane % nb1 + 1);
+            else if (lane < n1 + n2)
+                k = (int)(ent.y >> 16) * CH + 16 * __fns(ma2, 0, (lane - n1) / nb2 + 1) + __fns(mb2, 0, (lane - n1) % nb2 + 1);
+            if (k >= K)
+                k = -1;
+            const float4 *z4 = reinterpret_cast<const float4 *>(zrow);
+            const float4 *e4 = reinterpret_cast<const float4 *>(p.E + (size_t)(k < 0 ? 0 : k) * D);
+            float zz = 0.0f, acc = 0.0f;
+            for (int j = 0; j < D / 4; ++j) {             // oracle-order chains, ascending j
+                const float4 v = __ldg(z4 + j);
+                const float4 c = __ldg(e4 + j);
+                zz = fmaf(v.x, v.x, zz); zz = fmaf(v.y, v.y, zz); zz = fmaf(v.z, v.z, zz); zz = fmaf(v.w, v.w, zz);
+                acc = fmaf(v.x, c.x, acc); acc = fmaf(v.y, c.y, acc); acc = fmaf(v.z, c.z, acc); acc = fmaf(v.w, c.w, acc);
+            }
+            float best = __int_as_float(0x7f800000);
+            int bidx = 0x7fffffff;
+            if (k >= 0) {
+                best = ref_distance(zz, p.ee[k], acc);
+                bidx = k;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+                if (ob < best || (ob == best && oi < bidx)) {
+                    best = ob;
+                    bidx = oi;
+                }
+            }
+            code = bidx == 0x7fffffff ? 0 : bidx;
+        }
+        float r2 = 0.0f;
+        if (p.zq || p.need_sq) {
+            for (int j = lane; j < D; j += 32) {
+                float ej = __ldg(p.E + (size_t)code * D + j);
+                if (poisoned) {
+                    const int cnt = p.colcnt[j];
+                    if (!(cnt == 0 || (cnt == 1 && p.colwhich[j] == code + 1)))
+                        ej = __int_as_float(0x7fc00000);
+                }
+                const float zj = __ldg(zrow + j);
+                const float diff = __fsub_rn(ej, zj);
+                if (p.zq)
+                    p.zq[(size_t)row * D + j] = __fadd_rn(zj, diff);
+                r2 = fmaf(diff, diff, r2);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        }
+        if (lane == 0) {
+            p.idx[row] = code;
+            atomicAdd(p.counts + code, 1ULL);
+            sq += (double)r2;
+        }
+    }
+    __shared__ double red[8];
+    if (lane == 0)
+        red[warp] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w)
+            t += red[w];
+        partial_out[blockIdx.x] = p.accumulate ? partial_out[blockIdx.x] + t : t;
+    }
+}
+
+bool tcs_shape_supported(int K, int D) { return D >= 4 && D <= 128 && D % 4 == 0 && K >= 1 && K <= 16384; }
+
+size_t tcs_image_bytes(int K, int D)
+{
+    const int nc = (K + tcs::CH - 1) / tcs::CH, nd = (D + 31) / 32;
+    return tcs::img_bytes(nc, nd);
+}
+
+cudaError_t launch_fwd_tcs(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas, int *n_launches,
+                           cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end, bool image_ready)
+{
+    using namespace tcs;
+    if (!tcs_shape_supported(p.K, p.D) || !p.z.rows_contiguous(p.D) || p.z.n_rows >= (1ll << 31) || !p.idx)
+        return cudaErrorNotSupported;
+    const int nc = (p.K + CH - 1) / CH, nd = (p.D + 31) / 32;
+    unsigned char *img = reinterpret_cast<unsigned char *>(tc_scratch);
+    CUtensorMap map_z;
+    if (!tc::make_tensor_map_2d(&map_z, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.z.base, p.z.n_rows, p.D, TILE_M, 32,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+        return cudaErrorNotSupported;
+    cudaError_t err = cudaSuccess;
+    int launches = 0;
+    if (!image_ready) {
+        if ((err = cudaMemsetAsync(img + img_const_off(nc, nd), 0, sizeof(Consts), st)) != cudaSuccess)
+            return err;
+        vq_tcs_prep_kernel<<<(nc * CH + 127) / 128, 128, 0, st>>>(p.E, p.ee, p.K, p.D, nc, nd, img);
+        if ((err = cudaGetLastError()) != cudaSuccess)
+            return err;
+        ++launches;
+    }
+    const int64_t tiles = (p.z.n_rows + TILE_M - 1) / TILE_M;
+    int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    if (grid < 1)
+        grid = 1;
+    if (grid > WL_CTAS)
+        grid = WL_CTAS;
+    if (ev_begin)
+        cudaEventRecord(ev_begin, st);
+#define VQB_TCS_LAUNCH(NDV)                                                                                          \
+    do {                                                                                                             \
+        if (Cfg<NDV>::SMEM > max_smem)                                                                               \
+            return cudaErrorNotSupported;                                                                            \
+        err = cudaFuncSetAttribute(vq_fwd_tcs_kernel<NDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NDV>::SMEM); \
+        if (err != cudaSuccess)                                                                                      \
+            return err;                                                                                              \
+        vq_fwd_tcs_kernel<NDV><<<grid, Cfg<NDV>::THREADS, Cfg<NDV>::SMEM, st>>>(p, img, map_z, nc);                            \
+    } while (0)
+    switch (nd) {
+    case 1: VQB_TCS_LAUNCH(1); break;
+    case 2: VQB_TCS_LAUNCH(2); break;
+    case 3: VQB_TCS_LAUNCH(3); break;
+    default: VQB_TCS_LAUNCH(4); break;
+    }
+#undef VQB_TCS_LAUNCH
+    if ((err = cudaGetLastError()) != cudaSuccess)
+        return err;
+    vq_tcs_fixup_kernel<<<grid * FIX_SPLIT, 256, 0, st>>>(p, img, nc, nd, p.partials + grid);
+    if ((err = cudaGetLastError()) != cudaSuccess)
+        return err;
+    launches += 2;
+    *n_ctas = grid * (1 + FIX_SPLIT);        // partials [0, grid): main kernel, then one per fix-up CTA
+    if (ev_end)
+        cudaEventRecord(ev_end, st);
+    *n_launches = launches;
+    return cudaSuccess;
+}
+
+}  // namespace vqb

@@ -72,8 +72,9 @@ def _ws_ptr(ws: torch.Tensor) -> Tuple[int, int]:
 
 
 def _tc_eligible(n: int, k: int, d: int) -> bool:
-    """Shapes the tcgen05 kernel takes (vq_fwd_tc.cu: tc_shape_supported) once rows are contiguous."""
-    return 4 <= d <= 64 and d % 4 == 0 and 1 <= k <= 16384 and n >= 128
+    """Shapes the tcgen05 kernels take (vq_fwd_tc.cu: tc_shape_supported; vq_fwd_tcs.cu: tcs_shape_supported) once rows are
+    contiguous."""
+    return 4 <= d <= 128 and d % 4 == 0 and 1 <= k <= 16384 and n >= 128
 
 
 def pack_rows(z: torch.Tensor, d: int) -> torch.Tensor:
