@@ -47,7 +47,7 @@ __host__ inline size_t tc_scratch_floats(int k, int d)
     // tile-stationary path (vq_fwd_tcs.cu, tcs::img_bytes): one 40 KB operand block per (256-code chunk, 32-component
     // D-chunk), the scalar constants and queue counters (1 KB) and the per-CTA queues (16 bytes per entry)
     const size_t nc = (size_t)(k + 255) / 256, nd = (size_t)(d + 31) / 32;
-    const size_t tcs = (k > 256 || d > 64) ? nc * nd * 40960 + 1024 + 192 * 2048 * 16 : 0;
+    const size_t tcs = (k > 256 || d > 32) ? nc * nd * 40960 + 1024 + 192 * 2048 * 16 : 0;
     return (base > tcs ? base : tcs) / sizeof(float) + 64;
 }
 

@@ -1260,14 +1260,26 @@ cudaError_t launch_tc_finish_ids(const FwdParams &p, int sm_count, int *n_ctas, 
     return cudaGetLastError();
 }
 
+cudaError_t launch_fwd_tcs(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas, int *n_launches,
+                           cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end, bool image_ready);
+static bool wide_tcs_requested()
+{
+    static const bool v = [] { const char *e = getenv("VQB_WIDE_TCS"); return e && e[0] == '1'; }();
+    return v;
+}
+
 static unsigned long long *g_trace_buf = nullptr;   // debug only, see vqb_debug_set_tc_trace
 void set_tc_trace(unsigned long long *buf) { g_trace_buf = buf; }
+unsigned long long *tc_trace_buf() { return g_trace_buf; }
 size_t tc_trace_words() { return (size_t)kTraceCtas * kTraceTiles * kTraceEvents; }
 
 cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas,
                           int *n_launches, cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end, bool image_ready)
 {
     using namespace tc;
+    // (A/B switch: VQB_WIDE_TCS=1 sends 32 < D <= 64 to the tile-stationary kernel instead of the two-slot schedule below)
+    if (p.D > tc::D && p.idx && p.chunk_mode == 0 && wide_tcs_requested())
+        return launch_fwd_tcs(p, tc_scratch, sm_count, max_smem, n_ctas, n_launches, st, ev_begin, ev_end, false);
     // (row coordinates of the TMA boxes and the queue entries of the fix-up kernel are 32-bit)
     if (!tc_shape_supported(p.K, p.D) || !p.z.rows_contiguous(p.D) || SMEM_ALLOC > max_smem || p.z.n_rows >= (1ll << 31))
         return cudaErrorNotSupported;

@@ -55,7 +55,9 @@ constexpr int FIX_SPLIT = 8;
 template <int ND> struct Cfg {
     static constexpr int G = ND == 1 ? 2 : 1;         // tiles that share a B block
     static constexpr int NG = G;                      // epilogue groups (4 warps each)
-    static constexpr int THREADS = 128 * NG + 256;    // epilogue groups, 4 converter warps, 4 service warps
+    static constexpr int NE = ND == 1 ? 4 : 8;        // emit warps (z_q walk)
+    static constexpr int THREADS = 128 * NG + 256 + 32 * NE;   // epilogue groups, 4 converter, 4 service warps, emit warps
+    static constexpr int EPI_REGS = ND == 1 ? 136 : 168;       // 128 x (56 + 56) + 32 NE x 96 + 128 NG x EPI_REGS <= 640 x 96
     static constexpr int NZ = 3;                      // fp32 z slots (TMA targets, freed by the converters)
     static constexpr int NB = 2;                      // B ring stages of 40 KB
     static constexpr int OFF_Z = 0;
@@ -63,8 +65,8 @@ template <int ND> struct Cfg {
     static constexpr int OFF_B = OFF_A + NA * 16384;
     static constexpr int OFF_AAUG = OFF_B + NB * STAGE_B;
     static constexpr int OFF_ZZ = OFF_AAUG + 4096;
-    static constexpr int OFF_CODES = OFF_ZZ + ZZ_SLOTS * 512;        // int [2 groups][128]: the tile's codes for the z_q walk
-    static constexpr int OFF_HIST = OFF_CODES + 2 * 128 * 4;
+    static constexpr int OFF_CODES = OFF_ZZ + ZZ_SLOTS * 512;        // int [2 groups][2 slots][128]: the tile's codes for the z_q walk
+    static constexpr int OFF_HIST = OFF_CODES + 2 * 2 * 128 * 4;
     static constexpr int OFF_BARS = OFF_HIST + HIST_MAXK * 4;
     static constexpr int SMEM = OFF_BARS + 512;
 };
@@ -138,6 +140,57 @@ __device__ __forceinline__ float min16u(const uint32_t *v)
     return fminf(min3(__uint_as_float(v[15]), t0, t1), min3(t2, t3, t4));
 }
 
+// z_q = z + (e - z) and the squared residuals of one 128-row tile, walked by ET threads with coalesced 16-byte accesses.
+// Batches of 8 float4 per thread, every load of a batch issued before anything depends on it (code -> codebook row is a
+// dependent chain).  One warp issues one instruction every few clocks, so the walk is bound by its instruction count:
+// rows and columns come from shifts when D / 4 is a power of two (POW2), the poisoned-codebook test is compiled out of
+// the common instantiation, and the arithmetic runs on packed fp32 pairs (IEEE per lane).
+template <int ET, bool POW2, bool POISON>
+__device__ __forceinline__ float emit_tile(int t, int q4, int q4_shift, const int *codes_s, const float4 *__restrict__ z4,
+                                           const float4 *__restrict__ e4, float4 *__restrict__ o4, const int *colcnt,
+                                           const int *colwhich)
+{
+    float2 rs2 = make_float2(0.f, 0.f);
+    for (int f0 = t; f0 < TILE_M * q4; f0 += 8 * ET) {
+        int cd[8], cc[8];
+        float4 zv[8], ev[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int f = f0 + u * ET;
+            const int rr = POW2 ? f >> q4_shift : f / q4;
+            cc[u] = POW2 ? f & (q4 - 1) : f - rr * q4;
+            cd[u] = f < TILE_M * q4 ? codes_s[rr] : -1;
+            zv[u] = cd[u] >= 0 ? __ldcg(z4 + f) : make_float4(0.f, 0.f, 0.f, 0.f);   // (L2 only: L1 is a few KB beside 220 KB of smem)
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            ev[u] = cd[u] >= 0 ? __ldcg(e4 + (unsigned)(cd[u] * q4 + cc[u])) : zv[u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (cd[u] < 0)
+                continue;
+            if (POISON) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
+                float *evp = reinterpret_cast<float *>(&ev[u]);
+                for (int w = 0; w < 4; ++w) {
+                    const int j = 4 * cc[u] + w, cnt = colcnt[j];
+                    if (!(cnt == 0 || (cnt == 1 && colwhich[j] == cd[u] + 1)))
+                        evp[w] = __int_as_float(0x7fc00000);
+                }
+            }
+            const float2 d01 = __fadd2_rn(make_float2(ev[u].x, ev[u].y), make_float2(-zv[u].x, -zv[u].y));   // fl(e - z)
+            const float2 d23 = __fadd2_rn(make_float2(ev[u].z, ev[u].w), make_float2(-zv[u].z, -zv[u].w));
+            rs2 = __ffma2_rn(d01, d01, rs2);
+            rs2 = __ffma2_rn(d23, d23, rs2);
+            if (o4) {
+                const float2 o01 = __fadd2_rn(make_float2(zv[u].x, zv[u].y), d01);                            // fl(z + fl(e - z))
+                const float2 o23 = __fadd2_rn(make_float2(zv[u].z, zv[u].w), d23);
+                __stcs(o4 + f0 + u * ET, make_float4(o01.x, o01.y, o23.x, o23.y));
+            }
+        }
+    }
+    return rs2.x + rs2.y;
+}
+
 }  // namespace tcs
 
 // ---------------------------------------------------------------------------------------
@@ -198,20 +251,28 @@ __global__ void vq_tcs_prep_kernel(const float *__restrict__ E, const float *__r
 // ---------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------
-template <int ND>
+// TRACE: debug build that records clock64() of eight pipeline events per (tile, chunk) item (tools/tcs_trace.py)
+constexpr int kTcsTraceCtas = 4, kTcsTraceItems = 1024, kTcsTraceEvents = 8;
+template <int ND, bool TRACE>
 __global__ void __launch_bounds__(tcs::Cfg<ND>::THREADS, 1)
-vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __grid_constant__ CUtensorMap map_z, int nc)
+vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __grid_constant__ CUtensorMap map_z, int nc,
+                  unsigned long long *trace)
 {
     using namespace tcs;
     using namespace tc;
     using C = Cfg<ND>;
+    auto stamp = [&](int item, int ev) {
+        if (TRACE && blockIdx.x < kTcsTraceCtas && item < kTcsTraceItems)
+            atomicMax(&trace[((size_t)blockIdx.x * kTcsTraceItems + item) * kTcsTraceEvents + ev], (unsigned long long)clock64());
+    };
     constexpr int G = C::G, NG = C::NG, NZ = C::NZ, NB = C::NB;
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     if ((sbase & 1023u) != 0)
         __trap();
     enum { Z_FULL = 0, Z_EMPTY = Z_FULL + NZ, A_FULL = Z_EMPTY + NZ, A_EMPTY = A_FULL + NA, B_FULL = A_EMPTY + NA,
-           B_EMPTY = B_FULL + NB, T_FULL = B_EMPTY + NB, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2 };
+           B_EMPTY = B_FULL + NB, T_FULL = B_EMPTY + NB, T_EMPTY = T_FULL + 2, E_FULL = T_EMPTY + 2, E_EMPTY = E_FULL + 4,
+           N_BARS = E_EMPTY + 4 };   // E_*: [group][slot] code lists handed to the emit warps
     static_assert(8 * N_BARS + 16 <= 512, "barrier area");
     auto bar = [&](int i) { return sbase + C::OFF_BARS + 8 * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::OFF_BARS + 8 * N_BARS);
@@ -224,7 +285,7 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
     const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int K = p.K, D = p.D;
     const bool resident = nc * ND <= NB;              // every block of the image fits in the ring: load once
-    constexpr int W_CONV = 4 * NG, W_SVC = 4 * NG + 4, THREADS = C::THREADS;
+    constexpr int W_CONV = 4 * NG, W_SVC = 4 * NG + 4, W_EMIT = 4 * NG + 8, THREADS = C::THREADS;
     double sq = 0.0;
 
     if (warp == W_SVC && lane == 0) {
@@ -243,6 +304,10 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar(T_FULL + b), 1);
             mbar_init(bar(T_EMPTY + b), 128);
+        }
+        for (int b = 0; b < 4; ++b) {
+            mbar_init(bar(E_FULL + b), 128);
+            mbar_init(bar(E_EMPTY + b), 32 * C::NE);
         }
         fence_barrier_init();
     }
@@ -268,9 +333,55 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
     const uint32_t tmem_base = *tmem_slot;
     const Consts *cst = reinterpret_cast<const Consts *>(img + img_const_off(nc, ND));
 
-    if (warp >= W_SVC)
-        reg_dec<56>();      // (register pool: 128 x (56 + 56) + 128 * NG x 200 <= THREADS x registers at launch)
-    if (warp == W_SVC) {
+    // (the emit role branches off BEFORE any setmaxnreg: ptxas bounds a region by the smallest count that can reach it)
+    if (warp >= W_EMIT) {
+        // ================= emit warps: z_q = z + (e - z) and the squared residuals, tile by tile =================
+        // The tile was read from HBM a few microseconds ago, so these loads hit L2 (emit_tile above).
+        // (these warps keep the 96 registers of the launch)
+        if (p.zq || p.need_sq) {
+            constexpr int ET = 32 * C::NE;
+            const int t = tid - W_EMIT * 32;
+            const int q4 = D >> 2;                    // float4 per row
+            const int q4_shift = (q4 & (q4 - 1)) == 0 ? 31 - __clz(q4) : -1;
+            const float4 *e4 = reinterpret_cast<const float4 *>(p.E);
+            const bool poisoned = p.hdr_in->poisoned_columns != 0;
+            const int *codes_all = reinterpret_cast<const int *>(smem + C::OFF_CODES);
+            float sqf = 0.0f;
+            int run = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int e = NG == 2 ? (i & 1) : 0;
+                const unsigned tl = (unsigned)(i / NG);
+                const int slot = (int)(tl & 1u);
+                const uint32_t tile = blockIdx.x + (uint32_t)i * gridDim.x;
+                if ((t & 31) == 0)
+                    mbar_wait<64>(bar(E_FULL + e * 2 + slot), (uint32_t)((tl >> 1) & 1u));
+                __syncwarp();
+                if ((t & 31) == 0) stamp(i * nc + nc - 1, 6);
+                const int *codes_s = codes_all + (e * 2 + slot) * TILE_M;
+                const float4 *z4 = reinterpret_cast<const float4 *>(p.z.base) + (size_t)tile * TILE_M * q4;
+                float4 *o4 = p.zq ? reinterpret_cast<float4 *>(p.zq) + (size_t)tile * TILE_M * q4 : nullptr;
+                const float rs = q4_shift >= 0
+                                     ? (poisoned ? emit_tile<ET, true, true>(t, q4, q4_shift, codes_s, z4, e4, o4, p.colcnt, p.colwhich)
+                                                 : emit_tile<ET, true, false>(t, q4, q4_shift, codes_s, z4, e4, o4, nullptr, nullptr))
+                                     : (poisoned ? emit_tile<ET, false, true>(t, q4, q4_shift, codes_s, z4, e4, o4, p.colcnt, p.colwhich)
+                                                 : emit_tile<ET, false, false>(t, q4, q4_shift, codes_s, z4, e4, o4, nullptr, nullptr));
+                mbar_arrive(bar(E_EMPTY + e * 2 + slot));     // (the code list has been read: its slot may be rewritten)
+                if ((t & 31) == 0) stamp(i * nc + nc - 1, 7);
+                sqf += rs;
+                if (++run == 8) {                 // bounded fp32 run lengths, fp64 across them
+                    sq += (double)sqf;
+                    sqf = 0.0f;
+                    run = 0;
+                }
+            }
+            sq += (double)sqf;
+        }
+    } else if (warp >= W_SVC) {
+        reg_dec<56>();      // (register pool: Cfg::EPI_REGS)
+    }
+    if (warp >= W_EMIT) {
+        // (done above)
+    } else if (warp == W_SVC) {
         // ================= z loader: one 128 x 32 fp32 box per (tile, D-chunk) item =================
         const int n_items = my_tiles * ND;
         int s = 0;
@@ -338,6 +449,7 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
                         if (c == 0)
                             mbar_wait<32>(bar(A_FULL + as), (uint32_t)((ai / NA) & 1));
                         if (dc == 0) {
+                            if (lane == 0) stamp((g0 + j) * nc + c, 0);
                             mbar_wait<32>(bar(T_EMPTY + buf), (uint32_t)(((buf ? t_cnt1 : t_cnt0) & 1) ^ 1));
                             if (buf) ++t_cnt1; else ++t_cnt0;
                         }
@@ -360,6 +472,7 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
                             }
                         }
                         __syncwarp();
+                        if (dc == ND - 1 && lane == 0) stamp((g0 + j) * nc + c, 1);
                     }
                     if (!resident) {
                         if (elect_one())
@@ -438,22 +551,19 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
         }
     } else if (warp < 4 * NG) {
         // ================= epilogue groups: 4 warps each, thread = row (TMEM lane), all 256 columns of the chunk ==========
-        reg_inc<200>();
+        reg_inc<C::EPI_REGS>();
         const int e = warp >> 2;                  // group
         const int q = warp & 3;                   // TMEM lane quarter
         const int r = q * 32 + lane;              // row in tile
         unsigned *hist = reinterpret_cast<unsigned *>(smem + C::OFF_HIST);
-        int *codes_s = reinterpret_cast<int *>(smem + C::OFF_CODES) + e * TILE_M;
+        int *codes_s = reinterpret_cast<int *>(smem + C::OFF_CODES) + e * 2 * TILE_M;
         const bool poisoned = p.hdr_in->poisoned_columns != 0;
         const bool cb_bad = cst->nonfinite != 0 || poisoned || !(__uint_as_float(cst->emax2_bits) <= 1.0e37f);
         uint4 *wl = reinterpret_cast<uint4 *>(img + img_wl_off(nc, ND)) + (size_t)blockIdx.x * WL_CAP;
         const float big = 3.0e38f, inf = __int_as_float(0x7f800000);
-        const int q4 = D >> 2;                    // float4 per row
         unsigned n_slow_total = 0;
         unsigned t_cnt0 = 0u, t_cnt1 = 0u;        // accumulators consumed per TMEM buffer
         unsigned item = 0;
-        float sqf = 0.0f;
-        int run = 0;
         // tiles of this group: NG == 2: local tiles e, e + 2, ...; NG == 1: all
         for (int i = e; i < my_tiles; i += NG) {
             const uint32_t tile = blockIdx.x + (uint32_t)i * gridDim.x;
@@ -469,6 +579,7 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
                 if (buf) ++t_cnt1; else ++t_cnt0;
                 ++item;
                 tc_fence_after();
+                if (r == 0) stamp(i * nc + c, 2);
                 if (c == 0) {
                     const float eemax = __uint_as_float(cst->emax2_bits);
                     const float emax = sqrt_approx(eemax) * 1.00001f;
@@ -508,6 +619,7 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
                         } else {
                             tc_fence_before();
                             mbar_arrive(bar(T_EMPTY + buf));
+                            if (lane == 0) stamp(i * nc + c, 3);
                         }
                         reduce_slab(vb, sl + 1);
                     }
@@ -537,6 +649,7 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
                 } else {
                     m3 = fminf(m3, m);
                 }
+                if (lane == 0) stamp(i * nc + c, 4);
             }
             // ---- decision ----
             const unsigned ma1 = k1 & 0xffffu, mb1 = k1 >> 16;
@@ -577,61 +690,19 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
                 else
                     atomicAdd(p.counts + code, 1ULL);
             }
-            // ---- z_q and the squared residuals: the group walks the tile's rows with coalesced 16-byte accesses (the
-            // tile was read from HBM a few microseconds ago: these loads hit L2); queued rows are left to the fix-up ----
+            // ---- z_q and the squared residuals are produced by the emit warps from the tile's code list (queued rows: -1,
+            // left to the fix-up kernel) ----
             if (p.zq || p.need_sq) {
-                codes_s[r] = emit ? code : -1;
+                const unsigned tl = (unsigned)(i / NG);                  // tiles this group has finished
+                const int slot = (int)(tl & 1u);
+                if (q == 0)
+                    mbar_wait<64>(bar(E_EMPTY + e * 2 + slot), (uint32_t)(((tl >> 1) & 1u) ^ 1u));
                 named_bar_sync(2 + e, 128);
-                const float4 *z4 = reinterpret_cast<const float4 *>(p.z.base) + (size_t)tile * TILE_M * q4;
-                float4 *o4 = p.zq ? reinterpret_cast<float4 *>(p.zq) + (size_t)tile * TILE_M * q4 : nullptr;
-                float rs = 0.0f;
-                // batches of 8 float4 per thread, every load of a batch issued before anything depends on it (one element
-                // at a time the walk is latency-bound: code -> codebook row is a dependent chain)
-                for (int f0 = r; f0 < TILE_M * q4; f0 += 8 * TILE_M) {
-                    int cd[8], cc[8];
-                    float4 zv[8], ev[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int f = f0 + u * TILE_M;
-                        const int rr = f / q4;
-                        cc[u] = f - rr * q4;
-                        cd[u] = f < TILE_M * q4 ? codes_s[rr] : -1;
-                        zv[u] = cd[u] >= 0 ? __ldg(z4 + f) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        ev[u] = cd[u] >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)cd[u] * D) + cc[u]) : zv[u];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (cd[u] < 0)
-                            continue;
-                        if (poisoned) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
-                            float *evp = reinterpret_cast<float *>(&ev[u]);
-                            for (int t = 0; t < 4; ++t) {
-                                const int j = 4 * cc[u] + t, cnt = p.colcnt[j];
-                                if (!(cnt == 0 || (cnt == 1 && p.colwhich[j] == cd[u] + 1)))
-                                    evp[t] = __int_as_float(0x7fc00000);
-                            }
-                        }
-                        float4 o;
-                        float dj;
-                        dj = __fsub_rn(ev[u].x, zv[u].x); rs = fmaf(dj, dj, rs); o.x = __fadd_rn(zv[u].x, dj);
-                        dj = __fsub_rn(ev[u].y, zv[u].y); rs = fmaf(dj, dj, rs); o.y = __fadd_rn(zv[u].y, dj);
-                        dj = __fsub_rn(ev[u].z, zv[u].z); rs = fmaf(dj, dj, rs); o.z = __fadd_rn(zv[u].z, dj);
-                        dj = __fsub_rn(ev[u].w, zv[u].w); rs = fmaf(dj, dj, rs); o.w = __fadd_rn(zv[u].w, dj);
-                        if (o4)
-                            __stcs(o4 + f0 + u * TILE_M, o);
-                    }
-                }
-                sqf += rs;
-                if (++run == 8) {                 // bounded fp32 run lengths, fp64 across them
-                    sq += (double)sqf;
-                    sqf = 0.0f;
-                    run = 0;
-                }
+                codes_s[slot * TILE_M + r] = emit ? code : -1;
+                mbar_arrive(bar(E_FULL + e * 2 + slot));
+                if (lane == 0) stamp(i * nc + nc - 1, 5);
             }
         }
-        sq += (double)sqf;
         if (p.stats && n_slow_total && lane == 0)
             atomicAdd(p.stats + 1, (unsigned long long)n_slow_total);
     }
@@ -766,6 +837,8 @@ __global__ void __launch_bounds__(256) vq_tcs_fixup_kernel(const FwdParams p, co
     }
 }
 
+unsigned long long *tc_trace_buf();
+
 bool tcs_shape_supported(int K, int D) { return D >= 4 && D <= 128 && D % 4 == 0 && K >= 1 && K <= 16384; }
 
 size_t tcs_image_bytes(int K, int D)
@@ -808,13 +881,24 @@ cudaError_t launch_fwd_tcs(const FwdParams &p, float *tc_scratch, int sm_count, 
     do {                                                                                                             \
         if (Cfg<NDV>::SMEM > max_smem)                                                                               \
             return cudaErrorNotSupported;                                                                            \
-        err = cudaFuncSetAttribute(vq_fwd_tcs_kernel<NDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NDV>::SMEM); \
+        auto kern = vq_fwd_tcs_kernel<NDV, false>;                                                                   \
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NDV>::SMEM);               \
         if (err != cudaSuccess)                                                                                      \
             return err;                                                                                              \
-        vq_fwd_tcs_kernel<NDV><<<grid, Cfg<NDV>::THREADS, Cfg<NDV>::SMEM, st>>>(p, img, map_z, nc);                            \
+        kern<<<grid, Cfg<NDV>::THREADS, Cfg<NDV>::SMEM, st>>>(p, img, map_z, nc, nullptr);                           \
     } while (0)
     switch (nd) {
-    case 1: VQB_TCS_LAUNCH(1); break;
+    case 1:
+        if (tc_trace_buf()) {        // debug: the traced instantiation (ND = 1 only)
+            auto kern = vq_fwd_tcs_kernel<1, true>;
+            err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM);
+            if (err != cudaSuccess)
+                return err;
+            kern<<<grid, Cfg<1>::THREADS, Cfg<1>::SMEM, st>>>(p, img, map_z, nc, tc_trace_buf());
+        } else {
+            VQB_TCS_LAUNCH(1);
+        }
+        break;
     case 2: VQB_TCS_LAUNCH(2); break;
     case 3: VQB_TCS_LAUNCH(3); break;
     default: VQB_TCS_LAUNCH(4); break;
