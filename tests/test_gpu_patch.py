@@ -156,6 +156,12 @@ def test_bulk_builder_dedupe_gives_identical_ids(patch_golden):
     fast, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
     assert np.array_equal(plain, fast)
     assert calls == [12, 12, 12]            # 8 windows x 5 cycles = 40 rows hold 12 distinct cycles per batch
+    # once per data set: 28 distinct cycles in all, the second and third batch only add their 8 new ones each
+    calls.clear()
+    enc.dedupe = "dataset"
+    whole, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
+    assert np.array_equal(plain, whole)
+    assert calls == [12, 8, 8] and len(enc.cycle_cache) == 28
 
 
 def test_on_the_fly_tokenizer_matches_the_reference_dataset(patch_golden, bulk_golden):

@@ -166,3 +166,61 @@ def test_encoder_side_ops_refuse_cpu_tensors():
     # a layout-only helper: on CPU tensors it is torch's own copy, the quantiser behind it still refuses them
     v = torch.randn(3, 32, 16).permute(0, 2, 1)
     assert torch.equal(ops.pack_rows(v, 32), v.contiguous())
+
+
+def test_cycle_id_cache_encodes_every_distinct_cycle_once_per_dataset():
+    """dedupe = "dataset" (SURVEY.md section 8(f) row 2): windows with a stride of one cycle spread over several batches;
+    the cache hands every distinct cycle to the encoder once, and the ids equal the plain per-batch encode."""
+    from vqb200.dataloader import latentspace_dataloader as L
+    g = torch.Generator().manual_seed(11)
+    stream = torch.randn(70, 200, 2, generator=g)
+    stream[33] = stream[5]                                  # a repeat far apart (different batches)
+    windows = torch.stack([stream[i:i + 20] for i in range(50)])        # 50 windows x 20 cycles
+    seen = []
+    def encode(c):
+        seen.append(c.shape[0])
+        return torch.stack([(c.sum(dim=(1, 2)) * 1000).long(), (c[:, 0, 0] * 1000).long(), (c[:, -1, 1] * 1000).long()], dim=1)
+    for cap in (4 << 30, 70 * 1600 // 2, 0):                # representatives kept / dropped midway / fingerprints only
+        cache = L.CycleIdCache("cpu", max_rep_bytes=cap)
+        seen.clear()
+        outs = [cache.encode(encode, windows[b:b + 10].reshape(-1, 200, 2)) for b in range(0, 50, 10)]
+        want = encode(windows.reshape(-1, 200, 2))
+        assert torch.equal(torch.cat(outs), want)
+        assert sum(seen[:-1]) == 68 and len(cache) == 68    # 69 cycles touched, one pair identical
+        assert cache.hits + cache.misses == 1000 and cache.misses == 68
+    # a fingerprint that matches while the words differ is caught while the representatives are kept
+    cache = L.CycleIdCache("cpu")
+    a = torch.zeros(1, 200, 2); b = torch.ones(1, 200, 2)
+    cache.insert(a, L.cycle_fingerprints(a), torch.tensor([[1, 2, 3]]))
+    assert int(cache.lookup(b, L.cycle_fingerprints(a))[0]) == -1
+    assert int(cache.lookup(a, L.cycle_fingerprints(a))[0]) == 0
+
+
+def test_latent_dataset_pickle_is_the_reference_cache_format(tmp_path):
+    """save_latent_dataset writes what BaseDataloader.save_one_pickle_file would (dataloader/base_dataloader.py:236-246):
+    one pickle of (train, val, test), each an (x, y) pair, under quality_prediction_data/<dataset_name>/dataset.pickle."""
+    import pickle
+    from vqb200.dataloader import latentspace_dataloader as L
+    name = L.latent_dataset_name("autoregressive_ids", "VQ-VAE-Patch", 20, "abc123")
+    assert name == "autoregressive_ids_cycle_20_abc123"
+    assert L.latent_dataset_name("classification_ids", "VQ-VAE-Patch", 1, "m") == "asimow_ls_classification_ids_VQ-VAE-Patch_cycle_1_m"
+    with pytest.raises(ValueError):
+        L.latent_dataset_name("nope", "m", 1, "x")
+    splits = [(np.arange(12).reshape(3, 4), np.zeros(3)), (np.arange(4).reshape(1, 4), np.zeros(1)), (np.empty((0, 4), dtype=int), np.empty(0))]
+    file = L.save_latent_dataset(splits, str(tmp_path), name)
+    assert file == str(tmp_path / "quality_prediction_data" / name / "dataset.pickle")
+    with open(file, "rb") as f:
+        back = pickle.load(f)
+    assert isinstance(back, tuple) and len(back) == 3
+    for (x, y), (bx, by) in zip(splits, back):
+        assert np.array_equal(x, bx) and np.array_equal(y, by) and bx.dtype == x.dtype
+
+
+def test_async_host_writer_cpu_path_keeps_order_and_shapes():
+    from vqb200.dataloader import latentspace_dataloader as L
+    w = L._AsyncHostWriter("cpu")
+    parts = [torch.arange(24).view(2, 3, 4) + 100 * i for i in range(4)]
+    for t in parts:
+        w.put(t)
+    out = w.finish()
+    assert all(np.array_equal(o, t.numpy()) for o, t in zip(out, parts))

@@ -15,14 +15,18 @@ What changes underneath:
     fused VQ kernel in ONE call (cycles are independent: every op before the decoder is
     per token), results land in preallocated arrays, and only ids cross PCIe for the id tasks;
   * overlapping windows repeat cycles: with `dedupe = True` every distinct cycle of a batch is encoded once and its
-    ids are scattered to all its windows (encode_unique; identical arrays, up to 20x less encoder work);
+    ids are scattered to all its windows (encode_unique; identical arrays, up to 20x less encoder work); with
+    `dedupe = "dataset"` once per data set (CycleIdCache); ids leave through pinned staging buffers on a copy stream
+    (_AsyncHostWriter), and save_latent_dataset writes the reference's own pickle cache;
   * multi-GPU: batches are sharded across ranks (one process per GPU), the codebook and
     encoder weights are replicated, the only collectives are an optional gather of the ids and
     one K-element all-reduce of the code-usage histogram (bulk_encode_ids / gather_sharded).
 """
 from __future__ import annotations
 
-from typing import Callable, Iterable, Optional, Tuple
+import os
+import pickle
+from typing import Callable, Iterable, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -78,6 +82,159 @@ def encode_unique(encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: tor
     return encode_fn(cycles[rep])[inverse]
 
 
+def cycle_fingerprints(rows: torch.Tensor) -> torch.Tensor:
+    """(n, ...) float32 -> (n, 2) int64: two multiplicative hashes of the rows' bit patterns (the keys dedupe_rows groups by)."""
+    n = rows.shape[0]
+    wide = rows.reshape(n, -1).contiguous().view(torch.int32).to(torch.int64)
+    return torch.stack([(wide * _hash_weights(wide.shape[1], rows.device, s)).sum(dim=1) for s in _HASH_SEEDS], dim=1)
+
+
+class CycleIdCache:
+    """Whole-data-set de-duplication: the ids of every distinct cycle seen so far, keyed by
+    its 128-bit fingerprint.  A data set of overlapping windows (stride of one cycle, 20 cycles per window) repeats every
+    cycle up to 20 times ACROSS batches too; with the cache each distinct cycle passes through the encoder once per data
+    set.  Within a batch, identity is still decided word for word (dedupe_rows); across batches a hit is verified word for
+    word against the stored representative while the representatives fit in `max_rep_bytes` of device memory, and rests
+    on the fingerprint alone beyond that (two independent 64-bit hashes: ~n^2 / 2^128 expected false matches).
+    Device-resident: a sorted key column for torch.searchsorted, re-sorted when a batch adds new cycles."""
+
+    def __init__(self, device, max_rep_bytes: int = 4 << 30):
+        self.device = torch.device(device)
+        self.k1 = torch.empty(0, dtype=torch.int64, device=self.device)      # sorted
+        self.k2 = torch.empty(0, dtype=torch.int64, device=self.device)
+        self.slot = torch.empty(0, dtype=torch.int64, device=self.device)    # row of ids / reps for the sorted position
+        self.ids: Optional[torch.Tensor] = None                              # (m, T)
+        self.reps: Optional[torch.Tensor] = None                             # (m, words) int32 while they fit
+        self.max_rep_bytes = max_rep_bytes
+        self.hits = 0
+        self.misses = 0
+
+    def __len__(self) -> int:
+        return int(self.k1.numel())
+
+    def lookup(self, cycles: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
+        """(n,) int64: row of the cached ids for every cycle, -1 where the cycle is new."""
+        n = cycles.shape[0]
+        out = torch.full((n,), -1, dtype=torch.int64, device=self.device)
+        m = len(self)
+        if m == 0 or n == 0:
+            return out
+        pos = torch.searchsorted(self.k1, keys[:, 0].contiguous()).clamp_(max=m - 1)
+        hit = (self.k1[pos] == keys[:, 0]) & (self.k2[pos] == keys[:, 1])
+        rows = self.slot[pos]
+        if self.reps is not None and bool(hit.any()):
+            bits = cycles.reshape(n, -1).contiguous().view(torch.int32)
+            hit &= (self.reps[rows] == bits).all(dim=1)                      # word-for-word check
+        out[hit] = rows[hit]
+        return out
+
+    def insert(self, cycles: torch.Tensor, keys: torch.Tensor, ids: torch.Tensor) -> None:
+        """Remember the ids of `cycles` (distinct, not in the cache)."""
+        if cycles.shape[0] == 0:
+            return
+        m = 0 if self.ids is None else self.ids.shape[0]
+        self.ids = ids.clone() if self.ids is None else torch.cat([self.ids, ids], dim=0)
+        bits = cycles.reshape(cycles.shape[0], -1).contiguous().view(torch.int32)
+        if m == 0 and bits.numel() * 4 <= self.max_rep_bytes:
+            self.reps = bits.clone()
+        elif self.reps is not None:
+            if (self.reps.numel() + bits.numel()) * 4 <= self.max_rep_bytes:
+                self.reps = torch.cat([self.reps, bits], dim=0)
+            else:
+                self.reps = None                                             # from here on: fingerprints only
+        k1 = torch.cat([self.k1, keys[:, 0]])
+        order = torch.argsort(k1)
+        self.k1 = k1[order]
+        self.k2 = torch.cat([self.k2, keys[:, 1]])[order]
+        self.slot = torch.cat([self.slot, m + torch.arange(cycles.shape[0], device=self.device)])[order]
+
+    def encode(self, encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: torch.Tensor) -> torch.Tensor:
+        """ids of `cycles` ((n, ...) -> (n, T)): distinct cycles of the batch first (word for word), then the cache,
+        then the encoder for what is left."""
+        rep, inverse = dedupe_rows(cycles)
+        uniq = cycles[rep]
+        keys = cycle_fingerprints(uniq)
+        rows = self.lookup(uniq, keys)
+        new = (rows < 0).nonzero().view(-1)
+        self.hits += int(cycles.shape[0] - new.numel())
+        self.misses += int(new.numel())
+        if new.numel():
+            new_ids = encode_fn(uniq[new]).view(new.numel(), -1)
+            base = 0 if self.ids is None else self.ids.shape[0]
+            self.insert(uniq[new], keys[new], new_ids)
+            rows = rows.clone()
+            rows[new] = base + torch.arange(new.numel(), device=self.device)
+        return self.ids[rows][inverse]
+
+
+class _AsyncHostWriter:
+    """Device results -> host arrays through a small pool of pinned staging buffers on a copy stream: the D2H copy of batch
+    i overlaps the encoder work of batch i + 1 (the reference blocks on `.cpu()` once per cycle slice, :231-235)."""
+
+    def __init__(self, device, depth: int = 3):
+        self.cuda = torch.device(device).type == "cuda"
+        self.depth = depth
+        self.stream = torch.cuda.Stream(device=device) if self.cuda else None
+        self.pending: List[Tuple[torch.Tensor, Optional["torch.cuda.Event"], tuple]] = []
+        self.free: List[torch.Tensor] = []
+        self.out: List[np.ndarray] = []
+
+    def _retire(self) -> None:
+        buf, ev, shape = self.pending.pop(0)
+        if ev is not None:
+            ev.synchronize()
+        n = int(np.prod(shape))
+        self.out.append(buf[:n].view(shape).numpy().copy())
+        self.free.append(buf)
+
+    def put(self, t: torch.Tensor) -> None:
+        if not self.cuda:
+            self.out.append(t.cpu().numpy().copy())
+            return
+        while len(self.pending) >= self.depth:
+            self._retire()
+        n = t.numel()
+        buf = next((b for b in self.free if b.numel() >= n and b.dtype == t.dtype), None)
+        if buf is not None:
+            self.free.remove(buf)
+        else:
+            buf = torch.empty(max(n, 1), dtype=t.dtype, pin_memory=True)
+        self.stream.wait_stream(torch.cuda.current_stream(t.device))
+        with torch.cuda.stream(self.stream):
+            buf[:n].copy_(t.reshape(-1), non_blocking=True)
+            t.record_stream(self.stream)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.pending.append((buf, ev, tuple(t.shape)))
+
+    def finish(self) -> List[np.ndarray]:
+        while self.pending:
+            self._retire()
+        return self.out
+
+
+def latent_dataset_name(task: str, model_name: str, cycle_seq_number: int, model_id: str) -> str:
+    """The directory name the reference gives a latent data set (dataloader/latentspace_dataloader.py:21-26)."""
+    if task in ("classification", "classification_ids"):
+        return f"asimow_ls_{task}_{model_name}_cycle_{cycle_seq_number}_{model_id}"
+    if task in ("autoregressive_ids", "autoregressive_ids_classification"):
+        return f"{task}_cycle_{cycle_seq_number}_{model_id}"
+    raise ValueError(f"task {task} not supported")
+
+
+def save_latent_dataset(splits, data_directory_path: str, dataset_name: str) -> str:
+    """Writes (train, val, test) -- each an (x, y) pair of numpy arrays, what `preprocessing` returns (:79-98) -- where and how
+    the reference caches it: <data>/quality_prediction_data/<dataset_name>/dataset.pickle, one pickle.dump of the tuple
+    (dataloader/base_dataloader.py:149,236-246, dataloader/utils.py:38-42), so that the reference's `load_dataset` /
+    `get_data_loader` find a finished data set and skip their own encode loops."""
+    path = os.path.join(data_directory_path, "quality_prediction_data", dataset_name)
+    os.makedirs(path, exist_ok=True)
+    file = os.path.join(path, "dataset.pickle")
+    with open(file, "wb") as f:
+        pickle.dump(tuple((np.asarray(x), np.asarray(y)) for x, y in splits), f)
+    return file
+
+
 class LatentSpaceEncoder:
     """Encode-side of ``LatentSpaceDataLoader`` (reference :16-39 for the constructor fields
     that matter here: the model, ``window_size`` and the device)."""
@@ -100,7 +257,9 @@ class LatentSpaceEncoder:
         #: encode every distinct cycle of a batch once (overlapping windows repeat cycles; see encode_unique).  The ids
         #: are the same whenever the encoder is row-wise deterministic (eval mode; the fused encoder always is).  The
         #: code-usage histogram then counts distinct cycles.
+        #: "dataset": additionally across the batches of one create_latent_space_dataset_* call (CycleIdCache).
         self.dedupe = False
+        self.cycle_cache: Optional[CycleIdCache] = None
 
     # ---- single encode calls (:144-161) -------------------------------------------------
     def _encode(self, x, has_patch_embed: bool):
@@ -153,24 +312,32 @@ class LatentSpaceEncoder:
         """Token ids per window: (n, seq_len, enc_out_len) int64, labels (n,) (zeros when no_labels)."""
         model = self.latent_space_model
         enc_out_len = int(model.enc_out_len)
-        xs, ys = [], []
+        ys = []
         counts = None
+        writer = _AsyncHostWriter(self.device)          # ids leave through pinned buffers on a copy stream
+        cache = CycleIdCache(self.device) if self.dedupe == "dataset" else None
+        self.cycle_cache = cache
+        enc = lambda c: self.get_latent_space_IDs(c, has_patch_embed).view(c.shape[0], -1)
         model.eval()
         with torch.no_grad():
             for item in loader:
                 x, y = (item, None) if no_labels else item
                 b = x.shape[0]
                 cyc = self._cycles(x, seq_len).to(self.device, non_blocking=True)
-                if self.dedupe:
-                    ids = encode_unique(lambda c: self.get_latent_space_IDs(c, has_patch_embed).view(c.shape[0], -1), cyc)
+                model.vector_quantization.code_counts = None
+                if cache is not None:
+                    ids = cache.encode(enc, cyc)
+                elif self.dedupe:
+                    ids = encode_unique(enc, cyc)
                 else:
                     ids = self.get_latent_space_IDs(cyc, has_patch_embed)
                 c = getattr(model.vector_quantization, "code_counts", None)
                 if c is not None:
                     counts = c.clone() if counts is None else counts + c
-                xs.append(ids.view(b, seq_len, -1).cpu().numpy())
+                writer.put(ids.view(b, seq_len, -1))
                 if y is not None:
                     ys.append(np.asarray(y.cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64))
+        xs = writer.finish()
         self.code_counts = counts
         new_x = np.concatenate(xs, axis=0) if xs else np.empty((0, seq_len, enc_out_len), dtype=int)
         new_y = np.zeros(new_x.shape[0]) if no_labels else (np.concatenate(ys, axis=0) if ys else np.empty((0,)))
