@@ -157,6 +157,29 @@ int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const f
                      int64_t n_tokens, int k, int n, unsigned mode, void *stream);
 
 /*
+ * The same layer with THREE taps: the decoder's Conv1d(k = 3, pad = 1) along the positions of a cycle
+ * (model/vq_vae_patch_embedd.py:60-74 ResBlock inside CNNBlock(seperate=False), :142-147), on row-major tokens:
+ *     x[t] = sum_{tap = 0..2} w[:, tap * k_in : (tap + 1) * k_in] a[t + tap - 1]  + bias,   a[.] = 0 outside the token's cycle
+ * (cycles are runs of tokens_per_cycle consecutive tokens; n_tokens a multiple of it, 128 a multiple of it), then the
+ * epilogue of `mode` as in vqb_token_linear.  out_gelu = 0 stores out = bf16(x) (mode 0) / bf16(h) (modes 1, 2) instead
+ * of its GELU -- the last block's output feeds PatchEmbeddingInverse (:19-57), which starts with a (transposed)
+ * convolution, not a GELU.  w: (n, 3 * k_in) bf16 row-major, the three taps side by side (Conv1d weight (n, k_in, 3)
+ * permuted to (n, 3, k_in)); taps = 1 is vqb_token_linear with the out_gelu switch.  A transposed convolution with
+ * kernel = stride = s (PatchEmbeddingInverse.proj[0]) is the one-tap layer with n = s * channels.
+ */
+int vqb_token_conv(int device, const void *a_bf16, const void *w_bf16, const float *bias, float *h, void *out_bf16,
+                   int64_t n_tokens, int k_in, int n, unsigned mode, int taps, int tokens_per_cycle, int out_gelu,
+                   void *stream);
+
+/*
+ * PatchEmbeddingInverse.proj[3], ConvTranspose1d(hidden, 1, kernel = stride = p) (model/vq_vae_patch_embedd.py:24-29):
+ * out[r][j] = sum_c a[r][c] w[j][c] + bias for every row r of a (n_rows, hidden) bf16 activation; w (p, hidden) fp32
+ * (the weight (hidden, 1, p) transposed), out (n_rows, p) fp32.  hidden a multiple of 8, p <= 8.
+ */
+int vqb_token_out_proj(int device, const void *a_bf16, const float *w, float bias, float *out, int64_t n_rows, int hidden,
+                       int p, void *stream);
+
+/*
  * The whole residual-block chain of the patch encoder in one launch (model/vq_vae_patch_embedd.py:60-74 ResBlock,
  * :103-111 CNNBlock with seperate=True; n_layers = 2 * n_resblocks dense layers, the centre taps of the k=3 convs):
  *     for every block b:  h <- h + W[2b+1] gelu(W[2b] gelu(h) + bias[2b]) + bias[2b+1]

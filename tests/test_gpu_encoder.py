@@ -319,3 +319,81 @@ def test_fully_fused_encoder_launch(hidden, n_res, patch, B):
     # on a few elements each, so the bound is the bf16-operand tolerance of the path, not 2^-16
     assert (z_all - z_ref).abs().max().item() <= 0.02 * scale
     assert ((z_all - z_ref).abs().mean() / z_ref.abs().mean()).item() <= 2e-3
+
+
+# ---------------------------------------------------------------------------------------
+# decoder half on the fused layer kernels
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_cycles,tpc", [(1, 16), (8, 16), (9, 16), (300, 16), (50, 8), (7, 32)])
+@pytest.mark.parametrize("K,N", [(256, 256), (512, 512)])
+def test_token_conv_three_taps_matches_conv1d(n_cycles, tpc, K, N):
+    """vqb_token_conv (taps = 3) against torch's own Conv1d(k=3, pad=1) in fp32 on the same bf16-rounded operands: zero
+    padding at BOTH ends of every cycle, tiles that end inside the tensor, modes 0 / 1, with and without the output GELU."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(n_cycles * 31 + tpc + K)
+    T = n_cycles * tpc
+    a = torch.randn(T, K, device=dev, generator=g).to(torch.bfloat16)
+    w3 = (torch.randn(N, K, 3, device=dev, generator=g) * (2.0 / (3 * K)) ** 0.5).to(torch.bfloat16)     # Conv1d weight layout
+    bias = 0.1 * torch.randn(N, device=dev, generator=g)
+    w = w3.permute(0, 2, 1).reshape(N, 3 * K).contiguous()
+    x = a.float().view(n_cycles, tpc, K).permute(0, 2, 1)                                                # (cycles, K, positions)
+    conv = torch.nn.functional.conv1d(x, w3.float(), bias, padding=1).permute(0, 2, 1).reshape(T, N)
+    out = ops.token_conv(a, w, bias, mode=0, taps=3, tokens_per_cycle=tpc)
+    torch.testing.assert_close(out.float(), torch.nn.functional.gelu(conv), rtol=1.0 / 128, atol=2e-3)
+    out_lin = ops.token_conv(a, w, bias, mode=0, taps=3, tokens_per_cycle=tpc, out_gelu=False)
+    torch.testing.assert_close(out_lin.float(), conv, rtol=1.0 / 128, atol=2e-3)
+    h = torch.randn(T, N, device=dev, generator=g)
+    h0 = h.clone()
+    nxt = torch.empty(T, N, dtype=torch.bfloat16, device=dev)
+    ops.token_conv(a, w, bias, h=h, out=nxt, mode=1, taps=3, tokens_per_cycle=tpc, out_gelu=False)
+    torch.testing.assert_close(h, h0 + conv, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(nxt.float(), h0 + conv, rtol=1.0 / 128, atol=2e-3)
+    with pytest.raises(RuntimeError):                      # cycles must tile the 128-token tiles
+        ops.token_conv(a[: 2 * 24].contiguous(), w, bias, mode=0, taps=3, tokens_per_cycle=24)
+
+
+@pytest.mark.parametrize("R,H,P", [(1, 512, 5), (1000, 512, 5), (333, 256, 2), (64, 512, 8)])
+def test_token_out_proj_matches_fp32_reference(R, H, P):
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(R + H + P)
+    a = torch.randn(R, H, device=dev, generator=g).to(torch.bfloat16)
+    w = torch.randn(P, H, device=dev, generator=g) * H ** -0.5
+    out = ops.token_out_proj(a, w, 0.25)
+    torch.testing.assert_close(out, a.float() @ w.t() + 0.25, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("hidden,n_res,batch_norm", [(256, 2, False), (512, 1, True), (256, 3, True)])
+def test_fused_decoder_matches_the_torch_decoder(hidden, n_res, batch_norm):
+    """decoder_mode = "fused_bf16" against the stock PyTorch modules in fp32 on the same weights (eval mode, BatchNorm with
+    non-trivial running statistics): bf16 operands through 2 * n_res + 2 layers -- stated tolerance 2 % of the output's
+    largest magnitude (measured: below 1 %)."""
+    dev = _dev()
+    torch.manual_seed(hidden + n_res)
+    model = vqb200.VQVAEPatch(hidden_dim=hidden, input_dim=2, num_embeddings=64, embedding_dim=32, n_resblocks=n_res,
+                              learning_rate=1e-3, batch_norm=batch_norm).to(dev)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+    model.eval()
+    z_q = 0.5 * torch.randn(37, 16, 32, device=dev)
+    with torch.no_grad():
+        want = model.decode(z_q)
+        model.decoder_mode = "fused_bf16"
+        assert model._fused_decoder_ok(z_q)
+        got = model.decode(z_q)
+        assert got.shape == want.shape == (37, 200, 2)
+        err = (got - want).abs().max().item()
+        assert err <= 0.02 * want.abs().max().item(), (err, want.abs().max().item())
+        # the whole forward with both halves fused: same contract, reconstruction within the same tolerance
+        x = torch.randn(37, 200, 2, device=dev)
+        model.encoder_mode = "torch"
+        loss0, xhat0, ppl0 = model(x)
+        model.decoder_mode = "torch"
+        loss1, xhat1, ppl1 = model(x)
+        assert torch.equal(loss0, loss1) and torch.equal(ppl0, ppl1)
+        assert (xhat0 - xhat1).abs().max().item() <= 0.02 * xhat1.abs().max().item()
+    # training / autograd keep the PyTorch modules
+    model.decoder_mode = "fused_bf16"
+    model.train()
+    assert not model._fused_decoder_ok(z_q)

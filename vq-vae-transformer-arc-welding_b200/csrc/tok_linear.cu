@@ -12,6 +12,11 @@
 //              next block's leading GELU; out may be NULL after the last block)
 //     mode 2:  h   = A W^T + b  (fp32, written);   out = bf16( gelu(h) )   (patch embedding, K zero-padded to 64,
 //              + the first block's leading GELU)
+// Three-tap form (taps = 3; the DECODER's Conv1d(k = 3, pad = 1) along the 16 positions of a cycle,
+// model/vq_vae_patch_embedd.py:60-74,142-147): out[t] = sum_k W_k a[t + k - 1] with zeros beyond the ends of the
+// token's cycle.  Same kernel, K = 3 * K_in: the A operand of K-chunk (tap, c) is the TMA box at token offset tap - 1
+// of a 3-D map (K_in, tokens per cycle, cycles), whose out-of-range positions arrive as zeros -- no im2col copy.
+// out_gelu = 0 writes out = bf16(x) instead of bf16(gelu(x)) (the last block feeds the transposed convolutions).
 // A: (T, K) bf16 row-major activations, W: (N, K) bf16 row-major, fp32 accumulation in TMEM, erf-form GELU
 // evaluated through a fitted tanh argument (gelu_fast below, |error| <= 2.5e-5 + 2.5e-4 |x|, then rounded to bf16).  bf16 operands make this the reduced-precision encoder mode
 // (same operand precision as the reference under its own torch.set_float32_matmul_precision('medium'));
@@ -66,7 +71,7 @@ template <int MODE>
 __global__ void __launch_bounds__(tl::THREADS, 1)
 tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const float *__restrict__ bias, float *__restrict__ h, __nv_bfloat16 *__restrict__ out,
-                  int64_t n_tokens, int K, int N)
+                  int64_t n_tokens, int K, int N, int taps, int cyc_len, int out_gelu)
 {
     using namespace tc;
     using namespace tl;
@@ -120,7 +125,13 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     mbar_wait<32>(bar(EMPTY + s), (uint32_t)(((step / STAGES) & 1) ^ 1));
                     if (elect_one()) {
                         mbar_expect_tx(bar(FULL + s), A_BYTES + B_BYTES);
-                        tma_load_2d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), k * BK, (int)(mt * BM));
+                        if (taps == 1) {
+                            tma_load_2d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), k * BK, (int)(mt * BM));
+                        } else {          // K-chunk (tap, c): the tile's cycles, shifted by tap - 1 positions (zeros outside)
+                            const int kin = n_k / taps, tap = k / kin, c = k - tap * kin;
+                            tma_load_3d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), c * BK, tap - (taps >> 1),
+                                        (int)(mt * (BM / cyc_len)));
+                        }
                         tma_load_2d(sbase + OFF_B + s * B_BYTES, &map_w, bar(FULL + s), k * BK, nt * BN);
                     }
                     __syncwarp();
@@ -234,7 +245,8 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         hv[c] = x0;
                         hv[c + 1] = x1;
                     }
-                    const __nv_bfloat162 pk = __floats2bfloat162_rn(gelu_fast(x0), gelu_fast(x1));
+                    const __nv_bfloat162 pk = out_gelu ? __floats2bfloat162_rn(gelu_fast(x0), gelu_fast(x1))
+                                                       : __floats2bfloat162_rn(x0, x1);
                     packed[c >> 1] = *reinterpret_cast<const uint32_t *>(&pk);
                 }
                 if (MODE != 0) {
@@ -487,16 +499,27 @@ bool make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int cols, i
 bool tok_linear_supported(int K, int N) { return K >= tl::BK && K % tl::BK == 0 && N >= tl::BN && N % tl::BN == 0; }
 
 cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, float *h, void *out, int64_t n_tokens,
-                              int K, int N, int mode, int sm_count, int max_smem, cudaStream_t st)
+                              int K, int N, int mode, int sm_count, int max_smem, cudaStream_t st, int taps, int cyc_len,
+                              int out_gelu)
 {
     using namespace tl;
     const int smem_bytes = mode == 0 ? Plan<0>::SMEM_BYTES : Plan<1>::SMEM_BYTES;
     if (!tok_linear_supported(K, N) || smem_bytes > max_smem || (mode != 0 && !h) || (mode == 0 && !out))
         return cudaErrorNotSupported;
+    // three taps: whole cycles of cyc_len tokens, a 128-token tile holds whole cycles
+    if (taps != 1 && (taps != 3 || cyc_len < 1 || BM % cyc_len != 0 || n_tokens % cyc_len != 0 || cyc_len > 256))
+        return cudaErrorNotSupported;
     if (n_tokens == 0)
         return cudaSuccess;
     CUtensorMap map_a, map_w;
-    if (!make_bf16_map(&map_a, a, n_tokens, K, BM) || !make_bf16_map(&map_w, w, N, K, BN))
+    if (taps == 1) {
+        if (!make_bf16_map(&map_a, a, n_tokens, K, BM))
+            return cudaErrorNotSupported;
+    } else if (!tc::make_tensor_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, n_tokens / cyc_len, cyc_len, K, BM / cyc_len,
+                                       cyc_len, BK, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) {
+        return cudaErrorNotSupported;
+    }
+    if (!make_bf16_map(&map_w, w, N, taps * K, BN))
         return cudaErrorNotSupported;
     const int64_t items = (n_tokens + BM - 1) / BM * (N / BN);
     const int grid = (int)(items < sm_count ? items : sm_count);
@@ -504,7 +527,74 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (err != cudaSuccess)
         return err;
-    kern<<<grid, THREADS, smem_bytes, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, K, N);
+    kern<<<grid, THREADS, smem_bytes, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, taps * K, N, taps, cyc_len,
+                                            out_gelu);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// Last layer of the decoder: ConvTranspose1d(H, 1, kernel = stride = P) (model/vq_vae_patch_embedd.py:24-29,52-56) --
+// every row of a (rows, H) bf16 activation gives P fp32 samples: out[r][j] = sum_c a[r][c] w[j][c] + bias.
+// One warp per row (a row is 2 H bytes, read once), w resident in shared memory, fp32 accumulation.  HBM-bound: 2 H bytes
+// in, 4 P out per row.
+// ---------------------------------------------------------------------------------------
+constexpr int kOutProjMaxP = 8;
+__global__ void __launch_bounds__(256) tok_out_proj_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restrict__ w,
+                                                           float bias, float *__restrict__ out, int64_t n_rows, int H, int P)
+{
+    extern __shared__ float ws[];                       // [P][H]
+    for (int i = threadIdx.x; i < P * H; i += 256)
+        ws[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * 8) {
+        float acc[kOutProjMaxP];
+#pragma unroll
+        for (int j = 0; j < kOutProjMaxP; ++j)
+            acc[j] = 0.0f;
+        for (int c0 = lane * 8; c0 < H; c0 += 256) {    // 16 bytes per lane and step: a warp reads 512 contiguous bytes
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a + r * H + c0));
+            const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+            float x[8];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                x[2 * t] = __uint_as_float(vv[t] << 16);
+                x[2 * t + 1] = __uint_as_float(vv[t] & 0xffff0000u);
+            }
+#pragma unroll
+            for (int j = 0; j < kOutProjMaxP; ++j) {
+                if (j < P) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        acc[j] = fmaf(x[t], ws[j * H + c0 + t], acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kOutProjMaxP; ++j) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        }
+        if (lane == 0) {
+            for (int j = 0; j < P; ++j)
+                out[r * P + j] = acc[j] + bias;
+        }
+    }
+}
+
+bool tok_out_proj_supported(int H, int P) { return H >= 8 && H % 8 == 0 && P >= 1 && P <= kOutProjMaxP && (size_t)P * H * 4 <= 48 * 1024; }
+
+cudaError_t launch_tok_out_proj(const void *a, const float *w, float bias, float *out, int64_t n_rows, int H, int P, int sm_count,
+                                cudaStream_t st)
+{
+    if (!tok_out_proj_supported(H, P))
+        return cudaErrorNotSupported;
+    if (n_rows == 0)
+        return cudaSuccess;
+    const int64_t blocks = (n_rows + 7) / 8;
+    const int grid = (int)(blocks < (int64_t)sm_count * 8 ? blocks : (int64_t)sm_count * 8);
+    tok_out_proj_kernel<<<grid, 256, sizeof(float) * (size_t)P * H, st>>>((const __nv_bfloat16 *)a, w, bias, out, n_rows, H, P);
     return cudaGetLastError();
 }
 

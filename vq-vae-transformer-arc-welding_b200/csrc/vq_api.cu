@@ -283,6 +283,61 @@ int vqb_token_linear(int device, const void *a_bf16, const void *w_bf16, const f
     return VQB_OK;
 }
 
+int vqb_token_conv(int device, const void *a_bf16, const void *w_bf16, const float *bias, float *h, void *out_bf16,
+                   int64_t n_tokens, int k_in, int n, unsigned mode, int taps, int tokens_per_cycle, int out_gelu, void *stream)
+{
+    if (!a_bf16 || !w_bf16 || !bias || n_tokens < 0 || mode > 2u || (mode != 0u && !h) || (mode == 0u && !out_bf16) ||
+        (taps != 1 && taps != 3) || tokens_per_cycle < 1)
+        return VQB_E_ARG;
+    if (!tok_linear_supported(k_in, n) || !aligned(a_bf16, 16) || !aligned(w_bf16, 16) || !aligned(bias, 16) ||
+        (h && !aligned(h, 16)) || (out_bf16 && !aligned(out_bf16, 16)))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_tok_linear(a_bf16, w_bf16, bias, h, out_bf16, n_tokens, k_in, n, (int)mode, info.sm_count,
+                            info.max_smem_per_block, (cudaStream_t)stream, taps, tokens_per_cycle, out_gelu ? 1 : 0);
+    if (err == cudaErrorNotSupported)
+        return VQB_E_UNSUPPORTED;
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_tokens > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
+int vqb_token_out_proj(int device, const void *a_bf16, const float *w, float bias, float *out, int64_t n_rows, int hidden, int p,
+                       void *stream)
+{
+    if (!a_bf16 || !w || !out || n_rows < 0 || hidden <= 0 || p <= 0)
+        return VQB_E_ARG;
+    if (!tok_out_proj_supported(hidden, p) || !aligned(a_bf16, 16) || !aligned(w, 4) || !aligned(out, 4))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_tok_out_proj(a_bf16, w, bias, out, n_rows, hidden, p, info.sm_count, (cudaStream_t)stream);
+    if (err == cudaErrorNotSupported)
+        return VQB_E_UNSUPPORTED;
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_rows > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
 size_t vqb_encoder_chain_scratch_bytes(int device, int hidden)
 {
     vqb_device_info info;

@@ -108,6 +108,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+{   // signed coordinates: parts of the box outside the tensor (e.g. c1 = -1) arrive as zeros
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -256,6 +263,22 @@ inline bool make_tensor_map_2d(CUtensorMap *map, CUtensorMapDataType dtype, int 
     const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, dtype, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, l2,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// (n2, n1, cols) row-major tensor of `elem_bytes`-wide elements under boxes of box2 x box1 x box_cols
+inline bool make_tensor_map_3d(CUtensorMap *map, CUtensorMapDataType dtype, int elem_bytes, const void *base, int64_t n2,
+                               int64_t n1, int64_t cols, int box2, int box1, int box_cols, CUtensorMapSwizzle swizzle,
+                               CUtensorMapL2promotion l2)
+{
+    TensorMapEncodeTiledFn enc = tensor_map_encoder();
+    if (!enc)
+        return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)n1, (cuuint64_t)n2};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * (cuuint64_t)elem_bytes, (cuuint64_t)cols * (cuuint64_t)n1 * (cuuint64_t)elem_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box1, (cuuint32_t)box2};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, dtype, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, l2,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

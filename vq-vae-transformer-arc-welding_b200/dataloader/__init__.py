@@ -1,2 +1,2 @@
-from .latentspace_dataloader import (LatentSpaceEncoder, OnTheFlyTokenizer, bulk_encode_ids, gather_sharded, reduce_counts,  # noqa: F401
-                                     shard_range)
+from .latentspace_dataloader import (CycleIdCache, LatentSpaceEncoder, OnTheFlyTokenizer, bulk_encode_ids,  # noqa: F401
+                                     gather_sharded, latent_dataset_name, reduce_counts, save_latent_dataset, shard_range)

@@ -14,7 +14,8 @@ Encode half (the hot path):
                       the same values as a permuted view of (B, D, T), :83-91)
   * VectorQuantizer : fused CUDA kernel; contiguous rows go straight to the tcgen05 path, any strided view
                       (e.g. the reference encoder's permuted output) is accepted too.
-Decode half (out of the hot-path scope, stock PyTorch modules): :19-57, :142-147.
+Decode half (:19-57, :142-147): stock PyTorch modules by default; `decoder_mode = "fused_bf16"` runs inference on the same
+tcgen05 layer kernels (three-tap convolutions as shifted TMA boxes).
 """
 from __future__ import annotations
 
@@ -302,8 +303,104 @@ class VQVAEPatch(Autoencoder):
             z_e = self.encode(x)
             return self.vector_quantization.encode_indices(z_e).view(x.shape[0], -1)
 
+    # ---- decode half ---------------------------------------
+    #: "torch": stock PyTorch modules (training, fp32-faithful);
+    #: "fused_bf16": inference on the tcgen05 layer kernels -- the 1x1 input convolution, every three-tap convolution
+    #: of the residual blocks and the first transposed convolution as vqb_token_conv launches on row-major tokens
+    #: (bf16 operands, fp32 accumulation, fp32 residual stream, bias / eval-mode BatchNorm / GELU / residual in the
+    #: epilogues), the last transposed convolution as vqb_token_out_proj.  Selected like the encoder's mode.
+    decoder_mode = "torch"
+
+    def decode(self, z_q):
+        """z_q (B, T, D) -> x_hat (B, seq_len, input_dim)   (:164-165)."""
+        if self.decoder_mode == "fused_bf16" and self._fused_decoder_ok(z_q):
+            return self.decode_fused_bf16(z_q)
+        return self.reverse_patch_embed(self.decoder(z_q.permute(0, 2, 1)))
+
+    def _fused_decoder_ok(self, z_q) -> bool:
+        cnn = self.decoder[1]
+        rp = self.reverse_patch_embed.proj
+        hidden = self.decoder[0].out_channels
+        t = z_q.shape[1] if z_q.dim() == 3 else 0
+        return (z_q.is_cuda and z_q.dtype == torch.float32 and not self.training and not torch.is_grad_enabled()
+                and z_q.dim() == 3 and z_q.shape[2] <= 64 and t >= 1 and 128 % t == 0
+                and hidden % 256 == 0 and hidden <= 512 and not cnn.seperate
+                and all(b._centre_tap_ok() and b.kernel_size == 3 for b in cnn.shared_conv)
+                and rp[0].stride == rp[0].kernel_size and rp[3].stride == rp[3].kernel_size and rp[3].kernel_size[0] <= 8)
+
+    def _fused_decoder_weights(self):
+        """Operands of the fused decoder, rebuilt when a parameter or running statistic changes: every convolution as a
+        (out, taps * in) bf16 matrix with eval-mode BatchNorm folded in, biases fp32."""
+        tracked = [t for m in (self.decoder, self.reverse_patch_embed) for t in list(m.parameters()) + list(m.buffers())]
+        key = tuple((t.data_ptr(), t._version) for t in tracked)
+        cache = getattr(self, "_fused_dec_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+
+        def bn_fold(w, b, norm):          # w (out, ...), b (out): y = norm(conv(x)) is again a convolution
+            if isinstance(norm, nn.BatchNorm1d):
+                scale = norm.weight.float() / torch.sqrt(norm.running_var.float() + norm.eps)
+                w = w * scale.view(-1, *([1] * (w.dim() - 1)))
+                b = (b - norm.running_mean.float()) * scale + norm.bias.float()
+            return w, b
+
+        with torch.no_grad():
+            conv0 = self.decoder[0]
+            hidden, d = conv0.out_channels, conv0.in_channels
+            w0 = torch.zeros(hidden, 64, device=conv0.weight.device)
+            w0[:, :d] = conv0.weight[:, :, 0].float()
+            blocks = []
+            for blk in self.decoder[1].shared_conv:
+                pair = []
+                for conv, norm in ((blk.block[1], blk.block[2]), (blk.block[4], blk.block[5])):
+                    w, b = bn_fold(conv.weight.float(), conv.bias.float(), norm)          # (out, in, 3)
+                    pair += [w.permute(0, 2, 1).reshape(hidden, -1).to(torch.bfloat16).contiguous(), b.contiguous()]
+                blocks.append(tuple(pair))
+            rp = self.reverse_patch_embed.proj
+            k0 = rp[0].kernel_size[0]
+            # ConvTranspose1d(H, H, k0, stride k0): y[o, k0 t + j] = sum_c x[c, t] w[c, o, j] + b[o] -- a linear layer
+            # H -> k0 * H on tokens, row (j, o); BatchNorm acts per output channel o
+            wt = rp[0].weight.float().permute(2, 1, 0)                                    # (j, o, c)
+            bt = rp[0].bias.float().expand(k0, -1)
+            if isinstance(rp[1], nn.BatchNorm1d):
+                scale = rp[1].weight.float() / torch.sqrt(rp[1].running_var.float() + rp[1].eps)
+                wt = wt * scale.view(1, -1, 1)
+                bt = (bt - rp[1].running_mean.float()) * scale + rp[1].bias.float()
+            w_up = wt.reshape(k0 * hidden, hidden).to(torch.bfloat16).contiguous()
+            b_up = bt.reshape(-1).contiguous()
+            # ConvTranspose1d(H, 1, k1, stride k1): k1 samples per row
+            w_out = rp[3].weight.float()[:, 0, :].t().contiguous()                        # (k1, H)
+            b_out = float(rp[3].bias.float().item())
+            ops_ = dict(w0=w0.to(torch.bfloat16).contiguous(), b0=conv0.bias.float().contiguous(), blocks=blocks,
+                        w_up=w_up, b_up=b_up, w_out=w_out, b_out=b_out, k0=k0, hidden=hidden, d=d)
+        object.__setattr__(self, "_fused_dec_cache", (key, ops_))
+        return ops_
+
+    def decode_fused_bf16(self, z_q):
+        """Decoder + PatchEmbeddingInverse on the fused layer kernels (:142-147, :19-57): tokens (B*T, H) stay row-major,
+        the residual stream h is fp32, activations between the layers are bf16."""
+        from .. import ops
+        w = self._fused_decoder_weights()
+        b, t, d = z_q.shape
+        n = b * t
+        a0 = torch.zeros(n, 64, dtype=torch.bfloat16, device=z_q.device)
+        a0[:, :d] = z_q.reshape(n, d)
+        h = torch.empty(n, w["hidden"], dtype=torch.float32, device=z_q.device)
+        a = torch.empty(n, w["hidden"], dtype=torch.bfloat16, device=z_q.device)
+        u = torch.empty_like(a)
+        # h = W0 z_q + b0; a = gelu(h)   (Conv1d(D, H, 1), then the first block's leading GELU)
+        ops.token_conv(a0, w["w0"], w["b0"], h=h, out=a, mode=2, taps=1, tokens_per_cycle=1, out_gelu=bool(w["blocks"]))
+        for i, (w1, b1, w2, b2) in enumerate(w["blocks"]):
+            last = i + 1 == len(w["blocks"])
+            ops.token_conv(a, w1, b1, out=u, mode=0, taps=3, tokens_per_cycle=t)                       # u = gelu(conv1(a))
+            ops.token_conv(u, w2, b2, h=h, out=a, mode=1, taps=3, tokens_per_cycle=t, out_gelu=not last)   # h += conv2(u)
+        # first transposed convolution (+ BatchNorm + GELU): H -> k0 * H per token = k0 rows of H
+        up = ops.token_conv(a, w["w_up"], w["b_up"], mode=0, taps=1, tokens_per_cycle=1)
+        x = ops.token_out_proj(up.view(n * w["k0"], w["hidden"]), w["w_out"], w["b_out"])           # (n * k0, k1)
+        return x.view(b, -1, self.reverse_patch_embed.input_dim)
+
     def forward(self, x):
         z_e = self.encode(x)
         embedding_loss, z_q, perplexity, _, _ = self.vector_quantization(z_e)
-        x_hat = self.reverse_patch_embed(self.decoder(z_q.permute(0, 2, 1)))
+        x_hat = self.decode(z_q)
         return embedding_loss, x_hat, perplexity

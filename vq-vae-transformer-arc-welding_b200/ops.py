@@ -412,6 +412,52 @@ def token_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Option
     return out
 
 
+def token_conv(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None, mode: int = 0, taps: int = 3, tokens_per_cycle: int = 16,
+               out_gelu: bool = True) -> Optional[torch.Tensor]:
+    """token_linear with three taps along the positions of a cycle (vqb_token_conv: the decoder's Conv1d(k=3, pad=1),
+    model/vq_vae_patch_embedd.py:60-74,142-147): x[t] = sum_tap w[:, tap*K:(tap+1)*K] a[t + tap - 1] + bias with zeros
+    outside the token's cycle, then the epilogue of `mode`; out_gelu=False stores bf16(x) / bf16(h) without the GELU.
+    a (T, K) bf16, w (N, taps*K) bf16, bias (N,) fp32, h (T, N) fp32, out (T, N) bf16 -- all CUDA, contiguous."""
+    for t, name, dt in ((a, "a", torch.bfloat16), (w, "w", torch.bfloat16), (bias, "bias", torch.float32)):
+        if not t.is_cuda or t.dtype != dt or not t.is_contiguous():
+            raise RuntimeError(f"{name} must be a contiguous CUDA {dt} tensor (no CPU fallback)")
+    t_rows, k = a.shape
+    n = w.shape[0]
+    if w.shape[1] != taps * k or bias.numel() != n:
+        raise RuntimeError("token_conv: shape mismatch")
+    if mode == 0 and out is None:
+        out = torch.empty((t_rows, n), dtype=torch.bfloat16, device=a.device)
+    if mode != 0 and (h is None or h.dtype != torch.float32 or not h.is_contiguous() or tuple(h.shape) != (t_rows, n)):
+        raise RuntimeError("token_conv modes 1 and 2 need a contiguous fp32 h of shape (T, N)")
+    if out is not None and (out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape) != (t_rows, n)):
+        raise RuntimeError("token_conv: out must be a contiguous bf16 (T, N) tensor")
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.vqb_token_conv(a.device.index, a.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                h.data_ptr() if h is not None else None, out.data_ptr() if out is not None else None,
+                                t_rows, k, n, int(mode), int(taps), int(tokens_per_cycle), 1 if out_gelu else 0,
+                                torch.cuda.current_stream(a.device).cuda_stream)
+    _lib.check(rc, "vqb_token_conv")
+    return out
+
+
+def token_out_proj(a: torch.Tensor, w: torch.Tensor, bias: float) -> torch.Tensor:
+    """out[r, j] = sum_c a[r, c] w[j, c] + bias (vqb_token_out_proj: PatchEmbeddingInverse's last ConvTranspose1d,
+    model/vq_vae_patch_embedd.py:24-29).  a (R, H) bf16, w (P, H) fp32 -> (R, P) fp32."""
+    if not a.is_cuda or a.dtype != torch.bfloat16 or not a.is_contiguous() or a.dim() != 2:
+        raise RuntimeError("token_out_proj: a must be a contiguous CUDA bf16 (R, H) tensor (no CPU fallback)")
+    if not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous() or w.dim() != 2 or w.shape[1] != a.shape[1]:
+        raise RuntimeError("token_out_proj: w must be a contiguous CUDA fp32 (P, H) tensor")
+    out = torch.empty((a.shape[0], w.shape[0]), dtype=torch.float32, device=a.device)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.vqb_token_out_proj(a.device.index, a.data_ptr(), w.data_ptr(), float(bias), out.data_ptr(), a.shape[0],
+                                    a.shape[1], w.shape[0], torch.cuda.current_stream(a.device).cuda_stream)
+    _lib.check(rc, "vqb_token_out_proj")
+    return out
+
+
 def token_bias_gelu(h: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """h += bias (in place, fp32 (T, N)); returns bf16(gelu(h)) -- vqb_token_bias_gelu."""
     if not h.is_cuda or h.dtype != torch.float32 or not h.is_contiguous() or h.dim() != 2:
