@@ -351,6 +351,33 @@ def bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier):
     return out
 
 
+def sweep_corners_leg(args, torch, vqb200, dev, n):
+    """A few corners of BASELINE configs[1]'s K x D sweep (tools/sweep.py has the whole grid): the large-codebook and
+    wide-vector shapes run on the tile-stationary kernel (csrc/vq_fwd_tcs.cu)."""
+    from vqb200 import ops
+    rows = []
+    for K, D in ((512, 32), (1024, 32), (4096, 32), (256, 64), (256, 128)):
+        z = 0.1 * torch.randn(n, D, device=dev, generator=torch.Generator(device=dev).manual_seed(1234))
+        w = ((torch.rand(K, D, generator=torch.Generator().manual_seed(0)) * 2 - 1) / K).to(dev)
+        res = {"K": K, "D": D}
+        for name, kw in (("full_ms", {}), ("ids_only_ms", {"want_zq": False, "want_loss": False})):
+            for _ in range(2):
+                ops.forward(z, w, BETA, **kw)
+            reps = 3
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                ops.forward(z, w, BETA, **kw)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            res[name] = e0.elapsed_time(e1) / reps
+        res["hbm_gbs_full"] = n * (8 * D + 8) / res["full_ms"] / 1e6
+        res["algorithmic_tflops_ids_only"] = 2.0 * K * D * n / res["ids_only_ms"] / 1e9
+        rows.append(res)
+        del z
+    return {"N": n, "what": "ms per vqb_forward call (all outputs / ids only), device-timed, 3 calls after 2 warm-ups", "rows": rows}
+
+
 def config1_leg(args, torch, vqb200, dev):
     """BASELINE configs[0]: VQVAEPatch reconstruction forward, batch 256, fp32, eval."""
     model = default_model(torch, vqb200, dev)
@@ -372,6 +399,35 @@ def config1_leg(args, torch, vqb200, dev):
     gpu_ms = e0.elapsed_time(e1) / 5
     out = {"workload": "BASELINE configs[0]: VQVAEPatch.forward (encode + quantise + decode), batch 256, fp32 (TF32 off), eval",
            "gpu_ms": gpu_ms, "gpu_patches_per_s": 256 * 16 / (gpu_ms * 1e-3)}
+    # the same forward with BOTH halves on the hand-written tcgen05 layer kernels (bf16 operands, fp32 accumulation and
+    # residual streams; the quantiser stays exact), at the configuration's batch and at a batch that fills the GPU
+    with torch.no_grad():
+        model.encoder_mode = model.decoder_mode = "fused_bf16"
+        fused = {}
+        for name, xin in (("batch_256", xd), ("batch_8192", torch.randn(8192, 200, 2, device=dev,
+                                                                        generator=torch.Generator(device=dev).manual_seed(1)))):
+            for _ in range(2):
+                _, hat, _ = model(xin)
+            e0.record()
+            for _ in range(5):
+                model(xin)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / 5
+            fused[name] = {"gpu_ms": ms, "gpu_patches_per_s": xin.shape[0] * 16 / (ms * 1e-3)}
+        # decoder precision on IDENTICAL quantised latents (the two encoders differ on ~0.14 % of the ids, which would
+        # dominate a comparison of whole forwards): fused decoder against the fp32 PyTorch modules
+        z_q = model.vector_quantization(model.encode(xd))[1]
+        got = model.decode(z_q)
+        model.decoder_mode = "torch"
+        want = model.decode(z_q)
+        model.decoder_mode = "fused_bf16"
+        fused["decoder_max_abs_dev_vs_fp32"] = float((got - want).abs().max().item())
+        fused["decoder_out_max_abs"] = float(want.abs().max().item())
+        fused["precision"] = "encoder_mode = decoder_mode = 'fused_bf16' (vqb_encoder_chain, vqb_token_conv, vqb_token_out_proj)"
+        fused["decoder_flop_per_token"] = 2 * 32 * 512 + 16 * 2 * 1536 * 512 + 2 * 512 * 2560 + 5 * 2 * 512 * 5
+        model.encoder_mode = model.decoder_mode = "torch"
+    out["fused_bf16"] = fused
     if not args.no_cpu:
         from oracle import vq_oracle as O
         torch.set_float32_matmul_precision("highest")
@@ -591,6 +647,7 @@ def run_ours(args) -> None:
         return
 
     cfg1 = config1_leg(args, torch, vqb200, dev) if not args.no_config1 else None
+    corners = sweep_corners_leg(args, torch, vqb200, dev, n) if (rank == 0 and not args.no_sweep) else None
 
     # ---- index match rate on a sample (outside every timed region): against the C oracle and against the
     # reference's own torch op sequence (CPU), with the mismatches a near-tie explains counted separately ------
@@ -652,7 +709,7 @@ def run_ours(args) -> None:
                                                   "ops, matmul precision 'highest'", "rate": port_match,
                                           "mismatches": expl["mismatch"], "explained_by_fp32_near_tie": expl["explained"],
                                           "near_tie_explained_rate": (expl["explained"] / expl["mismatch"]) if expl["mismatch"] else 1.0}},
-        "bulk_encode": bulk, "config1_forward": cfg1,
+        "bulk_encode": bulk, "config1_forward": cfg1, "sweep_corners": corners,
         "check": {"loss": float(loss.item()), "perplexity": float(ppl.item()), "histogram_total": int(counts.sum().item())},
     }
     _emit(line)
@@ -674,6 +731,7 @@ def main():
     ap.add_argument("--no-bwd", action="store_true")
     ap.add_argument("--no-bulk", action="store_true")
     ap.add_argument("--no-config1", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--bulk-chunk", type=int, default=65536, help="cycles per encode call of the bulk-encode object")
     ap.add_argument("--bulk-chunks", type=int, default=8, help="timed encode calls per GPU")
     args = ap.parse_args()

@@ -174,7 +174,7 @@ int vqb_token_conv(int device, const void *a_bf16, const void *w_bf16, const flo
 /*
  * PatchEmbeddingInverse.proj[3], ConvTranspose1d(hidden, 1, kernel = stride = p) (model/vq_vae_patch_embedd.py:24-29):
  * out[r][j] = sum_c a[r][c] w[j][c] + bias for every row r of a (n_rows, hidden) bf16 activation; w (p, hidden) fp32
- * (the weight (hidden, 1, p) transposed), out (n_rows, p) fp32.  hidden a multiple of 8, p <= 8.
+ * (the weight (hidden, 1, p) transposed), out (n_rows, p) fp32.  hidden 256 or 512, p <= 8.
  */
 int vqb_token_out_proj(int device, const void *a_bf16, const float *w, float bias, float *out, int64_t n_rows, int hidden,
                        int p, void *stream);

@@ -535,55 +535,64 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
 // ---------------------------------------------------------------------------------------
 // Last layer of the decoder: ConvTranspose1d(H, 1, kernel = stride = P) (model/vq_vae_patch_embedd.py:24-29,52-56) --
 // every row of a (rows, H) bf16 activation gives P fp32 samples: out[r][j] = sum_c a[r][c] w[j][c] + bias.
-// One warp per row (a row is 2 H bytes, read once), w resident in shared memory, fp32 accumulation.  HBM-bound: 2 H bytes
-// in, 4 P out per row.
+// One warp per row (a row is 2 H bytes, read once), fp32 accumulation.  HBM-bound: 2 H bytes in, 4 P out per row.
 // ---------------------------------------------------------------------------------------
 constexpr int kOutProjMaxP = 8;
+// NS = H / 256 steps of 8 columns per lane; the lane's P x 8 NS weights live in registers (the first version read them from
+// shared memory with scalar loads: 8.2 ms per 5.2 M rows, LDS-bound; this one is bound by the row reads)
+template <int NS, int P>
 __global__ void __launch_bounds__(256) tok_out_proj_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restrict__ w,
-                                                           float bias, float *__restrict__ out, int64_t n_rows, int H, int P)
+                                                           float bias, float *__restrict__ out, int64_t n_rows)
 {
-    extern __shared__ float ws[];                       // [P][H]
-    for (int i = threadIdx.x; i < P * H; i += 256)
-        ws[i] = w[i];
-    __syncthreads();
+    constexpr int H = NS * 256;
     const int lane = threadIdx.x & 31;
-    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * 8) {
-        float acc[kOutProjMaxP];
+    float wr[NS][P][8];
 #pragma unroll
-        for (int j = 0; j < kOutProjMaxP; ++j)
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                wr[s][j][t] = __ldg(w + j * H + s * 256 + lane * 8 + t);
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * 8) {
+        uint4 v[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s)        // 16 bytes per lane and step: a warp reads 512 contiguous bytes
+            v[s] = __ldcs(reinterpret_cast<const uint4 *>(a + r * H + s * 256 + lane * 8));
+        float acc[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j)
             acc[j] = 0.0f;
-        for (int c0 = lane * 8; c0 < H; c0 += 256) {    // 16 bytes per lane and step: a warp reads 512 contiguous bytes
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a + r * H + c0));
-            const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-            float x[8];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const uint32_t vv[4] = {v[s].x, v[s].y, v[s].z, v[s].w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                x[2 * t] = __uint_as_float(vv[t] << 16);
-                x[2 * t + 1] = __uint_as_float(vv[t] & 0xffff0000u);
-            }
+                const float x0 = __uint_as_float(vv[t] << 16), x1 = __uint_as_float(vv[t] & 0xffff0000u);
 #pragma unroll
-            for (int j = 0; j < kOutProjMaxP; ++j) {
-                if (j < P) {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t)
-                        acc[j] = fmaf(x[t], ws[j * H + c0 + t], acc[j]);
+                for (int j = 0; j < P; ++j) {
+                    acc[j] = fmaf(x0, wr[s][j][2 * t], acc[j]);
+                    acc[j] = fmaf(x1, wr[s][j][2 * t + 1], acc[j]);
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < kOutProjMaxP; ++j) {
+        for (int j = 0; j < P; ++j) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
                 acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
         }
-        if (lane == 0) {
-            for (int j = 0; j < P; ++j)
-                out[r * P + j] = acc[j] + bias;
+        if (lane < P) {
+            float res = acc[0];
+#pragma unroll
+            for (int j = 1; j < P; ++j)
+                res = lane == j ? acc[j] : res;
+            out[r * P + lane] = res + bias;
         }
     }
 }
 
-bool tok_out_proj_supported(int H, int P) { return H >= 8 && H % 8 == 0 && P >= 1 && P <= kOutProjMaxP && (size_t)P * H * 4 <= 48 * 1024; }
+bool tok_out_proj_supported(int H, int P) { return (H == 256 || H == 512) && P >= 1 && P <= kOutProjMaxP; }
 
 cudaError_t launch_tok_out_proj(const void *a, const float *w, float bias, float *out, int64_t n_rows, int H, int P, int sm_count,
                                 cudaStream_t st)
@@ -594,7 +603,17 @@ cudaError_t launch_tok_out_proj(const void *a, const float *w, float bias, float
         return cudaSuccess;
     const int64_t blocks = (n_rows + 7) / 8;
     const int grid = (int)(blocks < (int64_t)sm_count * 8 ? blocks : (int64_t)sm_count * 8);
-    tok_out_proj_kernel<<<grid, 256, sizeof(float) * (size_t)P * H, st>>>((const __nv_bfloat16 *)a, w, bias, out, n_rows, H, P);
+    const __nv_bfloat16 *ab = (const __nv_bfloat16 *)a;
+#define VQB_OUT_PROJ(PV)                                                                                     \
+    case PV:                                                                                                 \
+        if (H == 256) tok_out_proj_kernel<1, PV><<<grid, 256, 0, st>>>(ab, w, bias, out, n_rows);            \
+        else tok_out_proj_kernel<2, PV><<<grid, 256, 0, st>>>(ab, w, bias, out, n_rows);                     \
+        break;
+    switch (P) {
+        VQB_OUT_PROJ(1) VQB_OUT_PROJ(2) VQB_OUT_PROJ(3) VQB_OUT_PROJ(4) VQB_OUT_PROJ(5) VQB_OUT_PROJ(6) VQB_OUT_PROJ(7)
+        VQB_OUT_PROJ(8)
+    }
+#undef VQB_OUT_PROJ
     return cudaGetLastError();
 }
 

@@ -440,7 +440,11 @@ __device__ __forceinline__ void merge_running(unsigned long long *run, int64_t r
 constexpr int kTraceCtas = 4, kTraceTiles = 1024, kTraceEvents = 8;
 // WIDE: 32 < D <= 64 (two pipeline items per tile); a separate instantiation keeps the D <= 32 kernel's hot loops free
 // of the wide-vector code.
-template <bool TRACE, bool WIDE>
+// PAIR: two CTAs of a cluster (one TPC) run every tcgen05.mma together (cta_group::2, M = 256): each CTA converts and
+// filters its own 128-vector tile, but holds only HALF of the codebook operand (codes 128 r .. 128 r + 127 for cluster
+// rank r), so the tensor core of each SM reads 8 KB instead of 12 KB of shared memory per MMA.  Only the leader issues;
+// the peer's converters and epilogue warps arrive on the leader's mbarriers, completions are multicast to both CTAs.
+template <bool TRACE, bool WIDE, bool PAIR>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const __grid_constant__ CUtensorMap map_z,
                  const __grid_constant__ CUtensorMap map_zq, int kp, unsigned long long *trace)
@@ -466,7 +470,14 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     const long long clk_begin = clock64();
     const int64_t n_rows = p.z.n_rows;
     const int64_t n_tiles = (n_rows + TILE_M - 1) / TILE_M;
-    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // PAIR: cluster c of n_cl works on the tile pairs 2 (c + i n_cl), + 1; its CTA of rank r takes the tile 2 (c + i n_cl) + r
+    // (a pair's second tile may lie beyond the tensor: its rows are masked like the rows of a ragged last tile)
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const uint32_t tile_first = PAIR ? 2u * (blockIdx.x >> 1) + crank : blockIdx.x;
+    const uint32_t tile_step = PAIR ? (gridDim.x & ~1u) : gridDim.x;
+    const int64_t n_units = PAIR ? (n_tiles + 1) / 2 : n_tiles, unit0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x,
+                  n_workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
+    const int64_t my_tiles = unit0 < n_units ? (n_units - unit0 + n_workers - 1) / n_workers : 0;
     // wide vectors (32 < D <= 64): every tile is two pipeline items (D-chunks of 32 components), each with its own
     // ring slot and converter pass; their products accumulate in the same TMEM buffer
     constexpr int nd = WIDE ? 2 : 1;
@@ -480,23 +491,39 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             mbar_init(bar(Q_DONE + s), 128);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bar(A_FULL + b), 128);
+            mbar_init(bar(A_FULL + b), PAIR ? 8 : 128);       // PAIR: one arrival per warp, the leader's barriers count both CTAs
             mbar_init(bar(A_EMPTY + b), 1);
-            mbar_init(bar(T_EMPTY + b), 128);
+            mbar_init(bar(T_EMPTY + b), PAIR ? 8 : 128);
         }
         for (int g = 0; g < GROUPS; ++g)
             mbar_init(bar(T_FULL + g), 1);
         fence_barrier_init();
     }
     if (warp == W_SVC + 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     // constant operands: copy the prepared image, build the ones tile, clear the histogram
     for (int i = tid; i < (IMG_EE + 1024) / 16; i += THREADS) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img) + i);
         // image order = smem order for BMAIN | BAUG, then EF32 | EE live after the AAUG tile
         const int off = i * 16;
+        int src = off;
+        if (PAIR && off < IMG_EF32) {
+            // a CTA of a pair holds the operand rows of ITS 128 codes at the start of BMAIN / BAUG
+            if (off < IMG_BAUG) {
+                if (off >= IMG_BAUG / 2) continue;
+                src = off + (int)crank * (IMG_BAUG / 2);
+            } else {
+                if (off - IMG_BAUG >= (IMG_EF32 - IMG_BAUG) / 2) continue;
+                src = off + (int)crank * ((IMG_EF32 - IMG_BAUG) / 2);
+            }
+        }
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img + src));
         const int dst = off < IMG_EF32 ? OFF_BMAIN + off : OFF_EF32 + (off - IMG_EF32);
         *reinterpret_cast<uint4 *>(smem + dst) = v;
     }
@@ -514,7 +541,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         *wl_count_s = 0u;
     fence_proxy_async();          // generic-proxy writes of the operands -> visible to tcgen05/TMA
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();       // the peer's barriers and operands are ready before anything is signalled across
+    else
+        __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -528,10 +558,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         // (idle: the ring is refilled by the store warp the moment it has released a slot)
     } else if (warp == W_SVC + 1) {
         // ================= MMA issuer: the whole warp runs the loop, one elected lane issues (vq_ptx.cuh: elect_one) ====
-        {
+        if (!PAIR || crank == 0) {
             // (Issuing the codebook as two N = kp/2 halves with an early commit was measured: the 14
             // half-width MMAs take ~2x the tensor time of 7 full-width ones, a net loss.)
-            const uint32_t idesc = idesc_bf16(kp);
+            const uint32_t idesc = PAIR ? idesc_bf16_mn(256, KMAX) : idesc_bf16(kp);
             const uint64_t bmain = desc_sw128(sbase + OFF_BMAIN);
             const uint64_t baug = desc_sw32(sbase + OFF_BAUG);
             const uint64_t aaug = desc_sw32(sbase + OFF_AAUG);
@@ -551,7 +581,21 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 tc_fence_after();
                 if (dc == 0 && lane == 0) stamp(i, 3);
                 const bool wide = p.D - 32 * dc > 16;                  // else components 16..31 of this chunk are padding
-                if (elect_one()) {
+                if (PAIR) {
+                    if (elect_one()) {
+                        const uint64_t a = a0 + (uint64_t)(ba * (16384 >> 4));
+                        const uint32_t d = tmem_base + b * KMAX;
+                        umma_bf16_2cta(d, a + 0, bmain + 0, idesc, 0);
+                        if (wide) umma_bf16_2cta(d, a + 2, bmain + 2, idesc, 1);
+                        umma_bf16_2cta(d, a + 0, bmain + 4, idesc, 1);
+                        if (wide) umma_bf16_2cta(d, a + 2, bmain + 6, idesc, 1);
+                        umma_bf16_2cta(d, a + 4, bmain + 0, idesc, 1);
+                        if (wide) umma_bf16_2cta(d, a + 6, bmain + 2, idesc, 1);
+                        umma_commit_2cta(bar(A_EMPTY + ba));
+                        umma_bf16_2cta(d, aaug, baug, idesc, 1);
+                        umma_commit_2cta(bar(T_FULL + g));
+                    }
+                } else if (elect_one()) {
                     const uint64_t a = a0 + (uint64_t)(ba * (16384 >> 4));
                     const uint64_t bm = dc ? bmain1 : bmain;
                     const uint32_t d = tmem_base + b * KMAX;
@@ -584,7 +628,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             auto load_item = [&](int it, int s) {
                 const int i = nd == 2 ? it >> 1 : it;
                 const int dc = nd == 2 ? (it & 1) : 0;
-                const uint32_t tile = blockIdx.x + (uint32_t)i * gridDim.x;
+                const uint32_t tile = tile_first + (uint32_t)i * tile_step;
                 if (elect_one()) {
                     mbar_expect_tx(bar(Z_FULL + s), TILE_M * D * 4);
                     tma_load_2d(sbase + OFF_ZRING + s * 16384, &map_z, bar(Z_FULL + s), dc * D, (int)(tile * TILE_M));
@@ -601,7 +645,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 if (p.zq) {
                     const int i = nd == 2 ? it >> 1 : it;
                     const int dc = nd == 2 ? (it & 1) : 0;
-                    const uint32_t tile = blockIdx.x + (uint32_t)i * gridDim.x;
+                    const uint32_t tile = tile_first + (uint32_t)i * tile_step;
                     if (elect_one()) {
                         tma_store_2d(&map_zq, sbase + OFF_ZRING + s * 16384, dc * D, (int)(tile * TILE_M));
                         tma_store_commit();
@@ -674,7 +718,13 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 reinterpret_cast<float *>(smem + OFF_ZZ + s * 512)[r] = t.x + t.y;
             }
             fence_proxy_async();
-            mbar_arrive(bar(A_FULL + b));
+            if (PAIR) {                                       // the leader issues for both tiles: one arrival per warp
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive_cluster(bar(A_FULL + b), 0);
+            } else {
+                mbar_arrive(bar(A_FULL + b));
+            }
             if (r == 0 && nd == 1) stamp(i, 2);
             if (++s == STAGES) {
                 s = 0;
@@ -699,6 +749,16 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         unsigned long long n_slow_total = 0;
         uint2 *wl = reinterpret_cast<uint2 *>(const_cast<unsigned char *>(img) + IMG_WL) + (size_t)blockIdx.x * WL_CAP;
 
+        // accumulator drained (this thread's share): in a pair the leader's barrier counts both CTAs' epilogue threads
+        auto t_empty_arrive = [&](int b) {
+            if (PAIR) {
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive_cluster(bar(T_EMPTY + b), 0);
+            } else {
+                mbar_arrive(bar(T_EMPTY + b));
+            }
+        };
         float sqf = 0.0f;
         const int n_my = (int)my_tiles;
         constexpr int s_step = (GROUPS * nd) % STAGES;
@@ -708,7 +768,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         for (int i = g; i < n_my; i += GROUPS, ph ^= 1u, s = s + s_step >= STAGES ? s + s_step - STAGES : s + s_step) {
             const int s1 = s + 1 == STAGES ? 0 : s + 1;       // second half of a wide tile
             const int b = i & 1;
-            const uint32_t tile = blockIdx.x + (uint32_t)i * gridDim.x;
+            const uint32_t tile = tile_first + (uint32_t)i * tile_step;
             const uint32_t row = tile * TILE_M + r;
             const bool ok = row < (uint32_t)n_rows;
 
@@ -748,7 +808,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                             tmem_ld32(taddr + (sl + 1) * 32, vb);
                         } else {
                             tc_fence_before();
-                            mbar_arrive(bar(T_EMPTY + b));
+                            t_empty_arrive(b);
                         }
                         reduce_slab(va, sl);
                         if (sl + 1 < n_slab) {
@@ -757,7 +817,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                                 tmem_ld32(taddr + (sl + 2) * 32, va);
                             } else {
                                 tc_fence_before();
-                                mbar_arrive(bar(T_EMPTY + b));
+                                t_empty_arrive(b);
                             }
                             reduce_slab(vb, sl + 1);
                         }
@@ -775,7 +835,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 }
             }
             tc_fence_before();
-            mbar_arrive(bar(T_EMPTY + b));        // accumulator drained: the next MMA may overwrite it
+            t_empty_arrive(b);        // accumulator drained: the next MMA may overwrite it
 #endif
             if (TRACE && lane == 0 && blockIdx.x < kTraceCtas && i < kTraceTiles)    // the last of the group's four warps
                 atomicMax(&trace[((size_t)blockIdx.x * kTraceTiles + i) * kTraceEvents + 5], (unsigned long long)clock64());
@@ -911,10 +971,17 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
 
     // ---- teardown ----------------------------------------------------------------------
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();       // neither CTA of a pair may leave (or free tensor memory) while the other still signals it
+    else
+        __syncthreads();
     tc_fence_after();
-    if (warp == W_SVC + 2)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (warp == W_SVC + 2) {
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
     if (!WIDE && p.chunk_mode == 0) {
         // ---- the CTA's own queue of uncertified vectors, decided here by all its warps (one warp per vector, one lane
         // per candidate code, exact oracle-order distances; codebook rows from shared memory, the vector from global
@@ -1262,6 +1329,12 @@ cudaError_t launch_tc_finish_ids(const FwdParams &p, int sm_count, int *n_ctas, 
 
 cudaError_t launch_fwd_tcs(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas, int *n_launches,
                            cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end, bool image_ready);
+// CTA pairs are an A/B switch while they are being measured: VQB_PAIR=1 in the environment
+static bool pair_mode_requested()
+{
+    static const bool v = [] { const char *e = getenv("VQB_PAIR"); return e && e[0] == '1'; }();
+    return v;
+}
 static bool wide_tcs_requested()
 {
     static const bool v = [] { const char *e = getenv("VQB_WIDE_TCS"); return e && e[0] == '1'; }();
@@ -1305,21 +1378,45 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
             return err;
     }
     const bool wide = p.D > tc::D;
-    auto kern = wide ? vq_fwd_tc_kernel<false, true> : g_trace_buf ? vq_fwd_tc_kernel<true, false> : vq_fwd_tc_kernel<false, false>;
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
-    if (err != cudaSuccess)
-        return err;
     const int64_t tiles = (p.z.n_rows + TILE_M - 1) / TILE_M;
     int grid = (int)(tiles < sm_count ? tiles : sm_count);
     if (grid < 1)
         grid = 1;
     if (grid > WL_CTAS)
         grid = WL_CTAS;
+    // CTA pairs (cta_group::2) for the plain pass over more than 128 codes: an even grid of 2-CTA clusters
+    const bool pair = !wide && p.chunk_mode == 0 && p.K > 128 && grid >= 2 && pair_mode_requested();
+    if (pair)
+        grid &= ~1;
+    auto kern = wide ? vq_fwd_tc_kernel<false, true, false>
+                     : g_trace_buf ? (pair ? vq_fwd_tc_kernel<true, false, true> : vq_fwd_tc_kernel<true, false, false>)
+                                   : pair ? vq_fwd_tc_kernel<false, false, true> : vq_fwd_tc_kernel<false, false, false>;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+    if (err != cudaSuccess)
+        return err;
     *n_ctas = grid * (1 + FIX_SPLIT);    // partials [0, grid): main kernel, then one per fix-up CTA
     if (ev_begin)
         cudaEventRecord(ev_begin, st);
-    kern<<<grid, THREADS, SMEM_ALLOC, st>>>(p, img, map_z, map_zq, kp, wide ? nullptr : g_trace_buf);
-    err = cudaGetLastError();
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = SMEM_ALLOC;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const unsigned char *img_c = img;
+        unsigned long long *trace_buf = g_trace_buf;
+        err = cudaLaunchKernelEx(&cfg, kern, p, img_c, map_z, map_zq, kp, trace_buf);
+    } else {
+        kern<<<grid, THREADS, SMEM_ALLOC, st>>>(p, img, map_z, map_zq, kp, wide ? nullptr : g_trace_buf);
+        err = cudaGetLastError();
+    }
     if (err != cudaSuccess)
         return err;
     if (wide || p.chunk_mode != 0) {   // (the plain D <= 32 pass decides its queued vectors itself, see the kernel's tail)

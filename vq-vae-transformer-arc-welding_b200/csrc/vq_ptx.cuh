@@ -138,6 +138,51 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the SMs of one TPC run ONE tcgen05.mma of M = 256: each supplies
+// its own 128 rows of A and HALF of the B operand from its own shared memory (same offsets in both), and receives its own
+// 128 accumulator rows in its own TMEM.  Only the leader (cluster rank 0) issues; completion is multicast to both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster (works for the own CTA too).
+// Default semantics (.release at CTA scope), as CUTLASS's ClusterBarrier::arrive does: what the waiter consumes are
+// shared-memory operands of the ARRIVING CTA's own SM (ordered by fence.proxy.async) and tensor-memory reads ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync.  (A .release.cluster arrive was measured first: ~1000 clocks per
+// arrival, it drains the thread's memory operations at cluster scope.)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t cta)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar)
+{   // arrives on the barrier at this offset in BOTH CTAs of the pair once all MMAs issued so far have completed
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+// kind::f16, A = B = BF16, D = F32, both K-major, M = m (256 for a CTA pair), N = n
+__host__ __device__ inline uint32_t idesc_bf16_mn(int m, int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(

@@ -324,7 +324,7 @@ class VQVAEPatch(Autoencoder):
         t = z_q.shape[1] if z_q.dim() == 3 else 0
         return (z_q.is_cuda and z_q.dtype == torch.float32 and not self.training and not torch.is_grad_enabled()
                 and z_q.dim() == 3 and z_q.shape[2] <= 64 and t >= 1 and 128 % t == 0
-                and hidden % 256 == 0 and hidden <= 512 and not cnn.seperate
+                and hidden in (256, 512) and not cnn.seperate
                 and all(b._centre_tap_ok() and b.kernel_size == 3 for b in cnn.shared_conv)
                 and rp[0].stride == rp[0].kernel_size and rp[3].stride == rp[3].kernel_size and rp[3].kernel_size[0] <= 8)
 
