@@ -193,7 +193,11 @@ class VQVAEPatch(Autoencoder):
     def encode(self, x):
         """x (B, seq_len, input_dim) -> z_e (B, T, D)."""
         if self.encoder_mode == "fused_bf16" and self._fused_ok(x):
-            return self.encode_fused_bf16(x)
+            torch.cuda.nvtx.range_push("vqb200.encode_fused_bf16")
+            try:
+                return self.encode_fused_bf16(x)
+            finally:
+                torch.cuda.nvtx.range_pop()
         return self.encoder(self.patch_embed(x))
 
     def _fused_ok(self, x) -> bool:
@@ -314,7 +318,11 @@ class VQVAEPatch(Autoencoder):
     def decode(self, z_q):
         """z_q (B, T, D) -> x_hat (B, seq_len, input_dim)   (:164-165)."""
         if self.decoder_mode == "fused_bf16" and self._fused_decoder_ok(z_q):
-            return self.decode_fused_bf16(z_q)
+            torch.cuda.nvtx.range_push("vqb200.decode_fused_bf16")
+            try:
+                return self.decode_fused_bf16(z_q)
+            finally:
+                torch.cuda.nvtx.range_pop()
         return self.reverse_patch_embed(self.decoder(z_q.permute(0, 2, 1)))
 
     def _fused_decoder_ok(self, z_q) -> bool:
