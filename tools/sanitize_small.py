@@ -66,5 +66,25 @@ conv = conv.to(dev)
 hh, act = ops.patch_embed(x, conv.weight, conv.bias, 25)
 assert torch.allclose(hh, r, rtol=1e-4, atol=1e-5)
 print("patch_embed ok")
+# tile-stationary kernel: large codebook / wide vectors against the exact FMA kernel
+for K_, D_ in ((700, 32), (300, 128)):
+    zz_ = 0.1 * torch.randn(128 * 3 + 5, D_, device=dev); ww_ = 0.1 * torch.randn(K_, D_, device=dev)
+    a, b = ops.forward(zz_, ww_, 0.25, path="fma"), ops.forward(zz_, ww_, 0.25, path="tc")
+    assert torch.equal(a[3], b[3]) and torch.equal(a[1], b[1]) and torch.equal(a[4], b[4])
+print("forward tile-stationary ok")
+# decoder: three-tap layer against Conv1d, then the whole fused decoder against the PyTorch modules
+a3 = torch.randn(5 * 16, 256, device=dev).to(torch.bfloat16)
+w3 = (torch.randn(256, 256, 3, device=dev) * 0.04).to(torch.bfloat16)
+b3 = 0.1 * torch.randn(256, device=dev)
+got = ops.token_conv(a3, w3.permute(0, 2, 1).reshape(256, 768).contiguous(), b3, mode=0, taps=3, tokens_per_cycle=16, out_gelu=False)
+want = torch.nn.functional.conv1d(a3.float().view(5, 16, 256).permute(0, 2, 1), w3.float(), b3, padding=1).permute(0, 2, 1).reshape(80, 256)
+assert torch.allclose(got.float(), want, rtol=1.0 / 128, atol=2e-3)
+with torch.no_grad():
+    zq_ = 0.3 * torch.randn(19, 16, 32, device=dev)
+    ref_hat = model.decode(zq_)
+    model.decoder_mode = "fused_bf16"
+    hat = model.decode(zq_)
+assert (hat - ref_hat).abs().max().item() <= 0.02 * ref_hat.abs().max().item()
+print("token_conv / fused decoder ok")
 torch.cuda.synchronize()
 print("all ok")
