@@ -92,6 +92,7 @@ constexpr int OFF_ZZ = OFF_HIST + 1024;                   // STAGES x 512    ||z
 constexpr int OFF_BARS = OFF_ZZ + STAGES * 512;           // 512             mbarriers + tmem base
 constexpr int SMEM_BYTES = OFF_BARS + 512;
 constexpr int SMEM_ALLOC = SMEM_BYTES;
+constexpr int SMEM_ALLOC_TF32 = SMEM_BYTES + (STAGES + 2) * TILE_M * 8 + 64;   // + the refiner lists (vq_fwd_tc_kernel, TF32)
 
 // image of the constant operands prepared once per call in global scratch
 constexpr int IMG_BMAIN = 0;
@@ -125,8 +126,10 @@ __device__ __forceinline__ int ef32_off(int k, int c) { return k * 128 + ((c ^ (
 // ---------------------------------------------------------------------------------------
 // prep: one thread per (padded) code builds the constant operand image in global scratch
 // ---------------------------------------------------------------------------------------
+// tf32: the operand image of the TF32 variant of the kernel (same regions, same sizes): BMAIN row k = -2 * tf32(E_k) as
+// 32 fp32 words, BAUG row k = ee_k as an exact three-way tf32 split (8 fp32 words)
 __global__ void vq_tc_prep_kernel(const float *__restrict__ E, const float *__restrict__ ee, int K, int d, int kp,
-                                  unsigned char *__restrict__ img)
+                                  unsigned char *__restrict__ img, int tf32)
 {
     using namespace tc;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,6 +146,14 @@ __global__ void vq_tc_prep_kernel(const float *__restrict__ E, const float *__re
         // main B operand: row k = [-2*E1 (32 bf16) | -2*E2 (32 bf16)], SW128; the second D-chunk of a wide
         // codebook (d > 32) takes the place of the fp32 copy, which wide codebooks read from global memory
         unsigned char *bm = img + (dc == 0 ? IMG_BMAIN : IMG_EF32);
+        if (tf32) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4 *>(bm + sw128(k, c)) =
+                    make_float4(-2.0f * tc::round_tf32(e[4 * c]), -2.0f * tc::round_tf32(e[4 * c + 1]),
+                                -2.0f * tc::round_tf32(e[4 * c + 2]), -2.0f * tc::round_tf32(e[4 * c + 3]));
+            continue;
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             __nv_bfloat16 out[8];
@@ -164,7 +175,12 @@ __global__ void vq_tc_prep_kernel(const float *__restrict__ E, const float *__re
     const float r1 = eef - __bfloat162float(a1);
     const __nv_bfloat16 a2 = __float2bfloat16_rn(r1);
     const __nv_bfloat16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
-    {
+    if (tf32) {
+        const float t1 = tc::round_tf32(eef), t2 = tc::round_tf32(eef - t1), t3 = tc::round_tf32((eef - t1) - t2);
+        const int sw = (k >> 2) & 1;   // SW32: 16-byte chunk index ^= bit 7 of the byte offset
+        *reinterpret_cast<float4 *>(img + IMG_BAUG + k * 32 + ((0 ^ sw) << 4)) = make_float4(t1, t2, t3, 0.0f);
+        *reinterpret_cast<float4 *>(img + IMG_BAUG + k * 32 + ((1 ^ sw) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
         __nv_bfloat16 out[8] = {a1, a2, a3, __float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f),
                                 __float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f)};
         const int sw = (k >> 2) & 1;   // SW32: 16-byte chunk index ^= bit 7 of the byte offset
@@ -444,12 +460,21 @@ constexpr int kTraceCtas = 4, kTraceTiles = 1024, kTraceEvents = 8;
 // filters its own 128-vector tile, but holds only HALF of the codebook operand (codes 128 r .. 128 r + 127 for cluster
 // rank r), so the tensor core of each SM reads 8 KB instead of 12 KB of shared memory per MMA.  Only the leader issues;
 // the peer's converters and epilogue warps arrive on the leader's mbarriers, completions are multicast to both CTAs.
-template <bool TRACE, bool WIDE, bool PAIR>
+// TF32 (experiment, VQB_TF32=1): ONE tf32 product straight off the TMA-written fp32 tile instead of three bf16 products
+// of a converted tile -- 4 MMAs of K = 8 + the norm slice = 5 tensor-pipe slots per tile instead of 7, and no converter
+// warps at all.  The price is a filter radius ~32x larger (the tensor core uses 11 significant bits of z and of E), i.e.
+// ~8 % of the vectors instead of ~0.25 % leave the filter uncertified; up to four candidate codes are then decided by
+// the vector's own thread right away (oracle-order distances against the fp32 codebook in shared memory), larger
+// candidate sets take the queue as before.  The decision stays the oracle's in every case.
+template <bool TRACE, bool WIDE, bool PAIR, bool TF32>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const __grid_constant__ CUtensorMap map_z,
                  const __grid_constant__ CUtensorMap map_zq, int kp, unsigned long long *trace)
 {
     using namespace tc;
+    // ring depth: the TF32 variant has no bf16 operand ring, its 32 KB hold two more fp32 slots (the refiner warps hold a
+    // slot ~2000 clocks longer than the epilogue alone)
+    constexpr int NST = TF32 ? STAGES + 2 : STAGES;
     auto stamp = [&](int i, int ev) {
         if (TRACE && blockIdx.x < kTraceCtas && i < kTraceTiles)
             trace[((size_t)blockIdx.x * kTraceTiles + i) * kTraceEvents + ev] = (unsigned long long)clock64();
@@ -459,8 +484,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     if ((sbase & 1023u) != 0)
         __trap();                  // SW128 operands and TMA boxes need a 1024-byte aligned base
     // barrier indices
-    enum { Z_FULL = 0, Q_DONE = Z_FULL + STAGES, A_FULL = Q_DONE + STAGES,
-           A_EMPTY = A_FULL + 2, T_FULL = A_EMPTY + 2, T_EMPTY = T_FULL + GROUPS, N_BARS = T_EMPTY + 2 };
+    enum { Z_FULL = 0, Q_DONE = Z_FULL + NST, A_FULL = Q_DONE + NST,
+           A_EMPTY = A_FULL + 2, T_FULL = A_EMPTY + 2, T_EMPTY = T_FULL + GROUPS, R_FULL = T_EMPTY + 2,
+           N_BARS = R_FULL + NST };
+    // R_FULL (TF32): the tile's list of uncertified rows is complete -- the refiner warps may take it
     // T_FULL is per epilogue GROUP (a waiter must see every phase of its barrier), T_EMPTY per TMEM buffer
     static_assert(8 * N_BARS + 8 <= 512, "barrier area");
     auto bar = [&](int i) { return sbase + OFF_BARS + 8 * i; };
@@ -486,9 +513,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
 
     // ---- one-time setup -----------------------------------------------------------------
     if (warp == W_SVC && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(bar(Z_FULL + s), 1);
-            mbar_init(bar(Q_DONE + s), 128);
+            mbar_init(bar(Q_DONE + s), TF32 ? 160 : 128);       // TF32: + the lanes of the tile's refiner warp
+            mbar_init(bar(R_FULL + s), 128);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar(A_FULL + b), PAIR ? 8 : 128);       // PAIR: one arrival per warp, the leader's barriers count both CTAs
@@ -531,7 +559,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
         __nv_bfloat16 out[8] = {one, one, one, zero, zero, zero, zero, zero};
         const int sw = (tid >> 2) & 1;
-        *reinterpret_cast<uint4 *>(smem + OFF_AAUG + tid * 32 + ((0 ^ sw) << 4)) = *reinterpret_cast<uint4 *>(out);
+        if (TF32)       // K = 8 tf32 per row: [1, 1, 1, 0 | 0, 0, 0, 0]
+            *reinterpret_cast<float4 *>(smem + OFF_AAUG + tid * 32 + ((0 ^ sw) << 4)) = make_float4(1.f, 1.f, 1.f, 0.f);
+        else
+            *reinterpret_cast<uint4 *>(smem + OFF_AAUG + tid * 32 + ((0 ^ sw) << 4)) = *reinterpret_cast<uint4 *>(out);
         *reinterpret_cast<uint4 *>(smem + OFF_AAUG + tid * 32 + ((1 ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
     }
     if (tid < KMAX)
@@ -539,6 +570,11 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
     unsigned *wl_count_s = reinterpret_cast<unsigned *>(smem + OFF_BARS + 8 * N_BARS + 4);
     if (tid == 0)
         *wl_count_s = 0u;
+    // TF32: per ring slot, the rows the filter left uncertified with at most four candidates (row in tile, masks)
+    uint2 *rlist = reinterpret_cast<uint2 *>(smem + SMEM_BYTES);                          // [NST][TILE_M]
+    unsigned *rcnt = reinterpret_cast<unsigned *>(smem + SMEM_BYTES + NST * TILE_M * 8);  // [NST]
+    if (TF32 && tid < NST)
+        rcnt[tid] = 0u;
     fence_proxy_async();          // generic-proxy writes of the operands -> visible to tcgen05/TMA
     tc_fence_before();
     if (PAIR)
@@ -558,7 +594,41 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         // (idle: the ring is refilled by the store warp the moment it has released a slot)
     } else if (warp == W_SVC + 1) {
         // ================= MMA issuer: the whole warp runs the loop, one elected lane issues (vq_ptx.cuh: elect_one) ====
-        if (!PAIR || crank == 0) {
+        if (TF32) {
+            // the ring slot the TMA wrote IS the A operand (fp32 words, SW128 K-major): no conversion, no operand ring
+            const uint32_t idesc = idesc_tf32(kp);
+            const uint64_t bmain = desc_sw128(sbase + OFF_BMAIN);
+            const uint64_t baug = desc_sw32(sbase + OFF_BAUG);
+            const uint64_t aaug = desc_sw32(sbase + OFF_AAUG);
+            const uint64_t z0 = desc_sw128(sbase + OFF_ZRING);
+            const int n_items = (int)my_items;
+            const int n_ks = (p.D + 7) >> 3;                         // K-slices of 8 components that hold data
+            int g = 0, s = 0;
+            uint32_t zph = 0;
+            for (int i = 0; i < n_items; ++i) {
+                const int b = i & 1;
+                mbar_wait<32>(bar(Z_FULL + s), zph);
+                mbar_wait<32>(bar(T_EMPTY + b), (uint32_t)(((i >> 1) & 1) ^ 1));
+                tc_fence_after();
+                if (lane == 0) stamp(i, 3);
+                if (elect_one()) {
+                    const uint64_t a = z0 + (uint64_t)(s * (16384 >> 4));
+                    const uint32_t d = tmem_base + b * KMAX;
+                    umma_tf32(d, a + 0, bmain + 0, idesc, 0);
+                    if (n_ks > 1) umma_tf32(d, a + 2, bmain + 2, idesc, 1);
+                    if (n_ks > 2) umma_tf32(d, a + 4, bmain + 4, idesc, 1);
+                    if (n_ks > 3) umma_tf32(d, a + 6, bmain + 6, idesc, 1);
+                    umma_tf32(d, aaug, baug, idesc, 1);                // + ee_k
+                    umma_commit(bar(T_FULL + g));
+                }
+                __syncwarp();
+                g = g + 1 == GROUPS ? 0 : g + 1;
+                if (++s == NST) {
+                    s = 0;
+                    zph ^= 1u;
+                }
+            }
+        } else if (!PAIR || crank == 0) {
             // (Issuing the codebook as two N = kp/2 halves with an early commit was measured: the 14
             // half-width MMAs take ~2x the tensor time of 7 full-width ones, a net loss.)
             const uint32_t idesc = PAIR ? idesc_bf16_mn(256, KMAX) : idesc_bf16(kp);
@@ -636,10 +706,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 __syncwarp();
                 if (dc == 0 && lane == 0) stamp(i, 0);
             };
-            for (int it = 0; it < n_items && it < STAGES; ++it)
+            for (int it = 0; it < n_items && it < NST; ++it)
                 load_item(it, it);
             int s = 0;
-            uint32_t qph = 0;                                            // parity of Q_DONE[s]: (it / STAGES) & 1
+            uint32_t qph = 0;                                            // parity of Q_DONE[s]: (it / NST) & 1
             for (int it = 0; it < n_items; ++it) {
                 mbar_wait<64>(bar(Q_DONE + s), qph);
                 if (p.zq) {
@@ -654,9 +724,9 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                     __syncwarp();
                 }
                 if ((nd == 1 || (it & 1)) && lane == 0) stamp(nd == 2 ? it >> 1 : it, 7);
-                if (it + STAGES < n_items)
-                    load_item(it + STAGES, s);
-                if (++s == STAGES) {
+                if (it + NST < n_items)
+                    load_item(it + NST, s);
+                if (++s == NST) {
                     s = 0;
                     qph ^= 1u;
                 }
@@ -667,12 +737,135 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         }
     } else if (warp >= W_CONV && warp < W_CONV + 4) {
         // ================= converters: fp32 -> bf16 hi/lo, thread = row =================
-        reg_dec<56>();
+        if (TF32)
+            reg_dec<80>();
+        else
+            reg_dec<56>();
+        if (TF32) {
+            // ================= refiner warps (TF32): warp w decides the uncertified rows of the tiles w, w + 4, ... ======
+            // One lane per listed row: the row's oracle-order ||z||^2, the oracle-order distances of its (at most four)
+            // candidate codes side by side (independent fmaf chains), lowest index among the smallest; then the row's
+            // outputs exactly as the epilogue writes them -- z_q in place in the ring slot, idx, histogram, residual.
+            const int w = warp - W_CONV;
+            const unsigned char *ef32 = smem + OFF_EF32;
+            const float *ees = reinterpret_cast<const float *>(smem + OFF_EE);
+            unsigned *hist = reinterpret_cast<unsigned *>(smem + OFF_HIST);
+            const int n_my = (int)my_tiles;
+            float sqf = 0.0f;
+            for (int i = w; i < n_my; i += 4) {
+                const int s = i % NST;
+                mbar_wait<64>(bar(R_FULL + s), (uint32_t)((i / NST) & 1));
+                if (lane == 0) stamp(i, 1);
+                const unsigned cnt = rcnt[s];
+                const uint32_t tile = tile_first + (uint32_t)i * tile_step;
+                unsigned char *zt = smem + OFF_ZRING + s * 16384;
+                // sixteen rows per pass, TWO LANES PER ROW: lane 2 j + t evaluates candidates 2 t and 2 t + 1 of row j (two fmaf
+                // chains side by side), the pair picks the lowest index among the smallest, then writes chunks 4 t .. 4 t + 3 of
+                // the row's z_q.  (One lane per row: a warp needs ~3500 clocks per pass whatever the number of active lanes --
+                // dependent chains -- and four warps could not keep up with ~10 rows per tile.)
+                const int t = lane & 1;
+                for (unsigned base = 0; base < cnt; base += 16) {
+                    const bool act = base + (lane >> 1) < cnt;
+                    const uint2 ent = act ? rlist[s * TILE_M + base + (lane >> 1)] : make_uint2(0u, 0u);
+                    const int rr = (int)ent.x, xr = (rr & 7) << 4;
+                    const unsigned ma = ent.y & 0xffffu, mb = ent.y >> 16;
+                    unsigned char *zrow = zt + rr * 128;
+                    float zreg[D];
+                    float zz = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ xr));
+                        zreg[4 * c] = v.x; zreg[4 * c + 1] = v.y; zreg[4 * c + 2] = v.z; zreg[4 * c + 3] = v.w;
+                        zz = fmaf(v.x, v.x, zz); zz = fmaf(v.y, v.y, zz); zz = fmaf(v.z, v.z, zz); zz = fmaf(v.w, v.w, zz);
+                    }
+                    // candidate u = (A-group u / nb, B-group u % nb), u = 0..3 in ascending code order; this lane: 2 t, 2 t + 1
+                    const int nb = __popc(mb), ncand = act ? __popc(ma) * nb : 0;
+                    int ga[4], gb[4];
+                    {
+                        unsigned ra = ma, rb = mb;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            ga[u] = ra ? __ffs(ra) - 1 : 0; ra &= ra - 1u;
+                            gb[u] = rb ? __ffs(rb) - 1 : 0; rb &= rb - 1u;
+                        }
+                    }
+                    int kc[2];
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const int u = 2 * t + v;
+                        const int ia = nb == 1 ? u : (nb == 2 ? u >> 1 : (nb == 3 ? (u == 3) : 0));
+                        const int ib = nb == 1 ? 0 : (nb == 2 ? u & 1 : (nb == 3 ? (u == 3 ? 0 : u) : u));
+                        const int a = ia == 0 ? ga[0] : (ia == 1 ? ga[1] : (ia == 2 ? ga[2] : ga[3]));
+                        const int b = ib == 0 ? gb[0] : (ib == 1 ? gb[1] : (ib == 2 ? gb[2] : gb[3]));
+                        const int k = (a << 4) | b;
+                        kc[v] = (u < ncand && k < K) ? k : -1;
+                    }
+                    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 e0 = *reinterpret_cast<const float4 *>(ef32 + ef32_off(kc[0] < 0 ? 0 : kc[0], c));
+                        const float4 e1 = *reinterpret_cast<const float4 *>(ef32 + ef32_off(kc[1] < 0 ? 0 : kc[1], c));
+                        acc0 = fmaf(zreg[4 * c], e0.x, acc0); acc1 = fmaf(zreg[4 * c], e1.x, acc1);
+                        acc0 = fmaf(zreg[4 * c + 1], e0.y, acc0); acc1 = fmaf(zreg[4 * c + 1], e1.y, acc1);
+                        acc0 = fmaf(zreg[4 * c + 2], e0.z, acc0); acc1 = fmaf(zreg[4 * c + 2], e1.z, acc1);
+                        acc0 = fmaf(zreg[4 * c + 3], e0.w, acc0); acc1 = fmaf(zreg[4 * c + 3], e1.w, acc1);
+                    }
+                    float best = __int_as_float(0x7f800000);
+                    int code = 0x7fffffff;
+                    if (kc[0] >= 0) { best = ref_distance(zz, ees[kc[0]], acc0); code = kc[0]; }
+                    if (kc[1] >= 0) {
+                        const float d1 = ref_distance(zz, ees[kc[1]], acc1);
+                        if (d1 < best) { best = d1; code = kc[1]; }          // ascending codes, strict <
+                    }
+                    {
+                        const float ob = __shfl_xor_sync(0xffffffffu, best, 1);
+                        const int oc = __shfl_xor_sync(0xffffffffu, code, 1);
+                        if (ob < best || (ob == best && oc < code)) {
+                            best = ob;
+                            code = oc;
+                        }
+                    }
+                    if (code == 0x7fffffff)
+                        code = 0;
+                    // the row's outputs: z_q = z + (e - z) in place (chunks 4 t .. 4 t + 3), residual, idx, histogram
+                    float r2 = 0.0f;
+                    if (act && (p.zq || p.need_sq)) {
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const int c = 4 * t + h;
+                            const float4 e = *reinterpret_cast<const float4 *>(ef32 + ef32_off(code, c));
+                            const float z0 = t ? zreg[16 + 4 * h] : zreg[4 * h], z1 = t ? zreg[17 + 4 * h] : zreg[4 * h + 1];
+                            const float z2 = t ? zreg[18 + 4 * h] : zreg[4 * h + 2], z3 = t ? zreg[19 + 4 * h] : zreg[4 * h + 3];
+                            const float d0 = __fsub_rn(e.x, z0), d1 = __fsub_rn(e.y, z1), d2 = __fsub_rn(e.z, z2), d3 = __fsub_rn(e.w, z3);
+                            r2 = fmaf(d0, d0, r2); r2 = fmaf(d1, d1, r2); r2 = fmaf(d2, d2, r2); r2 = fmaf(d3, d3, r2);
+                            if (p.zq)
+                                *reinterpret_cast<float4 *>(zrow + ((c << 4) ^ xr)) =
+                                    make_float4(__fadd_rn(z0, d0), __fadd_rn(z1, d1), __fadd_rn(z2, d2), __fadd_rn(z3, d3));
+                        }
+                    }
+                    r2 += __shfl_xor_sync(0xffffffffu, r2, 1);
+                    if (act && t == 0) {
+                        const uint32_t row = tile * TILE_M + (uint32_t)rr;
+                        if (p.idx)
+                            p.idx[row] = code;
+                        atomicAdd(hist + code, 1u);
+                        sqf += r2;
+                    }
+                }
+                sq += (double)sqf;
+                sqf = 0.0f;
+                // (the counter is cleared by the epilogue group when it takes the slot for its next tile)
+                if (p.zq)
+                    fence_proxy_async();               // z_q rows (generic proxy) -> visible to the TMA store
+                mbar_arrive(bar(Q_DONE + s));
+                if (lane == 0) stamp(i, 2);
+            }
+        }
         const int r = tid - W_CONV * 32;
         const int x = (r & 7) << 4;
-        const int n_items = (int)my_items;
+        const int n_items = TF32 ? 0 : (int)my_items;    // (TF32: nothing to convert)
         int s = 0;
-        uint32_t zph = 0;                                               // parity of Z_FULL[s]: (i / STAGES) & 1
+        uint32_t zph = 0;                                               // parity of Z_FULL[s]: (i / NST) & 1
         for (int i = 0; i < n_items; ++i) {              // i: pipeline item (= tile, or half a wide tile)
             const int b = i & 1;
             if (warp == W_CONV) {
@@ -726,14 +919,17 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
                 mbar_arrive(bar(A_FULL + b));
             }
             if (r == 0 && nd == 1) stamp(i, 2);
-            if (++s == STAGES) {
+            if (++s == NST) {
                 s = 0;
                 zph ^= 1u;
             }
         }
     } else if (warp >= W_EPI && warp < W_EPI + 4 * GROUPS) {
         // ================= epilogue groups =================
-        reg_inc<VQB_EPI_REGS>();
+        if (TF32)
+            reg_inc<120>();                       // (the refiner warps take 80 each: 128 x (40 + 80 + 3 x 120) = 61440)
+        else
+            reg_inc<VQB_EPI_REGS>();
         const int g = (warp - W_EPI) >> 2;            // tile i is handled by group i % GROUPS, TMEM buffer i & 1
         const int q = warp & 3;                   // TMEM lane quarter of this warp
         const int r = q * 32 + lane;              // row in tile = TMEM lane
@@ -761,19 +957,30 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
         };
         float sqf = 0.0f;
         const int n_my = (int)my_tiles;
-        constexpr int s_step = (GROUPS * nd) % STAGES;
-        int s = (g * nd) % STAGES;                            // ring slot of the tile (its first half if wide)
+        constexpr int s_step = (GROUPS * nd) % NST;
+        int s = (g * nd) % NST;                            // ring slot of the tile (its first half if wide)
         uint32_t ph = 0;                                      // parity of T_FULL[g]: (i / GROUPS) & 1
         int run = 0;
-        for (int i = g; i < n_my; i += GROUPS, ph ^= 1u, s = s + s_step >= STAGES ? s + s_step - STAGES : s + s_step) {
-            const int s1 = s + 1 == STAGES ? 0 : s + 1;       // second half of a wide tile
+        for (int i = g; i < n_my; i += GROUPS, ph ^= 1u, s = s + s_step >= NST ? s + s_step - NST : s + s_step) {
+            const int s1 = s + 1 == NST ? 0 : s + 1;       // second half of a wide tile
             const int b = i & 1;
             const uint32_t tile = tile_first + (uint32_t)i * tile_step;
             const uint32_t row = tile * TILE_M + r;
             const bool ok = row < (uint32_t)n_rows;
 
             // ---- filter: minima of the approximate scores over the 16 A-groups and the 16 B-groups ----
-            group_wait<64>(q == 0, bar(T_FULL + g), ph, 2 + g);
+            if (TF32) {
+                // (the accumulator is ready => the slot holds THIS tile => the previous tile's refiner warps are done with
+                // its list: the leader clears the counter before anyone of the group can push)
+                if (q == 0) {
+                    mbar_wait<64>(bar(T_FULL + g), ph);
+                    if (lane == 0)
+                        rcnt[s] = 0u;
+                }
+                named_bar_sync(2 + g, 128);
+            } else {
+                group_wait<64>(q == 0, bar(T_FULL + g), ph, 2 + g);
+            }
             tc_fence_after();
             if (r == 0) stamp(i, 4);
             const uint32_t taddr = tmem_base + b * KMAX + ((uint32_t)(q * 32) << 16);
@@ -847,9 +1054,22 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             unsigned char *zrow1 = zt1 + r * 128;
             // ||z||^2 comes from the converter that already had the row in registers (ordered before us
             // by A_FULL -> MMA -> T_FULL); it only bounds the filter radius, it is not part of the decision
-            float zz = reinterpret_cast<const float *>(smem + OFF_ZZ + s * 512)[r];
-            if (nd == 2)
-                zz += reinterpret_cast<const float *>(smem + OFF_ZZ + s1 * 512)[r];
+            float zz = 0.0f;
+            if (TF32) {
+                // no converter: the row's own thread sums the squares (it only bounds the filter radius)
+                float zp4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 v = *reinterpret_cast<const float4 *>(zrow + ((c << 4) ^ x));
+                    zp4[0] = fmaf(v.x, v.x, zp4[0]); zp4[1] = fmaf(v.y, v.y, zp4[1]);
+                    zp4[2] = fmaf(v.z, v.z, zp4[2]); zp4[3] = fmaf(v.w, v.w, zp4[3]);
+                }
+                zz = (zp4[0] + zp4[1]) + (zp4[2] + zp4[3]);
+            } else {
+                zz = reinterpret_cast<const float *>(smem + OFF_ZZ + s * 512)[r];
+                if (nd == 2)
+                    zz += reinterpret_cast<const float *>(smem + OFF_ZZ + s1 * 512)[r];
+            }
             // (sums of squares below 2^-120 are treated as 2^-120: the fp32 sum loses bits there -- it underflows to 0 for
             // components below 2^-75 -- and sqrt.approx.ftz would flush a sub-normal sum to 0; 2^-60 still bounds the norm)
             const float zn = sqrt_approx(fmaxf(zz, 7.52316385e-37f)) * 1.00001f;
@@ -863,7 +1083,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             //   =>  delta <= (12*2^-16 + 2^-17 + 2^-17 + D*2^-22) zn*emax + 2^-17 eemax + 2^-22 (zn+emax)^2
             //   + an absolute floor for sub-normal z entries (lost by the bf16 split and possibly flushed by the
             //     tensor core): each is < 2^-126, so they move a score by < 2*sqrt(D)*2^-126*emax
-            const float delta = 2.1e-4f * zn * emax + 8.0e-6f * eemax + 3.0e-7f * (zn + emax) * (zn + emax) +
+            // TF32 variant: the tensor core sees z truncated or rounded to 11 significant bits (|dz| <= 2^-10 |z|) and E rounded
+            // to nearest (|dE| <= 2^-11 |E|): eps <= 2 (2^-10 + 2^-11 + 2^-21) S + 2^-19 (2S + ee), so
+            //   delta <= (6*2^-10 + 2^-17 + D*2^-22) zn*emax + ... = 5.9e-3 zn*emax + (the same other terms)
+            const float delta = (TF32 ? 5.9e-3f : 2.1e-4f) * zn * emax + 8.0e-6f * eemax + 3.0e-7f * (zn + emax) * (zn + emax) +
                                 (1.0e-35f + 1.0e-36f * emax);
             // Decision on the group minima alone: with m the smallest approximate score and thr = m + delta, every code
             // whose approximate score lies within delta of m sits in an A-group AND a B-group whose minimum is <= thr.
@@ -890,7 +1113,22 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             // overflow, non-finite rows / codebooks, crowded candidate sets (exact ties of many codes) and a full queue
             // take the warp-wide exact scan of all K codes right here instead.
             bool slow = false, deferred = false;
-            if (!certain && ok) {
+            bool decided = certain;
+            bool refined = false;
+            if (TF32) {
+                // up to four candidate codes (the cross product of the qualifying A- and B-groups): the row goes to the tile's
+                // list and is decided -- and written -- by a refiner warp; this thread leaves the row alone
+                refined = !certain && ok && zz <= 1.0e37f && eemax <= 1.0e37f && !cb_bad &&
+                          __popc(ma) * __popc(mb) >= 1 && __popc(ma) * __popc(mb) <= 4;
+                if (refined) {
+                    const unsigned pos = atomicAdd(rcnt + s, 1u);
+                    rlist[s * TILE_M + pos] = make_uint2((unsigned)r, ma | (mb << 16));
+                    decided = true;
+                }
+                mbar_arrive(bar(R_FULL + s));      // this thread's entry (if any) is in the tile's list: the refiner warp
+                                                   // works on it while this thread writes its own row's outputs
+            }
+            if (!decided && ok) {
                 slow = true;
                 if (zz <= 1.0e37f && eemax <= 1.0e37f && !cb_bad) {
                     const int nc = __popc(ma) * __popc(mb);
@@ -906,6 +1144,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
             unsigned need = __ballot_sync(0xffffffffu, slow);
             n_slow_total += __popc(__ballot_sync(0xffffffffu, !certain && ok));
+            (void)decided;
             while (need) {
                 const int src = __ffs(need) - 1;
                 need &= need - 1;
@@ -930,7 +1169,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
 
             // ---- outputs: idx, histogram, loss, z_q (in place in the ring slot) ----
-            const bool emit = ok && !deferred;
+            const bool emit = ok && !deferred && !refined;
             if (emit) {
                 if (p.idx)
                     p.idx[row] = code;
@@ -938,8 +1177,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
             // (ids-only calls -- no z_q, no loss -- skip the gather and the residual altogether)
             float r2 = 0.0f;
-            if (p.zq || p.need_sq) {
+            if ((p.zq || p.need_sq) && !refined) {
                 if (nd == 1) {
+                    // (keeping the row in registers from the ||z||^2 pass for this write was measured: 108 bytes of spills at
+                    // 120 registers, 1.04 ms instead of 0.96)
                     r2 = poisoned ? emit_row<true>(zrow, x, ef32, code, p.zq != nullptr, p.colcnt, p.colwhich)
                                   : emit_row<false>(zrow, x, ef32, code, p.zq != nullptr, nullptr, nullptr);
                 } else if (poisoned) {
@@ -1329,6 +1570,12 @@ cudaError_t launch_tc_finish_ids(const FwdParams &p, int sm_count, int *n_ctas, 
 
 cudaError_t launch_fwd_tcs(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas, int *n_launches,
                            cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end, bool image_ready);
+// the single-product TF32 filter is an A/B switch while it is being measured: VQB_TF32=1 in the environment
+static bool tf32_mode_requested()
+{
+    static const bool v = [] { const char *e = getenv("VQB_TF32"); return e && e[0] == '1'; }();
+    return v;
+}
 // CTA pairs are an A/B switch while they are being measured: VQB_PAIR=1 in the environment
 static bool pair_mode_requested()
 {
@@ -1367,17 +1614,18 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
         map_zq = map_z;
     }
     const int kp = ((p.K + 31) / 32) * 32;
+    const bool wide = p.D > tc::D;
     // image_ready: the constant-operand image in tc_scratch was built by an earlier call for this very codebook
     // (the per-CTA queue counters need no reset: every CTA overwrites its own before anyone reads it)
     cudaError_t err = cudaSuccess;
     if (!image_ready) {
         if ((err = cudaMemsetAsync(img + IMG_CONST, 0, sizeof(Consts), st)) != cudaSuccess)
             return err;
-        vq_tc_prep_kernel<<<(KMAX + 127) / 128, 128, 0, st>>>(p.E, p.ee, p.K, p.D, kp, img);
+        vq_tc_prep_kernel<<<(KMAX + 127) / 128, 128, 0, st>>>(p.E, p.ee, p.K, p.D, kp, img,
+                                                              (!wide && p.chunk_mode == 0 && tf32_mode_requested()) ? 1 : 0);
         if ((err = cudaGetLastError()) != cudaSuccess)
             return err;
     }
-    const bool wide = p.D > tc::D;
     const int64_t tiles = (p.z.n_rows + TILE_M - 1) / TILE_M;
     int grid = (int)(tiles < sm_count ? tiles : sm_count);
     if (grid < 1)
@@ -1385,13 +1633,18 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
     if (grid > WL_CTAS)
         grid = WL_CTAS;
     // CTA pairs (cta_group::2) for the plain pass over more than 128 codes: an even grid of 2-CTA clusters
-    const bool pair = !wide && p.chunk_mode == 0 && p.K > 128 && grid >= 2 && pair_mode_requested();
+    const bool tf32 = !wide && p.chunk_mode == 0 && tf32_mode_requested();
+    const bool pair = !tf32 && !wide && p.chunk_mode == 0 && p.K > 128 && grid >= 2 && pair_mode_requested();
     if (pair)
         grid &= ~1;
-    auto kern = wide ? vq_fwd_tc_kernel<false, true, false>
-                     : g_trace_buf ? (pair ? vq_fwd_tc_kernel<true, false, true> : vq_fwd_tc_kernel<true, false, false>)
-                                   : pair ? vq_fwd_tc_kernel<false, false, true> : vq_fwd_tc_kernel<false, false, false>;
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+    auto kern = wide ? vq_fwd_tc_kernel<false, true, false, false>
+                : tf32 ? (g_trace_buf ? vq_fwd_tc_kernel<true, false, false, true> : vq_fwd_tc_kernel<false, false, false, true>)
+                : g_trace_buf ? (pair ? vq_fwd_tc_kernel<true, false, true, false> : vq_fwd_tc_kernel<true, false, false, false>)
+                              : pair ? vq_fwd_tc_kernel<false, false, true, false> : vq_fwd_tc_kernel<false, false, false, false>;
+    const int smem_alloc = tf32 ? SMEM_ALLOC_TF32 : SMEM_ALLOC;
+    if (smem_alloc > max_smem)
+        return cudaErrorNotSupported;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_alloc);
     if (err != cudaSuccess)
         return err;
     *n_ctas = grid * (1 + FIX_SPLIT);    // partials [0, grid): main kernel, then one per fix-up CTA
@@ -1414,7 +1667,7 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
         unsigned long long *trace_buf = g_trace_buf;
         err = cudaLaunchKernelEx(&cfg, kern, p, img_c, map_z, map_zq, kp, trace_buf);
     } else {
-        kern<<<grid, THREADS, SMEM_ALLOC, st>>>(p, img, map_z, map_zq, kp, wide ? nullptr : g_trace_buf);
+        kern<<<grid, THREADS, smem_alloc, st>>>(p, img, map_z, map_zq, kp, wide ? nullptr : g_trace_buf);
         err = cudaGetLastError();
     }
     if (err != cudaSuccess)
