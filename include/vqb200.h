@@ -261,6 +261,10 @@ int vqb_profile_collect(double *ms_sum, int *launches);
  * kernel records clock64() of eight pipeline events per tile there (tools/tc_trace.py). */
 int vqb_debug_set_tc_trace(unsigned long long *buf);
 size_t vqb_debug_tc_trace_words(void);
+/* Debug / A-B only: which filter the tcgen05 forward kernel (K <= 256, D <= 32) uses -- -1 automatic (TF32 single product for
+ * 16 < D <= 32, three bf16 products otherwise; the VQB_TF32 environment variable overrides), 0 bf16, 1 TF32.  The decision
+ * is the oracle's with either; a cached operand image (VQB_KEEP_TC_IMAGE) belongs to the filter it was built for. */
+int vqb_debug_set_filter(int mode);
 
 /* ---- host-buffer path (copies inside the call) --------------------------- */
 typedef struct vqb_host_ctx vqb_host_ctx;

@@ -36,6 +36,15 @@ def _to_dev(case):
     return z, logical, E
 
 
+@pytest.fixture(autouse=True, params=["auto", "bf16", "tf32"])
+def tc_filter(request):
+    """Every test of this module runs with both filters of the tcgen05 forward kernel (three bf16 products / one tf32
+    product, csrc/vq_fwd_tc.cu) forced, and with the automatic choice: the decision must be the oracle's with either."""
+    ops.set_filter(None if request.param == "auto" else request.param)
+    yield request.param
+    ops.set_filter(None)
+
+
 def _module(case, path, one_hot="dense"):
     vq = vqb200.VectorQuantizer(case["K"], case["D"], case["beta"], one_hot=one_hot, path=path).to(_dev())
     return vq

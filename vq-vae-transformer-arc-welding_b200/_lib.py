@@ -54,6 +54,7 @@ SIGNATURES = {
     "vqb_host_last_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "vqb_debug_set_tc_trace": (_i, [_vp]),
     "vqb_debug_tc_trace_words": (_sz, []),
+    "vqb_debug_set_filter": (_i, [_i]),
     "vqb_host_create": (_i, [_i, _i64, _i, _i, _i, ctypes.POINTER(_vp)]),
     "vqb_host_destroy": (_i, [_vp]),
     "vqb_host_set_codebook": (_i, [_vp, _vp]),

@@ -74,6 +74,14 @@ int vqb_debug_set_tc_trace(unsigned long long *buf)
 }
 size_t vqb_debug_tc_trace_words(void) { return tc_trace_words(); }
 
+int vqb_debug_set_filter(int mode)
+{
+    if (mode < -1 || mode > 1)
+        return VQB_E_ARG;
+    set_tc_filter(mode);
+    return VQB_OK;
+}
+
 int vqb_profile_enable(int on)
 {
     g_profile.store(on ? 1 : 0);

@@ -159,6 +159,7 @@ cudaError_t launch_ar_pairs(const int64_t *ids, int64_t n_windows, int n, int64_
                             int64_t *y, int sm_count, cudaStream_t st);
 void count_launches(int n);
 void set_tc_trace(unsigned long long *buf);
+void set_tc_filter(int mode);
 size_t tc_trace_words();
 
 // ---------------------------------------------------------------------------------------

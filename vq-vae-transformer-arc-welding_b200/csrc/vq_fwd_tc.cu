@@ -1570,11 +1570,17 @@ cudaError_t launch_tc_finish_ids(const FwdParams &p, int sm_count, int *n_ctas, 
 
 cudaError_t launch_fwd_tcs(const FwdParams &p, float *tc_scratch, int sm_count, int max_smem, int *n_ctas, int *n_launches,
                            cudaStream_t st, cudaEvent_t ev_begin, cudaEvent_t ev_end, bool image_ready);
-// the single-product TF32 filter is an A/B switch while it is being measured: VQB_TF32=1 in the environment
-static bool tf32_mode_requested()
+// The single-product TF32 filter is the default for 16 < D <= 32 (measured at N = 2^24: (256, 32) 0.975 ms against 1.033,
+// (128, 32) 0.825 / 0.848, (64, 32) 0.738 / 0.779; narrower vectors need fewer bf16 MMAs and stay on the three-product
+// filter: (256, 16) 0.795 against 0.883 with TF32).  VQB_TF32=0 in the environment selects the bf16 filter everywhere
+// (A/B runs), VQB_TF32=1 the TF32 filter for every D <= 32.
+static int g_filter_override = -1;        // vqb_debug_set_filter: -1 automatic, 0 bf16 three-product, 1 TF32 single-product
+void set_tc_filter(int mode) { g_filter_override = mode; }
+static bool tf32_mode_requested(int d)
 {
-    static const bool v = [] { const char *e = getenv("VQB_TF32"); return e && e[0] == '1'; }();
-    return v;
+    static const int env = [] { const char *e = getenv("VQB_TF32"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();
+    const int v = g_filter_override >= 0 ? g_filter_override : env;
+    return v < 0 ? d > 16 : v == 1;
 }
 // CTA pairs are an A/B switch while they are being measured: VQB_PAIR=1 in the environment
 static bool pair_mode_requested()
@@ -1622,7 +1628,7 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
         if ((err = cudaMemsetAsync(img + IMG_CONST, 0, sizeof(Consts), st)) != cudaSuccess)
             return err;
         vq_tc_prep_kernel<<<(KMAX + 127) / 128, 128, 0, st>>>(p.E, p.ee, p.K, p.D, kp, img,
-                                                              (!wide && p.chunk_mode == 0 && tf32_mode_requested()) ? 1 : 0);
+                                                              (!wide && p.chunk_mode == 0 && tf32_mode_requested(p.D)) ? 1 : 0);
         if ((err = cudaGetLastError()) != cudaSuccess)
             return err;
     }
@@ -1633,7 +1639,7 @@ cudaError_t launch_fwd_tc(const FwdParams &p, float *tc_scratch, int sm_count, i
     if (grid > WL_CTAS)
         grid = WL_CTAS;
     // CTA pairs (cta_group::2) for the plain pass over more than 128 codes: an even grid of 2-CTA clusters
-    const bool tf32 = !wide && p.chunk_mode == 0 && tf32_mode_requested();
+    const bool tf32 = !wide && p.chunk_mode == 0 && tf32_mode_requested(p.D);
     const bool pair = !tf32 && !wide && p.chunk_mode == 0 && p.K > 128 && grid >= 2 && pair_mode_requested();
     if (pair)
         grid &= ~1;

@@ -31,6 +31,14 @@ _ws_state = {}          # id(workspace tensor) -> (weakref to the weight tensor,
 _WS_MAX = 16
 
 
+def set_filter(mode: Optional[str]) -> None:
+    """Debug / A-B: the filter of the tcgen05 forward kernel -- None (automatic), "bf16" (three bf16 products) or "tf32"
+    (one tf32 product).  Cached operand images belong to a filter: the workspaces are dropped."""
+    code = {None: -1, "auto": -1, "bf16": 0, "tf32": 1}[mode]
+    _lib.check(_lib.load().vqb_debug_set_filter(code), "vqb_debug_set_filter")
+    clear_workspaces()
+
+
 def clear_workspaces() -> None:
     """Drop every cached kernel workspace (their memory returns to the caching allocator)."""
     _workspaces.clear()
