@@ -1576,7 +1576,16 @@ cudaError_t launch_fwd_tcs(const FwdParams &p, float *tc_scratch, int sm_count, 
 // (A/B runs), VQB_TF32=1 the TF32 filter for every D <= 32.
 static int g_filter_override = -1;        // vqb_debug_set_filter: -1 automatic, 0 bf16 three-product, 1 TF32 single-product
 void set_tc_filter(int mode) { g_filter_override = mode; }
-static bool tf32_mode_requested(int d)
+bool tc_filter_is_tf32(int d);
+static bool tf32_mode_requested(int d) { return tc_filter_is_tf32(d); }
+// forced (vqb_debug_set_filter(1) / VQB_TF32=1), not merely chosen by the automatic rule: the tile-stationary kernel
+// (vq_fwd_tcs.cu) takes its TF32 variant only then -- measured slower there (profiles/README.md, r02b)
+bool tc_filter_forced_tf32()
+{
+    static const int env = [] { const char *e = getenv("VQB_TF32"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();
+    return g_filter_override >= 0 ? g_filter_override == 1 : env == 1;
+}
+bool tc_filter_is_tf32(int d)
 {
     static const int env = [] { const char *e = getenv("VQB_TF32"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();
     const int v = g_filter_override >= 0 ? g_filter_override : env;
