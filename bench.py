@@ -702,6 +702,8 @@ def run_ours(args) -> None:
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(world, n), "path": args.path,
+        "filter": ("tf32 single product (default for 16 < D <= 32)" if os.environ.get("VQB_TF32", "") != "0" and 16 < DIM <= 32
+                   else "bf16 three products"),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "backward": bwd,
         "index_match": {"vs": "oracle (oracle/vq_oracle.c)", "rows": sample_rows, "rate": match,
