@@ -324,6 +324,44 @@ __device__ __forceinline__ float emit_row(unsigned char *zrow, int x, const unsi
 }
 
 
+// The same for the 32 rows of a warp (rows 32 q .. 32 q + 31 of the tile), EIGHT LANES PER ROW: lane = (row % 4, chunk) walks
+// rows 4 j + lane / 8, so that every quarter-warp reads one whole 128-byte row of z and one whole codebook row per
+// access -- conflict-free whatever codes the rows have.  (With one thread per row the codebook gather costs ~10
+// shared-memory wavefronts per LDS.128 instead of 4: 32 random rows, profiles/README.md r02b.)  `code_or_neg`: this
+// lane's OWN row's code, or -1 when that row is written elsewhere (queued / refined / beyond the tensor); the return
+// value is this lane's share of the squared residuals of the rows it walked (their sum over the warp is what counts).
+__device__ __forceinline__ float emit_rows_coop(unsigned char *ztile, int q, int lane, const unsigned char *ef32, int code_or_neg,
+                                                bool write_zq)
+{
+    const int c = lane & 7, sub = lane >> 3;
+    float2 rs01 = make_float2(0.f, 0.f), rs23 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int rr = 4 * j + sub;
+        const int cj = __shfl_sync(0xffffffffu, code_or_neg, rr);
+        // (branch-free: a skipped row is read like the others -- against code 0 -- and neither stored nor counted; with a
+        // branch per row the eight iterations serialise on their load latencies)
+        const bool on = cj >= 0;
+        float4 *zp4 = reinterpret_cast<float4 *>(ztile + (q * 32 + rr) * 128 + ((c ^ (rr & 7)) << 4));
+        const float4 zv = *zp4;
+        const float4 e = *reinterpret_cast<const float4 *>(ef32 + ef32_off(on ? cj : 0, c));
+        float2 d01 = __fadd2_rn(make_float2(e.x, e.y), make_float2(-zv.x, -zv.y));               // fl(e - z)
+        float2 d23 = __fadd2_rn(make_float2(e.z, e.w), make_float2(-zv.z, -zv.w));
+        if (write_zq && on) {
+            const float2 o01 = __fadd2_rn(make_float2(zv.x, zv.y), d01);                         // fl(z + fl(e - z))
+            const float2 o23 = __fadd2_rn(make_float2(zv.z, zv.w), d23);
+            *zp4 = make_float4(o01.x, o01.y, o23.x, o23.y);
+        }
+        if (!on) {
+            d01 = make_float2(0.f, 0.f);
+            d23 = make_float2(0.f, 0.f);
+        }
+        rs01 = __ffma2_rn(d01, d01, rs01);
+        rs23 = __ffma2_rn(d23, d23, rs23);
+    }
+    return (rs01.x + rs01.y) + (rs23.x + rs23.y);
+}
+
 // Oracle-order distance of one code for the vector in ring-slot row `zrow` (chunk passes of large codebooks:
 // the winners of the 256-code chunks are compared by their exact distances).
 __device__ __forceinline__ float exact_distance(const unsigned char *zrow, int x, const unsigned char *ef32,
@@ -1177,7 +1215,10 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             }
             // (ids-only calls -- no z_q, no loss -- skip the gather and the residual altogether)
             float r2 = 0.0f;
-            if ((p.zq || p.need_sq) && !refined) {
+            if ((p.zq || p.need_sq) && nd == 1 && !poisoned) {
+                // (the whole warp walks its 32 rows together; rows written elsewhere are skipped)
+                sqf += emit_rows_coop(zt, q, lane, ef32, emit ? code : -1, p.zq != nullptr);
+            } else if ((p.zq || p.need_sq) && !refined) {
                 if (nd == 1) {
                     // (keeping the row in registers from the ||z||^2 pass for this write was measured: 108 bytes of spills at
                     // 120 registers, 1.04 ms instead of 0.96)
