@@ -792,7 +792,7 @@ vq_fwd_tc_kernel(const FwdParams p, const unsigned char *__restrict__ img, const
             float sqf = 0.0f;
             for (int i = w; i < n_my; i += 4) {
                 const int s = i % NST;
-                mbar_wait<64>(bar(R_FULL + s), (uint32_t)((i / NST) & 1));
+                mbar_wait<512>(bar(R_FULL + s), (uint32_t)((i / NST) & 1));   // (long sleeps: this warp has three tile periods of slack, polling costs issue slots)
                 if (lane == 0) stamp(i, 1);
                 const unsigned cnt = rcnt[s];
                 const uint32_t tile = tile_first + (uint32_t)i * tile_step;
