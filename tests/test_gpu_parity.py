@@ -618,6 +618,31 @@ def test_tcs_degenerate_codebook_overflows_the_queue():
     assert int(out[3].max().item()) < 256
 
 
+@pytest.mark.parametrize("K,D,zscale", [(256, 32, 0.1), (256, 32, 30.0), (200, 24, 1.0), (512, 32, 0.1), (256, 64, 0.1)])
+def test_tc_twin_codes_at_every_scale(K, D, zscale):
+    """The certificate's boundary, probed at every scale at once: every code has a twin at a relative distance drawn
+    log-uniformly from 1e-8 .. 1e-1 (and a few exact twins), so that for every vector the runner-up is closer to the
+    winner than, near, or beyond the filter radius of either filter.  A radius that is too small for the tensor cores'
+    actual arithmetic shows up here as ids that differ from the exact CUDA-core kernel."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(K * 7 + D)
+    n = 1 << 20
+    base = 0.1 * torch.randn(K // 2, D, device=dev, generator=g)
+    rel = 10.0 ** (-8.0 + 7.0 * torch.rand(K // 2, 1, device=dev, generator=g))
+    twin = base * (1.0 + rel * torch.randn(K // 2, D, device=dev, generator=g))
+    twin[:4] = base[:4]                                          # exact twins: the lower index must win
+    E = torch.stack([base, twin], dim=1).reshape(-1, D).contiguous()
+    if E.shape[0] < K:
+        E = torch.cat([E, 0.1 * torch.randn(K - E.shape[0], D, device=dev, generator=g)])
+    z = zscale * torch.randn(n, D, device=dev, generator=g)
+    a = ops.forward(z, E, 0.25, path="tc", want_stats=True)
+    b = ops.forward(z, E, 0.25, path="fma")
+    assert int((a[3] != b[3]).sum().item()) == 0
+    assert torch.equal(a[1], b[1]) and torch.equal(a[4], b[4])
+    assert a[0].item() == pytest.approx(b[0].item(), rel=REL)
+    assert int(a[5][1].item()) > n // 50                          # the case does exercise the exact paths
+
+
 @pytest.mark.parametrize("K", [256, 100, 1])
 @pytest.mark.parametrize("n", [128, 129, 255, 1000, 128 * 148 * 2 + 77])
 def test_backward_tma_ring_kernel(K, n):
