@@ -292,6 +292,19 @@ def bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier):
         ref = enc.get_latent_space_IDs(sample, has_patch_embed=True).view(-1)
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
         match = float((got == ref).float().mean().item())
+        # the fp32-faithful fused encoder (VQVAEPatch's default for inference): one chunk timed, ids against the same fp32 ids
+        model.encoder_mode = "fused_fp32"
+        got32 = enc.get_latent_space_IDs(sample, has_patch_embed=True).view(-1)
+        enc.get_latent_space_IDs(pool[1], has_patch_embed=True)
+        torch.cuda.synchronize()
+        l1 = lib.vqb_launch_counter()
+        e0.record()
+        enc.get_latent_space_IDs(pool[0], has_patch_embed=True)
+        e1.record()
+        torch.cuda.synchronize()
+        fp32_ms, fp32_launches = e0.elapsed_time(e1), lib.vqb_launch_counter() - l1
+        match32 = float((got32 == ref).float().mean().item())
+        model.encoder_mode = "fused_bf16"
     if rank != 0:
         return None
     cycles = world * chunk * n_chunks
@@ -318,6 +331,13 @@ def bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier):
                              "and projection with bf16 hi+lo operand pairs = fp32-accurate to 2^-16, the 16 hidden layers "
                              "with bf16 operands, fp32 accumulation and fp32 residual stream), exact quantiser",
         "id_match_vs_fp32_encoder": {"rate": match, "rows": int(got.numel())},
+        "fp32_faithful": {"mode": "encoder_mode='fused_fp32' (VQVAEPatch's inference default): vqb_patch_embed (fp32 FMA) + "
+                                  "vqb_token_pair + 17 x vqb_token_linear_split (bf16 hi+lo operand pairs, three tcgen05 products "
+                                  "per layer, fp32 accumulation, erf GELU, fp32 residual stream), exact quantiser; rank 0, one chunk",
+                          "per_gpu": chunk * model.enc_out_len / (fp32_ms * 1e-3), "unit": UNIT, "ms_per_chunk": fp32_ms,
+                          "gpu_launches_per_chunk": fp32_launches,
+                          "id_match_vs_fp32_encoder": {"rate": match32, "rows": int(got32.numel())},
+                          "issued_tflops": 3.0 * chunk * CYCLE_FLOP / (fp32_ms * 1e-3) / 1e12},
         "gpu_launches_per_chunk": launches / n_chunks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "flop_per_cycle": CYCLE_FLOP, "peak_source": peak_src,

@@ -172,6 +172,22 @@ int vqb_token_conv(int device, const void *a_bf16, const void *w_bf16, const flo
                    void *stream);
 
 /*
+ * vqb_token_linear in its fp32-faithful form (the same reference layers, model/vq_vae_patch_embedd.py:60-74, :103-111, and
+ * -- as a mode-2 call on zero-padded rows -- the final projection SepCNNBlock, :83-91): every operand is a PAIR of bf16
+ * values, hi = bf16(x), lo = bf16(x - hi) (x to 2^-17), stored side by side:
+ *   a_pair (n_tokens, 2 k) = [a_hi | a_lo],  w_pair (n, 2 k) = [w_hi | w_lo],  out_pair (n_tokens, 2 n) = [g_hi | g_lo].
+ * The tensor cores accumulate a_hi w_hi + a_hi w_lo + a_lo w_hi in fp32 (operand precision 2^-16 instead of 2^-8, three
+ * times the tensor work); the GELU is the erf form torch evaluates (erff); modes as in vqb_token_linear, out_gelu as in
+ * vqb_token_conv (0: the pair of x / h itself).  bias (n) fp32, h (n_tokens, n) fp32.  Same shape / alignment rules.
+ */
+int vqb_token_linear_split(int device, const void *a_pair, const void *w_pair, const float *bias, float *h, void *out_pair,
+                           int64_t n_tokens, int k, int n, unsigned mode, int out_gelu, void *stream);
+
+/* out_pair (n_tokens, 2 n) = [bf16(g) | bf16(g - bf16(g))] with g = gelu(h) (erf form; apply_gelu != 0) or g = h:
+ * the operand pair of the first vqb_token_linear_split call, from the patch embedding's fp32 rows.  n a multiple of 4. */
+int vqb_token_pair(int device, const float *h, void *out_pair, int64_t n_tokens, int n, int apply_gelu, void *stream);
+
+/*
  * PatchEmbeddingInverse.proj[3], ConvTranspose1d(hidden, 1, kernel = stride = p) (model/vq_vae_patch_embedd.py:24-29):
  * out[r][j] = sum_c a[r][c] w[j][c] + bias for every row r of a (n_rows, hidden) bf16 activation; w (p, hidden) fp32
  * (the weight (hidden, 1, p) transposed), out (n_rows, p) fp32.  hidden 256 or 512, p <= 8.

@@ -57,6 +57,94 @@ def test_token_linear_matches_fp32_reference(T, K, N):
     assert torch.equal(h2, h)
 
 
+def _pair_value(p):
+    n = p.shape[1] // 2
+    return p[:, :n].double() + p[:, n:].double()
+
+
+@pytest.mark.parametrize("T", [1, 127, 129, 1000, 128 * 150 + 77])
+@pytest.mark.parametrize("K,N", [(512, 512), (64, 256), (256, 768)])
+def test_token_linear_split_is_fp32_faithful(T, K, N):
+    """vqb_token_linear_split against an fp64 reference on the SAME fp32 operands: hi + lo pairs carry 2^-17 per operand,
+    the dropped lo x lo term 2^-18, so the result must sit within ~2^-15 of |a| . |w| -- 200x tighter than the bf16 form,
+    and the same order as an fp32 GEMM's own rounding for these K."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(T * 11 + K + N)
+    x = torch.randn(T, K, device=dev, generator=g)
+    w = torch.randn(N, K, device=dev, generator=g) * (2.0 / K) ** 0.5
+    bias = 0.1 * torch.randn(N, device=dev, generator=g)
+    a = ops.token_pair(x, gelu=False)
+    assert (_pair_value(a) - x.double()).abs().max().item() <= 2.0 ** -16 * x.abs().max().item()
+    ag = ops.token_pair(x, gelu=True)
+    gx = torch.nn.functional.gelu(x.double())
+    assert bool(((_pair_value(ag) - gx).abs() <= 2.0 ** -17 * gx.abs() + 5e-7).all())      # erff + the pair's 2^-18
+    wp = ops.bf16_pair(w)
+    bound = 2.0 ** -14 * (x.double().abs() @ w.double().abs().t()) + 1e-6      # elementwise
+    acc = x.double() @ w.double().t() + bias.double()
+    # mode 0: pair of gelu(acc)
+    out = ops.token_linear_split(a, wp, bias, mode=0)
+    assert out.shape == (T, 2 * N)
+    assert bool(((_pair_value(out) - torch.nn.functional.gelu(acc)).abs() <= bound).all())
+    # mode 1: residual stream in place, pair of gelu(h) / of h itself
+    h = torch.randn(T, N, device=dev, generator=g)
+    h0 = h.clone()
+    nxt = torch.empty(T, 2 * N, dtype=torch.bfloat16, device=dev)
+    ops.token_linear_split(a, wp, bias, h=h, out=nxt, mode=1)
+    want = acc + h0.double()
+    assert bool(((h.double() - want).abs() <= bound + 2.0 ** -22 * want.abs()).all())
+    assert bool(((_pair_value(nxt) - torch.nn.functional.gelu(want)).abs() <= bound + 2.0 ** -16 * want.abs()).all())
+    h1 = h0.clone()
+    ops.token_linear_split(a, wp, bias, h=h1, out=nxt, mode=1, out_gelu=False)
+    assert torch.equal(h1, h)
+    assert bool(((_pair_value(nxt) - h.double()).abs() <= 2.0 ** -16 * h.double().abs() + 1e-30).all())
+    # mode 2: h written (not read), no activation output
+    h2 = torch.full((T, N), float("nan"), device=dev)
+    ops.token_linear_split(a, wp, bias, h=h2, mode=2, out_gelu=False)
+    assert bool(((h2.double() - acc).abs() <= bound).all())
+    # and the fp32-operand error is far below the bf16 form's on the same data
+    h16 = torch.empty(T, N, device=dev)
+    ops.token_linear(x.to(torch.bfloat16).contiguous(), w.to(torch.bfloat16).contiguous(), bias, h=h16, mode=2)
+    if T >= 127:
+        assert (h2.double() - acc).abs().max().item() * 50 < (h16.double() - acc).abs().max().item()
+
+
+def test_fused_fp32_encoder_matches_the_fp32_encoder():
+    """VQVAEPatch.encode in 'fused_fp32' mode at the repo-default architecture: z_e within 1e-5 of its range of the fp32
+    PyTorch layers, ids equal except where two codes are that close (none expected on 4800 tokens)."""
+    dev = _dev()
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    for hidden, n_res, bn in ((512, 8, False), (256, 2, True), (512, 0, False)):
+        model = vqb200.VQVAEPatch(hidden_dim=hidden, input_dim=2, num_embeddings=256, embedding_dim=32, n_resblocks=n_res,
+                                  learning_rate=1e-3, dropout_p=0.1, patch_size=25, batch_norm=bn).to(dev)
+        if bn:      # non-trivial running statistics, then eval mode (the statistics are folded into the weights)
+            model.train()
+            with torch.no_grad():
+                for _ in range(3):
+                    model.encode(torch.randn(64, 200, 2, device=dev))
+        model.eval()
+        x = torch.randn(300, 200, 2, device=dev)
+        with torch.no_grad():
+            model.encoder_mode = "torch"
+            z_ref = model.encode(x).double()
+            ids_ref = model.encode_ids(x)
+            model.encoder_mode = "fused_fp32"
+            assert model._fused_ok(x)
+            z = model.encode(x)
+            ids = model.encode_ids(x)
+        assert z.shape == z_ref.shape and z.is_contiguous() and z.dtype == torch.float32
+        err = (z.double() - z_ref).abs().max().item()
+        # (16 layers of 2^-18-per-operand pairs: measured ~1e-5 of the range; the bf16 form sits at ~1e-2)
+        assert err <= 1e-4 * z_ref.abs().max().item(), (hidden, n_res, err, z_ref.abs().max().item())
+        E = model.vector_quantization.embedding.weight.detach().cpu().numpy()
+        assert C.unexplained_mismatches(z_ref.float().cpu().numpy().reshape(-1, 32), E, ids.cpu().numpy().reshape(-1),
+                                        ids_ref.cpu().numpy().reshape(-1), rel=1e-4) == 0
+        assert (ids == ids_ref).float().mean().item() >= 0.9995
+        model.train()
+        assert not model._fused_ok(x)
+
+
 def test_token_linear_gelu_is_the_erf_form():
     """The epilogue's GELU is the exact (erf) form to bf16 accuracy, not the textbook two-term tanh approximation:
     |error| <= 2.5e-5 + 2.5e-4 |x| before the bf16 rounding (csrc/tok_linear.cu gelu_fast)."""
@@ -99,6 +187,7 @@ def test_fused_bf16_encoder_tracks_the_fp32_encoder():
     x = torch.randn(300, 200, 2, device=dev)
     with torch.no_grad():
         torch.backends.cuda.matmul.allow_tf32 = False
+        model.encoder_mode = "torch"
         z_ref = model.encode(x)
         ids_ref = model.encode_ids(x)
         model.encoder_mode = "fused_bf16"
@@ -157,6 +246,7 @@ def test_fused_bf16_encoder_folds_eval_batchnorm():
     model.eval()
     x = torch.randn(200, 200, 2, device=dev)
     with torch.no_grad():
+        model.encoder_mode = "torch"
         z_ref = model.encode(x)
         model.encoder_mode = "fused_bf16"
         assert model._fused_ok(x)
@@ -206,6 +296,7 @@ def _wide_model(patch_wide_golden, dev):
             wfull[:, :, 1] = torch.from_numpy(patch_wide_golden[k])
             sd[key] = wfull
     model.load_state_dict(sd, strict=True)
+    model.encoder_mode = "torch"
     return model.to(dev).eval()
 
 
@@ -240,6 +331,14 @@ def test_encoder_modes_against_the_reference_fixture(patch_wide_golden):
         assert np.abs(zf.cpu().numpy() - ref_z).max() <= 0.02 * np.abs(ref_z).max()
         rate = (idf == ref_ids).mean()
         assert rate >= 0.998, (chain, rate)
+    # fp32-faithful fused encoder (bf16 hi + lo pairs, three products per layer): the fp32 encoder's own tolerances
+    model.encoder_mode = "fused_fp32"
+    with torch.no_grad():
+        zs = model.encode(x)
+        ids_s = model.encode_ids(x).cpu().numpy().reshape(-1)
+    np.testing.assert_allclose(zs.cpu().numpy(), ref_z, rtol=1e-4, atol=1e-4 * np.abs(ref_z).max())
+    assert C.unexplained_mismatches(ref_z, E, ids_s, ref_ids, rel=1e-4) == 0
+    assert (ids_s == ref_ids).mean() >= 0.999
 
 
 @pytest.mark.parametrize("T,H,L", [(1, 512, 2), (127, 512, 4), (128 * 3 + 5, 512, 16), (128 * 150 + 77, 512, 16),
@@ -377,6 +476,7 @@ def test_fused_decoder_matches_the_torch_decoder(hidden, n_res, batch_norm):
             m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
     model.eval()
     z_q = 0.5 * torch.randn(37, 16, 32, device=dev)
+    model.encoder_mode = "torch"
     with torch.no_grad():
         want = model.decode(z_q)
         model.decoder_mode = "fused_bf16"

@@ -37,6 +37,8 @@ SIGNATURES = {
     "vqb_backward": (_i, [_i, _vp, _vp, _vp, _i64, _i64, _i, _i64, _i64, _i64, _vp, _vp, _i, _f,
                           _vp, _vp, _vp, _sz, _vp]),
     "vqb_token_linear": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _u, _vp]),
+    "vqb_token_linear_split": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _u, _i, _vp]),
+    "vqb_token_pair": (_i, [_i, _vp, _vp, _i64, _i, _i, _vp]),
     "vqb_token_conv": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _u, _i, _i, _i, _vp]),
     "vqb_token_out_proj": (_i, [_i, _vp, _vp, _f, _vp, _i64, _i, _i, _vp]),
     "vqb_token_bias_gelu": (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp]),

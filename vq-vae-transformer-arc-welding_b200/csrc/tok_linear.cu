@@ -22,6 +22,14 @@
 // (same operand precision as the reference under its own torch.set_float32_matmul_precision('medium'));
 // the quantiser behind it stays exact.
 //
+// Split form (SPLIT = true; vqb_token_linear_split, the fp32-faithful encoder mode): every operand is an exact-to-2^-17 PAIR
+// of bf16 values, A = [a_hi | a_lo] (T, 2 K_in) and W = [w_hi | w_lo] (N, 2 K_in) with hi = bf16(x), lo = bf16(x - hi); the
+// kernel accumulates the three products a_hi w_hi + a_hi w_lo + a_lo w_hi in the fp32 accumulator (K-chunk 3c + p of the
+// K = 3 K_in sweep reads the A box at column 64c + (p == 2) K_in and the W box at column 64c + (p == 1) K_in; the dropped
+// a_lo w_lo term is below 2^-16 of |a||w|), evaluates GELU in its erf form (gelu_erf: erff, ~1e-7), and writes `out` as the
+// same kind of pair, (T, 2 N) = [bf16(g) | bf16(g - bf16(g))].  Three times the tensor work of the bf16 form for 2^-16
+// instead of 2^-8 operand precision: ids equal to the fp32 encoder's except on ~1e-5 of the tokens.
+//
 // Tile 128 tokens x 256 outputs, K streamed in 64-element chunks through a 3-stage TMA ring (A 16 KB + W 32 KB per
 // stage, SWIZZLE_128B; tl::Plan), 4 tcgen05.mma (128 x 256 x 16) per chunk into one of two 256-column TMEM accumulators,
 // eight epilogue warps (TMEM lane quarter x column half) that overlap with the next tile's MMAs.
@@ -65,9 +73,12 @@ __device__ __forceinline__ float gelu_fast(float x)
     return fmaf(hx, t, hx);
 }
 
+// GELU in the form torch evaluates on fp32 tensors (x * 0.5 * (1 + erf(x / sqrt 2))): the split (fp32-faithful) layers
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
 }  // namespace tl
 
-template <int MODE>
+template <int MODE, bool SPLIT>
 __global__ void __launch_bounds__(tl::THREADS, 1)
 tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const float *__restrict__ bias, float *__restrict__ h, __nv_bfloat16 *__restrict__ out,
@@ -125,14 +136,20 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     mbar_wait<32>(bar(EMPTY + s), (uint32_t)(((step / STAGES) & 1) ^ 1));
                     if (elect_one()) {
                         mbar_expect_tx(bar(FULL + s), A_BYTES + B_BYTES);
-                        if (taps == 1) {
+                        if (SPLIT) {      // K-chunk 3c + p: (a_hi, w_hi), (a_hi, w_lo), (a_lo, w_hi) of input columns 64c ..
+                            const int c = k / 3, p = k - 3 * c, k_in = K / 3;
+                            tma_load_2d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), c * BK + (p == 2 ? k_in : 0),
+                                        (int)(mt * BM));
+                            tma_load_2d(sbase + OFF_B + s * B_BYTES, &map_w, bar(FULL + s), c * BK + (p == 1 ? k_in : 0), nt * BN);
+                        } else if (taps == 1) {
                             tma_load_2d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), k * BK, (int)(mt * BM));
                         } else {          // K-chunk (tap, c): the tile's cycles, shifted by tap - 1 positions (zeros outside)
                             const int kin = n_k / taps, tap = k / kin, c = k - tap * kin;
                             tma_load_3d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), c * BK, tap - (taps >> 1),
                                         (int)(mt * (BM / cyc_len)));
                         }
-                        tma_load_2d(sbase + OFF_B + s * B_BYTES, &map_w, bar(FULL + s), k * BK, nt * BN);
+                        if (!SPLIT)
+                            tma_load_2d(sbase + OFF_B + s * B_BYTES, &map_w, bar(FULL + s), k * BK, nt * BN);
                     }
                     __syncwarp();
                 }
@@ -227,6 +244,7 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                 }
                 uint32_t packed[16];
+                uint32_t packed_lo[SPLIT ? 16 : 1];
                 float bv[32];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -245,9 +263,17 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         hv[c] = x0;
                         hv[c + 1] = x1;
                     }
-                    const __nv_bfloat162 pk = out_gelu ? __floats2bfloat162_rn(gelu_fast(x0), gelu_fast(x1))
-                                                       : __floats2bfloat162_rn(x0, x1);
-                    packed[c >> 1] = *reinterpret_cast<const uint32_t *>(&pk);
+                    if (SPLIT) {
+                        const float g0 = out_gelu ? gelu_erf(x0) : x0, g1 = out_gelu ? gelu_erf(x1) : x1;
+                        const __nv_bfloat162 pk = __floats2bfloat162_rn(g0, g1);
+                        const __nv_bfloat162 pl = __floats2bfloat162_rn(g0 - __low2float(pk), g1 - __high2float(pk));
+                        packed[c >> 1] = *reinterpret_cast<const uint32_t *>(&pk);
+                        packed_lo[c >> 1] = *reinterpret_cast<const uint32_t *>(&pl);
+                    } else {
+                        const __nv_bfloat162 pk = out_gelu ? __floats2bfloat162_rn(gelu_fast(x0), gelu_fast(x1))
+                                                           : __floats2bfloat162_rn(x0, x1);
+                        packed[c >> 1] = *reinterpret_cast<const uint32_t *>(&pk);
+                    }
                 }
                 if (MODE != 0) {
                     __syncwarp();
@@ -266,19 +292,25 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 if (out) {
                     // bf16 rows are 64 bytes: chunk c of row r at r*64 + ((c ^ ((r >> 1) & 3)) << 4); global moves use
-                    // lane -> (row 8i + lane/4, chunk lane%4): 8 row segments of 64 bytes per instruction
-                    __syncwarp();
+                    // lane -> (row 8i + lane/4, chunk lane%4): 8 row segments of 64 bytes per instruction.
+                    // Split form: rows of `out` are 2 N wide, the hi slab goes to column col0, the lo slab to N + col0.
+                    const int64_t ld_out = SPLIT ? 2 * (int64_t)N : (int64_t)N;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        *reinterpret_cast<uint4 *>(xp + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
-                            make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-                    __syncwarp();
+                    for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+                        const uint32_t *pk = part == 0 ? packed : packed_lo;
+                        __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rr = 8 * i + (lane >> 2), cc = lane & 3;
-                        const uint4 t = *reinterpret_cast<const uint4 *>(xp + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
-                        if (row0 + rr < n_tokens)
-                            *reinterpret_cast<uint4 *>(out + (row0 + rr) * N + col0 + 8 * cc) = t;
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<uint4 *>(xp + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int rr = 8 * i + (lane >> 2), cc = lane & 3;
+                            const uint4 t = *reinterpret_cast<const uint4 *>(xp + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+                            if (row0 + rr < n_tokens)
+                                *reinterpret_cast<uint4 *>(out + (row0 + rr) * ld_out + part * N + col0 + 8 * cc) = t;
+                        }
                     }
                 }
             }
@@ -321,6 +353,40 @@ cudaError_t launch_tok_bias_gelu(float *h, const float *bias, void *out, int64_t
     const int64_t blocks = (n_vec4 + 255) / 256;
     const int grid = (int)(blocks < (int64_t)sm_count * 16 ? blocks : (int64_t)sm_count * 16);
     tok_bias_gelu_kernel<<<grid, 256, 0, st>>>(h, bias, (__nv_bfloat16 *)out, n_vec4, N / 4);
+    return cudaGetLastError();
+}
+
+// out = [bf16(g) | bf16(g - bf16(g))] (T, 2 N) with g = gelu_erf(h) or h itself: the operand pair the split layers read, made
+// from a fp32 (T, N) tensor (the patch embedding's output in front of the first block).  4 N bytes in, 4 N out per token.
+__global__ void __launch_bounds__(256) tok_pair_kernel(const float *__restrict__ h, __nv_bfloat16 *__restrict__ out,
+                                                       int64_t n_vec4, int n4, int apply_gelu)
+{
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n_vec4; t += (int64_t)gridDim.x * 256) {
+        float4 v = __ldcs(reinterpret_cast<const float4 *>(h) + t);
+        if (apply_gelu) {
+            v.x = tl::gelu_erf(v.x); v.y = tl::gelu_erf(v.y); v.z = tl::gelu_erf(v.z); v.w = tl::gelu_erf(v.w);
+        }
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+        const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+        const int64_t row = t / n4;
+        const int c4 = (int)(t - row * n4);
+        uint2 *o = reinterpret_cast<uint2 *>(out) + row * (2 * n4) + c4;
+        o[0] = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+        o[n4] = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+    }
+}
+
+cudaError_t launch_tok_pair(const float *h, void *out, int64_t n_tokens, int N, int apply_gelu, int sm_count, cudaStream_t st)
+{
+    if (N % 4 != 0)
+        return cudaErrorNotSupported;
+    const int64_t n_vec4 = n_tokens * (N / 4);
+    if (n_vec4 == 0)
+        return cudaSuccess;
+    const int64_t blocks = (n_vec4 + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)sm_count * 16 ? blocks : (int64_t)sm_count * 16);
+    tok_pair_kernel<<<grid, 256, 0, st>>>(h, (__nv_bfloat16 *)out, n_vec4, N / 4, apply_gelu);
     return cudaGetLastError();
 }
 
@@ -500,35 +566,38 @@ bool tok_linear_supported(int K, int N) { return K >= tl::BK && K % tl::BK == 0 
 
 cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, float *h, void *out, int64_t n_tokens,
                               int K, int N, int mode, int sm_count, int max_smem, cudaStream_t st, int taps, int cyc_len,
-                              int out_gelu)
+                              int out_gelu, int split)
 {
     using namespace tl;
     const int smem_bytes = mode == 0 ? Plan<0>::SMEM_BYTES : Plan<1>::SMEM_BYTES;
     if (!tok_linear_supported(K, N) || smem_bytes > max_smem || (mode != 0 && !h) || (mode == 0 && !out))
         return cudaErrorNotSupported;
     // three taps: whole cycles of cyc_len tokens, a 128-token tile holds whole cycles
+    if (split && taps != 1)
+        return cudaErrorNotSupported;
     if (taps != 1 && (taps != 3 || cyc_len < 1 || BM % cyc_len != 0 || n_tokens % cyc_len != 0 || cyc_len > 256))
         return cudaErrorNotSupported;
     if (n_tokens == 0)
         return cudaSuccess;
     CUtensorMap map_a, map_w;
     if (taps == 1) {
-        if (!make_bf16_map(&map_a, a, n_tokens, K, BM))
+        if (!make_bf16_map(&map_a, a, n_tokens, split ? 2 * K : K, BM))
             return cudaErrorNotSupported;
     } else if (!tc::make_tensor_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, n_tokens / cyc_len, cyc_len, K, BM / cyc_len,
                                        cyc_len, BK, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) {
         return cudaErrorNotSupported;
     }
-    if (!make_bf16_map(&map_w, w, N, taps * K, BN))
+    if (!make_bf16_map(&map_w, w, N, split ? 2 * K : taps * K, BN))
         return cudaErrorNotSupported;
     const int64_t items = (n_tokens + BM - 1) / BM * (N / BN);
     const int grid = (int)(items < sm_count ? items : sm_count);
-    auto kern = mode == 0 ? tok_linear_kernel<0> : mode == 1 ? tok_linear_kernel<1> : tok_linear_kernel<2>;
+    auto kern = split ? (mode == 0 ? tok_linear_kernel<0, true> : mode == 1 ? tok_linear_kernel<1, true> : tok_linear_kernel<2, true>)
+                      : (mode == 0 ? tok_linear_kernel<0, false> : mode == 1 ? tok_linear_kernel<1, false> : tok_linear_kernel<2, false>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (err != cudaSuccess)
         return err;
-    kern<<<grid, THREADS, smem_bytes, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, taps * K, N, taps, cyc_len,
-                                            out_gelu);
+    kern<<<grid, THREADS, smem_bytes, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, split ? 3 * K : taps * K, N, taps,
+                                            cyc_len, out_gelu);
     return cudaGetLastError();
 }
 

@@ -320,6 +320,57 @@ int vqb_token_conv(int device, const void *a_bf16, const void *w_bf16, const flo
     return VQB_OK;
 }
 
+int vqb_token_linear_split(int device, const void *a_pair, const void *w_pair, const float *bias, float *h, void *out_pair,
+                           int64_t n_tokens, int k, int n, unsigned mode, int out_gelu, void *stream)
+{
+    if (!a_pair || !w_pair || !bias || n_tokens < 0 || mode > 2u || (mode != 0u && !h) || (mode == 0u && !out_pair))
+        return VQB_E_ARG;
+    if (!tok_linear_supported(k, n) || !aligned(a_pair, 16) || !aligned(w_pair, 16) || !aligned(bias, 16) ||
+        (h && !aligned(h, 16)) || (out_pair && !aligned(out_pair, 16)))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_tok_linear(a_pair, w_pair, bias, h, out_pair, n_tokens, k, n, (int)mode, info.sm_count,
+                            info.max_smem_per_block, (cudaStream_t)stream, 1, 1, out_gelu ? 1 : 0, 1);
+    if (err == cudaErrorNotSupported)
+        return VQB_E_UNSUPPORTED;
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_tokens > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
+int vqb_token_pair(int device, const float *h, void *out_pair, int64_t n_tokens, int n, int apply_gelu, void *stream)
+{
+    if (!h || !out_pair || n_tokens < 0 || n <= 0)
+        return VQB_E_ARG;
+    if (n % 4 != 0 || !aligned(h, 16) || !aligned(out_pair, 8))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_tok_pair(h, out_pair, n_tokens, n, apply_gelu ? 1 : 0, info.sm_count, (cudaStream_t)stream);
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_tokens > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
 int vqb_token_out_proj(int device, const void *a_bf16, const float *w, float bias, float *out, int64_t n_rows, int hidden, int p,
                        void *stream)
 {

@@ -136,7 +136,8 @@ cudaError_t launch_fwd_tc_chunked(const FwdParams &p, float *tc_scratch, int sm_
 bool tok_linear_supported(int K, int N);
 cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, float *h, void *out, int64_t n_tokens,
                               int K, int N, int mode, int sm_count, int max_smem, cudaStream_t st, int taps = 1,
-                              int cyc_len = 1, int out_gelu = 1);
+                              int cyc_len = 1, int out_gelu = 1, int split = 0);
+cudaError_t launch_tok_pair(const float *h, void *out, int64_t n_tokens, int N, int apply_gelu, int sm_count, cudaStream_t st);
 bool tok_out_proj_supported(int H, int P);
 cudaError_t launch_tok_out_proj(const void *a, const float *w, float bias, float *out, int64_t n_rows, int H, int P, int sm_count,
                                 cudaStream_t st);

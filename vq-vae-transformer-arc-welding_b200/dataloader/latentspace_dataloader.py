@@ -262,7 +262,9 @@ class LatentSpaceEncoder:
         """encoder_mode: "auto" (default) selects the model's fused tcgen05 encoder ("fused_bf16": bf16 operands for the
         hidden layers, fp32 accumulation and residual stream) when the model offers it -- the reference builds its latent
         data sets under torch.set_float32_matmul_precision('medium') (train_transformer_mtasks.py:245), i.e. with bf16
-        matmuls too; "torch" keeps the fp32 PyTorch layers; None leaves the model's setting alone."""
+        matmuls too; "fused_fp32" is the fp32-faithful form of the same kernels (bf16 hi + lo operand pairs, ~3.5x slower,
+        ids equal to the fp32 layers' except on ~1e-5 of the tokens); "torch" keeps the fp32 PyTorch layers; None leaves
+        the model's setting alone (VQVAEPatch's own default is "auto" = "fused_fp32" for inference calls)."""
         if device is None:
             # the reference hard-codes cuda:0 (:34); one process per GPU uses its own device
             device = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"

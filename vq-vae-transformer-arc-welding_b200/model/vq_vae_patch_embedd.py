@@ -178,11 +178,15 @@ class VQVAEPatch(Autoencoder):
         self.apply(self.weights_init)
 
     # ---- encode half: the hot path ------------------------------------------------------
-    #: "torch": stock PyTorch layers in the ambient matmul precision (default, fp32-faithful);
+    #: "auto" (default): "fused_fp32" whenever the call qualifies (CUDA fp32 input, eval mode, no autograd, hidden size a
+    #: multiple of 256, centre-tap residual blocks), the PyTorch layers otherwise (training, CPU, narrow models);
+    #: "torch": stock PyTorch layers in the ambient matmul precision (fp32-faithful; the only mode that trains);
+    #: "fused_fp32": inference on the tcgen05 layer kernel with bf16 hi + lo operand pairs (three products per layer, fp32
+    #: accumulation, erf GELU): operand precision 2^-16, ids equal to the fp32 layers' except on ~1e-5 of the tokens;
     #: "fused_bf16": the residual blocks run on the fused tcgen05 layer kernel (csrc/tok_linear.cu) with bf16
     #: operands / fp32 accumulation -- the operand precision the reference itself selects with
     #: torch.set_float32_matmul_precision('medium') (train_*.py), without the element-wise passes.
-    encoder_mode = "torch"
+    encoder_mode = "auto"
     #: in "fused_bf16" mode: all residual blocks in one launch (csrc/enc_chain.cu) instead of one launch per layer
     fused_chain = True
     #: ... with the final H -> D projection fused into the same launch (operand bf16(h), weights exact to 2^-17)
@@ -192,6 +196,12 @@ class VQVAEPatch(Autoencoder):
 
     def encode(self, x):
         """x (B, seq_len, input_dim) -> z_e (B, T, D)."""
+        if self.encoder_mode in ("auto", "fused_fp32") and self._fused_ok(x):
+            torch.cuda.nvtx.range_push("vqb200.encode_fused_fp32")
+            try:
+                return self.encode_fused_fp32(x)
+            finally:
+                torch.cuda.nvtx.range_pop()
         if self.encoder_mode == "fused_bf16" and self._fused_ok(x):
             torch.cuda.nvtx.range_push("vqb200.encode_fused_bf16")
             try:
@@ -299,6 +309,85 @@ class VQVAEPatch(Autoencoder):
         proj = self.encoder[1].shared_conv
         z_e = F.linear(h, proj.weight[:, :, 0], proj.bias)
         return z_e.view(b, -1, z_e.shape[-1])
+
+    def _split_weights(self):
+        """Operands of the fp32-faithful fused encoder: every layer's centre tap (eval-mode BatchNorm folded in, in fp32) as a
+        bf16 hi + lo pair (ops.bf16_pair), the projection likewise on 256 zero-padded rows, the patch embedding as the
+        three-product operand of one bf16 GEMM.  Rebuilt when a parameter or running statistic changes."""
+        from .. import ops
+        blocks = list(self.encoder[0].shared_conv)
+        tracked = [t for blk in blocks for m in (blk.block[1], blk.block[2], blk.block[4], blk.block[5])
+                   for t in list(m.parameters()) + list(m.buffers())] + list(self.encoder[1].shared_conv.parameters()) \
+            + list(self.patch_embed.proj.parameters())
+        key = tuple((t.data_ptr(), t._version) for t in tracked)
+        cache = getattr(self, "_split_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+
+        def fold(conv, norm, c):
+            w, b = conv.weight[:, :, c].float(), conv.bias.float()
+            if isinstance(norm, nn.BatchNorm1d):
+                scale = norm.weight.float() / torch.sqrt(norm.running_var.float() + norm.eps)
+                w, b = w * scale[:, None], (b - norm.running_mean.float()) * scale + norm.bias.float()
+            return ops.bf16_pair(w), b.contiguous()
+
+        with torch.no_grad():
+            layers = []
+            for blk in blocks:
+                layers.append(fold(blk.block[1], blk.block[2], blk.padding) + fold(blk.block[4], blk.block[5], blk.padding))
+            proj = self.encoder[1].shared_conv
+            d, hidden = proj.weight.shape[0], proj.weight.shape[1]
+            wp = torch.zeros(256, hidden, device=proj.weight.device)
+            wp[:d] = proj.weight[:, :, 0].float()
+            bp = torch.zeros(256, device=proj.weight.device)
+            bp[:d] = proj.bias.float()
+            pe = self.patch_embed.proj
+            w_pe = None
+            if pe.kernel_size[0] <= 32:
+                # [a_hi | a_lo | a_hi | 0] (T, 128) against [w_hi | w_hi | w_lo | 0]: a_hi w_hi + a_lo w_hi + a_hi w_lo
+                wpe = pe.weight[:, 0, :].float()
+                hi = wpe.to(torch.bfloat16)
+                lo = (wpe - hi.float()).to(torch.bfloat16)
+                w_pe = torch.zeros(hidden, 128, dtype=torch.bfloat16, device=wpe.device)
+                w_pe[:, :wpe.shape[1]] = hi
+                w_pe[:, 32:32 + wpe.shape[1]] = hi
+                w_pe[:, 64:64 + wpe.shape[1]] = lo
+            ops_ = dict(layers=layers, wp=ops.bf16_pair(wp), bp=bp, d=d, w_pe=w_pe, b_pe=pe.bias.float().contiguous())
+        object.__setattr__(self, "_split_cache", (key, ops_))
+        return ops_
+
+    def encode_fused_fp32(self, x):
+        """The encoder on the tcgen05 layer kernel in its fp32-faithful form (vqb_token_linear_split): activations and
+        weights travel as bf16 hi + lo pairs (2^-17 each), three products per layer accumulate in fp32, GELU in the erf
+        form, fp32 residual stream.  ids equal the fp32 PyTorch encoder's except where two codes are within ~1e-5 of
+        each other (tests/test_gpu_encoder.py); ~3x the tensor work of `fused_bf16`, one launch per layer."""
+        from .. import ops
+        b = x.shape[0]
+        pe = self.patch_embed
+        hidden = pe.proj.out_channels
+        w = self._split_weights()
+        if hidden == 512 and pe.patch_size <= 64 and x.is_contiguous():
+            h, _ = ops.patch_embed(x, pe.proj.weight, pe.proj.bias, pe.patch_size, want_act=False)   # fp32 FMA arithmetic
+        elif w["w_pe"] is not None and x.is_contiguous():
+            a0 = ops.patch_split(x, pe.patch_size)                                    # (B*T, 64) = [hi | lo]
+            a0 = torch.cat([a0, a0[:, :32], torch.zeros_like(a0[:, :32])], dim=1)     # (B*T, 128)
+            h = torch.empty(a0.shape[0], hidden, dtype=torch.float32, device=x.device)
+            ops.token_linear(a0, w["w_pe"], w["b_pe"], h=h, mode=2)
+        else:
+            patches = x.permute(0, 2, 1).reshape(-1, pe.patch_size)
+            h = torch.addmm(pe.proj.bias, patches, pe.proj.weight[:, 0, :].t())
+        a = ops.token_pair(h, gelu=True)                                              # (B*T, 2H) pair of gelu(h)
+        u = torch.empty_like(a)
+        layers = w["layers"]
+        for i, (w1, b1, w2, b2) in enumerate(layers):
+            ops.token_linear_split(a, w1, b1, out=u, mode=0)                          # u = gelu(W1 a + b1)
+            # h += W2 u + b2; a = pair(gelu(h)) for the next block, pair(h) for the projection after the last one
+            ops.token_linear_split(u, w2, b2, h=h, out=a, mode=1, out_gelu=i + 1 < len(layers))
+        if not layers:
+            ops.token_pair(h, gelu=False, out=a)
+        z = torch.empty(h.shape[0], 256, dtype=torch.float32, device=x.device)
+        ops.token_linear_split(a, w["wp"], w["bp"], h=z, mode=2, out_gelu=False)                      # z[:, :D] = Wp h + bp
+        return z[:, :w["d"]].contiguous().view(b, -1, w["d"])
 
     def encode_ids(self, x):
         """Token ids (B, T) int64 -- the encode call of dataloader/latentspace_dataloader.py:154-161

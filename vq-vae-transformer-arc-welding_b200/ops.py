@@ -420,6 +420,60 @@ def token_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Option
     return out
 
 
+def bf16_pair(x: torch.Tensor) -> torch.Tensor:
+    """(R, C) fp32 -> (R, 2 C) bf16 = [bf16(x) | bf16(x - bf16(x))]: the operand pair of the split layers (weights; built once
+    per weight version with torch ops -- activations are paired by the kernels themselves)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=1).contiguous()
+
+
+def token_pair(h: torch.Tensor, gelu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(T, N) fp32 -> (T, 2 N) bf16 pair of gelu(h) (erf form) or of h itself -- vqb_token_pair."""
+    if not h.is_cuda or h.dtype != torch.float32 or not h.is_contiguous() or h.dim() != 2:
+        raise RuntimeError("token_pair: h must be a contiguous CUDA fp32 (T, N) tensor (no CPU fallback)")
+    t_rows, n = h.shape
+    if out is None:
+        out = torch.empty((t_rows, 2 * n), dtype=torch.bfloat16, device=h.device)
+    elif out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape) != (t_rows, 2 * n):
+        raise RuntimeError("token_pair: out must be a contiguous bf16 (T, 2 N) tensor")
+    lib = _lib.load()
+    with torch.cuda.device(h.device):
+        rc = lib.vqb_token_pair(h.device.index, h.data_ptr(), out.data_ptr(), t_rows, n, int(bool(gelu)),
+                                torch.cuda.current_stream(h.device).cuda_stream)
+    _lib.check(rc, "vqb_token_pair")
+    return out
+
+
+def token_linear_split(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Optional[torch.Tensor] = None,
+                       out: Optional[torch.Tensor] = None, mode: int = 0, out_gelu: bool = True) -> Optional[torch.Tensor]:
+    """token_linear on bf16 hi + lo operand pairs (vqb_token_linear_split): fp32-faithful to 2^-16 per product.
+    a (T, 2 K) = [a_hi | a_lo], w (N, 2 K) = [w_hi | w_lo] (bf16_pair), bias (N,) fp32, h (T, N) fp32,
+    out (T, 2 N) bf16 pair of gelu(x) (erf form), or of x itself with out_gelu = False."""
+    for t, name, dt in ((a, "a", torch.bfloat16), (w, "w", torch.bfloat16), (bias, "bias", torch.float32)):
+        if not t.is_cuda or t.dtype != dt or not t.is_contiguous():
+            raise RuntimeError(f"{name} must be a contiguous CUDA {dt} tensor (no CPU fallback)")
+    t_rows, k2 = a.shape
+    n = w.shape[0]
+    if w.shape[1] != k2 or k2 % 2 or bias.numel() != n:
+        raise RuntimeError("token_linear_split: shape mismatch")
+    if mode == 0 and out is None:
+        out = torch.empty((t_rows, 2 * n), dtype=torch.bfloat16, device=a.device)
+    if mode != 0 and (h is None or h.dtype != torch.float32 or not h.is_contiguous() or tuple(h.shape) != (t_rows, n)):
+        raise RuntimeError("token_linear_split modes 1 and 2 need a contiguous fp32 h of shape (T, N)")
+    if out is not None and (out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape) != (t_rows, 2 * n)):
+        raise RuntimeError("token_linear_split: out must be a contiguous bf16 (T, 2 N) tensor")
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.vqb_token_linear_split(a.device.index, a.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                        h.data_ptr() if h is not None else None,
+                                        out.data_ptr() if out is not None else None,
+                                        t_rows, k2 // 2, n, int(mode), int(bool(out_gelu)),
+                                        torch.cuda.current_stream(a.device).cuda_stream)
+    _lib.check(rc, "vqb_token_linear_split")
+    return out
+
+
 def token_conv(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Optional[torch.Tensor] = None,
                out: Optional[torch.Tensor] = None, mode: int = 0, taps: int = 3, tokens_per_cycle: int = 16,
                out_gelu: bool = True) -> Optional[torch.Tensor]:
