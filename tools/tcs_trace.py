@@ -9,7 +9,8 @@ from vqb200 import ops
 dev = torch.device("cuda:0")
 lib = vqb200._lib.load()
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-kw = {"want_zq": False, "want_loss": False} if (len(sys.argv) > 2 and sys.argv[2] == "ids") else {}
+mode = sys.argv[2] if len(sys.argv) > 2 else "full"
+kw = {"ids": {"want_zq": False, "want_loss": False}, "loss": {"want_zq": False}, "zq": {"want_loss": False}}.get(mode, {})
 n, D = 1 << 24, 32
 nc = (K + 255) // 256
 z = 0.1 * torch.randn(n, D, device=dev)

@@ -52,3 +52,10 @@ with torch.no_grad():
             z0 = z
         print(f"encode_ids {m}: {ms:.2f} ms per 65536 cycles = {65536 * 16 / ms / 1e3:.1f} M patches/s; ids equal to torch: "
               f"{(res[m] == res['torch']).double().mean().item():.7f}; max |z - z_torch| / range = {(z - z0).abs().max().item() / z0.abs().max().item():.2e}")
+from torch.profiler import profile, ProfilerActivity
+model.encoder_mode = "fused_fp32"
+with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(2):
+        model.encode_ids(x)
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=70))

@@ -197,6 +197,70 @@ __device__ __forceinline__ float emit_tile(int t, int q4, int q4_shift, const in
     return rs2.x + rs2.y;
 }
 
+// The same walk by ONE warp, software-pipelined (ND == 1: four emit warps, each with its own tile -- the four code lists
+// [group][slot] are four tiles in flight).  With all four warps on one tile (emit_tile<128>) a tile took ~3300 clocks, nearly
+// all of it the L2 latency of a single batch of loads, and at K = 512 the walk -- not the 14 MMAs of a tile pair -- set the
+// tile period (full outputs 2.08 ms against 1.39 ms for ids only).  Here a lane owns 4 q4 float4 of the tile in batches of 4;
+// the loads of batch b + 1 (z and codebook row: both addresses follow from the code list in shared memory) are in flight
+// while batch b is added and stored, so a tile exposes one L2 latency instead of one per batch.
+template <bool POW2, bool POISON>
+__device__ __forceinline__ float emit_tile_warp(int lane, int q4, int q4_shift, const int *codes_s, const float4 *__restrict__ z4,
+                                                const float4 *__restrict__ e4, float4 *__restrict__ o4, const int *colcnt,
+                                                const int *colwhich)
+{
+    float2 rs2 = make_float2(0.f, 0.f);
+    const int nb = q4;                                  // batches of 4 x 32 float4: 128 q4 float4 per tile
+    int cdA[4], ccA[4], cdB[4], ccB[4];
+    float4 zA[4], eA[4], zB[4], eB[4];
+    auto load = [&](int b, int (&cd)[4], int (&cc)[4], float4 (&zv)[4], float4 (&ev)[4]) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int f = b * 128 + u * 32 + lane;
+            const int rr = POW2 ? f >> q4_shift : f / q4;
+            cc[u] = POW2 ? f & (q4 - 1) : f - rr * q4;
+            cd[u] = b < nb ? codes_s[rr] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            zv[u] = cd[u] >= 0 ? __ldcg(z4 + b * 128 + u * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ev[u] = cd[u] >= 0 ? __ldcg(e4 + (unsigned)(cd[u] * q4 + cc[u])) : zv[u];
+        }
+    };
+    auto process = [&](int b, const int (&cd)[4], const int (&cc)[4], const float4 (&zv)[4], float4 (&ev)[4]) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (cd[u] < 0)
+                continue;
+            if (POISON) {   // gather-by-GEMM semantics for a non-finite codebook (oracle column_poison)
+                float *evp = reinterpret_cast<float *>(&ev[u]);
+                for (int w = 0; w < 4; ++w) {
+                    const int j = 4 * cc[u] + w, cnt = colcnt[j];
+                    if (!(cnt == 0 || (cnt == 1 && colwhich[j] == cd[u] + 1)))
+                        evp[w] = __int_as_float(0x7fc00000);
+                }
+            }
+            const float2 d01 = __fadd2_rn(make_float2(ev[u].x, ev[u].y), make_float2(-zv[u].x, -zv[u].y));   // fl(e - z)
+            const float2 d23 = __fadd2_rn(make_float2(ev[u].z, ev[u].w), make_float2(-zv[u].z, -zv[u].w));
+            rs2 = __ffma2_rn(d01, d01, rs2);
+            rs2 = __ffma2_rn(d23, d23, rs2);
+            if (o4) {
+                const float2 o01 = __fadd2_rn(make_float2(zv[u].x, zv[u].y), d01);                            // fl(z + fl(e - z))
+                const float2 o23 = __fadd2_rn(make_float2(zv[u].z, zv[u].w), d23);
+                __stcs(o4 + b * 128 + u * 32 + lane, make_float4(o01.x, o01.y, o23.x, o23.y));
+            }
+        }
+    };
+    load(0, cdA, ccA, zA, eA);
+#pragma unroll 1
+    for (int b = 0; b < nb; b += 2) {
+        load(b + 1, cdB, ccB, zB, eB);                  // (beyond the tile: predicated off)
+        process(b, cdA, ccA, zA, eA);
+        load(b + 2, cdA, ccA, zA, eA);
+        process(b + 1, cdB, ccB, zB, eB);
+    }
+    return rs2.x + rs2.y;
+}
+
 }  // namespace tcs
 
 // ---------------------------------------------------------------------------------------
@@ -331,7 +395,7 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
         }
         for (int b = 0; b < 4; ++b) {
             mbar_init(bar(E_FULL + b), TF32 ? 160 : 128);    // TF32: + the tile's refiner warp
-            mbar_init(bar(E_EMPTY + b), 32 * C::NE);
+            mbar_init(bar(E_EMPTY + b), C::NG == 2 ? 32 : 32 * C::NE);   // ND == 1: one emit warp per code list
         }
         fence_barrier_init();
     }
@@ -379,7 +443,11 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
             const int *codes_all = reinterpret_cast<const int *>(smem + C::OFF_CODES);
             float sqf = 0.0f;
             int run = 0;
-            for (int i = 0; i < my_tiles; ++i) {
+            // ND == 1: the code lists [group e][slot] are four tiles in flight, and emit warp w = 2 e + slot walks the tiles of
+            // list w on its own (emit_tile_warp); wider vectors: all eight warps walk one tile together (emit_tile)
+            constexpr bool PER_WARP = NG == 2;
+            const int ew = t >> 5;
+            for (int i = PER_WARP ? ((ew & 1) << 1 | (ew >> 1)) : 0; i < my_tiles; i += PER_WARP ? 4 : 1) {
                 const int e = NG == 2 ? (i & 1) : 0;
                 const unsigned tl = (unsigned)(i / NG);
                 const int slot = (int)(tl & 1u);
@@ -391,11 +459,21 @@ vq_fwd_tcs_kernel(const FwdParams p, unsigned char *__restrict__ img, const __gr
                 const int *codes_s = codes_all + (e * 2 + slot) * TILE_M;
                 const float4 *z4 = reinterpret_cast<const float4 *>(p.z.base) + (size_t)tile * TILE_M * q4;
                 float4 *o4 = p.zq ? reinterpret_cast<float4 *>(p.zq) + (size_t)tile * TILE_M * q4 : nullptr;
-                const float rs = q4_shift >= 0
-                                     ? (poisoned ? emit_tile<ET, true, true>(t, q4, q4_shift, codes_s, z4, e4, o4, p.colcnt, p.colwhich)
-                                                 : emit_tile<ET, true, false>(t, q4, q4_shift, codes_s, z4, e4, o4, nullptr, nullptr))
-                                     : (poisoned ? emit_tile<ET, false, true>(t, q4, q4_shift, codes_s, z4, e4, o4, p.colcnt, p.colwhich)
-                                                 : emit_tile<ET, false, false>(t, q4, q4_shift, codes_s, z4, e4, o4, nullptr, nullptr));
+                float rs;
+                if (PER_WARP) {
+                    const int ln = t & 31;
+                    rs = q4_shift >= 0
+                             ? (poisoned ? emit_tile_warp<true, true>(ln, q4, q4_shift, codes_s, z4, e4, o4, p.colcnt, p.colwhich)
+                                         : emit_tile_warp<true, false>(ln, q4, q4_shift, codes_s, z4, e4, o4, nullptr, nullptr))
+                             : (poisoned ? emit_tile_warp<false, true>(ln, q4, q4_shift, codes_s, z4, e4, o4, p.colcnt, p.colwhich)
+                                         : emit_tile_warp<false, false>(ln, q4, q4_shift, codes_s, z4, e4, o4, nullptr, nullptr));
+                } else {
+                    rs = q4_shift >= 0
+                             ? (poisoned ? emit_tile<ET, true, true>(t, q4, q4_shift, codes_s, z4, e4, o4, p.colcnt, p.colwhich)
+                                         : emit_tile<ET, true, false>(t, q4, q4_shift, codes_s, z4, e4, o4, nullptr, nullptr))
+                             : (poisoned ? emit_tile<ET, false, true>(t, q4, q4_shift, codes_s, z4, e4, o4, p.colcnt, p.colwhich)
+                                         : emit_tile<ET, false, false>(t, q4, q4_shift, codes_s, z4, e4, o4, nullptr, nullptr));
+                }
                 mbar_arrive(bar(E_EMPTY + e * 2 + slot));     // (the code list has been read: its slot may be rewritten)
                 if ((t & 31) == 0) stamp(i * nc + nc - 1, 7);
                 sqf += rs;
