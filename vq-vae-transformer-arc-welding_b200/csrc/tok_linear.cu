@@ -33,6 +33,7 @@
 // Tile 128 tokens x 256 outputs, K streamed in 64-element chunks through a 3-stage TMA ring (A 16 KB + W 32 KB per
 // stage, SWIZZLE_128B; tl::Plan), 4 tcgen05.mma (128 x 256 x 16) per chunk into one of two 256-column TMEM accumulators,
 // eight epilogue warps (TMEM lane quarter x column half) that overlap with the next tile's MMAs.
+#include <cstdlib>
 #include "vq_common.cuh"
 #include "vq_ptx.cuh"
 
@@ -42,17 +43,18 @@ namespace tl {
 
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-constexpr int THREADS = 128 + 256;                       // 4 service warps + 8 epilogue warps
+constexpr int THREADS = 128 + 256;                       // 4 service warps + 8 epilogue warps (EW = 16: 128 + 512)
 // Shared-memory plan per mode: three operand stages; modes 1 / 2 give every epilogue warp two 4 KB transposing buffers
 // (residual slab prefetch), mode 0 needs one.  (A fourth stage for mode 0 fits in 227 KB and was measured: 0.63 ms against
 // 0.58-0.61 ms -- with all of the SM's memory carved out as shared memory there is no L1 left for the bias / descriptor loads.)
-template <int MODE> struct Plan {
+// EW = 16 epilogue warps (TMEM lane quarter x column QUARTER, two slabs each): one 4 KB buffer per warp in every mode.
+template <int MODE, int EW = 8> struct Plan {
     static constexpr int STAGES = 3;
-    static constexpr int XPOSE_PER_WARP = MODE == 0 ? 4096 : 8192;
+    static constexpr int XPOSE_PER_WARP = (MODE == 0 || EW == 16) ? 4096 : 8192;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
     static constexpr int OFF_XPOSE = OFF_B + STAGES * B_BYTES;
-    static constexpr int OFF_BARS = OFF_XPOSE + 8 * XPOSE_PER_WARP;
+    static constexpr int OFF_BARS = OFF_XPOSE + EW * XPOSE_PER_WARP;
     static constexpr int SMEM_BYTES = OFF_BARS + 256;
 };
 
@@ -100,16 +102,16 @@ __device__ __forceinline__ float gelu_erf(float x)
 
 }  // namespace tl
 
-template <int MODE, bool SPLIT>
-__global__ void __launch_bounds__(tl::THREADS, 1)
+template <int MODE, bool SPLIT, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const float *__restrict__ bias, float *__restrict__ h, __nv_bfloat16 *__restrict__ out,
                   int64_t n_tokens, int K, int N, int taps, int cyc_len, int out_gelu)
 {
     using namespace tc;
     using namespace tl;
-    constexpr int STAGES = Plan<MODE>::STAGES, OFF_A = Plan<MODE>::OFF_A, OFF_B = Plan<MODE>::OFF_B,
-                  OFF_XPOSE = Plan<MODE>::OFF_XPOSE, OFF_BARS = Plan<MODE>::OFF_BARS;
+    using P = Plan<MODE, EW>;
+    constexpr int STAGES = P::STAGES, OFF_A = P::OFF_A, OFF_B = P::OFF_B, OFF_XPOSE = P::OFF_XPOSE, OFF_BARS = P::OFF_BARS;
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     if ((sbase & 1023u) != 0)
@@ -132,7 +134,7 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar(T_FULL + b), 1);
-            mbar_init(bar(T_EMPTY + b), 256);
+            mbar_init(bar(T_EMPTY + b), 32 * EW);
         }
         fence_barrier_init();
     }
@@ -207,11 +209,143 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 __syncwarp();
             }
         }
-    } else if (warp >= 4) {
+    } else if (EW == 16 && warp >= 4) {
+        // ================= epilogue, 16 warps: TMEM lane quarter x column quarter (64 columns = two 32-column slabs) ==========
+        // Four warps per scheduler instead of two hide the epilogue's dependent chains (the 8-warp epilogue issued at ~46 % with
+        // both of a scheduler's warps stalled on their own previous instruction most of the time).  640 threads leave 96
+        // registers per thread: a slab is worked on in two halves of 16 columns, and a warp has one 4 KB buffer (the residual
+        // slab of the NEXT slab is fetched once this slab's stores have left the buffer).
+        const int q = warp & 3;
+        const int cq = (warp - 4) >> 2;
+        unsigned char *xp = smem + OFF_XPOSE + (warp - 4) * 4096;
+        auto prefetch_h = [&](int64_t row0, int col0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = 4 * i + (lane >> 3), cc = lane & 7;
+                const bool in = row0 + rr < n_tokens;
+                const float *src = in ? h + (row0 + rr) * N + col0 + 4 * cc : h;
+                const uint32_t dst = smem_u32(xp + rr * 128 + ((cc ^ (rr & 7)) << 4));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int64_t it = 0; it < my_items; ++it) {
+            const int b = (int)(it & 1);
+            const int64_t item = blockIdx.x + it * gridDim.x;
+            const int64_t mt = item / n_ntiles;
+            const int nt = (int)(item % n_ntiles);
+            const int64_t row0 = mt * BM + q * 32;
+            if (MODE == 1)
+                prefetch_h(row0, nt * BN + cq * 64);
+            if (warp == 4)
+                mbar_wait<32>(bar(T_FULL + b), (uint32_t)((it >> 1) & 1));
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + b * BN + cq * 64 + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int sl = 0; sl < 2; ++sl) {
+                const int col0 = nt * BN + cq * 64 + sl * 32;
+                uint32_t packed[16];
+                uint32_t packed_lo[SPLIT ? 16 : 1];
+                if (MODE == 1) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + sl * 32 + half * 16, v);
+                    float hv[16], bv[16];
+                    if (MODE == 1) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int ck = half * 4 + c;
+                            const float4 t = *reinterpret_cast<const float4 *>(xp + lane * 128 + ((ck ^ (lane & 7)) << 4));
+                            hv[4 * c] = t.x; hv[4 * c + 1] = t.y; hv[4 * c + 2] = t.z; hv[4 * c + 3] = t.w;
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(bias + col0 + half * 16) + c);
+                        bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w;
+                    }
+                    tmem_wait_ld_fence16(v);
+#pragma unroll
+                    for (int c = 0; c < 16; c += 2) {
+                        float x0 = __uint_as_float(v[c]) + bv[c];
+                        float x1 = __uint_as_float(v[c + 1]) + bv[c + 1];
+                        if (MODE == 1) {
+                            x0 += hv[c];
+                            x1 += hv[c + 1];
+                        }
+                        if (MODE != 0) {
+                            hv[c] = x0;
+                            hv[c + 1] = x1;
+                        }
+                        if (SPLIT) {
+                            const float g0 = out_gelu ? gelu_erf(x0) : x0, g1 = out_gelu ? gelu_erf(x1) : x1;
+                            const __nv_bfloat162 pk = __floats2bfloat162_rn(g0, g1);
+                            const __nv_bfloat162 pl = __floats2bfloat162_rn(g0 - __low2float(pk), g1 - __high2float(pk));
+                            packed[half * 8 + (c >> 1)] = *reinterpret_cast<const uint32_t *>(&pk);
+                            packed_lo[half * 8 + (c >> 1)] = *reinterpret_cast<const uint32_t *>(&pl);
+                        } else {
+                            const __nv_bfloat162 pk = out_gelu ? __floats2bfloat162_rn(gelu_fast(x0), gelu_fast(x1))
+                                                               : __floats2bfloat162_rn(x0, x1);
+                            packed[half * 8 + (c >> 1)] = *reinterpret_cast<const uint32_t *>(&pk);
+                        }
+                    }
+                    if (MODE != 0) {        // (own row, own chunks: no other lane reads or writes them in this phase)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int ck = half * 4 + c;
+                            *reinterpret_cast<float4 *>(xp + lane * 128 + ((ck ^ (lane & 7)) << 4)) =
+                                make_float4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
+                        }
+                    }
+                }
+                if (MODE != 0) {
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + (lane >> 3), cc = lane & 7;
+                        const float4 t = *reinterpret_cast<const float4 *>(xp + rr * 128 + ((cc ^ (rr & 7)) << 4));
+                        if (row0 + rr < n_tokens)
+                            *reinterpret_cast<float4 *>(h + (row0 + rr) * N + col0 + 4 * cc) = t;
+                    }
+                }
+                if (out) {
+                    const int64_t ld_out = SPLIT ? 2 * (int64_t)N : (int64_t)N;
+#pragma unroll
+                    for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+                        const uint32_t *pk = part == 0 ? packed : packed_lo;
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<uint4 *>(xp + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int rr = 8 * i + (lane >> 2), cc = lane & 3;
+                            const uint4 t = *reinterpret_cast<const uint4 *>(xp + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+                            if (row0 + rr < n_tokens)
+                                *reinterpret_cast<uint4 *>(out + (row0 + rr) * ld_out + part * N + col0 + 8 * cc) = t;
+                        }
+                    }
+                }
+                if (MODE == 1 && sl == 0) {
+                    __syncwarp();                         // every lane has taken its stores' data out of the buffer
+                    prefetch_h(row0, col0 + 32);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(T_EMPTY + b));
+        }
+    } else if (EW == 8 && warp >= 4) {
         // ================= epilogue: TMEM -> bias (+ residual) -> GELU -> bf16 =================
         const int q = warp & 3;                           // TMEM lane quarter
         const int ch = (warp - 4) >> 2;                   // column half of the 256-column accumulator
-        unsigned char *xp0 = smem + OFF_XPOSE + (warp - 4) * Plan<MODE>::XPOSE_PER_WARP;
+        unsigned char *xp0 = smem + OFF_XPOSE + (warp - 4) * P::XPOSE_PER_WARP;
         // cp.async of the residual slab `sl` of the current item into buffer `buf` (lane -> row 4i + lane/8, chunk lane%8;
         // rows beyond the tensor are zero-filled): in flight while the tile's MMAs / the previous slab are worked on
         auto prefetch_h = [&](int64_t row0, int col0, int buf) {
@@ -249,7 +383,7 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 // global <-> buffer moves use lane -> (row 4i + lane/8, chunk lane%8), i.e. 4 full lines per instruction.
                 float hv[32];
                 const int64_t row0 = mt * BM + q * 32;
-                unsigned char *xp = xp0 + (MODE == 1 ? (sl & 1) * 4096 : 0);
+                unsigned char *xp = xp0 + (MODE == 1 ? (sl & 1) * 4096 : 0);   // (EW == 8: P::XPOSE_PER_WARP is 8 KB in mode 1)
                 if (MODE == 1) {
                     __syncwarp();                         // every lane is done with the buffer the next slab lands in
                     if (sl < 3) {
@@ -584,6 +718,16 @@ bool make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int cols, i
 
 }  // namespace
 
+// which launches take the 16-warp epilogue by default (measured)
+static bool tok_linear_default_ew16(int mode, int split, int taps)
+{
+    // T = 2^20 tokens, 512 x 512: bf16 form 0.614 / 1.291 ms (modes 0 / 1) against 0.660 / 1.389 with 8 warps; split form 1.547 /
+    // 2.251 against 1.528 / 2.049 -- its mode 0 is MMA-bound either way, and its mode 1 loses more to the single residual buffer
+    // (no prefetch across slabs, 104 bytes of spills at 96 registers) than it gains from the extra warps
+    (void)mode; (void)taps;
+    return !split;
+}
+
 bool tok_linear_supported(int K, int N) { return K >= tl::BK && K % tl::BK == 0 && N >= tl::BN && N % tl::BN == 0; }
 
 cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, float *h, void *out, int64_t n_tokens,
@@ -591,7 +735,11 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
                               int out_gelu, int split)
 {
     using namespace tl;
-    const int smem_bytes = mode == 0 ? Plan<0>::SMEM_BYTES : Plan<1>::SMEM_BYTES;
+    // 16 epilogue warps where measured faster (tools/tok_linear_time.py); VQB_TOK_EW=8 / 16 forces one for A/B runs
+    static const int ew_env = [] { const char *e = getenv("VQB_TOK_EW"); return e ? atoi(e) : 0; }();
+    const bool ew16 = ew_env == 16 || (ew_env != 8 && tok_linear_default_ew16(mode, split, taps));
+    const int smem_bytes = ew16 ? (mode == 0 ? Plan<0, 16>::SMEM_BYTES : Plan<1, 16>::SMEM_BYTES)
+                                : (mode == 0 ? Plan<0>::SMEM_BYTES : Plan<1>::SMEM_BYTES);
     if (!tok_linear_supported(K, N) || smem_bytes > max_smem || (mode != 0 && !h) || (mode == 0 && !out))
         return cudaErrorNotSupported;
     // three taps: whole cycles of cyc_len tokens, a 128-token tile holds whole cycles
@@ -613,12 +761,17 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
         return cudaErrorNotSupported;
     const int64_t items = (n_tokens + BM - 1) / BM * (N / BN);
     const int grid = (int)(items < sm_count ? items : sm_count);
-    auto kern = split ? (mode == 0 ? tok_linear_kernel<0, true> : mode == 1 ? tok_linear_kernel<1, true> : tok_linear_kernel<2, true>)
-                      : (mode == 0 ? tok_linear_kernel<0, false> : mode == 1 ? tok_linear_kernel<1, false> : tok_linear_kernel<2, false>);
+    using KernT = void (*)(const CUtensorMap, const CUtensorMap, const float *, float *, __nv_bfloat16 *, int64_t, int, int, int, int, int);
+    static const KernT table[2][2][3] = {
+        {{tok_linear_kernel<0, false, 8>, tok_linear_kernel<1, false, 8>, tok_linear_kernel<2, false, 8>},
+         {tok_linear_kernel<0, true, 8>, tok_linear_kernel<1, true, 8>, tok_linear_kernel<2, true, 8>}},
+        {{tok_linear_kernel<0, false, 16>, tok_linear_kernel<1, false, 16>, tok_linear_kernel<2, false, 16>},
+         {tok_linear_kernel<0, true, 16>, tok_linear_kernel<1, true, 16>, tok_linear_kernel<2, true, 16>}}};
+    KernT kern = table[ew16 ? 1 : 0][split ? 1 : 0][mode];
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (err != cudaSuccess)
         return err;
-    kern<<<grid, THREADS, smem_bytes, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, split ? 3 * K : taps * K, N, taps,
+    kern<<<grid, 128 + 32 * (ew16 ? 16 : 8), smem_bytes, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, split ? 3 * K : taps * K, N, taps,
                                             cyc_len, out_gelu);
     return cudaGetLastError();
 }
