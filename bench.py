@@ -406,19 +406,33 @@ def config1_leg(args, torch, vqb200, dev):
     tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    with torch.no_grad():
-        for _ in range(2):
-            model(xd)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            model(xd)
-        e1.record()
-        torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_forward():
+        with torch.no_grad():
+            for _ in range(2):
+                res = model(xd)
+            e0.record()
+            for _ in range(5):
+                model(xd)
+            e1.record()
+            torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / 5, res
+
+    model.encoder_mode = model.decoder_mode = "torch"          # the stock PyTorch layers around the fused quantiser
+    torch_ms, (_, hat_torch, _) = timed_forward()
+    model.encoder_mode = model.decoder_mode = "auto"           # the module's default: fp32-faithful tcgen05 layers for inference
+    gpu_ms, (_, hat_auto, _) = timed_forward()
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
-    gpu_ms = e0.elapsed_time(e1) / 5
     out = {"workload": "BASELINE configs[0]: VQVAEPatch.forward (encode + quantise + decode), batch 256, fp32 (TF32 off), eval",
-           "gpu_ms": gpu_ms, "gpu_patches_per_s": 256 * 16 / (gpu_ms * 1e-3)}
+           "gpu_ms": gpu_ms, "gpu_patches_per_s": 256 * 16 / (gpu_ms * 1e-3),
+           "modes": "encoder_mode = decoder_mode = 'auto' (the default) = 'fused_fp32': vqb_token_linear_split / vqb_token_conv_split "
+                    "(bf16 hi+lo operand pairs, three tcgen05 products per layer, fp32 accumulation and residual streams, erf GELU), "
+                    "exact quantiser",
+           "x_hat_max_abs_dev_vs_torch_layers": float((hat_auto - hat_torch).abs().max().item()),
+           "x_hat_max_abs": float(hat_torch.abs().max().item()),
+           "torch_layers": {"gpu_ms": torch_ms, "gpu_patches_per_s": 256 * 16 / (torch_ms * 1e-3),
+                            "modes": "encoder_mode = decoder_mode = 'torch' (stock PyTorch fp32 layers, fused quantiser)"}}
     # the same forward with BOTH halves on the hand-written tcgen05 layer kernels (bf16 operands, fp32 accumulation and
     # residual streams; the quantiser stays exact), at the configuration's batch and at a batch that fills the GPU
     with torch.no_grad():

@@ -183,6 +183,20 @@ int vqb_token_conv(int device, const void *a_bf16, const void *w_bf16, const flo
 int vqb_token_linear_split(int device, const void *a_pair, const void *w_pair, const float *bias, float *h, void *out_pair,
                            int64_t n_tokens, int k, int n, unsigned mode, int out_gelu, void *stream);
 
+/* vqb_token_conv in the fp32-faithful form (the decoder's Conv1d(k = 3, pad = 1) layers, its 1x1 input convolution and the first
+ * transposed convolution of PatchEmbeddingInverse; model/vq_vae_patch_embedd.py:19-57,60-74,142-147): operands as bf16 pairs like
+ * vqb_token_linear_split -- a_pair (n_tokens, 2 k_in) = [a_hi | a_lo], w_pair (n, taps * 2 k_in) = per tap [w_hi | w_lo],
+ * out_pair (n_tokens, 2 n).  Cycles, taps, modes and out_gelu as in vqb_token_conv. */
+int vqb_token_conv_split(int device, const void *a_pair, const void *w_pair, const float *bias, float *h, void *out_pair,
+                         int64_t n_tokens, int k_in, int n, unsigned mode, int taps, int tokens_per_cycle, int out_gelu,
+                         void *stream);
+
+/* vqb_token_out_proj on a bf16 pair: a_pair (n_tokens, 2 * group * hidden) = [hi | lo], each half `group` runs of `hidden`
+ * channels (the first transposed convolution's output: group = its kernel size); out (n_tokens * group, p) fp32 =
+ * (hi + lo) w^T + bias, the hi half first, the lo half added in a second pass. */
+int vqb_token_out_proj_pair(int device, const void *a_pair, const float *w, float bias, float *out, int64_t n_tokens, int group,
+                            int hidden, int p, void *stream);
+
 /* out_pair (n_tokens, 2 n) = [bf16(g) | bf16(g - bf16(g))] with g = gelu(h) (erf form; apply_gelu != 0) or g = h:
  * the operand pair of the first vqb_token_linear_split call, from the patch embedding's fp32 rows.  n a multiple of 4. */
 int vqb_token_pair(int device, const float *h, void *out_pair, int64_t n_tokens, int n, int apply_gelu, void *stream);

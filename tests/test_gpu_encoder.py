@@ -451,6 +451,43 @@ def test_token_conv_three_taps_matches_conv1d(n_cycles, tpc, K, N):
         ops.token_conv(a[: 2 * 24].contiguous(), w, bias, mode=0, taps=3, tokens_per_cycle=24)
 
 
+@pytest.mark.parametrize("n_cycles,tpc", [(1, 16), (9, 16), (300, 16), (50, 8)])
+@pytest.mark.parametrize("K,N", [(256, 256), (512, 512)])
+def test_token_conv_split_is_fp32_faithful(n_cycles, tpc, K, N):
+    """vqb_token_conv_split (three taps, bf16 hi + lo operand pairs) against Conv1d(k=3, pad=1) in fp64 on the same fp32
+    operands: within 2^-14 of sum |a||w| per element (measured ~100x tighter), padding at both ends of every cycle."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(n_cycles * 37 + tpc + K)
+    T = n_cycles * tpc
+    a32 = torch.randn(T, K, device=dev, generator=g)
+    w3 = torch.randn(N, K, 3, device=dev, generator=g) * (2.0 / (3 * K)) ** 0.5
+    bias = 0.1 * torch.randn(N, device=dev, generator=g)
+    a = ops.token_pair(a32, gelu=False)
+    w = ops.conv_pair(w3)
+    assert w.shape == (N, 6 * K)
+    x = a32.double().view(n_cycles, tpc, K).permute(0, 2, 1)
+    conv = torch.nn.functional.conv1d(x, w3.double(), bias.double(), padding=1).permute(0, 2, 1).reshape(T, N)
+    bound = 2.0 ** -14 * torch.nn.functional.conv1d(x.abs(), w3.double().abs(), None, padding=1).permute(0, 2, 1).reshape(T, N) + 1e-6
+    out = ops.token_conv_split(a, w, bias, mode=0, taps=3, tokens_per_cycle=tpc)
+    assert bool(((_pair_value(out) - torch.nn.functional.gelu(conv)).abs() <= bound).all())
+    h = torch.randn(T, N, device=dev, generator=g)
+    h0 = h.clone()
+    nxt = torch.empty(T, 2 * N, dtype=torch.bfloat16, device=dev)
+    ops.token_conv_split(a, w, bias, h=h, out=nxt, mode=1, taps=3, tokens_per_cycle=tpc, out_gelu=False)
+    want = h0.double() + conv
+    assert bool(((h.double() - want).abs() <= bound + 2.0 ** -22 * want.abs()).all())
+    assert bool(((_pair_value(nxt) - h.double()).abs() <= 2.0 ** -16 * h.double().abs() + 1e-30).all())
+    # the last transposed convolution on the pair: (hi + lo) w^T + bias, `group` runs of H channels per token
+    for hdim, group in ((256, 2), (512, 1)):
+        src = torch.randn(T, group * hdim, device=dev, generator=g)
+        pr = ops.token_pair(src, gelu=False)
+        w_out = torch.randn(5, hdim, device=dev, generator=g) * 0.1
+        got = ops.token_out_proj_pair(pr, w_out, 0.25, group)
+        ref = _pair_value(pr).view(T * group, hdim) @ w_out.double().t() + 0.25
+        assert got.shape == (T * group, 5)
+        torch.testing.assert_close(got.double(), ref, rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("R,H,P", [(1, 512, 5), (1000, 512, 5), (333, 256, 2), (64, 512, 8)])
 def test_token_out_proj_matches_fp32_reference(R, H, P):
     dev = _dev()
@@ -476,7 +513,7 @@ def test_fused_decoder_matches_the_torch_decoder(hidden, n_res, batch_norm):
             m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
     model.eval()
     z_q = 0.5 * torch.randn(37, 16, 32, device=dev)
-    model.encoder_mode = "torch"
+    model.encoder_mode = model.decoder_mode = "torch"
     with torch.no_grad():
         want = model.decode(z_q)
         model.decoder_mode = "fused_bf16"
@@ -493,6 +530,18 @@ def test_fused_decoder_matches_the_torch_decoder(hidden, n_res, batch_norm):
         loss1, xhat1, ppl1 = model(x)
         assert torch.equal(loss0, loss1) and torch.equal(ppl0, ppl1)
         assert (xhat0 - xhat1).abs().max().item() <= 0.02 * xhat1.abs().max().item()
+        # the fp32-faithful form of the same launches (the module's default for inference): 2^-18 operand pairs through the
+        # 2 n_res + 2 layers -- stated tolerance 1e-4 of the output's largest magnitude (measured ~1e-5)
+        for mode in ("fused_fp32", "auto"):
+            model.decoder_mode = mode
+            got32 = model.decode(z_q)
+            assert got32.shape == want.shape
+            err32 = (got32 - want).abs().max().item()
+            assert err32 <= 1e-4 * want.abs().max().item(), (mode, err32, want.abs().max().item())
+        model.encoder_mode = model.decoder_mode = "auto"
+        loss2, xhat2, ppl2 = model(x)
+        assert (xhat2 - xhat1).abs().max().item() <= 2e-4 * xhat1.abs().max().item()
+        assert loss2.item() == pytest.approx(loss1.item(), rel=1e-4)
     # training / autograd keep the PyTorch modules
     model.decoder_mode = "fused_bf16"
     model.train()

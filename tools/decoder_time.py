@@ -24,6 +24,14 @@ with torch.no_grad():
     model.decoder_mode = "fused_bf16"
     ms_f, got = timed(lambda: model.decode(z_q))
     print(f"fused_bf16 decoder: {ms_f:.3f} ms per {n} cycles = {flop / ms_f / 1e9:.0f} TFLOP/s, {n * 16 / ms_f / 1e3:.1f} M patches/s")
+    model.decoder_mode = "fused_fp32"
+    ms_s, got32 = timed(lambda: model.decode(z_q))
+    print(f"fused_fp32 decoder: {ms_s:.3f} ms per {n} cycles = {3 * flop / ms_s / 1e9:.0f} issued TFLOP/s, {n * 16 / ms_s / 1e3:.1f} M patches/s")
+    model.decoder_mode = "torch"
+    torch.backends.cuda.matmul.allow_tf32 = False; torch.backends.cudnn.allow_tf32 = False
+    want_s = model.decode(z_q[:1024])
+    print(f"max |fused_fp32 - fp32| = {(got32[:1024] - want_s).abs().max().item():.3e} at max |x_hat| = {want_s.abs().max().item():.3e}")
+    model.decoder_mode = "fused_bf16"
     if os.environ.get("DEC_NO_PROFILER") != "1":
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             model.decode(z_q); torch.cuda.synchronize()

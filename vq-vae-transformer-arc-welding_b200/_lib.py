@@ -38,6 +38,8 @@ SIGNATURES = {
                           _vp, _vp, _vp, _sz, _vp]),
     "vqb_token_linear": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _u, _vp]),
     "vqb_token_linear_split": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _u, _i, _vp]),
+    "vqb_token_conv_split": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _u, _i, _i, _i, _vp]),
+    "vqb_token_out_proj_pair": (_i, [_i, _vp, _vp, _f, _vp, _i64, _i, _i, _i, _vp]),
     "vqb_token_pair": (_i, [_i, _vp, _vp, _i64, _i, _i, _vp]),
     "vqb_token_conv": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _u, _i, _i, _i, _vp]),
     "vqb_token_out_proj": (_i, [_i, _vp, _vp, _f, _vp, _i64, _i, _i, _vp]),

@@ -161,10 +161,19 @@ tok_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (elect_one()) {
                         mbar_expect_tx(bar(FULL + s), A_BYTES + B_BYTES);
                         if (SPLIT) {      // K-chunk 3c + p: (a_hi, w_hi), (a_hi, w_lo), (a_lo, w_hi) of input columns 64c ..
-                            const int c = k / 3, p = k - 3 * c, k_in = K / 3;
-                            tma_load_2d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), c * BK + (p == 2 ? k_in : 0),
-                                        (int)(mt * BM));
-                            tma_load_2d(sbase + OFF_B + s * B_BYTES, &map_w, bar(FULL + s), c * BK + (p == 1 ? k_in : 0), nt * BN);
+                            const int c3 = k / 3, p = k - 3 * c3, k_in = K / (3 * taps);
+                            if (taps == 1) {
+                                tma_load_2d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), c3 * BK + (p == 2 ? k_in : 0),
+                                            (int)(mt * BM));
+                                tma_load_2d(sbase + OFF_B + s * B_BYTES, &map_w, bar(FULL + s), c3 * BK + (p == 1 ? k_in : 0),
+                                            nt * BN);
+                            } else {      // three taps: W rows are [tap][w_hi | w_lo], the A box is shifted by tap - 1 positions
+                                const int kc = k_in / BK, tap = c3 / kc, c = c3 - tap * kc;
+                                tma_load_3d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), c * BK + (p == 2 ? k_in : 0),
+                                            tap - (taps >> 1), (int)(mt * (BM / cyc_len)));
+                                tma_load_2d(sbase + OFF_B + s * B_BYTES, &map_w, bar(FULL + s),
+                                            tap * 2 * k_in + c * BK + (p == 1 ? k_in : 0), nt * BN);
+                            }
                         } else if (taps == 1) {
                             tma_load_2d(sbase + OFF_A + s * A_BYTES, &map_a, bar(FULL + s), k * BK, (int)(mt * BM));
                         } else {          // K-chunk (tap, c): the tile's cycles, shifted by tap - 1 positions (zeros outside)
@@ -743,8 +752,6 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
     if (!tok_linear_supported(K, N) || smem_bytes > max_smem || (mode != 0 && !h) || (mode == 0 && !out))
         return cudaErrorNotSupported;
     // three taps: whole cycles of cyc_len tokens, a 128-token tile holds whole cycles
-    if (split && taps != 1)
-        return cudaErrorNotSupported;
     if (taps != 1 && (taps != 3 || cyc_len < 1 || BM % cyc_len != 0 || n_tokens % cyc_len != 0 || cyc_len > 256))
         return cudaErrorNotSupported;
     if (n_tokens == 0)
@@ -753,11 +760,11 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
     if (taps == 1) {
         if (!make_bf16_map(&map_a, a, n_tokens, split ? 2 * K : K, BM))
             return cudaErrorNotSupported;
-    } else if (!tc::make_tensor_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, n_tokens / cyc_len, cyc_len, K, BM / cyc_len,
+    } else if (!tc::make_tensor_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, n_tokens / cyc_len, cyc_len, split ? 2 * K : K, BM / cyc_len,
                                        cyc_len, BK, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) {
         return cudaErrorNotSupported;
     }
-    if (!make_bf16_map(&map_w, w, N, split ? 2 * K : taps * K, BN))
+    if (!make_bf16_map(&map_w, w, N, (split ? 2 : 1) * taps * K, BN))
         return cudaErrorNotSupported;
     const int64_t items = (n_tokens + BM - 1) / BM * (N / BN);
     const int grid = (int)(items < sm_count ? items : sm_count);
@@ -771,7 +778,7 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (err != cudaSuccess)
         return err;
-    kern<<<grid, 128 + 32 * (ew16 ? 16 : 8), smem_bytes, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, split ? 3 * K : taps * K, N, taps,
+    kern<<<grid, 128 + 32 * (ew16 ? 16 : 8), smem_bytes, st>>>(map_a, map_w, bias, h, (__nv_bfloat16 *)out, n_tokens, (split ? 3 : 1) * taps * K, N, taps,
                                             cyc_len, out_gelu);
     return cudaGetLastError();
 }
@@ -786,7 +793,8 @@ constexpr int kOutProjMaxP = 8;
 // shared memory with scalar loads: 8.2 ms per 5.2 M rows, LDS-bound; this one is bound by the row reads)
 template <int NS, int P>
 __global__ void __launch_bounds__(256) tok_out_proj_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restrict__ w,
-                                                           float bias, float *__restrict__ out, int64_t n_rows)
+                                                           float bias, float *__restrict__ out, int64_t n_rows, int group,
+                                                           int64_t ld_group, int accumulate)
 {
     constexpr int H = NS * 256;
     const int lane = threadIdx.x & 31;
@@ -802,7 +810,7 @@ __global__ void __launch_bounds__(256) tok_out_proj_kernel(const __nv_bfloat16 *
         uint4 v[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s)        // 16 bytes per lane and step: a warp reads 512 contiguous bytes
-            v[s] = __ldcs(reinterpret_cast<const uint4 *>(a + r * H + s * 256 + lane * 8));
+            v[s] = __ldcs(reinterpret_cast<const uint4 *>(a + (r / group) * ld_group + (r % group) * H + s * 256 + lane * 8));
         float acc[P];
 #pragma unroll
         for (int j = 0; j < P; ++j)
@@ -831,27 +839,33 @@ __global__ void __launch_bounds__(256) tok_out_proj_kernel(const __nv_bfloat16 *
 #pragma unroll
             for (int j = 1; j < P; ++j)
                 res = lane == j ? acc[j] : res;
-            out[r * P + lane] = res + bias;
+            out[r * P + lane] = res + bias + (accumulate ? out[r * P + lane] : 0.0f);
         }
     }
 }
 
 bool tok_out_proj_supported(int H, int P) { return (H == 256 || H == 512) && P >= 1 && P <= kOutProjMaxP; }
 
+// group / ld_group: row r is the (r % group)-th run of H values of the (r / group)-th input row of ld_group elements (group = 1,
+// ld_group = H: plain rows); accumulate: out += instead of out = (the lo half of a bf16 pair after its hi half)
 cudaError_t launch_tok_out_proj(const void *a, const float *w, float bias, float *out, int64_t n_rows, int H, int P, int sm_count,
-                                cudaStream_t st)
+                                cudaStream_t st, int group, int64_t ld_group, int accumulate)
 {
     if (!tok_out_proj_supported(H, P))
         return cudaErrorNotSupported;
     if (n_rows == 0)
         return cudaSuccess;
+    if (group < 1)
+        group = 1;
+    if (ld_group <= 0)
+        ld_group = (int64_t)group * H;
     const int64_t blocks = (n_rows + 7) / 8;
     const int grid = (int)(blocks < (int64_t)sm_count * 8 ? blocks : (int64_t)sm_count * 8);
     const __nv_bfloat16 *ab = (const __nv_bfloat16 *)a;
 #define VQB_OUT_PROJ(PV)                                                                                     \
     case PV:                                                                                                 \
-        if (H == 256) tok_out_proj_kernel<1, PV><<<grid, 256, 0, st>>>(ab, w, bias, out, n_rows);            \
-        else tok_out_proj_kernel<2, PV><<<grid, 256, 0, st>>>(ab, w, bias, out, n_rows);                     \
+        if (H == 256) tok_out_proj_kernel<1, PV><<<grid, 256, 0, st>>>(ab, w, bias, out, n_rows, group, ld_group, accumulate); \
+        else tok_out_proj_kernel<2, PV><<<grid, 256, 0, st>>>(ab, w, bias, out, n_rows, group, ld_group, accumulate);          \
         break;
     switch (P) {
         VQB_OUT_PROJ(1) VQB_OUT_PROJ(2) VQB_OUT_PROJ(3) VQB_OUT_PROJ(4) VQB_OUT_PROJ(5) VQB_OUT_PROJ(6) VQB_OUT_PROJ(7)

@@ -397,6 +397,66 @@ int vqb_token_out_proj(int device, const void *a_bf16, const float *w, float bia
     return VQB_OK;
 }
 
+int vqb_token_conv_split(int device, const void *a_pair, const void *w_pair, const float *bias, float *h, void *out_pair,
+                         int64_t n_tokens, int k_in, int n, unsigned mode, int taps, int tokens_per_cycle, int out_gelu, void *stream)
+{
+    if (!a_pair || !w_pair || !bias || n_tokens < 0 || mode > 2u || (mode != 0u && !h) || (mode == 0u && !out_pair) ||
+        (taps != 1 && taps != 3) || tokens_per_cycle < 1)
+        return VQB_E_ARG;
+    if (!tok_linear_supported(k_in, n) || !aligned(a_pair, 16) || !aligned(w_pair, 16) || !aligned(bias, 16) ||
+        (h && !aligned(h, 16)) || (out_pair && !aligned(out_pair, 16)))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_tok_linear(a_pair, w_pair, bias, h, out_pair, n_tokens, k_in, n, (int)mode, info.sm_count,
+                            info.max_smem_per_block, (cudaStream_t)stream, taps, tokens_per_cycle, out_gelu ? 1 : 0, 1);
+    if (err == cudaErrorNotSupported)
+        return VQB_E_UNSUPPORTED;
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_tokens > 0)
+        count_launches(1);
+    return VQB_OK;
+}
+
+int vqb_token_out_proj_pair(int device, const void *a_pair, const float *w, float bias, float *out, int64_t n_tokens, int group,
+                            int hidden, int p, void *stream)
+{
+    if (!a_pair || !w || !out || n_tokens < 0 || hidden <= 0 || p <= 0 || group < 1)
+        return VQB_E_ARG;
+    if (!tok_out_proj_supported(hidden, p) || !aligned(a_pair, 16) || !aligned(w, 4) || !aligned(out, 4))
+        return VQB_E_UNSUPPORTED;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    if (info.cc_major != 10)
+        return VQB_E_DEVICE;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    const int64_t half = (int64_t)group * hidden;                 // elements of the hi half of a token's row
+    const uint16_t *a = (const uint16_t *)a_pair;                 // bf16 elements
+    err = launch_tok_out_proj(a, w, bias, out, n_tokens * group, hidden, p, info.sm_count, (cudaStream_t)stream, group, 2 * half, 0);
+    if (err == cudaSuccess)
+        err = launch_tok_out_proj(a + half, w, 0.0f, out, n_tokens * group, hidden, p, info.sm_count, (cudaStream_t)stream, group,
+                                  2 * half, 1);
+    if (err == cudaErrorNotSupported)
+        return VQB_E_UNSUPPORTED;
+    if (err != cudaSuccess)
+        return (int)err;
+    if (n_tokens > 0)
+        count_launches(2);
+    return VQB_OK;
+}
+
 size_t vqb_encoder_chain_scratch_bytes(int device, int hidden)
 {
     vqb_device_info info;

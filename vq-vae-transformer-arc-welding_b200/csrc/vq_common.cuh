@@ -140,7 +140,7 @@ cudaError_t launch_tok_linear(const void *a, const void *w, const float *bias, f
 cudaError_t launch_tok_pair(const float *h, void *out, int64_t n_tokens, int N, int apply_gelu, int sm_count, cudaStream_t st);
 bool tok_out_proj_supported(int H, int P);
 cudaError_t launch_tok_out_proj(const void *a, const float *w, float bias, float *out, int64_t n_rows, int H, int P, int sm_count,
-                                cudaStream_t st);
+                                cudaStream_t st, int group = 1, int64_t ld_group = 0, int accumulate = 0);
 cudaError_t launch_tok_bias_gelu(float *h, const float *bias, void *out, int64_t n_tokens, int N, int sm_count,
                                  cudaStream_t st);
 bool enc_chain_supported(int H, int L);

@@ -402,10 +402,19 @@ class VQVAEPatch(Autoencoder):
     #: of the residual blocks and the first transposed convolution as vqb_token_conv launches on row-major tokens
     #: (bf16 operands, fp32 accumulation, fp32 residual stream, bias / eval-mode BatchNorm / GELU / residual in the
     #: epilogues), the last transposed convolution as vqb_token_out_proj.  Selected like the encoder's mode.
-    decoder_mode = "torch"
+    #: "fused_fp32": the same launches in their fp32-faithful form (bf16 hi + lo operand pairs, three products per layer,
+    #: erf GELU: vqb_token_conv_split / vqb_token_out_proj_pair); "auto" (default) selects it for inference calls that
+    #: qualify, like the encoder's.
+    decoder_mode = "auto"
 
     def decode(self, z_q):
         """z_q (B, T, D) -> x_hat (B, seq_len, input_dim)   (:164-165)."""
+        if self.decoder_mode in ("auto", "fused_fp32") and self._fused_decoder_ok(z_q):
+            torch.cuda.nvtx.range_push("vqb200.decode_fused_fp32")
+            try:
+                return self.decode_fused_fp32(z_q)
+            finally:
+                torch.cuda.nvtx.range_pop()
         if self.decoder_mode == "fused_bf16" and self._fused_decoder_ok(z_q):
             torch.cuda.nvtx.range_push("vqb200.decode_fused_bf16")
             try:
@@ -494,6 +503,73 @@ class VQVAEPatch(Autoencoder):
         # first transposed convolution (+ BatchNorm + GELU): H -> k0 * H per token = k0 rows of H
         up = ops.token_conv(a, w["w_up"], w["b_up"], mode=0, taps=1, tokens_per_cycle=1)
         x = ops.token_out_proj(up.view(n * w["k0"], w["hidden"]), w["w_out"], w["b_out"])           # (n * k0, k1)
+        return x.view(b, -1, self.reverse_patch_embed.input_dim)
+
+    def _split_decoder_weights(self):
+        """Operands of the fp32-faithful fused decoder (bf16 hi + lo pairs of the BatchNorm-folded fp32 weights), rebuilt when a
+        parameter or running statistic changes."""
+        from .. import ops
+        tracked = [t for m in (self.decoder, self.reverse_patch_embed) for t in list(m.parameters()) + list(m.buffers())]
+        key = tuple((t.data_ptr(), t._version) for t in tracked)
+        cache = getattr(self, "_split_dec_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+
+        def bn_fold(w, b, norm):
+            if isinstance(norm, nn.BatchNorm1d):
+                scale = norm.weight.float() / torch.sqrt(norm.running_var.float() + norm.eps)
+                w = w * scale.view(-1, *([1] * (w.dim() - 1)))
+                b = (b - norm.running_mean.float()) * scale + norm.bias.float()
+            return w, b
+
+        with torch.no_grad():
+            conv0 = self.decoder[0]
+            hidden, d = conv0.out_channels, conv0.in_channels
+            w0 = torch.zeros(hidden, 64, device=conv0.weight.device)
+            w0[:, :d] = conv0.weight[:, :, 0].float()
+            blocks = []
+            for blk in self.decoder[1].shared_conv:
+                pair = []
+                for conv, norm in ((blk.block[1], blk.block[2]), (blk.block[4], blk.block[5])):
+                    w, b = bn_fold(conv.weight.float(), conv.bias.float(), norm)          # (out, in, 3)
+                    pair += [ops.conv_pair(w), b.contiguous()]
+                blocks.append(tuple(pair))
+            rp = self.reverse_patch_embed.proj
+            k0 = rp[0].kernel_size[0]
+            wt = rp[0].weight.float().permute(2, 1, 0)                                    # (j, o, c)
+            bt = rp[0].bias.float().expand(k0, -1)
+            if isinstance(rp[1], nn.BatchNorm1d):
+                scale = rp[1].weight.float() / torch.sqrt(rp[1].running_var.float() + rp[1].eps)
+                wt = wt * scale.view(1, -1, 1)
+                bt = (bt - rp[1].running_mean.float()) * scale + rp[1].bias.float()
+            ops_ = dict(w0=ops.bf16_pair(w0), b0=conv0.bias.float().contiguous(), blocks=blocks,
+                        w_up=ops.bf16_pair(wt.reshape(k0 * hidden, hidden).contiguous()), b_up=bt.reshape(-1).contiguous(),
+                        w_out=rp[3].weight.float()[:, 0, :].t().contiguous(), b_out=float(rp[3].bias.float().item()),
+                        k0=k0, hidden=hidden, d=d)
+        object.__setattr__(self, "_split_dec_cache", (key, ops_))
+        return ops_
+
+    def decode_fused_fp32(self, z_q):
+        """decode_fused_bf16's launches in their fp32-faithful form: activations and weights as bf16 hi + lo pairs, three tcgen05
+        products per layer in the fp32 accumulator, erf GELU, fp32 residual stream (vqb_token_conv_split); the last transposed
+        convolution reads the pair's two halves (vqb_token_out_proj_pair)."""
+        from .. import ops
+        w = self._split_decoder_weights()
+        b, t, d = z_q.shape
+        n = b * t
+        z64 = torch.zeros(n, 64, dtype=torch.float32, device=z_q.device)
+        z64[:, :d] = z_q.reshape(n, d)
+        a0 = ops.token_pair(z64, gelu=False)                                            # (n, 128)
+        h = torch.empty(n, w["hidden"], dtype=torch.float32, device=z_q.device)
+        a = torch.empty(n, 2 * w["hidden"], dtype=torch.bfloat16, device=z_q.device)
+        u = torch.empty_like(a)
+        ops.token_conv_split(a0, w["w0"], w["b0"], h=h, out=a, mode=2, taps=1, tokens_per_cycle=1, out_gelu=bool(w["blocks"]))
+        for i, (w1, b1, w2, b2) in enumerate(w["blocks"]):
+            last = i + 1 == len(w["blocks"])
+            ops.token_conv_split(a, w1, b1, out=u, mode=0, taps=3, tokens_per_cycle=t)
+            ops.token_conv_split(u, w2, b2, h=h, out=a, mode=1, taps=3, tokens_per_cycle=t, out_gelu=not last)
+        up = ops.token_conv_split(a, w["w_up"], w["b_up"], mode=0, taps=1, tokens_per_cycle=1)      # (n, 2 * k0 * H)
+        x = ops.token_out_proj_pair(up, w["w_out"], w["b_out"], w["k0"])                           # (n * k0, k1)
         return x.view(b, -1, self.reverse_patch_embed.input_dim)
 
     def forward(self, x):

@@ -504,6 +504,57 @@ def token_conv(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Optional
     return out
 
 
+def token_conv_split(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None, mode: int = 0, taps: int = 3, tokens_per_cycle: int = 16,
+                     out_gelu: bool = True) -> Optional[torch.Tensor]:
+    """token_conv on bf16 hi + lo operand pairs (vqb_token_conv_split; fp32-faithful like token_linear_split).
+    a (T, 2 K) = [a_hi | a_lo], w (N, taps * 2 K) = per tap [w_hi | w_lo] (conv_pair), bias (N,) fp32, h (T, N) fp32,
+    out (T, 2 N) bf16 pair."""
+    for t, name, dt in ((a, "a", torch.bfloat16), (w, "w", torch.bfloat16), (bias, "bias", torch.float32)):
+        if not t.is_cuda or t.dtype != dt or not t.is_contiguous():
+            raise RuntimeError(f"{name} must be a contiguous CUDA {dt} tensor (no CPU fallback)")
+    t_rows, k2 = a.shape
+    n = w.shape[0]
+    if w.shape[1] != taps * k2 or k2 % 2 or bias.numel() != n:
+        raise RuntimeError("token_conv_split: shape mismatch")
+    if mode == 0 and out is None:
+        out = torch.empty((t_rows, 2 * n), dtype=torch.bfloat16, device=a.device)
+    if mode != 0 and (h is None or h.dtype != torch.float32 or not h.is_contiguous() or tuple(h.shape) != (t_rows, n)):
+        raise RuntimeError("token_conv_split modes 1 and 2 need a contiguous fp32 h of shape (T, N)")
+    if out is not None and (out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape) != (t_rows, 2 * n)):
+        raise RuntimeError("token_conv_split: out must be a contiguous bf16 (T, 2 N) tensor")
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.vqb_token_conv_split(a.device.index, a.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                      h.data_ptr() if h is not None else None, out.data_ptr() if out is not None else None,
+                                      t_rows, k2 // 2, n, int(mode), int(taps), int(tokens_per_cycle), 1 if out_gelu else 0,
+                                      torch.cuda.current_stream(a.device).cuda_stream)
+    _lib.check(rc, "vqb_token_conv_split")
+    return out
+
+
+def conv_pair(w: torch.Tensor) -> torch.Tensor:
+    """Conv1d weight (N, K, taps) fp32 -> (N, taps * 2 K) bf16: per tap [bf16(w) | bf16(w - bf16(w))], the weight operand of
+    token_conv_split."""
+    return torch.cat([bf16_pair(w[:, :, t].contiguous()) for t in range(w.shape[2])], dim=1).contiguous()
+
+
+def token_out_proj_pair(a: torch.Tensor, w: torch.Tensor, bias: float, group: int) -> torch.Tensor:
+    """token_out_proj on a bf16 pair (vqb_token_out_proj_pair): a (T, 2 * group * H) = [hi | lo] -> (T * group, P) fp32."""
+    if not a.is_cuda or a.dtype != torch.bfloat16 or not a.is_contiguous() or a.dim() != 2:
+        raise RuntimeError("token_out_proj_pair: a must be a contiguous CUDA bf16 (T, 2 * group * H) tensor (no CPU fallback)")
+    hdim = w.shape[1]
+    if not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous() or w.dim() != 2 or a.shape[1] != 2 * group * hdim:
+        raise RuntimeError("token_out_proj_pair: w must be a contiguous CUDA fp32 (P, H) tensor with 2 * group * H = a.shape[1]")
+    out = torch.empty((a.shape[0] * group, w.shape[0]), dtype=torch.float32, device=a.device)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.vqb_token_out_proj_pair(a.device.index, a.data_ptr(), w.data_ptr(), float(bias), out.data_ptr(), a.shape[0],
+                                         int(group), hdim, w.shape[0], torch.cuda.current_stream(a.device).cuda_stream)
+    _lib.check(rc, "vqb_token_out_proj_pair")
+    return out
+
+
 def token_out_proj(a: torch.Tensor, w: torch.Tensor, bias: float) -> torch.Tensor:
     """out[r, j] = sum_c a[r, c] w[j, c] + bias (vqb_token_out_proj: PatchEmbeddingInverse's last ConvTranspose1d,
     model/vq_vae_patch_embedd.py:24-29).  a (R, H) bf16, w (P, H) fp32 -> (R, P) fp32."""
