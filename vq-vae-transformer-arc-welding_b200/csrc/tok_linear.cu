@@ -732,7 +732,8 @@ static bool tok_linear_default_ew16(int mode, int split, int taps)
 {
     // T = 2^20 tokens, 512 x 512: bf16 form 0.614 / 1.291 ms (modes 0 / 1) against 0.660 / 1.389 with 8 warps; split form 1.547 /
     // 2.251 against 1.528 / 2.049 -- its mode 0 is MMA-bound either way, and its mode 1 loses more to the single residual buffer
-    // (no prefetch across slabs, 104 bytes of spills at 96 registers) than it gains from the extra warps
+    // (no prefetch across slabs, 104 bytes of spills at 96 registers) than it gains from the extra warps.  (Rejected for mode 1 of both
+    // forms: a cp.async.bulk.prefetch.L2 of the next item's residual slab one tile ahead -- 1.378 / 2.201 ms instead of 1.291 / 2.049.)
     (void)mode; (void)taps;
     return !split;
 }

@@ -196,7 +196,7 @@ class VQVAEPatch(Autoencoder):
 
     def encode(self, x):
         """x (B, seq_len, input_dim) -> z_e (B, T, D)."""
-        if self.encoder_mode in ("auto", "fused_fp32") and self._fused_ok(x):
+        if self.encoder_mode in ("auto", "fused_fp32") and self._fused_ok(x) and self.encoder[1].shared_conv.out_channels <= 256:
             torch.cuda.nvtx.range_push("vqb200.encode_fused_fp32")
             try:
                 return self.encode_fused_fp32(x)
