@@ -177,6 +177,28 @@ def test_token_linear_rejects_bad_arguments():
                          torch.zeros(256, 48, device=dev, dtype=torch.bfloat16), b)   # K not a multiple of 64
 
 
+def test_split_entry_points_reject_bad_arguments():
+    dev = _dev()
+    a = torch.zeros(8, 128, device=dev, dtype=torch.bfloat16)
+    w = torch.zeros(256, 128, device=dev, dtype=torch.bfloat16)
+    b = torch.zeros(256, device=dev)
+    with pytest.raises(RuntimeError):
+        ops.token_linear_split(a.float(), w, b)
+    with pytest.raises(RuntimeError):
+        ops.token_linear_split(a, w, b, mode=1)                                   # no residual stream
+    with pytest.raises(RuntimeError):
+        ops.token_linear_split(a, w, b, out=torch.empty(8, 256, device=dev, dtype=torch.bfloat16))   # out must be the (T, 2 N) pair
+    with pytest.raises(RuntimeError):
+        ops.token_linear_split(torch.zeros(8, 96, device=dev, dtype=torch.bfloat16),
+                               torch.zeros(256, 96, device=dev, dtype=torch.bfloat16), b)            # K = 48 not a multiple of 64
+    with pytest.raises(RuntimeError):
+        ops.token_conv_split(torch.zeros(48, 128, device=dev, dtype=torch.bfloat16),
+                             torch.zeros(256, 384, device=dev, dtype=torch.bfloat16), b, taps=3, tokens_per_cycle=24)
+    with pytest.raises(RuntimeError):
+        ops.token_pair(torch.zeros(4, 6, device=dev))                             # n not a multiple of 4
+    assert ops.token_linear_split(torch.zeros(0, 128, device=dev, dtype=torch.bfloat16), w, b).shape == (0, 512)   # empty input
+
+
 def test_fused_bf16_encoder_tracks_the_fp32_encoder():
     """VQVAEPatch.encode in 'fused_bf16' mode: same shapes, z_e within bf16-operand error of the fp32 encoder,
     ids equal for the overwhelming majority of tokens (the quantiser itself is exact on whatever z_e it gets)."""

@@ -166,6 +166,64 @@ def test_encoder_side_ops_refuse_cpu_tensors():
     # a layout-only helper: on CPU tensors it is torch's own copy, the quantiser behind it still refuses them
     v = torch.randn(3, 32, 16).permute(0, 2, 1)
     assert torch.equal(ops.pack_rows(v, 32), v.contiguous())
+    # the fp32-faithful (split) entry points likewise
+    pair = torch.randn(256, 1024).to(torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.token_linear_split(pair, torch.randn(512, 1024).to(torch.bfloat16), b)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.token_conv_split(pair, torch.randn(512, 3 * 1024).to(torch.bfloat16), b)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.token_pair(torch.randn(4, 512))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.token_out_proj_pair(pair, torch.randn(5, 512), 0.0, 1)
+
+
+def test_bf16_pairs_carry_fp32_values_to_2_pow_minus_17():
+    """Host side of the fp32-faithful layers: weights are split once per weight version with torch ops (ops.bf16_pair /
+    ops.conv_pair); hi + lo reproduces the fp32 value to 2^-17 relative, and the layouts are the ones the kernels index."""
+    import torch
+    from vqb200 import ops
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(64, 128, generator=g) * torch.logspace(-6, 3, 128)
+    p = ops.bf16_pair(w)
+    assert p.shape == (64, 256) and p.dtype == torch.bfloat16 and p.is_contiguous()
+    assert torch.equal(p[:, :128], w.to(torch.bfloat16))
+    val = p[:, :128].double() + p[:, 128:].double()
+    assert bool(((val - w.double()).abs() <= 2.0 ** -17 * w.double().abs()).all())
+    w3 = torch.randn(32, 64, 3, generator=g)
+    c = ops.conv_pair(w3)
+    assert c.shape == (32, 3 * 128)
+    for tap in range(3):
+        assert torch.equal(c[:, tap * 128:(tap + 1) * 128], ops.bf16_pair(w3[:, :, tap].contiguous()))
+
+
+def test_auto_modes_keep_the_pytorch_layers_off_the_gpu_and_in_training():
+    """encoder_mode = decoder_mode = "auto" (the default) selects the fused fp32-faithful launches only for calls that qualify;
+    CPU tensors, training mode and autograd take the PyTorch layers (same values as the explicit "torch" mode)."""
+    import torch
+    import vqb200
+    torch.manual_seed(3)
+    model = vqb200.VQVAEPatch(hidden_dim=256, input_dim=2, num_embeddings=32, embedding_dim=16, n_resblocks=1,
+                              learning_rate=1e-3, patch_size=25, batch_norm=False).eval()
+    assert model.encoder_mode == "auto" and model.decoder_mode == "auto"
+    x = torch.randn(3, 200, 2)
+    with torch.no_grad():
+        assert not model._fused_ok(x) and not model._fused_decoder_ok(torch.randn(3, 16, 16))
+        z_auto = model.encode(x)
+        model.encoder_mode = "torch"
+        assert torch.equal(model.encode(x), z_auto)
+        zq = torch.randn(3, 16, 16)
+        model.decoder_mode = "auto"
+        y_auto = model.decode(zq)
+        model.decoder_mode = "torch"
+        assert torch.equal(model.decode(zq), y_auto)
+    # the operand cache of the split layers is plain torch code: built on CPU weights too, rebuilt when a weight changes
+    w0 = model._split_weights()
+    assert model._split_weights() is w0
+    with torch.no_grad():
+        model.encoder[1].shared_conv.weight.add_(1.0)
+    w1 = model._split_weights()
+    assert w1 is not w0 and w1["wp"].shape == (256, 512) and w1["layers"][0][0].shape == (256, 512)
 
 
 def test_cycle_id_cache_encodes_every_distinct_cycle_once_per_dataset():

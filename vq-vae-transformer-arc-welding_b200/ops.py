@@ -437,6 +437,8 @@ def token_pair(h: torch.Tensor, gelu: bool = True, out: Optional[torch.Tensor] =
         out = torch.empty((t_rows, 2 * n), dtype=torch.bfloat16, device=h.device)
     elif out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape) != (t_rows, 2 * n):
         raise RuntimeError("token_pair: out must be a contiguous bf16 (T, 2 N) tensor")
+    if t_rows == 0:
+        return out
     lib = _lib.load()
     with torch.cuda.device(h.device):
         rc = lib.vqb_token_pair(h.device.index, h.data_ptr(), out.data_ptr(), t_rows, n, int(bool(gelu)),
@@ -463,6 +465,8 @@ def token_linear_split(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: 
         raise RuntimeError("token_linear_split modes 1 and 2 need a contiguous fp32 h of shape (T, N)")
     if out is not None and (out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape) != (t_rows, 2 * n)):
         raise RuntimeError("token_linear_split: out must be a contiguous bf16 (T, 2 N) tensor")
+    if t_rows == 0:
+        return out
     lib = _lib.load()
     with torch.cuda.device(a.device):
         rc = lib.vqb_token_linear_split(a.device.index, a.data_ptr(), w.data_ptr(), bias.data_ptr(),
@@ -523,6 +527,8 @@ def token_conv_split(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, h: Op
         raise RuntimeError("token_conv_split modes 1 and 2 need a contiguous fp32 h of shape (T, N)")
     if out is not None and (out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape) != (t_rows, 2 * n)):
         raise RuntimeError("token_conv_split: out must be a contiguous bf16 (T, 2 N) tensor")
+    if t_rows == 0:
+        return out
     lib = _lib.load()
     with torch.cuda.device(a.device):
         rc = lib.vqb_token_conv_split(a.device.index, a.data_ptr(), w.data_ptr(), bias.data_ptr(),
