@@ -283,7 +283,10 @@ int vqb_one_hot(int device, const int64_t *idx, int64_t n, int k, float *onehot,
 long long vqb_launch_counter(void);
 /* While enabled, vqb_forward brackets its dominant kernel (the fused distance/argmin/gather
  * kernel) with CUDA events on the caller's stream; vqb_profile_collect waits for them and
- * returns the summed duration and the number of bracketed launches, then forgets them. */
+ * returns the summed duration and the number of bracketed launches, then forgets them.
+ * Brackets are kept per device: collect returns (and forgets) those of launches whose `device`
+ * argument equals the calling thread's current device, so a process that drives several GPUs
+ * does not mix them. */
 int vqb_profile_enable(int on);
 int vqb_profile_collect(double *ms_sum, int *launches);
 

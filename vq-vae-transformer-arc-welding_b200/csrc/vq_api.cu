@@ -51,7 +51,13 @@ int device_info(int device, vqb_device_info *out)
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_profile{0};
 std::mutex g_prof_mu;
-std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+// brackets are kept per device: vqb_profile_collect returns those of the calling thread's current device only,
+// so processes that drive several GPUs do not mix their launches
+struct ProfBracket {
+    int dev;
+    cudaEvent_t first, second;
+};
+std::vector<ProfBracket> g_prof_events;
 
 inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -90,10 +96,20 @@ int vqb_profile_enable(int on)
 
 int vqb_profile_collect(double *ms_sum, int *launches)
 {
+    int dev = 0;
+    cudaError_t derr = cudaGetDevice(&dev);
+    if (derr != cudaSuccess)
+        return (int)derr;
     std::lock_guard<std::mutex> lock(g_prof_mu);
     double total = 0.0;
     int n = 0;
+    cudaError_t first_err = cudaSuccess;
+    std::vector<ProfBracket> other;
     for (auto &pr : g_prof_events) {
+        if (pr.dev != dev) {
+            other.push_back(pr);
+            continue;
+        }
         float ms = 0.f;
         cudaError_t err = cudaEventSynchronize(pr.second);
         if (err == cudaSuccess)
@@ -101,13 +117,16 @@ int vqb_profile_collect(double *ms_sum, int *launches)
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
         if (err != cudaSuccess) {
-            g_prof_events.clear();
-            return (int)err;
+            if (first_err == cudaSuccess)
+                first_err = err;
+            continue;
         }
         total += ms;
         ++n;
     }
-    g_prof_events.clear();
+    g_prof_events.swap(other);
+    if (first_err != cudaSuccess)
+        return (int)first_err;
     if (ms_sum) *ms_sum = total;
     if (launches) *launches = n;
     return VQB_OK;
@@ -229,7 +248,10 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (g_profile.load()) {
             if ((err = cudaEventCreate(&ev0)) != cudaSuccess) return (int)err;
-            if ((err = cudaEventCreate(&ev1)) != cudaSuccess) return (int)err;
+            if ((err = cudaEventCreate(&ev1)) != cudaSuccess) {
+                cudaEventDestroy(ev0);
+                return (int)err;
+            }
         }
         int launches = 1;
         if (path == VQB_PATH_TC) {
@@ -246,11 +268,17 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
             err = launch_fwd_fma(p, info.sm_count, info.max_smem_per_block, &n_ctas, st);
             if (ev1) cudaEventRecord(ev1, st);
         }
-        if (err != cudaSuccess) return (int)err;
+        if (err != cudaSuccess) {
+            if (ev0) {
+                cudaEventDestroy(ev0);
+                cudaEventDestroy(ev1);
+            }
+            return (int)err;
+        }
         count_launches(launches);
         if (ev0) {
             std::lock_guard<std::mutex> lock(g_prof_mu);
-            g_prof_events.emplace_back(ev0, ev1);
+            g_prof_events.push_back(ProfBracket{device, ev0, ev1});
         }
     } else {
         if ((err = cudaMemsetAsync(partials, 0, sizeof(double), st)) != cudaSuccess) return (int)err;
