@@ -257,6 +257,55 @@ def default_model(torch, vqb200, dev):
                              learning_rate=1e-3, dropout_p=0.1, patch_size=25, batch_norm=False).to(dev).eval()
 
 
+def bulk_e2e_leg(torch, dist, enc, model, dev, rank, world, barrier, resident_ms_per_cycle):
+    """configs[2] end to end through the reference-facing call: loader batches of windows in PINNED HOST memory ->
+    LatentSpaceEncoder.create_latent_space_dataset_VQ_VAE_IDs -> the int64 ids as ONE numpy array on the host.  The timed
+    region (wall clock, device idle on both sides) holds every host->device copy of the cycles, the encoder and quantiser
+    launches, the device->host copies of the ids and the host-side assembly of the array.  Two batch geometries: the
+    reference's own (512 windows of 20 cycles per loader batch, train_transformer_mtasks.py:214,
+    dataloader/latentspace_dataloader.py:225-238) and large batches (4096 windows of 16 cycles = the resident leg's chunk).
+    All ranks run at once on their own data; the time is the maximum over ranks."""
+    T = int(model.enc_out_len)
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(2000 + rank)
+    for name, windows, seq_len, n_batches, pinned in (("reference_batches", 512, 20, 52, True),
+                                                       ("large_batches", 4096, 16, 8, True),
+                                                       ("large_batches_pageable", 4096, 16, 8, False)):
+        if not pinned and world > 1:
+            continue                          # the staging copy of pageable batches uses every host thread: one rank only
+        hosts = []
+        for _ in range(3):                    # three distinct host batches, cycled through the loader list
+            h = torch.empty(windows, seq_len * 200, 2, dtype=torch.float32, pin_memory=pinned)
+            h.copy_(torch.randn(windows, seq_len * 200, 2, device=dev, generator=g))
+            hosts.append(h)
+        loader = [hosts[i % 3] for i in range(n_batches)]
+        times = []
+        for rep in range(3):                  # first pass untimed (pinned staging buffers of the id writer, allocator)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            ids, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
+            dt = time.perf_counter() - t0
+            if rep:
+                times.append(dt)
+        assert ids.shape == (windows * n_batches, seq_len, T) and str(ids.dtype) == "int64"
+        t = torch.tensor([min(times)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+        cycles = windows * seq_len * n_batches
+        out[name] = {"value": world * cycles * T / sec, "unit": UNIT, "per_gpu": cycles * T / sec,
+                     "ms_per_data_set": sec * 1e3, "cycles_per_gpu": cycles, "loader_batch": [windows, seq_len * 200, 2],
+                     "loader_batches": n_batches, "host_memory": "pinned" if pinned else "pageable (staged through pinned buffers)",
+                     "h2d_bytes_per_data_set": cycles * 200 * 2 * 4, "d2h_bytes_per_data_set": cycles * T * 8,
+                     "frac_of_resident_rate": resident_ms_per_cycle * 1e-3 * cycles / sec}
+        del hosts, loader, ids
+    out["what"] = ("wall clock around LatentSpaceEncoder.create_latent_space_dataset_VQ_VAE_IDs(loader, no_labels=True): host batches "
+                   "in, one int64 numpy array out; H2D of batch i + 1 on a copy stream under the encode of batch i, ids back "
+                   "through pinned buffers on a second copy stream; best of 2 timed passes after one warm-up, max over ranks")
+    return out
+
+
 def bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier):
     from vqb200.dataloader import LatentSpaceEncoder
     chunk, n_chunks = args.bulk_chunk, args.bulk_chunks
@@ -305,6 +354,7 @@ def bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier):
         fp32_ms, fp32_launches = e0.elapsed_time(e1), lib.vqb_launch_counter() - l1
         match32 = float((got32 == ref).float().mean().item())
         model.encoder_mode = "fused_bf16"
+        e2e = bulk_e2e_leg(torch, dist, enc, model, dev, rank, world, barrier, ms_max / n_chunks / chunk)
     if rank != 0:
         return None
     cycles = world * chunk * n_chunks
@@ -339,6 +389,7 @@ def bulk_encode_leg(args, torch, dist, vqb200, lib, dev, rank, world, barrier):
                           "id_match_vs_fp32_encoder": {"rate": match32, "rows": int(got32.numel())},
                           "issued_tflops": 3.0 * chunk * CYCLE_FLOP / (fp32_ms * 1e-3) / 1e12},
         "gpu_launches_per_chunk": launches / n_chunks,
+        "e2e": e2e,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "flop_per_cycle": CYCLE_FLOP, "peak_source": peak_src,
                      "traffic": chain_traffic, "kernel": "enc_chain_kernel<512> (vqb_encoder_chain: one launch per chunk)"},

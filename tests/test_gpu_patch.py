@@ -137,6 +137,49 @@ def test_bulk_loops_equal_per_cycle_reference_loop(patch_golden):
     np.testing.assert_allclose(zq.reshape(n_windows, seq_len, model.enc_out_len, -1), E[ids], rtol=0, atol=1e-6)
 
 
+def test_bulk_loop_prefetch_over_every_kind_of_loader_batch(patch_golden):
+    """The bulk loops copy batch i + 1 to the device on a copy stream while batch i is encoded (_DevicePrefetcher):
+    pageable and pinned tensors, numpy arrays, windows longer than seq_len cycles (strided source), batches of changing
+    size (slots are re-sized), a single batch and an empty loader -- ids equal to one direct encode call per batch, many
+    batches so that every slot is recycled several times."""
+    case = C.PATCH_CASES[0]
+    model = _load(case, patch_golden).eval()
+    enc = LatentSpaceEncoder(model, window_size=200, device=DEV)
+    rs = np.random.RandomState(11)
+    seq_len = 2
+    sizes = [3, 7, 1, 16, 5, 16, 2, 9, 16, 4, 11, 6]
+    kinds = ["pageable", "pinned", "numpy", "long", "long_pinned", "cuda"]
+    loader, direct = [], []
+    for i, b in enumerate(sizes):
+        kind = kinds[i % len(kinds)]
+        extra = 37 if kind.startswith("long") else 0              # the loop reads the first seq_len * 200 samples only
+        x = torch.from_numpy(rs.standard_normal((b, seq_len * 200 + extra, 2)).astype(np.float32))
+        with torch.no_grad():
+            cyc = x[:, : seq_len * 200, :].reshape(b * seq_len, 200, 2).to(DEV)
+            direct.append(enc.get_latent_space_IDs(cyc, True).cpu().numpy().reshape(b, seq_len, -1))
+        if kind in ("pinned", "long_pinned"):
+            x = x.pin_memory()
+        elif kind == "numpy":
+            x = x.numpy()
+        elif kind == "cuda":
+            x = x.to(DEV)
+        loader.append(x)
+    want = np.concatenate(direct, axis=0)
+    for _ in range(2):
+        ids, y = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
+        assert ids.shape == want.shape and np.array_equal(ids, want)
+        assert np.array_equal(y, np.zeros(sum(sizes)))
+    one, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader[3:4], seq_len=seq_len, has_patch_embed=True, no_labels=True)
+    assert np.array_equal(one, direct[3])
+    none, y0 = enc.create_latent_space_dataset_VQ_VAE_IDs([], seq_len=seq_len, has_patch_embed=True, no_labels=True)
+    assert none.shape == (0, seq_len, model.enc_out_len) and y0.shape == (0,)
+    labelled = [(x, np.full(len(x), float(i))) for i, x in enumerate(loader)]
+    zq, yl = enc.create_latent_space_dataset_VQ_VAE(labelled, seq_len=seq_len, has_patch_embed=True)
+    E = model.vector_quantization.embedding.weight.detach().cpu().numpy()
+    np.testing.assert_allclose(zq.reshape(sum(sizes), seq_len, model.enc_out_len, -1), E[want], rtol=0, atol=1e-6)
+    assert np.array_equal(yl, np.concatenate([np.full(b, float(i)) for i, b in enumerate(sizes)]))
+
+
 def test_bulk_builder_dedupe_gives_identical_ids(patch_golden):
     """Overlapping windows (stride of one cycle): with `dedupe = True` every distinct cycle is encoded once and the ids
     array is identical to the plain loop's (SURVEY.md section 8(f) row 2)."""

@@ -281,4 +281,14 @@ def test_async_host_writer_cpu_path_keeps_order_and_shapes():
     for t in parts:
         w.put(t)
     out = w.finish()
-    assert all(np.array_equal(o, t.numpy()) for o, t in zip(out, parts))
+    assert out.shape == (8, 3, 4) and out.dtype == np.int64
+    assert np.array_equal(out, torch.cat(parts).numpy())
+    # a batch-count hint sizes the array up front; a hint that was too small grows it; batches of changing size; dtype conversion
+    for hint in (None, 1, 2, 4, 9):
+        w = L._AsyncHostWriter("cpu", n_batches_hint=hint, out_dtype=np.float64)
+        ragged = [torch.full((r, 5), float(r)) for r in (3, 1, 7, 2, 6)]
+        for t in ragged:
+            w.put(t)
+        out = w.finish()
+        assert out.dtype == np.float64 and np.array_equal(out, torch.cat(ragged).numpy().astype(np.float64))
+    assert L._AsyncHostWriter("cpu").finish() is None

@@ -186,35 +186,54 @@ class CycleIdCache:
 
 
 class _AsyncHostWriter:
-    """Device results -> host arrays through a small pool of pinned staging buffers on a copy stream: the D2H copy of batch
-    i overlaps the encoder work of batch i + 1 (the reference blocks on `.cpu()` once per cycle slice, :231-235)."""
+    """Device results -> ONE host array through a small pool of pinned staging buffers on a copy stream: the D2H copy of
+    batch i overlaps the encoder work of batch i + 1 (the reference blocks on `.cpu()` once per cycle slice, :231-235, and
+    `np.append`s, :238).  A retired batch is copied once, straight into its rows of the output array (converted to
+    `out_dtype` on the way); the array is sized from `n_batches_hint` x the first batch (exact for the equal batches a
+    DataLoader yields) and doubles if that was too small."""
 
-    def __init__(self, device, depth: int = 3):
+    def __init__(self, device, depth: int = 3, n_batches_hint: Optional[int] = None, out_dtype=None):
         self.cuda = torch.device(device).type == "cuda"
         self.depth = depth
         self.stream = torch.cuda.Stream(device=device) if self.cuda else None
         self.pending: List[Tuple[torch.Tensor, Optional["torch.cuda.Event"], tuple]] = []
         self.free: List[torch.Tensor] = []
-        self.out: List[np.ndarray] = []
+        self.n_batches_hint, self.out_dtype = n_batches_hint, out_dtype
+        self.arr: Optional[np.ndarray] = None
+        self.n = 0
+
+    def _append(self, a: np.ndarray) -> None:
+        b = a.shape[0]
+        if self.arr is None:
+            cap = max(b * (self.n_batches_hint or 1), b, 1)
+            self.arr = np.empty((cap,) + a.shape[1:], dtype=self.out_dtype or a.dtype)
+        elif self.n + b > self.arr.shape[0]:
+            grown = np.empty((max(self.n + b, 2 * self.arr.shape[0]),) + self.arr.shape[1:], dtype=self.arr.dtype)
+            grown[: self.n] = self.arr[: self.n]
+            self.arr = grown
+        self.arr[self.n: self.n + b] = a
+        self.n += b
 
     def _retire(self) -> None:
         buf, ev, shape = self.pending.pop(0)
         if ev is not None:
             ev.synchronize()
         n = int(np.prod(shape))
-        self.out.append(buf[:n].view(shape).numpy().copy())
+        self._append(buf[:n].view(shape).numpy())
         self.free.append(buf)
 
     def put(self, t: torch.Tensor) -> None:
         if not self.cuda:
-            self.out.append(t.cpu().numpy().copy())
+            self._append(t.cpu().numpy())
             return
-        while len(self.pending) >= self.depth:
+        # retire what has arrived (its rows are written while the GPU works on the next batches, not at the end), and
+        # whatever must go to keep the pool at `depth` buffers
+        while self.pending and (len(self.pending) >= self.depth or self.pending[0][1].query()):
             self._retire()
         n = t.numel()
-        buf = next((b for b in self.free if b.numel() >= n and b.dtype == t.dtype), None)
-        if buf is not None:
-            self.free.remove(buf)
+        k = next((i for i, b in enumerate(self.free) if b.numel() >= n and b.dtype == t.dtype), None)
+        if k is not None:
+            buf = self.free.pop(k)         # (by position: list.remove would compare tensors element-wise)
         else:
             buf = torch.empty(max(n, 1), dtype=t.dtype, pin_memory=True)
         self.stream.wait_stream(torch.cuda.current_stream(t.device))
@@ -225,10 +244,107 @@ class _AsyncHostWriter:
             ev.record(self.stream)
         self.pending.append((buf, ev, tuple(t.shape)))
 
-    def finish(self) -> List[np.ndarray]:
+    def finish(self) -> Optional[np.ndarray]:
+        """All rows written so far (None if there were none)."""
         while self.pending:
             self._retire()
-        return self.out
+        return None if self.arr is None else self.arr[: self.n]
+
+
+def _n_batches(loader) -> Optional[int]:
+    try:
+        return len(loader)
+    except TypeError:
+        return None
+
+
+class _DevicePrefetcher:
+    """Loader batches -> their cycles on the device, ONE BATCH AHEAD: the host->device copy of batch i + 1 runs on a copy
+    stream while the encoder works on batch i (the reference copies one cycle slice at a time on the compute stream and
+    then blocks on it, :231-232).  A pageable loader tensor (or one whose windows are longer than seq_len cycles) first
+    goes through a pinned staging buffer -- `copy_` on CPU tensors of this size runs on all host threads -- a pinned,
+    exactly-sized one is copied as it is.  Three device slots rotate (being encoded / handed out / being filled); a slot
+    is overwritten only after the compute stream has passed the work that read it (`consumed` events), a staging buffer
+    only after its copy has finished.  On a CPU device it degenerates to the plain `.to(device)`.
+
+    Yields (cycles_on_device (b * seq_len, window, C), item) with `item` exactly what the loader produced."""
+
+    SLOTS = 3
+
+    def __init__(self, loader: Iterable, device, seq_len: int, window_size: int, no_labels: bool = False):
+        self.loader, self.device = loader, torch.device(device)
+        self.seq_len, self.window = seq_len, window_size
+        self.no_labels = no_labels
+        self.cuda = self.device.type == "cuda"
+        if self.cuda:
+            self.stream = torch.cuda.Stream(device=self.device)
+            self.dev: List[Optional[torch.Tensor]] = [None] * self.SLOTS
+            self.stage: List[Optional[torch.Tensor]] = [None] * self.SLOTS
+            self.consumed: List[Optional["torch.cuda.Event"]] = [None] * self.SLOTS
+            self.copied: List[Optional["torch.cuda.Event"]] = [None] * self.SLOTS
+        self.n = 0
+
+    @staticmethod
+    def _fit(buf: Optional[torch.Tensor], n: int, dtype, **kw) -> torch.Tensor:
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(max(n, 1), dtype=dtype, **kw)
+        return buf
+
+    def _issue(self, item):
+        x = item if self.no_labels else item[0]
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(x)
+        b, c = x.shape[0], x.shape[2]
+        src = x[:, : self.seq_len * self.window, :]
+        shape = (b * self.seq_len, self.window, c)
+        if not self.cuda or x.is_cuda:                     # nothing to overlap: a CPU run, or cycles that are on a GPU already
+            return src.reshape(shape).to(self.device), item, -1, None
+        k = self.n % self.SLOTS
+        self.n += 1
+        n = src.numel()
+        if not (src.is_contiguous() and src.is_pinned()):
+            if self.copied[k] is not None:
+                self.copied[k].synchronize()               # the copy that last read this staging buffer
+            self.stage[k] = self._fit(self.stage[k], n, src.dtype, pin_memory=True)
+            host = self.stage[k][:n].view(src.shape)
+            host.copy_(src)
+        else:
+            host = src
+        with torch.cuda.device(self.device):
+            old = self.dev[k]
+            self.dev[k] = self._fit(old, n, src.dtype, device=self.device)
+            if self.dev[k] is not old:                     # a block the allocator may be recycling from the compute stream
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            if self.consumed[k] is not None:
+                self.stream.wait_event(self.consumed[k])   # the encoder work that read this slot three batches ago
+            with torch.cuda.stream(self.stream):
+                out = self.dev[k][:n].view(shape)
+                out.copy_(host.reshape(shape), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+        self.copied[k] = ev
+        return out, item, k, ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._issue(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = self._issue(next(it))                # its copy overlaps the encode of `cur` the caller launches next
+            except StopIteration:
+                nxt = None
+            cyc, item, k, ready = cur
+            if k >= 0:
+                torch.cuda.current_stream(self.device).wait_event(ready)
+            yield cyc, item
+            if k >= 0:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self.consumed[k] = ev
 
 
 def latent_dataset_name(task: str, model_name: str, cycle_seq_number: int, model_id: str) -> str:
@@ -315,20 +431,19 @@ class LatentSpaceEncoder:
         model = self.latent_space_model
         width = int(model.embedding_dim * model.enc_out_len)
         ys = []
-        writer = _AsyncHostWriter(self.device)
+        writer = _AsyncHostWriter(self.device, n_batches_hint=_n_batches(loader), out_dtype=np.float64)
         model.eval()
         with torch.no_grad():
-            for x, y in loader:
+            for cyc, (x, y) in _DevicePrefetcher(loader, self.device, seq_len, self.window_size):
                 b = x.shape[0]
                 with nvtx_range("vqb200.encode_batch"):
-                    cyc = self._cycles(x, seq_len).to(self.device, non_blocking=True)
                     z_q = self.get_latent_space(cyc, has_patch_embed=has_patch_embed)
                 writer.put(z_q.reshape(b, seq_len, -1))
                 ys.append(np.asarray(y.cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64))
-        xs = [a.astype(np.float64) for a in writer.finish()]
-        if not xs:
+        new_x = writer.finish()
+        if new_x is None:
             return np.empty((0, seq_len, width)), np.empty((0,))
-        return np.concatenate(xs, axis=0), np.concatenate(ys, axis=0)
+        return new_x, np.concatenate(ys, axis=0)
 
     def create_latent_space_dataset_VQ_VAE_IDs(self, loader: Iterable, seq_len: int, has_patch_embed: bool = False,
                                                no_labels: bool = False):
@@ -337,18 +452,17 @@ class LatentSpaceEncoder:
         enc_out_len = int(model.enc_out_len)
         ys = []
         counts = None
-        writer = _AsyncHostWriter(self.device)          # ids leave through pinned buffers on a copy stream
+        writer = _AsyncHostWriter(self.device, n_batches_hint=_n_batches(loader))   # ids leave through pinned buffers on a copy stream
         cache = CycleIdCache(self.device) if self.dedupe == "dataset" else None
         self.cycle_cache = cache
         enc = lambda c: self.get_latent_space_IDs(c, has_patch_embed).view(c.shape[0], -1)
         model.eval()
         with torch.no_grad():
-            for item in loader:
+            for cyc, item in _DevicePrefetcher(loader, self.device, seq_len, self.window_size, no_labels=no_labels):
                 x, y = (item, None) if no_labels else item
                 b = x.shape[0]
                 model.vector_quantization.code_counts = None
                 with nvtx_range("vqb200.encode_batch"):
-                    cyc = self._cycles(x, seq_len).to(self.device, non_blocking=True)
                     if cache is not None:
                         ids = cache.encode(enc, cyc)
                     elif self.dedupe:
@@ -361,9 +475,10 @@ class LatentSpaceEncoder:
                 writer.put(ids.view(b, seq_len, -1))
                 if y is not None:
                     ys.append(np.asarray(y.cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64))
-        xs = writer.finish()
+        new_x = writer.finish()
         self.code_counts = counts
-        new_x = np.concatenate(xs, axis=0) if xs else np.empty((0, seq_len, enc_out_len), dtype=int)
+        if new_x is None:
+            new_x = np.empty((0, seq_len, enc_out_len), dtype=int)
         new_y = np.zeros(new_x.shape[0]) if no_labels else (np.concatenate(ys, axis=0) if ys else np.empty((0,)))
         return new_x, new_y
 
