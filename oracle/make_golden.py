@@ -219,6 +219,36 @@ def run_bulk_case(VQVAEPatch):
     return out, meta
 
 
+def run_sequence_case(VQVAEPatch):
+    """The reference's window builder (`ASIMoWDataLoader.create_sequence_ds`, dataloader/asimow_dataloader.py:185-206: windows
+    of seq_len consecutive cycles with a stride of one cycle, n - seq_len of them, label of window i = y[i + seq_len]) on a
+    stream of cycles, its data-set class's float32 cast (dataloader/base_dataloader.py:29), and the reference's id loop
+    (dataloader/latentspace_dataloader.py:205-243) over those windows -- what a builder that encodes every cycle ONCE and
+    windows the ids has to reproduce."""
+    import types
+    from dataloader.asimow_dataloader import ASIMoWDataLoader as A  # type: ignore
+    from dataloader.latentspace_dataloader import LatentSpaceDataLoader as L  # type: ignore
+    case = C.BULK_CASE
+    name = case["name"]
+    mcase = next(c for c in C.PATCH_CASES if c["name"] == case["model"])
+    model = build_ref_model(VQVAEPatch, mcase)
+    stream, cycle_labels = C.make_stream(case)
+    wx, wy = A.create_sequence_ds(types.SimpleNamespace(window_size=200, window_offset=0), stream.astype(np.float64),
+                                  cycle_labels, case["seq_len"])
+    win_t, lab_t = torch.tensor(wx, dtype=torch.float32), torch.tensor(wy, dtype=torch.long)
+    loader = [(win_t[lo:lo + case["batch"]], lab_t[lo:lo + case["batch"]]) for lo in range(0, len(win_t), case["batch"])]
+    me = types.SimpleNamespace(latent_space_model=model, device="cpu", window_size=200, task="classification_ids")
+    me.get_latent_space = types.MethodType(L.get_latent_space, me)
+    me.get_latent_space_IDs = types.MethodType(L.get_latent_space_IDs, me)
+    ids, y = L.create_latent_space_dataset_VQ_VAE_IDs(me, loader, seq_len=case["seq_len"], has_patch_embed=True)
+    zq, y2 = L.create_latent_space_dataset_VQ_VAE(me, loader, seq_len=case["seq_len"], has_patch_embed=True)
+    assert np.array_equal(y, y2)
+    out = {f"{name}/seq_ids": ids, f"{name}/seq_labels": y, f"{name}/seq_zq": zq}
+    meta = {k.split("/")[1]: dict(shape=list(v.shape), dtype=str(v.dtype)) for k, v in out.items()}
+    print(f"{name:18s} create_sequence_ds windows {wx.shape} -> ids {ids.shape} labels {y.shape}")
+    return out, meta
+
+
 def default_config_keys(VQVAEPatch):
     """State-dict layout of the repo-default model (train_reconstruction_embedding.py:220-230)."""
     res = {}
@@ -244,6 +274,9 @@ def main():
     w_out, w_meta = run_wide_case(VQVAEPatch)
     np.savez_compressed(os.path.join(GOLDEN, "patch_wide_golden.npz"), **w_out)
     b_out, b_meta = run_bulk_case(VQVAEPatch)
+    s_out, s_meta = run_sequence_case(VQVAEPatch)
+    b_out.update(s_out)
+    b_meta.update(s_meta)
     np.savez_compressed(os.path.join(GOLDEN, "bulk_golden.npz"), **b_out)
     manifest = dict(
         generator="oracle/make_golden.py",

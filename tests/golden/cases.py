@@ -152,6 +152,14 @@ PATCH_WIDE_CASE = dict(name="patch_wide", hidden_dim=256, input_dim=2, num_embed
 BULK_CASE = dict(name="bulk_overlap", model="patch_small", seq_len=4, n_stream=15, batch=4, seed=105)
 
 
+def make_stream(case: dict):
+    """-> (cycles (n_stream, 200, 2) float32 -- the stream make_windows slides over --, one label per CYCLE (n_stream,) float64)."""
+    rs = np.random.RandomState(case["seed"])
+    stream = rs.standard_normal((case["n_stream"], 200, 2)).astype(np.float32)
+    cycle_labels = np.random.RandomState(case["seed"] + 1).randint(0, 2, case["n_stream"]).astype(np.float64)
+    return stream, cycle_labels
+
+
 def make_windows(case: dict):
     """-> (windows (n, seq_len*200, 2) float32, labels (n,) float32, list of (lo, hi) batch slices)."""
     rs = np.random.RandomState(case["seed"])

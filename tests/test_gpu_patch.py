@@ -180,7 +180,46 @@ def test_bulk_loop_prefetch_over_every_kind_of_loader_batch(patch_golden):
     assert np.array_equal(yl, np.concatenate([np.full(b, float(i)) for i, b in enumerate(sizes)]))
 
 
-def test_bulk_builder_dedupe_gives_identical_ids(patch_golden):
+def test_data_sets_from_the_cycle_stream_match_the_reference_window_builder(patch_golden, bulk_golden):
+    """create_latent_space_dataset_from_cycles (every cycle encoded once, windows as a sliding view of the result) against
+    the arrays the unmodified reference produced with its own window builder (ASIMoWDataLoader.create_sequence_ds,
+    dataloader/asimow_dataloader.py:185-206) and its own loops over those windows (tests/golden: bulk_overlap/seq_*)."""
+    case = C.BULK_CASE
+    name = case["name"]
+    model = _load(next(c for c in C.PATCH_CASES if c["name"] == case["model"]), patch_golden).eval()
+    enc = LatentSpaceEncoder(model, window_size=200, device=DEV, encoder_mode="torch")
+    stream, cycle_labels = C.make_stream(case)
+    calls = []
+    inner = enc.get_latent_space_IDs
+    enc.get_latent_space_IDs = lambda x, p=False: (calls.append(x.shape[0]), inner(x, p))[1]
+    for cyc in (stream, stream.astype(np.float64), torch.from_numpy(stream)):
+        ids, y = enc.create_latent_space_dataset_from_cycles(cyc, cycle_labels, seq_len=case["seq_len"], has_patch_embed=True,
+                                                             batch=4)
+        assert ids.dtype == np.int64 and np.array_equal(ids, bulk_golden[f"{name}/seq_ids"])
+        assert y.dtype == np.float64 and np.array_equal(y, bulk_golden[f"{name}/seq_labels"])
+    assert calls == [4, 4, 4, 3] * 3                    # 15 cycles, each encoded once (the reference: 11 windows x 4)
+    ar, y0 = enc.create_latent_space_dataset_from_cycles(stream, None, seq_len=case["seq_len"], has_patch_embed=True, kind="ar_ids")
+    assert np.array_equal(ar, bulk_golden[f"{name}/seq_ids"].reshape(ar.shape[0], -1)) and np.array_equal(y0, np.zeros(len(ar)))
+    zq, y2 = enc.create_latent_space_dataset_from_cycles(stream, cycle_labels, seq_len=case["seq_len"], has_patch_embed=True,
+                                                         kind="latents")
+    assert zq.dtype == np.float64 and zq.shape == bulk_golden[f"{name}/seq_zq"].shape
+    np.testing.assert_allclose(zq, bulk_golden[f"{name}/seq_zq"], rtol=0, atol=1e-6)
+    assert np.array_equal(y2, bulk_golden[f"{name}/seq_labels"])
+    # the windows of the older fixture (n - seq_len + 1 of them) are the same sliding view, one window longer
+    assert np.array_equal(bulk_golden[f"{name}/ids"][: len(ids)], ids)
+    # seq_len = 1: the cycles themselves (dataloader/asimow_dataloader.py:173); fewer cycles than a window: nothing
+    one, y1 = enc.create_latent_space_dataset_from_cycles(stream, cycle_labels, seq_len=1, has_patch_embed=True)
+    assert one.shape == (len(stream), 1, model.enc_out_len) and np.array_equal(y1, cycle_labels)
+    assert np.array_equal(one[:, 0, :][np.arange(len(ids))[:, None] + np.arange(case["seq_len"])[None, :]], ids)
+    none, yn = enc.create_latent_space_dataset_from_cycles(stream[:3], cycle_labels[:3], seq_len=4, has_patch_embed=True)
+    assert none.shape == (0, 4, model.enc_out_len) and yn.shape == (0,)
+    with pytest.raises(ValueError):
+        enc.create_latent_space_dataset_from_cycles(stream, cycle_labels[:-1], seq_len=2, has_patch_embed=True)
+    with pytest.raises(ValueError):
+        enc.create_latent_space_dataset_from_cycles(stream, None, seq_len=2, has_patch_embed=True, kind="one_hot")
+
+
+
     """Overlapping windows (stride of one cycle): with `dedupe = True` every distinct cycle is encoded once and the ids
     array is identical to the plain loop's (SURVEY.md section 8(f) row 2)."""
     case = C.PATCH_CASES[0]

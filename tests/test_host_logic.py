@@ -292,3 +292,47 @@ def test_async_host_writer_cpu_path_keeps_order_and_shapes():
         out = w.finish()
         assert out.dtype == np.float64 and np.array_equal(out, torch.cat(ragged).numpy().astype(np.float64))
     assert L._AsyncHostWriter("cpu").finish() is None
+
+
+def test_data_set_from_cycle_stream_windows_like_create_sequence_ds():
+    """Host logic of create_latent_space_dataset_from_cycles on the CPU with a stand-in per-cycle encoder: window i = cycles
+    i .. i + seq_len - 1, n - seq_len windows, label y[i + seq_len] (dataloader/asimow_dataloader.py:185-206), every
+    cycle encoded once, and the bulk loops' CPU path (prefetcher and writer degenerate to plain copies)."""
+    import types
+    from vqb200.dataloader import LatentSpaceEncoder
+
+    class Stub(torch.nn.Module):
+        enc_out_len, embedding_dim = 3, 2
+        vector_quantization = types.SimpleNamespace(code_counts=None)
+
+    enc = LatentSpaceEncoder(Stub(), window_size=5, device="cpu", encoder_mode=None)
+    seen = []
+
+    def fake_ids(x, has_patch_embed=False):           # ids of a cycle = a function of its samples alone
+        seen.append(x.shape[0])
+        s = x[:, :5, :].sum(dim=(1, 2))
+        return torch.stack([(s * (j + 1)).round().long() for j in range(3)], dim=1).view(-1, 1)
+
+    enc.get_latent_space_IDs = fake_ids
+    rs = np.random.RandomState(3)
+    n, seq_len = 23, 4
+    cycles = rs.randint(-9, 9, (n, 5, 2)).astype(np.float64)
+    y = rs.randint(0, 2, n).astype(np.float64)
+    ids, labels = enc.create_latent_space_dataset_from_cycles(cycles, y, seq_len=seq_len, has_patch_embed=True, batch=10)
+    assert seen == [10, 10, 3]
+    per_cycle = fake_ids(torch.from_numpy(cycles).float()).view(n, 3).numpy()
+    assert ids.shape == (n - seq_len, seq_len, 3) and ids.dtype == np.int64 and ids.flags["C_CONTIGUOUS"]
+    for i in range(n - seq_len):
+        assert np.array_equal(ids[i], per_cycle[i:i + seq_len])
+    assert np.array_equal(labels, y[seq_len:])
+    # the same windows through the loop over MATERIALISED windows (what the reference feeds its loop with)
+    win = np.stack([cycles[i:i + seq_len].reshape(seq_len * 5, 2) for i in range(n - seq_len)]).astype(np.float32)
+    loop_ids, _ = enc.create_latent_space_dataset_VQ_VAE_IDs([torch.from_numpy(win[i:i + 6]) for i in range(0, len(win), 6)],
+                                                             seq_len=seq_len, has_patch_embed=True, no_labels=True)
+    assert np.array_equal(loop_ids, ids)
+    flat, zeros = enc.create_latent_space_dataset_from_cycles(cycles, None, seq_len=seq_len, kind="ar_ids")
+    assert np.array_equal(flat, ids.reshape(n - seq_len, -1)) and np.array_equal(zeros, np.zeros(n - seq_len))
+    one, y1 = enc.create_latent_space_dataset_from_cycles(cycles, y, seq_len=1)
+    assert np.array_equal(one[:, 0, :], per_cycle) and np.array_equal(y1, y)
+    with pytest.raises(ValueError):
+        enc.create_latent_space_dataset_from_cycles(cycles[:, :4, :], y, seq_len=2)

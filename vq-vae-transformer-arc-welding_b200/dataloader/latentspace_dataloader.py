@@ -490,6 +490,68 @@ class LatentSpaceEncoder:
         return new_x.reshape((new_x.shape[0], -1)), new_y
 
 
+    # ---- the same data sets from the CYCLE STREAM ---------------------------------
+    def create_latent_space_dataset_from_cycles(self, cycles, labels=None, seq_len: int = 1, has_patch_embed: bool = False,
+                                                kind: str = "ids", batch: int = 65536):
+        """The arrays the loops above build from the reference's windows, built from the cycles the windows are made of.
+
+        The reference slides a window of `seq_len` cycles with a stride of ONE cycle over the (n, window, C) cycle array
+        (`ASIMoWDataLoader.create_sequence_ds`, dataloader/asimow_dataloader.py:185-206: n - seq_len windows, window i =
+        cycles i .. i + seq_len - 1, label y[i + seq_len]; with seq_len = 1 the cycles themselves, :173) and then encodes
+        every window cycle by cycle (:225-238) -- every cycle seq_len times.  Every op before the decoder is per cycle, so
+        the ids (latents) of a window are the ids (latents) of its cycles: each cycle is encoded ONCE, in `batch`-cycle
+        calls through the loops above, and the windows are a sliding view of the result.  Same arrays, seq_len times
+        less encoder work and host->device traffic (test: the reference's own create_sequence_ds + loop fixture).
+
+        cycles: (n, window, C) numpy array or tensor, already scaled the way the loader's windows are (the reference's
+                scaler is per channel, dataloader/utils.py:81-93, so scaling commutes with windowing); float64 is cast
+                to float32 as the reference's Dataset classes do (dataloader/base_dataloader.py:29,72)
+        labels: (n,) per-cycle labels or None (zeros, as the loops return for no_labels)
+        kind:   "ids"      -> (n_windows, seq_len, enc_out_len) int64           (create_latent_space_dataset_VQ_VAE_IDs)
+                "ar_ids"   -> (n_windows, seq_len * enc_out_len) int64          (..._VQ_VAE_autoreggressive)
+                "latents"  -> (n_windows, seq_len, embedding_dim * enc_out_len) float64   (create_latent_space_dataset_VQ_VAE)
+        Returns (array, labels (n_windows,) float64)."""
+        if kind not in ("ids", "ar_ids", "latents"):
+            raise ValueError(f"kind must be 'ids', 'ar_ids' or 'latents', got {kind!r}")
+        if seq_len < 1:
+            raise ValueError("seq_len must be >= 1")
+        if isinstance(cycles, np.ndarray):
+            cycles = torch.from_numpy(cycles)
+        if cycles.dim() != 3 or cycles.shape[1] < self.window_size:
+            raise ValueError(f"cycles must be (n, >= {self.window_size}, C), got {tuple(cycles.shape)}")
+        if cycles.dtype != torch.float32:
+            cycles = cycles.to(torch.float32)
+        n = cycles.shape[0]
+        n_windows = n if seq_len == 1 else max(n - seq_len, 0)
+        if labels is None:
+            new_y = np.zeros(n_windows)
+        else:
+            y = np.asarray(labels.cpu().numpy() if isinstance(labels, torch.Tensor) else labels, dtype=np.float64)
+            if y.shape != (n,):
+                raise ValueError(f"labels must be ({n},), got {y.shape}")
+            new_y = y.copy() if seq_len == 1 else y[seq_len:].copy()
+        loader = [cycles[s: s + batch] for s in range(0, n, batch)]
+        if kind == "latents":
+            per_cycle, _ = self.create_latent_space_dataset_VQ_VAE([(c, np.zeros(c.shape[0])) for c in loader], seq_len=1,
+                                                                   has_patch_embed=has_patch_embed)
+        else:
+            per_cycle, _ = self.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=1, has_patch_embed=has_patch_embed,
+                                                                       no_labels=True)
+        per_cycle = per_cycle.reshape(n, -1)                       # (n, T) ids or (n, D * T) latents
+        if seq_len == 1:
+            new_x = per_cycle.reshape(n, 1, -1)
+        elif n_windows == 0:
+            new_x = np.empty((0, seq_len, per_cycle.shape[1]), dtype=per_cycle.dtype)
+        else:
+            # (n - seq_len + 1, width, seq_len) sliding view -> the windows as their own array, seq_len x the per-cycle
+            # result (what the reference's format asks for); torch's strided copy runs on all host threads
+            view = torch.from_numpy(np.ascontiguousarray(per_cycle)).unfold(0, seq_len, 1)
+            new_x = view[:n_windows].permute(0, 2, 1).contiguous().numpy()
+        if kind == "ar_ids":
+            new_x = new_x.reshape(new_x.shape[0], -1)
+        return new_x, new_y
+
+
 class OnTheFlyTokenizer:
     """Windows of raw cycles -> the transformer's training batch, on the GPU, per step:
     what the reference prepares offline as a pickled data set -- the id loop of dataloader/latentspace_dataloader.py:
