@@ -269,6 +269,19 @@ int vqb_pack_rows(int device, const float *z, int64_t n_outer, int64_t n_inner, 
 int vqb_ar_pairs(int device, const int64_t *ids, int64_t n_windows, int n_tokens, int64_t start_token, int64_t end_token,
                  int64_t *x, int64_t *y, void *stream);
 
+/* De-duplicating data-set builder (the reference encodes every cycle of every overlapping
+ * window, dataloader/latentspace_dataloader.py:225-238 over dataloader/asimow_dataloader.py:185-206).
+ * vqb_row_keys: two 64-bit fingerprints per row of `words` 32-bit words: keys[2 i + s] = sum_j int64(rows[i][j]) *
+ * mult[s * words + j] (mod 2^64; mult = 2 x words multipliers).  One pass over the rows.
+ * vqb_dedupe_first: first[i] = the smallest row index whose two keys equal row i's (i itself if it is the first; also i
+ * itself in the 2^-64 case of a row that shares key 0, but not key 1, with an earlier row) -- deterministic.  scratch: vqb_dedupe_scratch_bytes(n)
+ * of device memory, contents irrelevant.  The caller verifies rows against `first` word for word. */
+int vqb_row_keys(int device, const void *rows, int64_t n_rows, int words, const unsigned long long *mult,
+                 unsigned long long *keys, void *stream);
+size_t vqb_dedupe_scratch_bytes(int64_t n_rows);
+int vqb_dedupe_first(int device, const unsigned long long *keys, int64_t n_rows, void *scratch, size_t scratch_bytes,
+                     int64_t *first, void *stream);
+
 /* out[i] = codebook[idx[i]] (n, d).  Out-of-range indices yield NaN rows and set
  * *bad_index (device int, may be NULL) to 1. */
 int vqb_gather(int device, const int64_t *idx, int64_t n, const float *codebook, int k, int d,

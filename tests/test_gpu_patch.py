@@ -140,8 +140,8 @@ def test_bulk_loops_equal_per_cycle_reference_loop(patch_golden):
 def test_bulk_loop_prefetch_over_every_kind_of_loader_batch(patch_golden):
     """The bulk loops copy batch i + 1 to the device on a copy stream while batch i is encoded (_DevicePrefetcher):
     pageable and pinned tensors, numpy arrays, windows longer than seq_len cycles (strided source), batches of changing
-    size (slots are re-sized), a single batch and an empty loader -- ids equal to one direct encode call per batch, many
-    batches so that every slot is recycled several times."""
+    size (slots are re-sized), a single batch and an empty loader, consecutive batches grouped into one encoder call or
+    not -- ids equal to one direct encode call per batch, many batches so that every slot is recycled several times."""
     case = C.PATCH_CASES[0]
     model = _load(case, patch_golden).eval()
     enc = LatentSpaceEncoder(model, window_size=200, device=DEV)
@@ -165,10 +165,12 @@ def test_bulk_loop_prefetch_over_every_kind_of_loader_batch(patch_golden):
             x = x.to(DEV)
         loader.append(x)
     want = np.concatenate(direct, axis=0)
-    for _ in range(2):
+    for group in (65536, 65536, 1, 30, 33):                      # one call per run of host batches ... one per loader batch
+        enc.group_cycles = group
         ids, y = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
         assert ids.shape == want.shape and np.array_equal(ids, want)
         assert np.array_equal(y, np.zeros(sum(sizes)))
+    enc.group_cycles = 24
     one, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader[3:4], seq_len=seq_len, has_patch_embed=True, no_labels=True)
     assert np.array_equal(one, direct[3])
     none, y0 = enc.create_latent_space_dataset_VQ_VAE_IDs([], seq_len=seq_len, has_patch_embed=True, no_labels=True)
@@ -231,6 +233,9 @@ def test_data_sets_from_the_cycle_stream_match_the_reference_window_builder(patc
     data = torch.stack([stream[i:i + seq_len].reshape(seq_len * 200, 2) for i in range(n_windows)])
     loader = [data[i:i + 8] for i in range(0, n_windows, 8)]
     plain, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
+    enc.group_cycles = 1                    # one encoder call per loader batch (the default groups consecutive batches)
+    assert np.array_equal(plain, enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True,
+                                                                            no_labels=True)[0])
     calls = []
     inner = enc.get_latent_space_IDs
     enc.get_latent_space_IDs = lambda x, p=False: (calls.append(x.shape[0]), inner(x, p))[1]
@@ -244,6 +249,18 @@ def test_data_sets_from_the_cycle_stream_match_the_reference_window_builder(patc
     whole, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
     assert np.array_equal(plain, whole)
     assert calls == [12, 8, 8] and len(enc.cycle_cache) == 28
+    # grouped (the default: up to 65536 cycles per call): the three batches are one call, and the per-call de-duplication
+    # already sees the overlap between them
+    enc.group_cycles = 65536
+    for mode in (True, "dataset"):
+        calls.clear()
+        enc.dedupe = mode
+        grouped, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
+        assert np.array_equal(plain, grouped) and calls == [28]
+    enc.group_cycles = 80                   # two loader batches per call
+    calls.clear()
+    grouped, _ = enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True, no_labels=True)
+    assert np.array_equal(plain, grouped) and calls == [20, 8]
 
 
 def test_on_the_fly_tokenizer_matches_the_reference_dataset(patch_golden, bulk_golden):
@@ -276,3 +293,57 @@ def test_on_the_fly_tokenizer_matches_the_reference_dataset(patch_golden, bulk_g
     assert bool((xx[:, 0] == 50).all()) and bool((yy[:, -1] == 51).all())
     with pytest.raises(RuntimeError):
         ops.ar_pairs(ids.cpu(), 50, 51)
+
+
+def test_row_keys_and_dedupe_kernels_against_the_host_formulas(monkeypatch):
+    """vqb_row_keys == the torch evaluation of the same sums (wrapping int64), row widths with and without the 16-byte path,
+    -0.0 / NaN payloads kept apart; vqb_dedupe_first == first occurrence by key pair (checked against a Python dict), on
+    many duplicates, and the whole dedupe_rows on CUDA == the CPU path, incl. useless hashes (one group, word-for-word
+    split) and a key-0-only collision."""
+    from vqb200 import ops
+    from vqb200.dataloader import latentspace_dataloader as L
+    g = torch.Generator().manual_seed(21)
+    for n, words in ((1, 4), (37, 400), (1000, 402), (5000, 7), (4096, 400)):
+        rows = torch.randn(n, words, generator=g)
+        if n > 8:
+            rows[3, 0], rows[5, 0] = 0.0, -0.0
+            rows[7] = rows[2]
+            rows[8, 1] = float("nan")
+        want = L.cycle_fingerprints(rows)                                  # CPU: torch ops
+        got = L.cycle_fingerprints(rows.to(DEV))                           # CUDA: vqb_row_keys
+        assert got.dtype == torch.int64 and torch.equal(got.cpu(), want)
+    # first occurrence per key pair
+    stream = torch.randn(700, 50, generator=g)
+    idx = torch.randint(0, 700, (20000,), generator=g)
+    rows = stream[idx].to(DEV)
+    keys = L.cycle_fingerprints(rows)
+    first = ops.dedupe_first(keys).cpu().tolist()
+    seen, want_first = {}, []
+    for i, k in enumerate(map(tuple, keys.cpu().tolist())):
+        want_first.append(seen.setdefault(k, i))
+    assert first == want_first
+    assert ops.dedupe_first(keys).cpu().tolist() == first                  # deterministic
+    for r in (rows, rows[:1], rows[:0], torch.randn(300, 200, 2, generator=g).to(DEV)):
+        rep, inv = L.dedupe_rows(r)
+        rep_c, inv_c = L.dedupe_rows(r.cpu())
+        assert torch.equal(rep.cpu(), torch.sort(rep_c).values)            # the same representatives (first occurrences)
+        if r.shape[0]:
+            assert torch.equal(r[rep[inv]].view(torch.int32), r.view(torch.int32))
+            assert torch.equal(rep, torch.sort(rep).values) and int(inv.max()) == rep.numel() - 1
+    # key 0 equal for every row, key 1 honest: rows fall back to themselves unless both keys agree
+    honest = L._hash_weights
+    monkeypatch.setattr(L, "_hash_weights", lambda width, device, seed: (
+        torch.zeros(width, dtype=torch.int64, device=device) if seed == L._HASH_SEEDS[0] else honest(width, device, seed)))
+    L._weight_cache.clear()
+    small = torch.randn(64, 12, generator=g)
+    small[40] = small[10]
+    small[50] = small[0]
+    rep, inv = L.dedupe_rows(small.to(DEV))
+    # (every row shares key 0 with row 0: only rows whose key 1 equals row 0's -- row 50 -- are grouped; 10 / 40 stay apart)
+    assert torch.equal(small.to(DEV)[rep[inv]], small.to(DEV)) and rep.numel() == 63
+    # both hashes useless: one group, split again word for word
+    monkeypatch.setattr(L, "_hash_weights", lambda width, device, seed: torch.zeros(width, dtype=torch.int64, device=device))
+    L._weight_cache.clear()
+    rep, inv = L.dedupe_rows(small.to(DEV))
+    assert torch.equal(small.to(DEV)[rep[inv]], small.to(DEV)) and rep.numel() == 63      # only row 50 == row 0 is found
+    L._weight_cache.clear()

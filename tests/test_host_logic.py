@@ -283,9 +283,9 @@ def test_async_host_writer_cpu_path_keeps_order_and_shapes():
     out = w.finish()
     assert out.shape == (8, 3, 4) and out.dtype == np.int64
     assert np.array_equal(out, torch.cat(parts).numpy())
-    # a batch-count hint sizes the array up front; a hint that was too small grows it; batches of changing size; dtype conversion
-    for hint in (None, 1, 2, 4, 9):
-        w = L._AsyncHostWriter("cpu", n_batches_hint=hint, out_dtype=np.float64)
+    # a row-count hint sizes the array up front; a hint that was too small grows it; batches of changing size; dtype conversion
+    for hint in (None, 1, 2, 4, 19, 40):
+        w = L._AsyncHostWriter("cpu", rows_hint=hint, out_dtype=np.float64)
         ragged = [torch.full((r, 5), float(r)) for r in (3, 1, 7, 2, 6)]
         for t in ragged:
             w.put(t)

@@ -6,7 +6,7 @@ every batch goes through the prefetcher's pinned staging copy.  Prints wall-cloc
 the way the reference counts: every cycle of every window) per mode, and checks that the three id arrays are equal;
 then the same data set through create_latent_space_dataset_from_cycles (the cycle stream in, every cycle encoded once).
 
-    python tools/dataset_build_time.py [n_cycles]"""
+    python tools/dataset_build_time.py [n_cycles [group_cycles]]"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, vqb200
@@ -19,11 +19,13 @@ torch.manual_seed(0)
 model = vqb200.VQVAEPatch(hidden_dim=512, input_dim=2, num_embeddings=256, embedding_dim=32, n_resblocks=8,
                           learning_rate=1e-3, dropout_p=0.1, patch_size=25, batch_norm=False).to(dev).eval()
 enc = LatentSpaceEncoder(model, window_size=200, device=str(dev))
+if len(sys.argv) > 2:
+    enc.group_cycles = int(sys.argv[2])
 stream = torch.randn(n_cycles * 200, 2, generator=torch.Generator().manual_seed(1))
 n_windows = n_cycles - SEQ + 1
 windows = stream.as_strided((n_windows, SEQ * 200, 2), (200 * 2, 2, 1))
 loader = [windows[i:i + BATCH] for i in range(0, n_windows, BATCH)]
-out, ref = {"n_cycles": n_cycles, "n_windows": n_windows, "batches": len(loader)}, None
+out, ref = {"group_cycles": enc.group_cycles, "n_cycles": n_cycles, "n_windows": n_windows, "batches": len(loader)}, None
 for mode in (False, True, "dataset"):
     enc.dedupe = mode
     best = None

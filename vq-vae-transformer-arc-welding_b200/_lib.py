@@ -50,6 +50,9 @@ SIGNATURES = {
     "vqb_pack_rows": (_i, [_i, _vp, _i64, _i64, _i, _i64, _i64, _i64, _vp, _vp]),
     "vqb_patch_embed": (_i, [_i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "vqb_ar_pairs": (_i, [_i, _vp, _i64, _i, _i64, _i64, _vp, _vp, _vp]),
+    "vqb_row_keys": (_i, [_i, _vp, _i64, _i, _vp, _vp, _vp]),
+    "vqb_dedupe_scratch_bytes": (_sz, [_i64]),
+    "vqb_dedupe_first": (_i, [_i, _vp, _i64, _vp, _sz, _vp, _vp]),
     "vqb_gather": (_i, [_i, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     "vqb_one_hot": (_i, [_i, _vp, _i64, _i, _vp, _vp]),
     "vqb_launch_counter": (ctypes.c_longlong, []),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libvqb200.so")
-SOURCES = ["vq_api.cu", "vq_fwd_fma.cu", "vq_fwd_tc.cu", "vq_fwd_tcs.cu", "vq_bwd.cu", "vq_hostpipe.cu", "tok_linear.cu", "vq_pack.cu", "enc_chain.cu"]
+SOURCES = ["vq_api.cu", "vq_fwd_fma.cu", "vq_fwd_tc.cu", "vq_fwd_tcs.cu", "vq_bwd.cu", "vq_hostpipe.cu", "tok_linear.cu", "vq_pack.cu", "vq_dedupe.cu", "enc_chain.cu"]
 HEADERS = ["vq_common.cuh", "vq_ptx.cuh", os.path.join("..", "..", "include", "vqb200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

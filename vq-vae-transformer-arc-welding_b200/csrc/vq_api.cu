@@ -651,6 +651,52 @@ int vqb_ar_pairs(int device, const int64_t *ids, int64_t n_windows, int n_tokens
     return VQB_OK;
 }
 
+int vqb_row_keys(int device, const void *rows, int64_t n_rows, int words, const unsigned long long *mult,
+                 unsigned long long *keys, void *stream)
+{
+    if (n_rows < 0 || words <= 0 || !mult || (n_rows > 0 && (!rows || !keys)) || !aligned(rows, 4) || !aligned(mult, 8) ||
+        !aligned(keys, 8))
+        return VQB_E_ARG;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_row_keys(rows, n_rows, words, mult, keys, info.sm_count, (cudaStream_t)stream);
+    if (err != cudaSuccess)
+        return (int)err;
+    count_launches(n_rows > 0 ? 1 : 0);
+    return VQB_OK;
+}
+
+size_t vqb_dedupe_scratch_bytes(int64_t n_rows) { return dedupe_scratch_bytes(n_rows); }
+
+int vqb_dedupe_first(int device, const unsigned long long *keys, int64_t n_rows, void *scratch, size_t scratch_bytes,
+                     int64_t *first, void *stream)
+{
+    if (n_rows < 0 || (n_rows > 0 && (!keys || !scratch || !first)) || !aligned(keys, 8) || !aligned(scratch, 8) ||
+        !aligned(first, 8))
+        return VQB_E_ARG;
+    if (n_rows >= 0x7F000000ll)                  // row indices live in 32-bit table entries
+        return VQB_E_UNSUPPORTED;
+    if (scratch_bytes < dedupe_scratch_bytes(n_rows))
+        return VQB_E_WORKSPACE;
+    vqb_device_info info;
+    int rc = device_info(device, &info);
+    if (rc != VQB_OK)
+        return rc;
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return (int)err;
+    err = launch_dedupe_first(keys, n_rows, scratch, first, info.sm_count, (cudaStream_t)stream);
+    if (err != cudaSuccess)
+        return (int)err;
+    count_launches(n_rows > 0 ? 2 : 0);
+    return VQB_OK;
+}
+
 int vqb_backward(int device, const float *g_zq, const float *g_loss,
                  const float *z, int64_t n_outer, int64_t n_inner, int d,
                  int64_t stride_outer, int64_t stride_inner, int64_t stride_d,

@@ -156,6 +156,12 @@ cudaError_t launch_patch_embed(const float *x, const float *w, const float *bias
 bool pack_rows_supported(int64_t n_inner, int d, int64_t s_outer, int64_t s_inner, int64_t s_d);
 cudaError_t launch_pack_rows(const float *src, float *dst, int64_t n_outer, int64_t n_inner, int d, int64_t s_outer,
                              int64_t s_inner, int64_t s_d, int sm_count, cudaStream_t st);
+// vq_dedupe.cu
+cudaError_t launch_row_keys(const void *rows, int64_t n, int words, const unsigned long long *mult, unsigned long long *keys,
+                            int sm_count, cudaStream_t st);
+size_t dedupe_scratch_bytes(int64_t n);
+cudaError_t launch_dedupe_first(const unsigned long long *keys, int64_t n, void *scratch, int64_t *first, int sm_count,
+                                cudaStream_t st);
 cudaError_t launch_ar_pairs(const int64_t *ids, int64_t n_windows, int n, int64_t start_token, int64_t end_token, int64_t *x,
                             int64_t *y, int sm_count, cudaStream_t st);
 void count_launches(int n);

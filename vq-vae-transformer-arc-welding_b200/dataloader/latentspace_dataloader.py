@@ -26,6 +26,8 @@ from __future__ import annotations
 
 import os
 import pickle
+import queue
+import threading
 from typing import Callable, Iterable, List, Optional, Tuple
 
 import numpy as np
@@ -62,49 +64,75 @@ def nvtx_range(name: str):
 _HASH_SEEDS = (0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F)
 
 
+_weight_cache: dict = {}
+
+
 def _hash_weights(width: int, device, seed: int) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed & 0x7FFFFFFF)
     w = torch.randint(-(1 << 62), 1 << 62, (width,), generator=g, dtype=torch.int64)
     return (w | 1).to(device)                 # odd multipliers; int64 arithmetic wraps
 
 
+def _hash_weight_pair(width: int, device) -> torch.Tensor:
+    """(2, width) int64: the multipliers of both hashes on `device`, built once per (width, device)."""
+    key = (width, str(device), _HASH_SEEDS)
+    w = _weight_cache.get(key)
+    if w is None:
+        w = torch.stack([_hash_weights(width, device, s) for s in _HASH_SEEDS]).contiguous()
+        _weight_cache[key] = w
+    return w
+
+
+def cycle_fingerprints(rows: torch.Tensor) -> torch.Tensor:
+    """(n, ...) float32 -> (n, 2) int64: two multiplicative hashes of the rows' bit patterns, key_s = sum_j int64(word_j) *
+    w_s[j] (wrapping).  CUDA rows: one pass of vqb_row_keys (the rows are read once); CPU rows (host-logic tests): the
+    same sums as torch ops."""
+    n = rows.shape[0]
+    if rows.is_cuda:
+        from .. import ops
+        bits = rows.reshape(n, -1)
+        return ops.row_keys(bits, _hash_weight_pair(bits.shape[1], rows.device))
+    wide = rows.reshape(n, -1).contiguous().view(torch.int32).to(torch.int64)
+    return torch.stack([(wide * _hash_weights(wide.shape[1], rows.device, s)).sum(dim=1) for s in _HASH_SEEDS], dim=1)
+
+
 def dedupe_rows(rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """rows (n, ...) float32 -> (rep, inverse): rep (u,) int64 indices of one representative per group of bit-identical
     rows (the first occurrence), inverse (n,) int64 with rows[i] bit-identical to rows[rep[inverse[i]]].  Rows that a
-    hash collision put into a foreign group come back as their own representatives."""
+    hash collision put into a foreign group come back as their own representatives.
+
+    CUDA rows: fingerprints (vqb_row_keys) -> first row with the same fingerprints (vqb_dedupe_first: a hash table in
+    device memory) -> word-for-word check against that row -> representatives in ascending row order; ONE host
+    synchronisation (the number of representatives).  CPU rows (host-logic tests): the same grouping with torch.unique."""
     n = rows.shape[0]
     if n == 0:
         e = torch.empty(0, dtype=torch.int64, device=rows.device)
         return e, e
     bits = rows.reshape(n, -1).contiguous().view(torch.int32)
-    wide = bits.to(torch.int64)
-    keys = torch.stack([(wide * _hash_weights(bits.shape[1], rows.device, s)).sum(dim=1) for s in _HASH_SEEDS], dim=1)
-    _, inverse = torch.unique(keys, dim=0, return_inverse=True)
-    u = int(inverse.max().item()) + 1
+    keys = cycle_fingerprints(rows)
     ar = torch.arange(n, device=rows.device)
-    rep = torch.full((u,), n, dtype=torch.int64, device=rows.device).scatter_reduce_(0, inverse, ar, reduce="amin")
-    same = (bits == bits[rep[inverse]]).all(dim=1)            # word-for-word check against the representative
-    if not bool(same.all()):
-        stray = (~same).nonzero().view(-1)                    # collided rows: each becomes its own group
-        inverse = inverse.clone()
-        inverse[stray] = u + torch.arange(stray.numel(), device=rows.device)
-        rep = torch.cat([rep, stray])
-    return rep, inverse
+    if rows.is_cuda:
+        from .. import ops
+        first = ops.dedupe_first(keys)
+    else:
+        _, group = torch.unique(keys, dim=0, return_inverse=True)
+        u = int(group.max().item()) + 1
+        first = torch.full((u,), n, dtype=torch.int64, device=rows.device).scatter_reduce_(0, group, ar, reduce="amin")[group]
+    same = (bits == bits[first]).all(dim=1)                   # word-for-word check against the row it was grouped with
+    first = torch.where(same, first, ar)                      # collided rows: each becomes its own group
+    is_rep = first == ar
+    rank = torch.cumsum(is_rep, dim=0) - 1                    # position of a representative among the representatives
+    rep = is_rep.nonzero().view(-1)                           # ascending row order (the one synchronisation)
+    return rep, rank[first]
 
 
-def encode_unique(encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: torch.Tensor) -> torch.Tensor:
-    """encode_fn(cycles) for a per-cycle encode_fn ((b, ...) -> (b, T)), evaluated once per distinct cycle."""
-    rep, inverse = dedupe_rows(cycles)
+def encode_unique(encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: torch.Tensor, pre=None) -> torch.Tensor:
+    """encode_fn(cycles) for a per-cycle encode_fn ((b, ...) -> (b, T)), evaluated once per distinct cycle.
+    pre: dedupe_rows(cycles) if the caller has it already (the bulk loops compute it one batch ahead)."""
+    rep, inverse = dedupe_rows(cycles) if pre is None else pre
     if rep.numel() == cycles.shape[0]:
         return encode_fn(cycles)
     return encode_fn(cycles[rep])[inverse]
-
-
-def cycle_fingerprints(rows: torch.Tensor) -> torch.Tensor:
-    """(n, ...) float32 -> (n, 2) int64: two multiplicative hashes of the rows' bit patterns (the keys dedupe_rows groups by)."""
-    n = rows.shape[0]
-    wide = rows.reshape(n, -1).contiguous().view(torch.int32).to(torch.int64)
-    return torch.stack([(wide * _hash_weights(wide.shape[1], rows.device, s)).sum(dim=1) for s in _HASH_SEEDS], dim=1)
 
 
 class CycleIdCache:
@@ -166,10 +194,10 @@ class CycleIdCache:
         self.k2 = torch.cat([self.k2, keys[:, 1]])[order]
         self.slot = torch.cat([self.slot, m + torch.arange(cycles.shape[0], device=self.device)])[order]
 
-    def encode(self, encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: torch.Tensor) -> torch.Tensor:
+    def encode(self, encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: torch.Tensor, pre=None) -> torch.Tensor:
         """ids of `cycles` ((n, ...) -> (n, T)): distinct cycles of the batch first (word for word), then the cache,
-        then the encoder for what is left."""
-        rep, inverse = dedupe_rows(cycles)
+        then the encoder for what is left.  pre: dedupe_rows(cycles) if the caller has it already."""
+        rep, inverse = dedupe_rows(cycles) if pre is None else pre
         uniq = cycles[rep]
         keys = cycle_fingerprints(uniq)
         rows = self.lookup(uniq, keys)
@@ -189,23 +217,23 @@ class _AsyncHostWriter:
     """Device results -> ONE host array through a small pool of pinned staging buffers on a copy stream: the D2H copy of
     batch i overlaps the encoder work of batch i + 1 (the reference blocks on `.cpu()` once per cycle slice, :231-235, and
     `np.append`s, :238).  A retired batch is copied once, straight into its rows of the output array (converted to
-    `out_dtype` on the way); the array is sized from `n_batches_hint` x the first batch (exact for the equal batches a
-    DataLoader yields) and doubles if that was too small."""
+    `out_dtype` on the way); the array is sized from `rows_hint` (the loops set it to the loader's length x its first batch: exact
+    for the equal batches a DataLoader yields) and doubles if that was too small."""
 
-    def __init__(self, device, depth: int = 3, n_batches_hint: Optional[int] = None, out_dtype=None):
+    def __init__(self, device, depth: int = 3, rows_hint: Optional[int] = None, out_dtype=None):
         self.cuda = torch.device(device).type == "cuda"
         self.depth = depth
         self.stream = torch.cuda.Stream(device=device) if self.cuda else None
         self.pending: List[Tuple[torch.Tensor, Optional["torch.cuda.Event"], tuple]] = []
         self.free: List[torch.Tensor] = []
-        self.n_batches_hint, self.out_dtype = n_batches_hint, out_dtype
+        self.rows_hint, self.out_dtype = rows_hint, out_dtype
         self.arr: Optional[np.ndarray] = None
         self.n = 0
 
     def _append(self, a: np.ndarray) -> None:
         b = a.shape[0]
         if self.arr is None:
-            cap = max(b * (self.n_batches_hint or 1), b, 1)
+            cap = max(self.rows_hint or 0, b, 1)
             self.arr = np.empty((cap,) + a.shape[1:], dtype=self.out_dtype or a.dtype)
         elif self.n + b > self.arr.shape[0]:
             grown = np.empty((max(self.n + b, 2 * self.arr.shape[0]),) + self.arr.shape[1:], dtype=self.arr.dtype)
@@ -259,92 +287,165 @@ def _n_batches(loader) -> Optional[int]:
 
 
 class _DevicePrefetcher:
-    """Loader batches -> their cycles on the device, ONE BATCH AHEAD: the host->device copy of batch i + 1 runs on a copy
-    stream while the encoder works on batch i (the reference copies one cycle slice at a time on the compute stream and
-    then blocks on it, :231-232).  A pageable loader tensor (or one whose windows are longer than seq_len cycles) first
-    goes through a pinned staging buffer -- `copy_` on CPU tensors of this size runs on all host threads -- a pinned,
-    exactly-sized one is copied as it is.  Three device slots rotate (being encoded / handed out / being filled); a slot
-    is overwritten only after the compute stream has passed the work that read it (`consumed` events), a staging buffer
-    only after its copy has finished.  On a CPU device it degenerates to the plain `.to(device)`.
+    """Loader batches -> their cycles on the device, in GROUPS of up to `group_cycles` cycles, one group ahead.
 
-    Yields (cycles_on_device (b * seq_len, window, C), item) with `item` exactly what the loader produced."""
+    The host->device copy of every loader batch runs on a copy stream, straight into its rows of the group's device slot,
+    while the encoder works on the previous group (the reference copies one cycle slice at a time on the compute stream
+    and then blocks on it, :231-232).  A pageable loader tensor (or one whose windows are longer than seq_len cycles)
+    first goes through one of three pinned staging buffers -- `copy_` on CPU tensors of this size runs on all host
+    threads -- a pinned, exactly-sized one is copied as it is.  Three device slots rotate (being encoded / handed out /
+    being filled); a slot is overwritten only after the compute stream has passed the work that read it (`consumed`
+    events), a staging buffer only after its copy has finished.  The loader is walked and the copies are issued by a
+    helper thread.  Grouping amortises the per-call host work of the encoder over several loader batches (a batch of 512
+    windows x 20 cycles keeps the GPU busy for 1.5 ms, about what its launches cost the host) and lets the
+    de-duplication see the overlap BETWEEN consecutive batches.  On a CPU device, or for batches that are on a GPU
+    already, it degenerates to `.to(device)` per batch.
+
+    Yields (cycles_on_device (rows, window, C), items) with `items` the list of what the loader produced for the group,
+    rows = sum over the items of batch size x seq_len, in loader order."""
 
     SLOTS = 3
 
-    def __init__(self, loader: Iterable, device, seq_len: int, window_size: int, no_labels: bool = False):
+    def __init__(self, loader: Iterable, device, seq_len: int, window_size: int, no_labels: bool = False,
+                 group_cycles: int = 65536):
         self.loader, self.device = loader, torch.device(device)
         self.seq_len, self.window = seq_len, window_size
         self.no_labels = no_labels
+        self.group_cycles = max(int(group_cycles), 1)
         self.cuda = self.device.type == "cuda"
         if self.cuda:
             self.stream = torch.cuda.Stream(device=self.device)
             self.dev: List[Optional[torch.Tensor]] = [None] * self.SLOTS
-            self.stage: List[Optional[torch.Tensor]] = [None] * self.SLOTS
             self.consumed: List[Optional["torch.cuda.Event"]] = [None] * self.SLOTS
+            self.stage: List[Optional[torch.Tensor]] = [None] * self.SLOTS
             self.copied: List[Optional["torch.cuda.Event"]] = [None] * self.SLOTS
-        self.n = 0
+        self.n_groups = 0
+        self.n_staged = 0
 
-    @staticmethod
-    def _fit(buf: Optional[torch.Tensor], n: int, dtype, **kw) -> torch.Tensor:
-        if buf is None or buf.numel() < n or buf.dtype != dtype:
-            buf = torch.empty(max(n, 1), dtype=dtype, **kw)
-        return buf
-
-    def _issue(self, item):
+    def _source(self, item) -> torch.Tensor:
         x = item if self.no_labels else item[0]
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(x)
-        b, c = x.shape[0], x.shape[2]
-        src = x[:, : self.seq_len * self.window, :]
-        shape = (b * self.seq_len, self.window, c)
-        if not self.cuda or x.is_cuda:                     # nothing to overlap: a CPU run, or cycles that are on a GPU already
-            return src.reshape(shape).to(self.device), item, -1, None
-        k = self.n % self.SLOTS
-        self.n += 1
-        n = src.numel()
+        return x[:, : self.seq_len * self.window, :]
+
+    def _copy_in(self, src: torch.Tensor, dst: torch.Tensor) -> None:
+        """One loader batch (b, seq_len * window, C) on the host -> its rows `dst` (b * seq_len, window, C) of a slot."""
         if not (src.is_contiguous() and src.is_pinned()):
+            k = self.n_staged % self.SLOTS
+            self.n_staged += 1
             if self.copied[k] is not None:
                 self.copied[k].synchronize()               # the copy that last read this staging buffer
-            self.stage[k] = self._fit(self.stage[k], n, src.dtype, pin_memory=True)
+            n = src.numel()
+            if self.stage[k] is None or self.stage[k].numel() < n or self.stage[k].dtype != src.dtype:
+                self.stage[k] = torch.empty(max(n, 1), dtype=src.dtype, pin_memory=True)
             host = self.stage[k][:n].view(src.shape)
             host.copy_(src)
         else:
-            host = src
-        with torch.cuda.device(self.device):
-            old = self.dev[k]
-            self.dev[k] = self._fit(old, n, src.dtype, device=self.device)
-            if self.dev[k] is not old:                     # a block the allocator may be recycling from the compute stream
-                self.stream.wait_stream(torch.cuda.current_stream(self.device))
-            if self.consumed[k] is not None:
-                self.stream.wait_event(self.consumed[k])   # the encoder work that read this slot three batches ago
-            with torch.cuda.stream(self.stream):
-                out = self.dev[k][:n].view(shape)
-                out.copy_(host.reshape(shape), non_blocking=True)
+            k, host = -1, src
+        with torch.cuda.stream(self.stream):
+            dst.copy_(host.reshape(dst.shape), non_blocking=True)
+            if k >= 0:
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
-        self.copied[k] = ev
-        return out, item, k, ev
+                self.copied[k] = ev
+
+    def _groups(self):
+        """The loader's items in groups of at most group_cycles cycles (a single larger batch is a group of its own)."""
+        group, rows = [], 0
+        for item in self.loader:
+            src = self._source(item)
+            r = src.shape[0] * self.seq_len
+            if group and (rows + r > self.group_cycles or src.is_cuda != group[0][1].is_cuda or
+                          src.dtype != group[0][1].dtype or src.shape[2] != group[0][1].shape[2]):
+                yield group
+                group, rows = [], 0
+            group.append((item, src))
+            rows += r
+        if group:
+            yield group
+
+    def _issue(self, group):
+        items = [it for it, _ in group]
+        srcs = [s for _, s in group]
+        c, dtype = srcs[0].shape[2], srcs[0].dtype
+        rows = [s.shape[0] * self.seq_len for s in srcs]
+        if not self.cuda or srcs[0].is_cuda:               # nothing to overlap: a CPU run, or cycles that are on a GPU already
+            parts = [s.reshape(r, self.window, c).to(self.device) for s, r in zip(srcs, rows)]
+            return (parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)), items, -1, None
+        k = self.n_groups % self.SLOTS
+        self.n_groups += 1
+        per_row = self.window * c
+        total = sum(rows)
+        with torch.cuda.device(self.device):
+            old = self.dev[k]
+            if old is None or old.numel() < total * per_row or old.dtype != dtype:
+                self.dev[k] = torch.empty(max(total, min(self.group_cycles, 1 << 20)) * per_row, dtype=dtype, device=self.device)
+                # (a block the allocator may be recycling from the compute stream)
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            if self.consumed[k] is not None:
+                self.stream.wait_event(self.consumed[k])   # the encoder work that read this slot three groups ago
+            out = self.dev[k][: total * per_row].view(total, self.window, c)
+            lo = 0
+            for s, r in zip(srcs, rows):
+                self._copy_in(s, out[lo: lo + r])
+                lo += r
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        return out, items, k, ready
 
     def __iter__(self):
-        it = iter(self.loader)
-        try:
-            nxt = self._issue(next(it))
-        except StopIteration:
+        if not self.cuda:
+            for group in self._groups():
+                cyc, items, _k, _ready = self._issue(group)
+                yield cyc, items
             return
-        while nxt is not None:
-            cur = nxt
+        # A helper thread walks the loader and issues the copies (ATen's host copy and the CUDA calls release the GIL), so the
+        # staging of the next group overlaps the launches -- and, in the de-duplicating modes, the synchronisations -- of
+        # this one on the consumer's thread.  The queue holds one issued group: one handed out + one queued + one being
+        # issued = SLOTS.
+        q: "queue.Queue" = queue.Queue(maxsize=self.SLOTS - 2)
+        stop = threading.Event()
+        end = object()
+
+        def walk():
             try:
-                nxt = self._issue(next(it))                # its copy overlaps the encode of `cur` the caller launches next
-            except StopIteration:
-                nxt = None
-            cyc, item, k, ready = cur
-            if k >= 0:
-                torch.cuda.current_stream(self.device).wait_event(ready)
-            yield cyc, item
-            if k >= 0:
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream(self.device))
-                self.consumed[k] = ev
+                torch.cuda.set_device(self.device)
+                for group in self._groups():
+                    if stop.is_set():
+                        break
+                    q.put(self._issue(group))
+            except BaseException as e:           # handed to the consumer, raised there
+                q.put(e)
+            finally:
+                q.put(end)
+
+        worker = threading.Thread(target=walk, name="vqb200-prefetch", daemon=True)
+        worker.start()
+        try:
+            while True:
+                got = q.get()
+                if got is end:
+                    break
+                if isinstance(got, BaseException):
+                    raise got
+                cyc, items, k, ready = got
+                here = torch.cuda.current_stream(self.device)
+                if k >= 0:
+                    here.wait_event(ready)
+                    cyc.record_stream(here)
+                yield cyc, items
+                if k >= 0:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(self.device))
+                    self.consumed[k] = ev        # set before the next q.get() lets the helper move on to this slot
+        finally:
+            stop.set()
+            while worker.is_alive():             # a consumer that stops early: let the helper run into `stop`
+                try:
+                    q.get(timeout=0.05)
+                except queue.Empty:
+                    pass
+            worker.join()
 
 
 def latent_dataset_name(task: str, model_name: str, cycle_seq_number: int, model_id: str) -> str:
@@ -396,6 +497,9 @@ class LatentSpaceEncoder:
         #: "dataset": additionally across the batches of one create_latent_space_dataset_* call (CycleIdCache).
         self.dedupe = False
         self.cycle_cache: Optional[CycleIdCache] = None
+        #: the bulk loops hand the encoder up to this many cycles per call: consecutive loader batches are copied into one
+        #: device buffer (_DevicePrefetcher); 1 = one call per loader batch.  Same arrays either way (every op is per cycle).
+        self.group_cycles = 65536
 
     # ---- single encode calls (:144-161) -------------------------------------------------
     def _encode(self, x, has_patch_embed: bool):
@@ -431,15 +535,18 @@ class LatentSpaceEncoder:
         model = self.latent_space_model
         width = int(model.embedding_dim * model.enc_out_len)
         ys = []
-        writer = _AsyncHostWriter(self.device, n_batches_hint=_n_batches(loader), out_dtype=np.float64)
+        writer = _AsyncHostWriter(self.device, out_dtype=np.float64)
+        n_batches = _n_batches(loader)
         model.eval()
         with torch.no_grad():
-            for cyc, (x, y) in _DevicePrefetcher(loader, self.device, seq_len, self.window_size):
-                b = x.shape[0]
+            for cyc, items in _DevicePrefetcher(loader, self.device, seq_len, self.window_size, group_cycles=self.group_cycles):
+                if writer.rows_hint is None and n_batches:
+                    writer.rows_hint = n_batches * int(items[0][0].shape[0])
                 with nvtx_range("vqb200.encode_batch"):
                     z_q = self.get_latent_space(cyc, has_patch_embed=has_patch_embed)
-                writer.put(z_q.reshape(b, seq_len, -1))
-                ys.append(np.asarray(y.cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64))
+                writer.put(z_q.reshape(cyc.shape[0] // seq_len, seq_len, -1))
+                for _x, y in items:
+                    ys.append(np.asarray(y.cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64))
         new_x = writer.finish()
         if new_x is None:
             return np.empty((0, seq_len, width)), np.empty((0,))
@@ -452,15 +559,18 @@ class LatentSpaceEncoder:
         enc_out_len = int(model.enc_out_len)
         ys = []
         counts = None
-        writer = _AsyncHostWriter(self.device, n_batches_hint=_n_batches(loader))   # ids leave through pinned buffers on a copy stream
+        writer = _AsyncHostWriter(self.device)          # ids leave through pinned buffers on a copy stream
+        n_batches = _n_batches(loader)
         cache = CycleIdCache(self.device) if self.dedupe == "dataset" else None
         self.cycle_cache = cache
         enc = lambda c: self.get_latent_space_IDs(c, has_patch_embed).view(c.shape[0], -1)
         model.eval()
         with torch.no_grad():
-            for cyc, item in _DevicePrefetcher(loader, self.device, seq_len, self.window_size, no_labels=no_labels):
-                x, y = (item, None) if no_labels else item
-                b = x.shape[0]
+            for cyc, items in _DevicePrefetcher(loader, self.device, seq_len, self.window_size, no_labels=no_labels,
+                                                group_cycles=self.group_cycles):
+                b = cyc.shape[0] // seq_len
+                if writer.rows_hint is None and n_batches:
+                    writer.rows_hint = n_batches * int((items[0] if no_labels else items[0][0]).shape[0])
                 model.vector_quantization.code_counts = None
                 with nvtx_range("vqb200.encode_batch"):
                     if cache is not None:
@@ -473,8 +583,9 @@ class LatentSpaceEncoder:
                 if c is not None:
                     counts = c.clone() if counts is None else counts + c
                 writer.put(ids.view(b, seq_len, -1))
-                if y is not None:
-                    ys.append(np.asarray(y.cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64))
+                if not no_labels:
+                    for _x, y in items:
+                        ys.append(np.asarray(y.cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64))
         new_x = writer.finish()
         self.code_counts = counts
         if new_x is None:
@@ -531,12 +642,16 @@ class LatentSpaceEncoder:
                 raise ValueError(f"labels must be ({n},), got {y.shape}")
             new_y = y.copy() if seq_len == 1 else y[seq_len:].copy()
         loader = [cycles[s: s + batch] for s in range(0, n, batch)]
-        if kind == "latents":
-            per_cycle, _ = self.create_latent_space_dataset_VQ_VAE([(c, np.zeros(c.shape[0])) for c in loader], seq_len=1,
-                                                                   has_patch_embed=has_patch_embed)
-        else:
-            per_cycle, _ = self.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=1, has_patch_embed=has_patch_embed,
-                                                                       no_labels=True)
+        keep, self.group_cycles = self.group_cycles, batch         # one encoder call per `batch` cycles
+        try:
+            if kind == "latents":
+                per_cycle, _ = self.create_latent_space_dataset_VQ_VAE([(c, np.zeros(c.shape[0])) for c in loader], seq_len=1,
+                                                                       has_patch_embed=has_patch_embed)
+            else:
+                per_cycle, _ = self.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=1, has_patch_embed=has_patch_embed,
+                                                                           no_labels=True)
+        finally:
+            self.group_cycles = keep
         per_cycle = per_cycle.reshape(n, -1)                       # (n, T) ids or (n, D * T) latents
         if seq_len == 1:
             new_x = per_cycle.reshape(n, 1, -1)

@@ -261,6 +261,44 @@ def ar_pairs(ids: torch.Tensor, start_token: int, end_token: int):
     return x, y
 
 
+def row_keys(rows: torch.Tensor, mult: torch.Tensor) -> torch.Tensor:
+    """(n, 2) int64 fingerprints of the bit patterns of `rows` ((n, ...) of a 4-byte dtype, CUDA): keys[i, s] =
+    sum_j int64(word_ij) * mult[s, j] (wrapping) with mult (2, words) int64 -- vqb_row_keys, one pass over the rows."""
+    if not isinstance(rows, torch.Tensor) or not rows.is_cuda:
+        raise RuntimeError("row_keys: rows must be a CUDA tensor; there is no CPU fallback")
+    if rows.element_size() != 4:
+        raise RuntimeError(f"row_keys: rows must have a 4-byte dtype, got {rows.dtype}")
+    n = rows.shape[0]
+    flat = rows.reshape(n, -1).contiguous()
+    words = flat.shape[1]
+    if mult.dtype != torch.int64 or tuple(mult.shape) != (2, words) or mult.device != rows.device or not mult.is_contiguous():
+        raise RuntimeError(f"row_keys: mult must be a contiguous (2, {words}) int64 tensor on {rows.device}")
+    lib = _lib.load()
+    with torch.cuda.device(rows.device):
+        keys = torch.empty((n, 2), dtype=torch.int64, device=rows.device)
+        rc = lib.vqb_row_keys(rows.device.index, flat.data_ptr(), n, words, mult.data_ptr(), keys.data_ptr(),
+                              torch.cuda.current_stream(rows.device).cuda_stream)
+    _lib.check(rc, "vqb_row_keys")
+    return keys
+
+
+def dedupe_first(keys: torch.Tensor) -> torch.Tensor:
+    """(n,) int64: for every row the smallest row index with the same (n, 2) int64 key pair (CUDA) -- vqb_dedupe_first."""
+    if not isinstance(keys, torch.Tensor) or not keys.is_cuda or keys.dtype != torch.int64 or keys.dim() != 2 or keys.shape[1] != 2:
+        raise RuntimeError("dedupe_first: keys must be an (n, 2) int64 CUDA tensor; there is no CPU fallback")
+    keys = keys.contiguous()
+    n = keys.shape[0]
+    lib = _lib.load()
+    with torch.cuda.device(keys.device):
+        nbytes = int(lib.vqb_dedupe_scratch_bytes(n))
+        scratch = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=keys.device)
+        first = torch.empty(n, dtype=torch.int64, device=keys.device)
+        rc = lib.vqb_dedupe_first(keys.device.index, keys.data_ptr(), n, scratch.data_ptr(), scratch.numel() * 8,
+                                  first.data_ptr(), torch.cuda.current_stream(keys.device).cuda_stream)
+    _lib.check(rc, "vqb_dedupe_first")
+    return first
+
+
 def one_hot(indices: torch.Tensor, k: int) -> torch.Tensor:
     """(N, k) fp32 one-hot of (N, 1) int64 indices (model/vector_quantizer.py:98-100)."""
     if not isinstance(indices, torch.Tensor) or indices.dtype != torch.int64:
