@@ -257,6 +257,48 @@ def default_model(torch, vqb200, dev):
                              learning_rate=1e-3, dropout_p=0.1, patch_size=25, batch_norm=False).to(dev).eval()
 
 
+def overlapping_windows_leg(torch, enc, model, n_cycles: int = 50_000, seq_len: int = 20, batch: int = 512):
+    """The reference's data-set geometry: windows of 20 cycles with a stride of ONE cycle over a stream of cycles
+    (dataloader/asimow_dataloader.py:185-206), loader batches of 512 windows (pageable: strided views of the host stream).
+    Patches are counted the way the reference produces them (every cycle of every window).  Rank 0 only (the staging copies
+    of pageable batches use every host thread)."""
+    import numpy as np
+    T = int(model.enc_out_len)
+    stream = torch.randn(n_cycles * 200, 2, generator=torch.Generator().manual_seed(7))
+    n_windows = n_cycles - seq_len + 1
+    windows = stream.as_strided((n_windows, seq_len * 200, 2), (200 * 2, 2, 1))
+    loader = [windows[i:i + batch] for i in range(0, n_windows, batch)]
+    res, ref = {"cycles": n_cycles, "windows": n_windows, "loader_batches": len(loader), "unit": UNIT}, None
+
+    def best_of(fn, reps=3):
+        best, val = None, None
+        for rep in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            val = fn()
+            dt = time.perf_counter() - t0
+            best = dt if best is None or (rep and dt < best) else best
+        return best, val
+
+    keep = enc.dedupe
+    for name, mode in (("every_window_encoded", False), ("dedupe_per_call", True), ("dedupe_per_data_set", "dataset")):
+        enc.dedupe = mode
+        sec, (ids, _) = best_of(lambda: enc.create_latent_space_dataset_VQ_VAE_IDs(loader, seq_len=seq_len, has_patch_embed=True,
+                                                                                  no_labels=True))
+        ref = ids if ref is None else ref
+        res[name] = {"value": n_windows * seq_len * T / sec, "ms": sec * 1e3, "ids_equal": bool(np.array_equal(ids, ref))}
+    enc.dedupe = keep
+    sec, (ids, _) = best_of(lambda: enc.create_latent_space_dataset_from_cycles(stream.view(n_cycles, 200, 2), None, seq_len=seq_len,
+                                                                                has_patch_embed=True))
+    res["from_cycle_stream"] = {"value": ids.shape[0] * seq_len * T / sec, "ms": sec * 1e3, "windows": int(ids.shape[0]),
+                                "ids_equal": bool(np.array_equal(ids, ref[: ids.shape[0]]))}
+    res["what"] = ("create_latent_space_dataset_VQ_VAE_IDs over the windows with dedupe off / True / 'dataset' (vqb_row_keys + "
+                   "vqb_dedupe_first: every distinct cycle of a call / of the data set encoded once), and "
+                   "create_latent_space_dataset_from_cycles on the stream itself (every cycle encoded once, windows as a sliding "
+                   "view of the ids; the reference's create_sequence_ds keeps n - seq_len windows); wall clock, best of 2 after a warm-up")
+    return res
+
+
 def bulk_e2e_leg(torch, dist, enc, model, dev, rank, world, barrier, resident_ms_per_cycle):
     """configs[2] end to end through the reference-facing call: loader batches of windows in PINNED HOST memory ->
     LatentSpaceEncoder.create_latent_space_dataset_VQ_VAE_IDs -> the int64 ids as ONE numpy array on the host.  The timed
@@ -300,6 +342,8 @@ def bulk_e2e_leg(torch, dist, enc, model, dev, rank, world, barrier, resident_ms
                      "h2d_bytes_per_data_set": cycles * 200 * 2 * 4, "d2h_bytes_per_data_set": cycles * T * 8,
                      "frac_of_resident_rate": resident_ms_per_cycle * 1e-3 * cycles / sec}
         del hosts, loader, ids
+    if rank == 0:
+        out["overlapping_windows"] = overlapping_windows_leg(torch, enc, model)
     out["what"] = ("wall clock around LatentSpaceEncoder.create_latent_space_dataset_VQ_VAE_IDs(loader, no_labels=True): host batches "
                    "in, one int64 numpy array out; H2D of batch i + 1 on a copy stream under the encode of batch i, ids back "
                    "through pinned buffers on a second copy stream; best of 2 timed passes after one warm-up, max over ranks")

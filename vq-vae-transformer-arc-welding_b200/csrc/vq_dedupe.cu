@@ -17,8 +17,6 @@
 
 namespace vqb {
 
-namespace {
-
 constexpr unsigned long long kEmpty = 0xFFFFFFFFFFFFFFFFull;        // what cudaMemset(0xFF) leaves in the key column
 
 __device__ __forceinline__ unsigned long long table_key(unsigned long long k) { return k == kEmpty ? kEmpty - 1 : k; }
@@ -97,8 +95,6 @@ __global__ void __launch_bounds__(256) vq_dedupe_resolve_kernel(const unsigned l
         first[i] = keys[2 * (int64_t)r + 1] == keys[2 * i + 1] ? (int64_t)r : i;
     }
 }
-
-}  // namespace
 
 cudaError_t launch_row_keys(const void *rows, int64_t n, int words, const unsigned long long *mult, unsigned long long *keys,
                             int sm_count, cudaStream_t st)
