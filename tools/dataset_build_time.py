@@ -25,7 +25,10 @@ stream = torch.randn(n_cycles * 200, 2, generator=torch.Generator().manual_seed(
 n_windows = n_cycles - SEQ + 1
 windows = stream.as_strided((n_windows, SEQ * 200, 2), (200 * 2, 2, 1))
 loader = [windows[i:i + BATCH] for i in range(0, n_windows, BATCH)]
-out, ref = {"group_cycles": enc.group_cycles, "n_cycles": n_cycles, "n_windows": n_windows, "batches": len(loader)}, None
+if os.environ.get("SHUFFLE") == "1":       # the reference's train loader is shuffled (dataloader/asimow_dataloader.py:141-142)
+    perm = torch.randperm(n_windows, generator=torch.Generator().manual_seed(2))
+    loader = [windows[perm[i:i + BATCH]] for i in range(0, n_windows, BATCH)]      # materialised, contiguous, pageable
+out, ref = {"shuffled": os.environ.get("SHUFFLE") == "1", "group_cycles": enc.group_cycles, "n_cycles": n_cycles, "n_windows": n_windows, "batches": len(loader)}, None
 for mode in (False, True, "dataset"):
     enc.dedupe = mode
     best = None
@@ -39,6 +42,8 @@ for mode in (False, True, "dataset"):
         ref = ids
     out[str(mode)] = {"ms": best * 1e3, "windows_per_s": n_windows / best, "patches_per_s": n_windows * SEQ * 16 / best,
                       "ms_per_batch": best * 1e3 / len(loader), "ids_equal_to_plain": bool(np.array_equal(ids, ref))}
+if os.environ.get("SHUFFLE") == "1":
+    print(json.dumps(out)); sys.exit(0)
 # the same data set from the cycle stream: every cycle encoded once, windows as a sliding view of the ids (the reference's
 # create_sequence_ds keeps n - seq_len windows: the last window of the loader above is not part of it)
 cycles = stream.view(n_cycles, 200, 2)
