@@ -271,7 +271,7 @@ int vqb_ar_pairs(int device, const int64_t *ids, int64_t n_windows, int n_tokens
 
 /* De-duplicating data-set builder (the reference encodes every cycle of every overlapping
  * window, dataloader/latentspace_dataloader.py:225-238 over dataloader/asimow_dataloader.py:185-206).
- * vqb_row_keys: two 64-bit fingerprints per row of `words` 32-bit words: keys[2 i + s] = sum_j int64(rows[i][j]) *
+ * vqb_row_keys: two 64-bit fingerprints per row of `words` 32-bit words: keys[2 i + s] = sum_j uint32(rows[i][j]) *
  * mult[s * words + j] (mod 2^64; mult = 2 x words multipliers).  One pass over the rows.
  * vqb_dedupe_first: first[i] = the smallest row index whose two keys equal row i's (i itself if it is the first; also i
  * itself in the 2^-64 case of a row that shares key 0, but not key 1, with an earlier row) -- deterministic.  scratch: vqb_dedupe_scratch_bytes(n)

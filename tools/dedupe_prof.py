@@ -47,3 +47,24 @@ for name, fn in (("prefetch only", only_prefetch), ("+ dedupe_rows", prefetch_de
                  ("+ encode + scatter", prefetch_dedupe_encode), ("encode 531 cycles alone", encode_small),
                  ("encode 10240 cycles alone", encode_big)):
     print(f"{name:44s} {wall(fn):.3f} ms per batch")
+
+# the kernels alone (CUDA events, 65536 cycles = 105 MB: larger than... no, smaller than L2 -- so two buffers alternate)
+from vqb200 import ops
+rows = [torch.randn(65536 * 4, 400, device=dev) for _ in range(2)]        # 2 x 419 MB: larger than L2
+mult = L._hash_weight_pair(400, torch.device(dev))
+def ev_time(fn, reps=10):
+    for i in range(3): fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps): fn(i)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+ms = ev_time(lambda i: ops.row_keys(rows[i & 1], mult))
+nbytes = rows[0].numel() * 4
+print(f"vqb_row_keys      {rows[0].shape[0]} rows x 1600 B: {ms:.4f} ms = {nbytes / ms / 1e6:.0f} GB/s")
+keys = ops.row_keys(rows[0], mult)
+dup = keys[torch.randint(0, 20000, (keys.shape[0],), device=dev)].contiguous()        # ~13 rows per distinct key
+for name, k in (("all distinct", keys), ("20000 distinct", dup)):
+    ms = ev_time(lambda i: ops.dedupe_first(k))
+    print(f"vqb_dedupe_first  {k.shape[0]} keys, {name}: {ms:.4f} ms = {k.shape[0] / ms / 1e3:.0f} M rows/s")

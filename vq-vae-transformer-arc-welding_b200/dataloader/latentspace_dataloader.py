@@ -84,15 +84,15 @@ def _hash_weight_pair(width: int, device) -> torch.Tensor:
 
 
 def cycle_fingerprints(rows: torch.Tensor) -> torch.Tensor:
-    """(n, ...) float32 -> (n, 2) int64: two multiplicative hashes of the rows' bit patterns, key_s = sum_j int64(word_j) *
-    w_s[j] (wrapping).  CUDA rows: one pass of vqb_row_keys (the rows are read once); CPU rows (host-logic tests): the
+    """(n, ...) float32 -> (n, 2) int64: two multiplicative hashes of the rows' bit patterns, key_s = sum_j uint32(word_j) *
+    w_s[j] (wrapping; the 32-bit words zero-extended).  CUDA rows: one pass of vqb_row_keys (the rows are read once); CPU rows (host-logic tests): the
     same sums as torch ops."""
     n = rows.shape[0]
     if rows.is_cuda:
         from .. import ops
         bits = rows.reshape(n, -1)
         return ops.row_keys(bits, _hash_weight_pair(bits.shape[1], rows.device))
-    wide = rows.reshape(n, -1).contiguous().view(torch.int32).to(torch.int64)
+    wide = rows.reshape(n, -1).contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
     return torch.stack([(wide * _hash_weights(wide.shape[1], rows.device, s)).sum(dim=1) for s in _HASH_SEEDS], dim=1)
 
 

@@ -263,7 +263,7 @@ def ar_pairs(ids: torch.Tensor, start_token: int, end_token: int):
 
 def row_keys(rows: torch.Tensor, mult: torch.Tensor) -> torch.Tensor:
     """(n, 2) int64 fingerprints of the bit patterns of `rows` ((n, ...) of a 4-byte dtype, CUDA): keys[i, s] =
-    sum_j int64(word_ij) * mult[s, j] (wrapping) with mult (2, words) int64 -- vqb_row_keys, one pass over the rows."""
+    sum_j uint32(word_ij) * mult[s, j] (wrapping, words zero-extended) with mult (2, words) int64 -- vqb_row_keys, one pass over the rows."""
     if not isinstance(rows, torch.Tensor) or not rows.is_cuda:
         raise RuntimeError("row_keys: rows must be a CUDA tensor; there is no CPU fallback")
     if rows.element_size() != 4:
