@@ -21,7 +21,8 @@ on this box's host cores (oracle port, bounded sample).
 Further objects on the same line (each measured in this run, none part of `value`): `bulk_encode` = BASELINE
 configs[2], bulk latent-dataset encoding through LatentSpaceEncoder (synthetic cycles in, ids out, fused encoder chain
 + fused quantiser) with its tensor-roofline fraction, id match against the fp32 encoder and the reference's loop on
-host cores; `config1_forward` = BASELINE configs[0], the whole VQVAEPatch.forward at batch 256 on the GPU next to the
+host cores, and `bulk_encode.e2e`: the same workload through create_latent_space_dataset_VQ_VAE_IDs from loader batches in
+host memory to the ids on the host (+ at N = 1 the reference's overlapping-window geometry, de-duplicated and not); `config1_forward` = BASELINE configs[0], the whole VQVAEPatch.forward at batch 256 on the GPU next to the
 reference's op sequence on host cores; `backward` = the straight-through backward call.
 
 --impl reference times that CPU port alone (the reference is a Python/PyTorch program whose
@@ -260,8 +261,8 @@ def default_model(torch, vqb200, dev):
 def overlapping_windows_leg(torch, enc, model, n_cycles: int = 50_000, seq_len: int = 20, batch: int = 512):
     """The reference's data-set geometry: windows of 20 cycles with a stride of ONE cycle over a stream of cycles
     (dataloader/asimow_dataloader.py:185-206), loader batches of 512 windows (pageable: strided views of the host stream).
-    Patches are counted the way the reference produces them (every cycle of every window).  Rank 0 only (the staging copies
-    of pageable batches use every host thread)."""
+    Patches are counted the way the reference produces them (every cycle of every window).  Single-GPU runs only (the
+    staging copies of pageable batches use every host thread)."""
     import numpy as np
     T = int(model.enc_out_len)
     stream = torch.randn(n_cycles * 200, 2, generator=torch.Generator().manual_seed(7))
@@ -342,7 +343,7 @@ def bulk_e2e_leg(torch, dist, enc, model, dev, rank, world, barrier, resident_ms
                      "h2d_bytes_per_data_set": cycles * 200 * 2 * 4, "d2h_bytes_per_data_set": cycles * T * 8,
                      "frac_of_resident_rate": resident_ms_per_cycle * 1e-3 * cycles / sec}
         del hosts, loader, ids
-    if rank == 0:
+    if world == 1:        # (pageable loader batches: their staging copies use every host thread, torchrun gives a rank one)
         out["overlapping_windows"] = overlapping_windows_leg(torch, enc, model)
     out["what"] = ("wall clock around LatentSpaceEncoder.create_latent_space_dataset_VQ_VAE_IDs(loader, no_labels=True): host batches "
                    "in, one int64 numpy array out; H2D of batch i + 1 on a copy stream under the encode of batch i, ids back "
