@@ -347,3 +347,17 @@ def test_row_keys_and_dedupe_kernels_against_the_host_formulas(monkeypatch):
     rep, inv = L.dedupe_rows(small.to(DEV))
     assert torch.equal(small.to(DEV)[rep[inv]], small.to(DEV)) and rep.numel() == 63      # only row 50 == row 0 is found
     L._weight_cache.clear()
+
+
+def test_forward_without_the_one_hot_is_the_same_call():
+    """VectorQuantizer.forward(z, need_one_hot=False) -- what VQVAEPatch.forward uses, the reference drops min_encodings
+    there (model/vq_vae_patch_embedd.py:161) -- returns the same loss, z_q, perplexity and ids, and None for the one-hot."""
+    torch.manual_seed(3)
+    vq = vqb200.VectorQuantizer(64, 16, 0.25).to(DEV)
+    z = torch.randn(7, 16, 16, device=DEV) * 0.02
+    full = vq(z)
+    lean = vq(z, need_one_hot=False)
+    assert lean[3] is None and full[3].shape == (7 * 16, 64)
+    for a, b in zip((full[0], full[1], full[2], full[4]), (lean[0], lean[1], lean[2], lean[4])):
+        assert torch.equal(a, b)
+    assert vqb200.VectorQuantizer(64, 16, 0.25, one_hot="none").to(DEV)(z, need_one_hot=True)[3].shape == (7 * 16, 64)

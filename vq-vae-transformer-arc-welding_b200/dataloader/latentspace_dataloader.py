@@ -96,18 +96,19 @@ def cycle_fingerprints(rows: torch.Tensor) -> torch.Tensor:
     return torch.stack([(wide * _hash_weights(wide.shape[1], rows.device, s)).sum(dim=1) for s in _HASH_SEEDS], dim=1)
 
 
-def dedupe_rows(rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def dedupe_rows(rows: torch.Tensor, return_keys: bool = False):
     """rows (n, ...) float32 -> (rep, inverse): rep (u,) int64 indices of one representative per group of bit-identical
     rows (the first occurrence), inverse (n,) int64 with rows[i] bit-identical to rows[rep[inverse[i]]].  Rows that a
     hash collision put into a foreign group come back as their own representatives.
 
     CUDA rows: fingerprints (vqb_row_keys) -> first row with the same fingerprints (vqb_dedupe_first: a hash table in
     device memory) -> word-for-word check against that row -> representatives in ascending row order; ONE host
-    synchronisation (the number of representatives).  CPU rows (host-logic tests): the same grouping with torch.unique."""
+    synchronisation (the number of representatives).  CPU rows (host-logic tests): the same grouping with torch.unique.
+    return_keys: also the (n, 2) fingerprints of all rows (the data-set cache keys its entries by them)."""
     n = rows.shape[0]
     if n == 0:
         e = torch.empty(0, dtype=torch.int64, device=rows.device)
-        return e, e
+        return (e, e, torch.empty((0, 2), dtype=torch.int64, device=rows.device)) if return_keys else (e, e)
     bits = rows.reshape(n, -1).contiguous().view(torch.int32)
     keys = cycle_fingerprints(rows)
     ar = torch.arange(n, device=rows.device)
@@ -123,7 +124,7 @@ def dedupe_rows(rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     is_rep = first == ar
     rank = torch.cumsum(is_rep, dim=0) - 1                    # position of a representative among the representatives
     rep = is_rep.nonzero().view(-1)                           # ascending row order (the one synchronisation)
-    return rep, rank[first]
+    return (rep, rank[first], keys) if return_keys else (rep, rank[first])
 
 
 def encode_unique(encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: torch.Tensor, pre=None) -> torch.Tensor:
@@ -168,7 +169,7 @@ class CycleIdCache:
         pos = torch.searchsorted(self.k1, keys[:, 0].contiguous()).clamp_(max=m - 1)
         hit = (self.k1[pos] == keys[:, 0]) & (self.k2[pos] == keys[:, 1])
         rows = self.slot[pos]
-        if self.reps is not None and bool(hit.any()):
+        if self.reps is not None:
             bits = cycles.reshape(n, -1).contiguous().view(torch.int32)
             hit &= (self.reps[rows] == bits).all(dim=1)                      # word-for-word check
         out[hit] = rows[hit]
@@ -196,10 +197,10 @@ class CycleIdCache:
 
     def encode(self, encode_fn: Callable[[torch.Tensor], torch.Tensor], cycles: torch.Tensor, pre=None) -> torch.Tensor:
         """ids of `cycles` ((n, ...) -> (n, T)): distinct cycles of the batch first (word for word), then the cache,
-        then the encoder for what is left.  pre: dedupe_rows(cycles) if the caller has it already."""
-        rep, inverse = dedupe_rows(cycles) if pre is None else pre
+        then the encoder for what is left.  pre: dedupe_rows(cycles, return_keys=True) if the caller has it already."""
+        rep, inverse, all_keys = dedupe_rows(cycles, return_keys=True) if pre is None else pre
         uniq = cycles[rep]
-        keys = cycle_fingerprints(uniq)
+        keys = all_keys[rep]
         rows = self.lookup(uniq, keys)
         new = (rows < 0).nonzero().view(-1)
         self.hits += int(cycles.shape[0] - new.numel())

@@ -47,16 +47,20 @@ class VectorQuantizer(LightningModule):
         # dict keeps its single key `embedding.weight` and DDP has no extra buffer to broadcast
         self.code_counts = None
 
-    def forward(self, z):
+    def forward(self, z, need_one_hot=None):
         """z: fp32 CUDA tensor whose trailing elements group into vectors of ``e_dim``
         (any shape, may be a non-contiguous view; read in place).
 
         Returns (loss, z_q, perplexity, min_encodings, min_encoding_indices), :119.
+        need_one_hot: False = return None for min_encodings in this call whatever ``one_hot`` says (a caller that
+        drops it, like VQVAEPatch.forward -- model/vq_vae_patch_embedd.py:161 --, saves the 4 * n_e bytes per vector
+        of its write); None = as configured.
         """
         loss, z_q, perplexity, indices, counts = ops.VQStraightThrough.apply(
             z, self.embedding.weight, self.beta, self.path)
         self.code_counts = counts
-        min_encodings = ops.one_hot(indices, self.n_e) if self.one_hot == "dense" else None
+        dense = self.one_hot == "dense" if need_one_hot is None else bool(need_one_hot)
+        min_encodings = ops.one_hot(indices, self.n_e) if dense else None
         return loss, z_q, perplexity, min_encodings, indices
 
     def encode_indices(self, z):

@@ -574,6 +574,8 @@ class VQVAEPatch(Autoencoder):
 
     def forward(self, x):
         z_e = self.encode(x)
-        embedding_loss, z_q, perplexity, _, _ = self.vector_quantization(z_e)
+        vq = self.vector_quantization
+        # (the (N, n_e) one-hot is dropped here, :161 of the reference: the fused quantiser does not write it)
+        embedding_loss, z_q, perplexity, _, _ = vq(z_e, need_one_hot=False) if isinstance(vq, VectorQuantizer) else vq(z_e)
         x_hat = self.decode(z_q)
         return embedding_loss, x_hat, perplexity
