@@ -90,3 +90,41 @@ def test_ddp_step_equals_single_gpu_on_the_concatenated_batch(tmp_path, patch_go
         assert float(r["g_loss"]) == pytest.approx(float(emb_loss), rel=1e-5)
         assert float(r["g_ppl"]) == pytest.approx(float(ppl), rel=1e-5)
     assert 0.5 * (float(r0["loss"]) + float(r1["loss"])) == pytest.approx(float(loss), rel=1e-5)
+
+
+def _stream_worker(rank, world, port, patch_sd, case, stream, labels, seq_len, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from vqb200.dataloader import LatentSpaceEncoder
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        enc = LatentSpaceEncoder(_build(patch_sd, case, dev), window_size=200, device=str(dev), encoder_mode="torch")
+        ids, y = enc.create_latent_space_dataset_from_cycles(stream, labels, seq_len=seq_len, has_patch_embed=True, batch=4,
+                                                             shard=True)
+        np.savez(os.path.join(out_dir, f"s{rank}.npz"), ids=ids, y=y)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_data_set_from_the_cycle_stream_matches_the_reference_fixture(tmp_path, patch_golden, bulk_golden):
+    """Bulk latent-dataset building batch-sharded over two GPUs (north star: codebook and encoder replicated, every rank
+    encodes its shard of the cycles, the ids are all-gathered over NCCL): both ranks hold the arrays the unmodified
+    reference built from its own windows (tests/golden: bulk_overlap/seq_*)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    case = C.BULK_CASE
+    mcase = next(c for c in C.PATCH_CASES if c["name"] == case["model"])
+    pre = f"{mcase['name']}/sd/"
+    sd = {k[len(pre):]: torch.from_numpy(patch_golden[k]) for k in patch_golden.files if k.startswith(pre)}
+    stream, cycle_labels = C.make_stream(case)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_stream_worker, args=(2, port, sd, mcase, stream, cycle_labels, case["seq_len"], str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        got = np.load(os.path.join(tmp_path, f"s{r}.npz"))
+        assert np.array_equal(got["ids"], bulk_golden[f"{case['name']}/seq_ids"])
+        assert np.array_equal(got["y"], bulk_golden[f"{case['name']}/seq_labels"])

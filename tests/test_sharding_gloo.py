@@ -86,6 +86,48 @@ def test_two_rank_bulk_encode_equals_single_process(tmp_path, n):
         assert abs(float(r["g_ppl"]) - float(want_ppl)) < 1e-5
 
 
+def _stream_worker(rank, world, port, n, seq_len, out_dir):
+    """create_latent_space_dataset_from_cycles(shard=True) on two gloo ranks with a stand-in per-cycle encoder."""
+    import types
+    import numpy as np
+    from vqb200.dataloader import LatentSpaceEncoder
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class Stub(torch.nn.Module):
+            enc_out_len, embedding_dim = 4, 2
+            vector_quantization = types.SimpleNamespace(code_counts=None)
+        enc = LatentSpaceEncoder(Stub(), window_size=8, device="cpu", encoder_mode=None)
+        seen = []
+        enc.get_latent_space_IDs = lambda x, p=False: (seen.append(x.shape[0]), _fake_encode(x).view(-1, 1))[1]
+        cycles = torch.randn(n, 8, 2, generator=torch.Generator().manual_seed(5))
+        y = np.arange(n, dtype=np.float64)
+        ids, labels = enc.create_latent_space_dataset_from_cycles(cycles, y, seq_len=seq_len, batch=5, shard=True)
+        torch.save(dict(ids=torch.from_numpy(ids), labels=torch.from_numpy(labels), encoded=sum(seen)),
+                   os.path.join(out_dir, f"s{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,seq_len", [(23, 4), (9, 1), (1, 1), (3, 4)])
+def test_two_rank_data_set_from_the_cycle_stream(tmp_path, n, seq_len):
+    """Every rank encodes its shard of the cycles once, the per-cycle ids are all-gathered, and both ranks hold the windows
+    a single process builds (n - seq_len windows, window i = cycles i .. i + seq_len - 1, label y[i + seq_len])."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_stream_worker, args=(2, port, n, seq_len, str(tmp_path)), nprocs=2, join=True)
+    cycles = torch.randn(n, 8, 2, generator=torch.Generator().manual_seed(5))
+    per_cycle = _fake_encode(cycles)
+    n_windows = n if seq_len == 1 else max(n - seq_len, 0)
+    want = torch.stack([per_cycle[i:i + seq_len] for i in range(n_windows)]) if n_windows else torch.empty(0, seq_len, 4, dtype=torch.int64)
+    r0, r1 = (torch.load(os.path.join(tmp_path, f"s{r}.pt")) for r in range(2))
+    for r in (r0, r1):
+        assert tuple(r["ids"].shape) == (n_windows, seq_len, 4) and torch.equal(r["ids"], want)
+        assert torch.equal(r["labels"], torch.arange(n, dtype=torch.float64)[(seq_len if seq_len > 1 else 0):][:n_windows])
+    assert r0["encoded"] + r1["encoded"] == n and abs(r0["encoded"] - r1["encoded"]) <= 1      # each cycle once, on one rank
+
+
 def test_single_process_paths():
     cycles = torch.randn(10, 8, 2)
     ids = bulk_encode_ids(_fake_encode, cycles, batch=3)

@@ -604,7 +604,7 @@ class LatentSpaceEncoder:
 
     # ---- the same data sets from the CYCLE STREAM ---------------------------------
     def create_latent_space_dataset_from_cycles(self, cycles, labels=None, seq_len: int = 1, has_patch_embed: bool = False,
-                                                kind: str = "ids", batch: int = 65536):
+                                                kind: str = "ids", batch: int = 65536, shard: bool = False):
         """The arrays the loops above build from the reference's windows, built from the cycles the windows are made of.
 
         The reference slides a window of `seq_len` cycles with a stride of ONE cycle over the (n, window, C) cycle array
@@ -622,6 +622,9 @@ class LatentSpaceEncoder:
         kind:   "ids"      -> (n_windows, seq_len, enc_out_len) int64           (create_latent_space_dataset_VQ_VAE_IDs)
                 "ar_ids"   -> (n_windows, seq_len * enc_out_len) int64          (..._VQ_VAE_autoreggressive)
                 "latents"  -> (n_windows, seq_len, embedding_dim * enc_out_len) float64   (create_latent_space_dataset_VQ_VAE)
+        shard:  with an initialised process group of several ranks (one process per GPU), every rank encodes its
+                contiguous shard of the cycles (shard_range) and the per-cycle results are all-gathered -- 128 bytes per
+                cycle for the ids -- so that every rank returns the whole data set; no other collective
         Returns (array, labels (n_windows,) float64)."""
         if kind not in ("ids", "ar_ids", "latents"):
             raise ValueError(f"kind must be 'ids', 'ar_ids' or 'latents', got {kind!r}")
@@ -642,7 +645,11 @@ class LatentSpaceEncoder:
             if y.shape != (n,):
                 raise ValueError(f"labels must be ({n},), got {y.shape}")
             new_y = y.copy() if seq_len == 1 else y[seq_len:].copy()
-        loader = [cycles[s: s + batch] for s in range(0, n, batch)]
+        model = self.latent_space_model
+        width = int(model.enc_out_len) * (int(model.embedding_dim) if kind == "latents" else 1)
+        sharded = shard and _dist_ready()
+        lo, hi = shard_range(n, dist.get_rank(), dist.get_world_size()) if sharded else (0, n)
+        loader = [cycles[s: min(s + batch, hi)] for s in range(lo, hi, batch)]
         keep, self.group_cycles = self.group_cycles, batch         # one encoder call per `batch` cycles
         try:
             if kind == "latents":
@@ -653,7 +660,9 @@ class LatentSpaceEncoder:
                                                                            no_labels=True)
         finally:
             self.group_cycles = keep
-        per_cycle = per_cycle.reshape(n, -1)                       # (n, T) ids or (n, D * T) latents
+        per_cycle = per_cycle.reshape(hi - lo, width)              # (n, T) ids or (n, D * T) latents
+        if sharded:
+            per_cycle = gather_sharded(torch.from_numpy(np.ascontiguousarray(per_cycle)).to(self.device), n).cpu().numpy()
         if seq_len == 1:
             new_x = per_cycle.reshape(n, 1, -1)
         elif n_windows == 0:
