@@ -2,8 +2,9 @@
 synthetic welding cycles randn(n, 200, 2) generated on the device in 65536-cycle chunks, random-init
 VQ-VAE-Patch (repo defaults, seed 0), ids out (what the id tasks keep).  Reports patches/s for the encode call
 (patchify + encoder + fused VQ) per encoder precision, the share of the fused VQ kernel, and the index match
-rate against the fp32 ('highest') encoder on the first chunk.  The encoder is stock PyTorch GEMMs (SURVEY.md
-section 8(f) row 1 is the fused token-MLP that would replace it); the quantiser is the tcgen05 kernel.
+rate against the fp32 ('highest') encoder on the first chunk.  Modes: the stock PyTorch layers in fp32 / TF32 / bf16
+autocast (round 1's baseline rows) and `fused_bf16` = the one-launch tcgen05 encoder chain (SURVEY.md section 8(f) row 1);
+the quantiser is the tcgen05 kernel in all of them.  `bench.py`'s `bulk_encode` object is the figure of record.
 
     python tools/bulk_encode.py [n_cycles]            (torchrun: every rank encodes its own n_cycles)"""
 import json, os, sys, time
