@@ -28,7 +28,9 @@ loader = [windows[i:i + BATCH] for i in range(0, n_windows, BATCH)]
 if os.environ.get("SHUFFLE") == "1":       # the reference's train loader is shuffled (dataloader/asimow_dataloader.py:141-142)
     perm = torch.randperm(n_windows, generator=torch.Generator().manual_seed(2))
     loader = [windows[perm[i:i + BATCH]] for i in range(0, n_windows, BATCH)]      # materialised, contiguous, pageable
-out, ref = {"shuffled": os.environ.get("SHUFFLE") == "1", "group_cycles": enc.group_cycles, "n_cycles": n_cycles, "n_windows": n_windows, "batches": len(loader)}, None
+if os.environ.get("PINNED") == "1":        # what DataLoader(pin_memory=True) hands over: contiguous pinned batches, no staging copy
+    loader = [b.contiguous().pin_memory() for b in loader]
+out, ref = {"pinned": os.environ.get("PINNED") == "1", "shuffled": os.environ.get("SHUFFLE") == "1", "group_cycles": enc.group_cycles, "n_cycles": n_cycles, "n_windows": n_windows, "batches": len(loader)}, None
 for mode in (False, True, "dataset"):
     enc.dedupe = mode
     best = None
