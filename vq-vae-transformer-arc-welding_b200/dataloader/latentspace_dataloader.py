@@ -310,6 +310,8 @@ class _DevicePrefetcher:
     def __init__(self, loader: Iterable, device, seq_len: int, window_size: int, no_labels: bool = False,
                  group_cycles: int = 65536):
         self.loader, self.device = loader, torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:      # "cuda": the caller's current device, by number
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.seq_len, self.window = seq_len, window_size
         self.no_labels = no_labels
         self.group_cycles = max(int(group_cycles), 1)
