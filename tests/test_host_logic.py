@@ -330,6 +330,9 @@ def test_data_set_from_cycle_stream_windows_like_create_sequence_ds():
     loop_ids, _ = enc.create_latent_space_dataset_VQ_VAE_IDs([torch.from_numpy(win[i:i + 6]) for i in range(0, len(win), 6)],
                                                              seq_len=seq_len, has_patch_embed=True, no_labels=True)
     assert np.array_equal(loop_ids, ids)
+    view, _ = enc.create_latent_space_dataset_from_cycles(cycles, y, seq_len=seq_len, has_patch_embed=True, materialize=False)
+    assert view.shape == ids.shape and np.array_equal(view, ids) and not view.flags["OWNDATA"] and not view.flags["WRITEABLE"]
+    assert np.array_equal(view[7], ids[7]) and np.array_equal(view[[1, 5, 2]], ids[[1, 5, 2]])      # what a Dataset does with it
     flat, zeros = enc.create_latent_space_dataset_from_cycles(cycles, None, seq_len=seq_len, kind="ar_ids")
     assert np.array_equal(flat, ids.reshape(n - seq_len, -1)) and np.array_equal(zeros, np.zeros(n - seq_len))
     one, y1 = enc.create_latent_space_dataset_from_cycles(cycles, y, seq_len=1)

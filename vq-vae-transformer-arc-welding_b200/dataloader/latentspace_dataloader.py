@@ -606,7 +606,8 @@ class LatentSpaceEncoder:
 
     # ---- the same data sets from the CYCLE STREAM ---------------------------------
     def create_latent_space_dataset_from_cycles(self, cycles, labels=None, seq_len: int = 1, has_patch_embed: bool = False,
-                                                kind: str = "ids", batch: int = 65536, shard: bool = False):
+                                                kind: str = "ids", batch: int = 65536, shard: bool = False,
+                                                materialize: bool = True):
         """The arrays the loops above build from the reference's windows, built from the cycles the windows are made of.
 
         The reference slides a window of `seq_len` cycles with a stride of ONE cycle over the (n, window, C) cycle array
@@ -627,6 +628,9 @@ class LatentSpaceEncoder:
         shard:  with an initialised process group of several ranks (one process per GPU), every rank encodes its
                 contiguous shard of the cycles (shard_range) and the per-cycle results are all-gathered -- 128 bytes per
                 cycle for the ids -- so that every rank returns the whole data set; no other collective
+        materialize: False returns the windows as a read-only sliding VIEW of the per-cycle array (same shape and values,
+                no seq_len-fold copy: the reference's Dataset classes only index it, dataloader/base_dataloader.py:14-72);
+                "ar_ids" flattens the windows and is always materialised
         Returns (array, labels (n_windows,) float64)."""
         if kind not in ("ids", "ar_ids", "latents"):
             raise ValueError(f"kind must be 'ids', 'ar_ids' or 'latents', got {kind!r}")
@@ -672,8 +676,11 @@ class LatentSpaceEncoder:
         else:
             # (n - seq_len + 1, width, seq_len) sliding view -> the windows as their own array, seq_len x the per-cycle
             # result (what the reference's format asks for); torch's strided copy runs on all host threads
-            view = torch.from_numpy(np.ascontiguousarray(per_cycle)).unfold(0, seq_len, 1)
-            new_x = view[:n_windows].permute(0, 2, 1).contiguous().numpy()
+            if materialize or kind == "ar_ids":
+                view = torch.from_numpy(np.ascontiguousarray(per_cycle)).unfold(0, seq_len, 1)
+                new_x = view[:n_windows].permute(0, 2, 1).contiguous().numpy()
+            else:
+                new_x = np.lib.stride_tricks.sliding_window_view(per_cycle, seq_len, axis=0)[:n_windows].transpose(0, 2, 1)
         if kind == "ar_ids":
             new_x = new_x.reshape(new_x.shape[0], -1)
         return new_x, new_y
