@@ -243,7 +243,8 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
                            n < (1ll << 31);
         if (path == VQB_PATH_TC && !tc_ok)
             return VQB_E_UNSUPPORTED;
-        if (path == VQB_PATH_AUTO)
+        const bool was_auto = path == VQB_PATH_AUTO;
+        if (was_auto)
             path = (tc_ok && n >= 128) ? VQB_PATH_TC : VQB_PATH_FMA;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (g_profile.load()) {
@@ -263,7 +264,23 @@ int vqb_forward(int device, const float *z, int64_t n_outer, int64_t n_inner, in
             else
                 err = launch_fwd_tc_chunked(p, (float *)(ws + L.off_tc), info.sm_count, info.max_smem_per_block, &n_ctas,
                                             &launches, st, ev0, ev1);
-        } else {
+            // the launcher could not set the tcgen05 kernel up (tensor-map encode, driver entry point, shared-memory limit):
+            // nothing of it has run; a call that left the choice to the library takes the exact CUDA-core kernel instead,
+            // one that asked for the tcgen05 path is told so
+            if (err == cudaErrorNotSupported) {
+                (void)cudaGetLastError();
+                if (!was_auto) {
+                    if (ev0) {
+                        cudaEventDestroy(ev0);
+                        cudaEventDestroy(ev1);
+                    }
+                    return VQB_E_UNSUPPORTED;
+                }
+                path = VQB_PATH_FMA;
+                launches = 1;
+            }
+        }
+        if (path != VQB_PATH_TC) {
             if (ev0) cudaEventRecord(ev0, st);
             err = launch_fwd_fma(p, info.sm_count, info.max_smem_per_block, &n_ctas, st);
             if (ev1) cudaEventRecord(ev1, st);
