@@ -339,3 +339,28 @@ def test_data_set_from_cycle_stream_windows_like_create_sequence_ds():
     assert np.array_equal(one[:, 0, :], per_cycle) and np.array_equal(y1, y)
     with pytest.raises(ValueError):
         enc.create_latent_space_dataset_from_cycles(cycles[:, :4, :], y, seq_len=2)
+
+
+def test_prefetcher_groups_consecutive_loader_batches_in_order():
+    """_DevicePrefetcher (CPU path): loader batches are concatenated into groups of at most group_cycles cycles -- never split,
+    never reordered, a larger batch is a group of its own -- and the rows of a group are the cycles of its batches in order."""
+    from vqb200.dataloader import latentspace_dataloader as L
+    rs = np.random.RandomState(0)
+    sizes = [3, 7, 1, 16, 5, 2, 2, 9]
+    seq_len, window = 2, 4
+    loader = [torch.from_numpy(rs.standard_normal((b, seq_len * window + 3, 2)).astype(np.float32)) for b in sizes]
+    want = torch.cat([x[:, : seq_len * window, :].reshape(-1, window, 2) for x in loader])
+    for group_cycles, expect in ((1, [[3], [7], [1], [16], [5], [2], [2], [9]]),
+                                 (20, [[3, 7], [1], [16], [5, 2, 2], [9]]),
+                                 (32, [[3, 7, 1], [16], [5, 2, 2], [9]]),
+                                 (10 ** 6, [sizes])):
+        got, groups = [], []
+        for cyc, items in L._DevicePrefetcher(loader, "cpu", seq_len, window, no_labels=True, group_cycles=group_cycles):
+            assert cyc.shape == (sum(int(x.shape[0]) for x in items) * seq_len, window, 2)
+            got.append(cyc)
+            groups.append([int(x.shape[0]) for x in items])
+        assert groups == expect and torch.equal(torch.cat(got), want)
+    labelled = [(x, torch.full((x.shape[0],), float(i))) for i, x in enumerate(loader)]
+    ys = [float(y[0]) for _cyc, items in L._DevicePrefetcher(labelled, "cpu", seq_len, window, group_cycles=20) for _x, y in items]
+    assert ys == [float(i) for i in range(len(sizes))]
+    assert list(L._DevicePrefetcher([], "cpu", seq_len, window, no_labels=True)) == []
