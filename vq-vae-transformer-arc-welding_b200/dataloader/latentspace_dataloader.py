@@ -150,14 +150,41 @@ class CycleIdCache:
         self.k1 = torch.empty(0, dtype=torch.int64, device=self.device)      # sorted
         self.k2 = torch.empty(0, dtype=torch.int64, device=self.device)
         self.slot = torch.empty(0, dtype=torch.int64, device=self.device)    # row of ids / reps for the sorted position
-        self.ids: Optional[torch.Tensor] = None                              # (m, T)
-        self.reps: Optional[torch.Tensor] = None                             # (m, words) int32 while they fit
+        self._ids: Optional[torch.Tensor] = None                             # (capacity, T): rows [0, m) are used
+        self._reps: Optional[torch.Tensor] = None                            # (capacity, words) int32 while they fit
+        self._keep_reps = True
         self.max_rep_bytes = max_rep_bytes
         self.hits = 0
         self.misses = 0
 
     def __len__(self) -> int:
         return int(self.k1.numel())
+
+    @property
+    def ids(self) -> Optional[torch.Tensor]:
+        """(m, T): the ids of the cached cycles."""
+        return None if self._ids is None else self._ids[: len(self)]
+
+    @property
+    def reps(self) -> Optional[torch.Tensor]:
+        """(m, words) int32: the cached cycles themselves, while they fit max_rep_bytes."""
+        return None if self._reps is None else self._reps[: len(self)]
+
+    @staticmethod
+    def _append(buf: Optional[torch.Tensor], used: int, rows: torch.Tensor, cap_rows: Optional[int] = None) -> torch.Tensor:
+        """rows appended behind buf[:used]; the buffer doubles when it is full (amortised: no copy of the whole store
+        per call), up to cap_rows."""
+        need = used + rows.shape[0]
+        if buf is None or buf.shape[0] < need:
+            cap = max(need, 2 * (0 if buf is None else buf.shape[0]), 1024)
+            if cap_rows is not None:
+                cap = max(min(cap, cap_rows), need)
+            grown = torch.empty((cap,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+            if used:
+                grown[:used] = buf[:used]
+            buf = grown
+        buf[used:need] = rows
+        return buf
 
     def lookup(self, cycles: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
         """(n,) int64: row of the cached ids for every cycle, -1 where the cycle is new."""
@@ -179,16 +206,15 @@ class CycleIdCache:
         """Remember the ids of `cycles` (distinct, not in the cache)."""
         if cycles.shape[0] == 0:
             return
-        m = 0 if self.ids is None else self.ids.shape[0]
-        self.ids = ids.clone() if self.ids is None else torch.cat([self.ids, ids], dim=0)
+        m = len(self)
+        self._ids = self._append(self._ids, m, ids)
         bits = cycles.reshape(cycles.shape[0], -1).contiguous().view(torch.int32)
-        if m == 0 and bits.numel() * 4 <= self.max_rep_bytes:
-            self.reps = bits.clone()
-        elif self.reps is not None:
-            if (self.reps.numel() + bits.numel()) * 4 <= self.max_rep_bytes:
-                self.reps = torch.cat([self.reps, bits], dim=0)
+        if self._keep_reps:
+            row_bytes = bits.shape[1] * 4
+            if (m + bits.shape[0]) * row_bytes <= self.max_rep_bytes:
+                self._reps = self._append(self._reps, m, bits, cap_rows=self.max_rep_bytes // max(row_bytes, 1))
             else:
-                self.reps = None                                             # from here on: fingerprints only
+                self._reps, self._keep_reps = None, False                    # from here on: fingerprints only
         k1 = torch.cat([self.k1, keys[:, 0]])
         order = torch.argsort(k1)
         self.k1 = k1[order]
@@ -207,7 +233,7 @@ class CycleIdCache:
         self.misses += int(new.numel())
         if new.numel():
             new_ids = encode_fn(uniq[new]).view(new.numel(), -1)
-            base = 0 if self.ids is None else self.ids.shape[0]
+            base = len(self)
             self.insert(uniq[new], keys[new], new_ids)
             rows = rows.clone()
             rows[new] = base + torch.arange(new.numel(), device=self.device)
