@@ -134,3 +134,32 @@ def test_encoder_port_reproduces_the_reference_encoder(patch_golden):
         assert np.array_equal(z.contiguous().numpy(), patch_golden[f"{case['name']}/z_e"])
         ids = O.torch_port_forward(z, sd["vector_quantization.embedding.weight"], case["beta"])[4]
         assert np.array_equal(ids.numpy().reshape(-1), patch_golden[f"{case['name']}/idx"])
+
+
+def test_port_ids_of_the_cycle_stream_window_into_the_reference_data_set(patch_golden, bulk_golden):
+    """The oracle port on the CYCLES of the bulk fixture's stream, windowed the way the reference's create_sequence_ds does
+    (dataloader/asimow_dataloader.py:185-206: n - seq_len windows, window i = cycles i .. i + seq_len - 1, label
+    y[i + seq_len]) == what the unmodified reference built from its own windows (bulk_overlap/seq_*): the property
+    create_latent_space_dataset_from_cycles rests on (every op before the decoder is per cycle), pinned on the CPU."""
+    import torch
+    import cases as C
+    from oracle import vq_oracle as O
+    case = C.BULK_CASE
+    mcase = next(c for c in C.PATCH_CASES if c["name"] == case["model"])
+    if mcase["batch_norm"]:
+        pytest.skip("the encoder port covers the models without BatchNorm")
+    pre = f"{mcase['name']}/sd/"
+    sd = {k[len(pre):]: torch.from_numpy(patch_golden[k]) for k in patch_golden.files if k.startswith(pre)}
+    stream, cycle_labels = C.make_stream(case)
+    with torch.no_grad():
+        z = O.torch_port_encode(sd, torch.from_numpy(stream), mcase["patch_size"])
+        per_cycle = O.torch_port_forward(z, sd["vector_quantization.embedding.weight"], mcase["beta"])[4].numpy().reshape(len(stream), -1)
+    seq_len = case["seq_len"]
+    want = bulk_golden[f"{case['name']}/seq_ids"]
+    n_windows = len(stream) - seq_len
+    assert want.shape == (n_windows, seq_len, per_cycle.shape[1])
+    got = np.stack([per_cycle[i:i + seq_len] for i in range(n_windows)])
+    assert np.array_equal(got, want)
+    assert np.array_equal(bulk_golden[f"{case['name']}/seq_labels"], cycle_labels[seq_len:])
+    # and the older fixture (the repo's own n - seq_len + 1 windows through the reference's loop) is the same view, one longer
+    assert np.array_equal(bulk_golden[f"{case['name']}/ids"][:n_windows], want)
