@@ -326,7 +326,8 @@ class _DevicePrefetcher:
     helper thread.  Grouping amortises the per-call host work of the encoder over several loader batches (a batch of 512
     windows x 20 cycles keeps the GPU busy for 1.5 ms, about what its launches cost the host) and lets the
     de-duplication see the overlap BETWEEN consecutive batches.  On a CPU device, or for batches that are on a GPU
-    already, it degenerates to `.to(device)` per batch.
+    already, it degenerates to `.to(device)` per batch.  (A pinned batch is read by the copy engine after the loader has
+    moved on: like any non_blocking copy this wants loaders that hand out a batch and leave it alone -- DataLoader does.)
 
     Yields (cycles_on_device (rows, window, C), items) with `items` the list of what the loader produced for the group,
     rows = sum over the items of batch size x seq_len, in loader order."""
