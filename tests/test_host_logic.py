@@ -115,7 +115,8 @@ def test_dedupe_rows_and_encode_unique():
     calls.clear()
     L.encode_unique(encode, base[[0, 1, 2]])
     assert calls == [3]
-    assert L.dedupe_rows(cycles[:0])[0].numel() == 0
+    assert L.dedupe_rows(cycles[:0])[0].numel() == 0 and tuple(L.cycle_fingerprints(cycles[:0]).shape) == (0, 2)
+    assert tuple(L.dedupe_rows(cycles[:0], return_keys=True)[2].shape) == (0, 2)
 
 
 def test_dedupe_rows_survives_hash_collisions(monkeypatch):

@@ -88,6 +88,8 @@ def cycle_fingerprints(rows: torch.Tensor) -> torch.Tensor:
     w_s[j] (wrapping; the 32-bit words zero-extended).  CUDA rows: one pass of vqb_row_keys (the rows are read once); CPU rows (host-logic tests): the
     same sums as torch ops."""
     n = rows.shape[0]
+    if n == 0:
+        return torch.empty((0, 2), dtype=torch.int64, device=rows.device)
     if rows.is_cuda:
         from .. import ops
         bits = rows.reshape(n, -1)
