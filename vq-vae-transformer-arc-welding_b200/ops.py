@@ -269,6 +269,8 @@ def row_keys(rows: torch.Tensor, mult: torch.Tensor) -> torch.Tensor:
     if rows.element_size() != 4:
         raise RuntimeError(f"row_keys: rows must have a 4-byte dtype, got {rows.dtype}")
     n = rows.shape[0]
+    if n == 0:
+        return torch.empty((0, 2), dtype=torch.int64, device=rows.device)
     flat = rows.reshape(n, -1).contiguous()
     words = flat.shape[1]
     if mult.dtype != torch.int64 or tuple(mult.shape) != (2, words) or mult.device != rows.device or not mult.is_contiguous():
